@@ -1,0 +1,217 @@
+/*
+ * b200nn.h — C ABI of libb200nn.so: the B200 (sm_100a) numeric core behind neuralnetlib's
+ * Python Layer / Optimizer / Sequential API.
+ *
+ * The upstream reference (marcpinet/neuralnetlib, pure NumPy) has no FFI; each entry point below
+ * replaces a NumPy code region of the reference's `Sequential.fit` hot path and cites it
+ * (paths relative to /root/reference/neuralnetlib/). INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every tensor is float32, row-major, images are NHWC;
+ *  - the C side never allocates or frees tensors: the caller owns every device buffer;
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *    capturable into a CUDA graph, and returns 0 on success or a negative B200NN_E* code;
+ *    the message of the last failure on the calling thread is available from b200nn_last_error;
+ *  - "lazy clip": the reference clips every error tensor to L2 norm <= 1 before every layer's
+ *    backward (models.py:214, preprocessing.py:220-224). All backward ops are linear in the
+ *    error, so producers accumulate the sum of squares of what they emit into a float64 slot
+ *    (`ss_out`, one atomicAdd per CTA) and consumers turn a *chain* of such slots into one
+ *    multiplier applied on load.  A chain is (`ss`, `chain`): `ss` points at the slot array,
+ *    `chain` packs n (bits 0-7) and up to four 12-bit slot indices (bits 8.., 20.., 32.., 44..).
+ *        acc = 1; for i < n: n2 = acc*acc*ss[slot_i]; if (n2 > 1) acc *= rsqrt(n2);
+ *    n == 0 (or ss == NULL) means "no clip". Slots must be zeroed before the producer runs
+ *    (b200nn_step_begin, or b200nn_zero_f64).
+ */
+#ifndef B200NN_H_
+#define B200NN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NN_OK 0
+#define B200NN_EINVAL (-1)   /* bad argument / unsupported geometry */
+#define B200NN_ECUDA (-2)    /* CUDA runtime error (launch, capture, ...) */
+#define B200NN_ENOTSUP (-3)  /* valid request that this build cannot serve */
+
+/* activation kinds (activations.py:33-109) */
+#define B200NN_ACT_NONE 0      /* Linear                     activations.py:81-89  */
+#define B200NN_ACT_RELU 1      /* max(0,x); f' = x>0         activations.py:46-54  */
+#define B200NN_ACT_SIGMOID 2   /* 1/(1+exp(-clip(x,+-50)))   activations.py:33-43  */
+#define B200NN_ACT_TANH 3      /*                            activations.py:57-65  */
+#define B200NN_ACT_LEAKYRELU 4 /* max(x, a*x); f' = x>0?1:a  activations.py:92-109 */
+
+/* loss kinds (losses.py:79-120) */
+#define B200NN_LOSS_MSE 0
+#define B200NN_LOSS_BCE 1
+#define B200NN_LOSS_CCE 2
+
+/* GEMM math modes */
+#define B200NN_MATH_FP32 0 /* FFMA, fp32 accumulate: parity path (rel 1e-5)                    */
+#define B200NN_MATH_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM: perf path (rel 2e-3) */
+
+int b200nn_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+size_t b200nn_last_error(char* buf, size_t cap);
+/* 1 when tcgen05 GEMM kernels are compiled in */
+int b200nn_has_tcgen05(void);
+
+/* ---- step bookkeeping --------------------------------------------------------------------- */
+/* Zero `n_slots` float64 sum-of-squares slots and `n_acc` float64 accumulators (loss, counters)
+ * and add `inc` to the device counter *counter (int64, nullable). First node of a captured train
+ * step: the counter is Adam's `t` (optimizers.py:236), advanced on the device by the number of
+ * layers the step will update so that a replayed graph needs no host-side argument. */
+int b200nn_step_begin(double* ss, int n_slots, double* acc, int n_acc, long long* counter, long long inc,
+                      void* stream);
+/* dst[r, :] = src[idx[r], :] for r < rows (row_elems floats per row): the shuffled mini-batch gather of
+ * Sequential.fit (models.py:386-402, utils.py:34-50) done on the device against a resident dataset. */
+int b200nn_gather_rows(const float* src, const long long* idx, float* dst, long long rows, long long row_elems,
+                       void* stream);
+int b200nn_zero_f64(double* p, int n, void* stream);
+
+/* ---- CUDA graph helpers (capture every launch made on `stream` between begin and end) ------ */
+int b200nn_graph_begin(void* stream);
+int b200nn_graph_end(void* stream, void** graph_exec_out);
+int b200nn_graph_launch(void* graph_exec, void* stream);
+int b200nn_graph_destroy(void* graph_exec);
+
+/* ---- elementwise -------------------------------------------------------------------------- */
+/* Activation.forward_pass (layers.py:231-234): y = f(x). */
+int b200nn_act_fwd(int act, float alpha, const float* x, float* y, long long n, void* stream);
+/* Activation.backward_pass (layers.py:236-237) with the preceding clip (models.py:214) folded in:
+ * dx = chain(err) * f'(.)  where f' is evaluated from the cached OUTPUT y (equivalent for every
+ * activation above). ss_out (nullable) += sum(dx^2). */
+int b200nn_act_bwd(int act, float alpha, const float* y, const float* err, const double* ss, uint64_t chain,
+                   float* dx, double* ss_out, long long n, void* stream);
+/* clip_gradients (preprocessing.py:220-224) materialised: out = chain(in). */
+int b200nn_scale_apply(const float* in, const double* ss, uint64_t chain, float* out, long long n, void* stream);
+/* ss_out += sum(x^2) */
+int b200nn_sumsq(const float* x, long long n, double* ss_out, void* stream);
+/* Softmax over axis 1 (activations.py:69-71). */
+int b200nn_softmax_fwd(const float* x, float* p, int rows, int cols, void* stream);
+/* Loss value + error for the last layer (models.py:255-256, 198-210):
+ *   loss_acc[0] += the loss numerator (host divides: CCE by rows, BCE/MSE by rows*cols);
+ *   fused_pair != 0 (Softmax+CCE or Sigmoid+BCE): err = p - y (models.py:200-205, not /B);
+ *   fused_pair == 0: err = LossFunction.derivative(y, p) (losses.py:83-84, 96-99, 111-115);
+ *   loss_acc[1] += number of rows whose argmax(p) == argmax(y) (cols == 1: (p >= 0.5) == y)
+ *   (metrics.py:84-89, first-index tie break);  ss_out (nullable) += sum(err^2). */
+int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
+                        double* ss_out, int rows, int cols, void* stream);
+
+/* ---- Dense (layers.py:152-198) ------------------------------------------------------------- */
+/* y[M,N] = act(x[M,K] . w[K,N] + b[N])   layers.py:173 (+ the Activation Sequential.add appends).
+ * `ws` is a float workspace of at least b200nn_dense_ws_bytes(M,N,K) bytes (split-K partials; the same
+ * size serves the forward and the backward of that layer). */
+size_t b200nn_dense_ws_bytes(int M, int N, int K);
+int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
+                     int act, float alpha, float* ws, void* stream);
+/* g = chain(err)[M,N];  dx[M,K] = g . w^T (layers.py:189);  dw[K,N] = x^T . g (:196);  db[N] = sum_rows g (:197).
+ * dx == NULL skips dx (first parametrised layer inside fit). If prev_act != NONE the backward of the
+ * PRECEDING Activation layer (whose output is this layer's input x) is fused into the dx epilogue:
+ *   ss_out[0] += sum(dx^2) (the tensor the reference clips before Activation.backward_pass),
+ *   dx <- dx * f'(x),  ss_out[1] += sum(dx^2).   With prev_act == NONE only ss_out[0] is written.
+ * The caller then chains {slot0, slot1}. */
+int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err, const double* ss, uint64_t chain,
+                     float* dx, float* dw, float* db, int M, int N, int K, int prev_act, float prev_alpha,
+                     double* ss_out0, double* ss_out1, float* ws, void* stream);
+
+/* ---- Conv2D (layers.py:442-530, preprocessing.py:34-126) ----------------------------------- */
+typedef struct {
+    int N, H, W, C;      /* input NHWC */
+    int F, kh, kw;       /* filters, kernel */
+    int sh, sw;          /* strides */
+    int ph, pw;          /* symmetric zero pad (layers.py:450-465) */
+    int OH, OW;          /* output spatial size */
+} b200nn_conv_geom;
+/* y = act(conv(x, w) + b). w is the reference's (kh,kw,C,F) buffer READ with K order (c,ky,kx)
+ * (preprocessing.py:77 vs layers.py:474 — SURVEY Q1). */
+size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g);
+int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* b, float* y,
+                      int act, float alpha, float* ws, void* stream);
+/* layers.py:513-528: db[F] = sum g, dw (same K-order view), dx = col2im(g . w^T). Same dx epilogue
+ * contract as b200nn_dense_bwd. */
+int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* err,
+                      const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
+                      float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream);
+
+/* ---- Conv2DTranspose (layers.py:2588-2659) ------------------------------------------------- */
+typedef struct {
+    int N, H, W, C;      /* input NHWC */
+    int F, kh, kw, sh, sw;
+    int pt, pl;          /* crop offsets of the forward (layers.py:2597-2609) */
+    int OH, OW;          /* output spatial size after the crop */
+} b200nn_convt_geom;
+/* w is (kh,kw,F,C). y = act(scatter(x,w)[crop] + b). */
+size_t b200nn_convt_ws_bytes(const b200nn_convt_geom* g);
+int b200nn_convt_fwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* b,
+                     float* y, int act, float alpha, float* ws, void* stream);
+/* Reference backward: windows read from the cropped error with NO pad offset; an input pixel whose
+ * kh x kw window is truncated by the border gets zero d_input and contributes nothing to dw
+ * (layers.py:2651). db = sum over (n,h,w). */
+int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* err,
+                     const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
+                     float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream);
+
+/* ---- BatchNormalization (layers.py:1230-1276): statistics per POSITION over axis 0 ---------- */
+/* x viewed as [B, P]. Training: xc = clip(x,+-10); mean, var over B; batch_var = var + eps;
+ * running = momentum*running + (1-momentum)*{mean, batch_var}; std = sqrt(batch_var + eps);
+ * y = gamma*(xc-mean)/std + beta. Saves mean[P] and invstd[P] for the backward. */
+int b200nn_bn_fwd_train(const float* x, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float* save_mean, float* save_invstd, float* y, int B, long long P,
+                        float momentum, float eps, void* stream);
+/* Inference: mean/var = running stats, std = sqrt(running_var + eps). */
+int b200nn_bn_fwd_infer(const float* x, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float* y, int B, long long P, float eps, void* stream);
+/* e = chain(err); dgamma = sum e*xhat; dbeta = sum e;
+ * dx = gamma*invstd*(e - xhat*dgamma/B - dbeta/B)  (algebraically layers.py:1264-1274; the
+ * mean(-2*centered) term is identically 0). xhat is recomputed from x, save_mean, save_invstd.
+ * Fused dx epilogue as in b200nn_dense_bwd (prev_act evaluated on x, the BN input = activation output). */
+int b200nn_bn_bwd(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                  const float* save_mean, const float* save_invstd, float* dx, float* dgamma, float* dbeta, int B,
+                  long long P, int prev_act, float prev_alpha, double* ss_out0, double* ss_out1, void* stream);
+
+/* ---- MaxPooling2D (layers.py:570-643) ------------------------------------------------------ */
+typedef struct {
+    int N, H, W, C;
+    int ph, pw, sh, sw;  /* pool size, strides */
+    int pad_h, pad_w;    /* zero padding ('same'; value 0 not -inf, layers.py:582-585) */
+    int OH, OW;
+} b200nn_pool_geom;
+int b200nn_maxpool_fwd(const b200nn_pool_geom* g, const float* x, float* y, void* stream);
+/* dx[n,h,w,c] = sum over windows containing (h,w) of chain(err)[window] * (x == window max):
+ * EVERY tied maximum receives the gradient (layers.py:631-637). y is the forward output. */
+int b200nn_maxpool_bwd(const b200nn_pool_geom* g, const float* x, const float* y, const float* err,
+                       const double* ss, uint64_t chain, float* dx, double* ss_out, void* stream);
+
+/* ---- optimizers (optimizers.py:47-50, 167-245) and gradient clip (models.py:240-242) -------- */
+typedef struct {
+    float* p;          /* parameter tensor (updated in place, optimizers.py:223) */
+    const float* g;    /* gradient */
+    float* m;          /* Adam first moment  (unused by SGD) */
+    float* v;          /* Adam second moment (unused by SGD) */
+    long long n;       /* elements */
+    int t_index;       /* Adam: 1-based position j of this tensor's LAYER among the L layers updated per step,
+                          last layer first; t = *t_counter - L + j (optimizers.py:236) */
+    int clip;          /* 1: scale g by 1/||g|| when ||g|| > 1 (models.py:240-242) */
+} b200nn_param;
+/* `params` is a DEVICE array of n_params descriptors; `gss` a device array of n_params float64
+ * scratch slots (zeroed and filled by this call with ||g||^2); hyper is a DEVICE float64 array
+ * {lr, beta1, beta2, eps} (device-resident so a LearningRateScheduler can change lr without
+ * re-capturing the step graph); *t_counter is Adam's device-resident `t` AFTER this step's updates (the
+ * caller advanced it by n_layers, e.g. through b200nn_step_begin). block_map is a DEVICE
+ * array of total_blocks (tensor index, chunk index) int pairs, total_blocks = sum over tensors of
+ * ceil(n / B200NN_OPT_CHUNK). */
+#define B200NN_OPT_CHUNK 4096
+int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
+                      const long long* t_counter, const int* block_map, int total_blocks, void* stream);
+int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
+                     const int* block_map, int total_blocks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NN_H_ */

@@ -1,0 +1,233 @@
+"""Tensor-level wrappers over the C ABI (include/b200nn.h): torch tensors in, raw pointers out.
+
+Nothing here computes: each function validates shapes, packs the lazy-clip chain and calls libb200nn.
+`ss` is the float64 slot tensor of the calling plan; slots are ints, chains are tuples of ints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _backend as B
+from ._backend import ConvGeom, ConvTGeom, PoolGeom, check, lib, ptr, stream
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKYRELU = 0, 1, 2, 3, 4
+LOSS_MSE, LOSS_BCE, LOSS_CCE = 0, 1, 2
+MATH_FP32, MATH_TF32 = 0, 1
+
+
+def pack_chain(chain) -> int:
+    chain = tuple(chain or ())
+    if len(chain) > 4:
+        raise ValueError("clip chain longer than 4 slots")
+    v = len(chain)
+    for i, s in enumerate(chain):
+        if not 0 <= s < 4096:
+            raise ValueError("clip slot out of range")
+        v |= int(s) << (8 + 12 * i)
+    return v
+
+
+def _slot_ptr(ss, slot):
+    return None if (ss is None or slot is None) else ss.data_ptr() + 8 * int(slot)
+
+
+def _f32(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError("b200nn ops need contiguous float32 tensors")
+
+
+# ---- bookkeeping ------------------------------------------------------------------------------------
+def step_begin(ss, acc, counter=None, inc=0):
+    check(lib().b200nn_step_begin(ptr(ss), 0 if ss is None else ss.numel(), ptr(acc), 0 if acc is None else acc.numel(),
+                                  ptr(counter), int(inc), stream()))
+
+
+def zero_f64(t):
+    check(lib().b200nn_zero_f64(ptr(t), t.numel(), stream()))
+
+
+def gather_rows(src, idx, dst):
+    _f32(src, dst)
+    rows = idx.numel()
+    row_elems = src.numel() // src.shape[0]
+    assert idx.dtype == torch.int64 and dst.numel() == rows * row_elems
+    check(lib().b200nn_gather_rows(ptr(src), ptr(idx), ptr(dst), rows, row_elems, stream()))
+
+
+def graph_begin():
+    check(lib().b200nn_graph_begin(stream()))
+
+
+def graph_end():
+    h = C.c_void_p()
+    check(lib().b200nn_graph_end(stream(), C.byref(h)))
+    return h.value
+
+
+def graph_launch(h):
+    check(lib().b200nn_graph_launch(h, stream()))
+
+
+def graph_destroy(h):
+    if h:
+        check(lib().b200nn_graph_destroy(h))
+
+
+# ---- elementwise -------------------------------------------------------------------------------------
+def act_fwd(act, alpha, x, y):
+    _f32(x, y)
+    check(lib().b200nn_act_fwd(act, alpha, ptr(x), ptr(y), x.numel(), stream()))
+
+
+def act_bwd(act, alpha, y, err, ss, chain, dx, slot_out):
+    _f32(y, err, dx)
+    check(lib().b200nn_act_bwd(act, alpha, ptr(y), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), _slot_ptr(ss, slot_out),
+                               err.numel(), stream()))
+
+
+def scale_apply(inp, ss, chain, out):
+    _f32(inp, out)
+    check(lib().b200nn_scale_apply(ptr(inp), ptr(ss), pack_chain(chain), ptr(out), inp.numel(), stream()))
+
+
+def sumsq(x, ss, slot):
+    _f32(x)
+    check(lib().b200nn_sumsq(ptr(x), x.numel(), _slot_ptr(ss, slot), stream()))
+
+
+def softmax_fwd(x, p):
+    _f32(x, p)
+    check(lib().b200nn_softmax_fwd(ptr(x), ptr(p), x.shape[0], x.numel() // x.shape[0], stream()))
+
+
+def loss_fwd_bwd(loss, fused_pair, p, y, err, acc, ss, slot_out):
+    _f32(p, y, err)
+    rows = p.shape[0]
+    check(lib().b200nn_loss_fwd_bwd(loss, int(fused_pair), ptr(p), ptr(y), ptr(err), ptr(acc), _slot_ptr(ss, slot_out),
+                                    rows, p.numel() // rows, stream()))
+
+
+# ---- Dense -------------------------------------------------------------------------------------------
+def dense_ws_bytes(M, N, K):
+    return int(lib().b200nn_dense_ws_bytes(M, N, K))
+
+
+def dense_fwd(math, x, w, b, y, act, alpha, ws):
+    _f32(x, w, b, y)
+    K, N = w.shape
+    M = x.numel() // K
+    check(lib().b200nn_dense_fwd(math, ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, alpha, ptr(ws), stream()))
+
+
+def dense_bwd(math, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, ws):
+    _f32(x, w, err, dx, dw, db)
+    K, N = w.shape
+    M = x.numel() // K
+    check(lib().b200nn_dense_bwd(math, ptr(x), ptr(w), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), ptr(dw), ptr(db),
+                                 M, N, K, prev_act, prev_alpha, _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), ptr(ws),
+                                 stream()))
+
+
+# ---- Conv2D / Conv2DTranspose ------------------------------------------------------------------------
+def conv2d_ws_bytes(g: ConvGeom):
+    return int(lib().b200nn_conv2d_ws_bytes(C.byref(g)))
+
+
+def conv2d_fwd(math, g, x, w, b, y, act, alpha, ws):
+    _f32(x, w, b, y)
+    check(lib().b200nn_conv2d_fwd(math, C.byref(g), ptr(x), ptr(w), ptr(b), ptr(y), act, alpha, ptr(ws), stream()))
+
+
+def conv2d_bwd(math, g, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, ws):
+    _f32(x, w, err, dx, dw, db)
+    check(lib().b200nn_conv2d_bwd(math, C.byref(g), ptr(x), ptr(w), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), ptr(dw),
+                                  ptr(db), prev_act, prev_alpha, _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), ptr(ws),
+                                  stream()))
+
+
+def convt_ws_bytes(g: ConvTGeom):
+    return int(lib().b200nn_convt_ws_bytes(C.byref(g)))
+
+
+def convt_fwd(math, g, x, w, b, y, act, alpha, ws):
+    _f32(x, w, b, y)
+    check(lib().b200nn_convt_fwd(math, C.byref(g), ptr(x), ptr(w), ptr(b), ptr(y), act, alpha, ptr(ws), stream()))
+
+
+def convt_bwd(math, g, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, ws):
+    _f32(x, w, err, dx, dw, db)
+    check(lib().b200nn_convt_bwd(math, C.byref(g), ptr(x), ptr(w), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), ptr(dw),
+                                 ptr(db), prev_act, prev_alpha, _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), ptr(ws),
+                                 stream()))
+
+
+# ---- BatchNorm / MaxPool -----------------------------------------------------------------------------
+def bn_fwd_train(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y, momentum, eps):
+    _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y)
+    Bn = x.shape[0]
+    check(lib().b200nn_bn_fwd_train(ptr(x), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(save_mean), ptr(save_invstd),
+                                    ptr(y), Bn, x.numel() // Bn, momentum, eps, stream()))
+
+
+def bn_fwd_infer(x, gamma, beta, rmean, rvar, y, eps):
+    _f32(x, gamma, beta, rmean, rvar, y)
+    Bn = x.shape[0]
+    check(lib().b200nn_bn_fwd_infer(ptr(x), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(y), Bn, x.numel() // Bn, eps,
+                                    stream()))
+
+
+def bn_bwd(x, err, ss, chain, gamma, save_mean, save_invstd, dx, dgamma, dbeta, prev_act, prev_alpha, slot0, slot1):
+    _f32(x, err, gamma, save_mean, save_invstd, dx, dgamma, dbeta)
+    Bn = x.shape[0]
+    check(lib().b200nn_bn_bwd(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(save_mean), ptr(save_invstd),
+                              ptr(dx), ptr(dgamma), ptr(dbeta), Bn, x.numel() // Bn, prev_act, prev_alpha,
+                              _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), stream()))
+
+
+def maxpool_fwd(g: PoolGeom, x, y):
+    _f32(x, y)
+    check(lib().b200nn_maxpool_fwd(C.byref(g), ptr(x), ptr(y), stream()))
+
+
+def maxpool_bwd(g: PoolGeom, x, y, err, ss, chain, dx, slot_out):
+    _f32(x, y, err, dx)
+    check(lib().b200nn_maxpool_bwd(C.byref(g), ptr(x), ptr(y), ptr(err), ptr(ss), pack_chain(chain), ptr(dx),
+                                   _slot_ptr(ss, slot_out), stream()))
+
+
+# ---- optimizers --------------------------------------------------------------------------------------
+class OptPlan:
+    """Device-resident descriptor table for the multi-tensor optimizer kernels.
+    entries: list of (p, g, m, v, t_index, clip) tensors (m, v may be None for SGD)."""
+
+    def __init__(self, entries, n_layers):
+        self.keep = entries  # keep tensors alive
+        self.n_layers = int(n_layers)
+        desc = np.zeros(len(entries), dtype=B.PARAM_DTYPE)
+        pairs = []
+        for i, (p, g, m, v, t_index, clip) in enumerate(entries):
+            _f32(p, g, m, v)
+            assert p.numel() == g.numel()
+            desc[i] = (p.data_ptr(), g.data_ptr(), 0 if m is None else m.data_ptr(), 0 if v is None else v.data_ptr(),
+                       p.numel(), t_index, int(clip))
+            for c in range((p.numel() + B.OPT_CHUNK - 1) // B.OPT_CHUNK):
+                pairs.append((i, c))
+        self.n_params = len(entries)
+        self.total_blocks = len(pairs)
+        self.desc = torch.from_numpy(desc.view(np.uint8).copy()).to(B.device())
+        self.block_map = torch.from_numpy(np.asarray(pairs, dtype=np.int32).reshape(-1).copy()).to(B.device())
+        self.gss = B.zeros((self.n_params,), dtype=torch.float64)
+
+
+def adam_multi(plan: OptPlan, hyper, t_counter):
+    check(lib().b200nn_adam_multi(ptr(plan.desc), plan.n_params, plan.n_layers, ptr(plan.gss), ptr(hyper), ptr(t_counter),
+                                  ptr(plan.block_map), plan.total_blocks, stream()))
+
+
+def sgd_multi(plan: OptPlan, hyper):
+    check(lib().b200nn_sgd_multi(ptr(plan.desc), plan.n_params, ptr(plan.gss), ptr(hyper), ptr(plan.block_map),
+                                 plan.total_blocks, stream()))

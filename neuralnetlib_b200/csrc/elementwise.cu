@@ -1,0 +1,457 @@
+// elementwise.cu — API basics, step bookkeeping, CUDA-graph helpers, activations, clip helpers,
+// softmax / losses, and the fused multi-tensor optimizers. All HBM-bound: 128-bit vector access,
+// grid-stride loops sized in multiples of the SM count, one fp64 atomic per CTA for norms.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200nn {
+
+static thread_local char g_last_error[512] = {0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+static inline int grid_for(long long work_items, int threads, int items_per_thread = 4, int max_waves = 8) {
+    long long blocks = (work_items + (long long)threads * items_per_thread - 1) / ((long long)threads * items_per_thread);
+    if (blocks < 1) blocks = 1;
+    const long long cap = (long long)kNumSMs * max_waves;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void step_begin_kernel(double* ss, int n_slots, double* acc, int n_acc, long long* counter, long long inc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) ss[i] = 0.0;
+    if (i < n_acc) acc[i] = 0.0;
+    if (i == 0 && counter != nullptr) *counter += inc;
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+                                                          float* __restrict__ dst, long long rows, long long row_elems) {
+    // one warp per 128-float chunk of a row; rows are contiguous so every access is a coalesced line
+    const long long chunks_per_row = (row_elems + 127) / 128;
+    const long long total = rows * chunks_per_row;
+    const int lane = threadIdx.x & 31;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
+         w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const long long r = w / chunks_per_row, c = w % chunks_per_row;
+        const float* s = src + idx[r] * row_elems + c * 128;
+        float* d = dst + r * row_elems + c * 128;
+        const long long left = row_elems - c * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = lane + j * 32;
+            if (e < left) d[e] = s[e];
+        }
+    }
+}
+
+__global__ void zero_f64_kernel(double* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_fwd_kernel(int act, float alpha, const float* __restrict__ x,
+                                                      float* __restrict__ y, long long n) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = x4[i];
+        v.x = act_apply(act, v.x, alpha); v.y = act_apply(act, v.y, alpha);
+        v.z = act_apply(act, v.z, alpha); v.w = act_apply(act, v.w, alpha);
+        y4[i] = v;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = act_apply(act, x[i], alpha);
+}
+
+// dx = s * err * f'(y); ss_out += sum(dx^2).  has_y == false => f' = 1 (pure scale / sumsq of scaled err)
+template <bool kWrite>
+__global__ void __launch_bounds__(256) act_bwd_kernel(int act, float alpha, const float* __restrict__ y,
+                                                      const float* __restrict__ err, const double* __restrict__ ss,
+                                                      uint64_t chain, float* __restrict__ dx, double* ss_out,
+                                                      long long n) {
+    __shared__ double scratch[32];
+    const float s = chain_scale(ss, chain);
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float4* e4 = reinterpret_cast<const float4*>(err);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float4* d4 = reinterpret_cast<float4*>(dx);
+    float acc = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 e = e4[i];
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (y != nullptr) {
+            const float4 yy = y4[i];
+            g.x = act_grad_from_y(act, yy.x, alpha); g.y = act_grad_from_y(act, yy.y, alpha);
+            g.z = act_grad_from_y(act, yy.z, alpha); g.w = act_grad_from_y(act, yy.w, alpha);
+        }
+        e.x = s * e.x * g.x; e.y = s * e.y * g.y; e.z = s * e.z * g.z; e.w = s * e.w * g.w;
+        acc += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+        if (kWrite) d4[i] = e;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float g = y != nullptr ? act_grad_from_y(act, y[i], alpha) : 1.0f;
+        const float e = s * err[i] * g;
+        acc += e * e;
+        if (kWrite) dx[i] = e;
+    }
+    if (ss_out != nullptr) block_accumulate(acc, ss_out, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one warp per row; cols arbitrary
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ x, float* __restrict__ p, int rows,
+                                                      int cols) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + (long long)warp * cols;
+    float* pr = p + (long long)warp * cols;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int c = lane; c < cols; c += 32) sum += expf(xr[c] - mx);
+    sum = warp_sum(sum);
+    for (int c = lane; c < cols; c += 32) pr[c] = expf(xr[c] - mx) / sum;
+}
+
+__device__ __forceinline__ float loss_term(int loss, float y, float p) {
+    if (loss == B200NN_LOSS_MSE) return (y - p) * (y - p);
+    const float pc = fminf(fmaxf(p, 1e-15f), 1.0f);  // 1 - 1e-15 rounds to 1 in fp32
+    if (loss == B200NN_LOSS_CCE) return -y * logf(pc);
+    const float q = fmaxf(1.0f - pc, 1.1102230246251565e-15f);  // fp64 value of 1-(1-1e-15)
+    return -(y * logf(pc) + (1.0f - y) * logf(q));
+}
+__device__ __forceinline__ float loss_deriv(int loss, float y, float p, float inv_size) {
+    if (loss == B200NN_LOSS_MSE) return 2.0f * (p - y) * inv_size;
+    const float pc = fminf(fmaxf(p, 1e-15f), 1.0f);
+    if (loss == B200NN_LOSS_CCE) return -y / pc;
+    const float q = fmaxf(1.0f - pc, 1.1102230246251565e-15f);
+    return (pc - y) / (pc * q);
+}
+
+// warp per row (cols > 1) or thread per element (cols == 1)
+__global__ void __launch_bounds__(256) loss_kernel(int loss, int fused_pair, const float* __restrict__ p,
+                                                   const float* __restrict__ y, float* __restrict__ err,
+                                                   double* loss_acc, double* ss_out, int rows, int cols) {
+    __shared__ double scratch[32];
+    float lsum = 0.0f, esq = 0.0f, correct = 0.0f;
+    const float inv_size = 1.0f / ((float)rows * (float)cols);
+    if (cols == 1) {
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+            const float pv = p[r], yv = y[r];
+            lsum += loss_term(loss, yv, pv);
+            const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size);
+            if (err != nullptr) err[r] = e;
+            esq += e * e;
+            correct += ((pv >= 0.5f ? 1.0f : 0.0f) == yv) ? 1.0f : 0.0f;
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const int nwarps = (gridDim.x * blockDim.x) >> 5;
+        for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+            const float* pr = p + (long long)r * cols;
+            const float* yr = y + (long long)r * cols;
+            float bp = -INFINITY, by = -INFINITY;
+            int ip = 0x7fffffff, iy = 0x7fffffff;
+            for (int c = lane; c < cols; c += 32) {
+                const float pv = pr[c], yv = yr[c];
+                lsum += loss_term(loss, yv, pv);
+                const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size);
+                if (err != nullptr) err[(long long)r * cols + c] = e;
+                esq += e * e;
+                if (pv > bp) { bp = pv; ip = c; }  // strict > keeps the first index within a lane
+                if (yv > by) { by = yv; iy = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // first-index tie break across lanes (np.argmax)
+                const float obp = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int oip = __shfl_xor_sync(0xffffffffu, ip, o);
+                if (obp > bp || (obp == bp && oip < ip)) { bp = obp; ip = oip; }
+                const float oby = __shfl_xor_sync(0xffffffffu, by, o);
+                const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
+                if (oby > by || (oby == by && oiy < iy)) { by = oby; iy = oiy; }
+            }
+            if (lane == 0 && ip == iy) correct += 1.0f;
+        }
+    }
+    const double l = block_sum_to_double(lsum, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[0], l);
+    const double c = block_sum_to_double(correct, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[1], c);
+    if (ss_out != nullptr) block_accumulate(esq, ss_out, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-tensor optimizers. block_map holds (tensor, chunk) pairs; one CTA per 4096-element chunk.
+__global__ void __launch_bounds__(256) sumsq_multi_kernel(const b200nn_param* __restrict__ params,
+                                                          const int* __restrict__ block_map, double* gss) {
+    __shared__ double scratch[32];
+    const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
+    const b200nn_param P = params[ti];
+    const long long base = (long long)chunk * B200NN_OPT_CHUNK;
+    const long long end = min(P.n, base + B200NN_OPT_CHUNK);
+    float acc = 0.0f;
+    if ((reinterpret_cast<uintptr_t>(P.g) & 15) == 0) {
+        const long long e4 = base + ((end - base) & ~3LL);
+        for (long long i = base + threadIdx.x * 4; i < e4; i += 256 * 4) {
+            const float4 g = *reinterpret_cast<const float4*>(P.g + i);
+            acc += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+        }
+        for (long long i = e4 + threadIdx.x; i < end; i += 256) acc += P.g[i] * P.g[i];
+    } else {
+        for (long long i = base + threadIdx.x; i < end; i += 256) acc += P.g[i] * P.g[i];
+    }
+    block_accumulate(acc, &gss[ti], scratch);
+}
+
+struct OptScalars {
+    float clip, lr, b1, b2, omb1, omb2, inv_bc1, inv_bc2, eps;
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const OptScalars& s) {
+    g *= s.clip;
+    m = s.b1 * m + s.omb1 * g;
+    v = s.b2 * v + s.omb2 * g * g;
+    const float mh = m * s.inv_bc1;
+    const float vh = v * s.inv_bc2;
+    const float denom = fmaxf(sqrtf(vh) + s.eps, 1e-16f);
+    float upd = s.lr * mh / denom;
+    if (!isfinite(upd)) upd = 0.0f;  // np.nan_to_num(update, nan=0, posinf=0, neginf=0), optimizers.py:222
+    p -= upd;
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __restrict__ params, int n_layers,
+                                                         const double* __restrict__ gss,
+                                                         const double* __restrict__ hyper,
+                                                         const long long* __restrict__ step,
+                                                         const int* __restrict__ block_map) {
+    __shared__ OptScalars sh;
+    const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
+    const b200nn_param P = params[ti];
+    if (threadIdx.x == 0) {
+        const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+        const double n2 = gss[ti];
+        const double t = (double)(*step - (long long)n_layers + P.t_index);  // optimizers.py:236 (Q3)
+        sh.clip = (P.clip && n2 > 1.0) ? (float)rsqrt(n2) : 1.0f;                   // models.py:240-242
+        sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;
+        sh.omb1 = (float)(1.0 - b1); sh.omb2 = (float)(1.0 - b2);
+        sh.inv_bc1 = (float)(1.0 / (1.0 - pow(b1, t)));
+        sh.inv_bc2 = (float)(1.0 / (1.0 - pow(b2, t)));
+        sh.eps = (float)eps;
+    }
+    __syncthreads();
+    const OptScalars s = sh;
+    const long long base = (long long)chunk * B200NN_OPT_CHUNK;
+    const long long end = min(P.n, base + B200NN_OPT_CHUNK);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(P.p) | reinterpret_cast<uintptr_t>(P.g) |
+                           reinterpret_cast<uintptr_t>(P.m) | reinterpret_cast<uintptr_t>(P.v)) & 15) == 0;
+    long long tail = base;
+    if (aligned) {
+        const long long e4 = base + ((end - base) & ~3LL);
+        for (long long i = base + threadIdx.x * 4; i < e4; i += 256 * 4) {
+            float4 p = *reinterpret_cast<float4*>(P.p + i);
+            const float4 g = *reinterpret_cast<const float4*>(P.g + i);
+            float4 m = *reinterpret_cast<float4*>(P.m + i);
+            float4 v = *reinterpret_cast<float4*>(P.v + i);
+            adam_elem(p.x, g.x, m.x, v.x, s); adam_elem(p.y, g.y, m.y, v.y, s);
+            adam_elem(p.z, g.z, m.z, v.z, s); adam_elem(p.w, g.w, m.w, v.w, s);
+            *reinterpret_cast<float4*>(P.p + i) = p;
+            *reinterpret_cast<float4*>(P.m + i) = m;
+            *reinterpret_cast<float4*>(P.v + i) = v;
+        }
+        tail = e4;
+    }
+    for (long long i = tail + threadIdx.x; i < end; i += 256) {
+        float p = P.p[i], m = P.m[i], v = P.v[i];
+        adam_elem(p, P.g[i], m, v, s);
+        P.p[i] = p; P.m[i] = m; P.v[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const b200nn_param* __restrict__ params,
+                                                        const double* __restrict__ gss,
+                                                        const double* __restrict__ hyper,
+                                                        const int* __restrict__ block_map) {
+    const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
+    const b200nn_param P = params[ti];
+    const double n2 = gss[ti];
+    const float scale = (float)hyper[0] * ((P.clip && n2 > 1.0) ? (float)rsqrt(n2) : 1.0f);
+    const long long base = (long long)chunk * B200NN_OPT_CHUNK;
+    const long long end = min(P.n, base + B200NN_OPT_CHUNK);
+    for (long long i = base + threadIdx.x; i < end; i += 256) P.p[i] -= scale * P.g[i];  // optimizers.py:48
+}
+
+}  // namespace b200nn
+
+using namespace b200nn;
+
+extern "C" {
+
+int b200nn_version(void) { return 100; }
+
+#ifndef B200NN_HAS_TCGEN05
+#define B200NN_HAS_TCGEN05 0
+#endif
+int b200nn_has_tcgen05(void) { return B200NN_HAS_TCGEN05; }
+
+size_t b200nn_last_error(char* buf, size_t cap) {
+    const size_t n = strlen(g_last_error);
+    if (buf != nullptr && cap > 0) {
+        const size_t c = n < cap - 1 ? n : cap - 1;
+        memcpy(buf, g_last_error, c);
+        buf[c] = 0;
+    }
+    return n;
+}
+
+int b200nn_gather_rows(const float* src, const long long* idx, float* dst, long long rows, long long row_elems,
+                       void* stream) {
+    if (rows <= 0 || row_elems <= 0) return B200NN_OK;
+    const long long warps = rows * ((row_elems + 127) / 128);
+    long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    gather_rows_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, idx, dst, rows, row_elems);
+    B200NN_LAUNCH_CHECK("gather_rows");
+    return B200NN_OK;
+}
+
+int b200nn_step_begin(double* ss, int n_slots, double* acc, int n_acc, long long* counter, long long inc, void* stream) {
+    int n = n_slots > n_acc ? n_slots : n_acc;
+    if (n < 1) n = 1;
+    const int threads = 128, blocks = (n + threads - 1) / threads;
+    step_begin_kernel<<<blocks, threads, 0, as_stream(stream)>>>(ss, n_slots, acc, n_acc, counter, inc);
+    B200NN_LAUNCH_CHECK("step_begin");
+    return B200NN_OK;
+}
+
+int b200nn_zero_f64(double* p, int n, void* stream) {
+    if (n <= 0) return B200NN_OK;
+    zero_f64_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p, n);
+    B200NN_LAUNCH_CHECK("zero_f64");
+    return B200NN_OK;
+}
+
+int b200nn_graph_begin(void* stream) {
+    B200NN_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+    return B200NN_OK;
+}
+
+int b200nn_graph_end(void* stream, void** graph_exec_out) {
+    cudaGraph_t graph = nullptr;
+    B200NN_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        return B200NN_ECUDA;
+    }
+    *graph_exec_out = exec;
+    return B200NN_OK;
+}
+
+int b200nn_graph_launch(void* graph_exec, void* stream) {
+    B200NN_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+    return B200NN_OK;
+}
+
+int b200nn_graph_destroy(void* graph_exec) {
+    if (graph_exec != nullptr) B200NN_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+    return B200NN_OK;
+}
+
+int b200nn_act_fwd(int act, float alpha, const float* x, float* y, long long n, void* stream) {
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "act_fwd: unknown activation %d", act);
+    B200NN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                   "act_fwd: buffers must be 16-byte aligned");
+    if (n <= 0) return B200NN_OK;
+    act_fwd_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(act, alpha, x, y, n);
+    B200NN_LAUNCH_CHECK("act_fwd");
+    return B200NN_OK;
+}
+
+int b200nn_act_bwd(int act, float alpha, const float* y, const float* err, const double* ss, uint64_t chain,
+                   float* dx, double* ss_out, long long n, void* stream) {
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "act_bwd: unknown activation %d", act);
+    B200NN_REQUIRE(act != B200NN_ACT_LEAKYRELU || alpha > 0.0f, "act_bwd: LeakyReLU needs alpha > 0 (got %g)", alpha);
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+                   "act_bwd: buffers must be 16-byte aligned");
+    if (n <= 0) return B200NN_OK;
+    act_bwd_kernel<true><<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(act, alpha, y, err, ss, chain, dx, ss_out, n);
+    B200NN_LAUNCH_CHECK("act_bwd");
+    return B200NN_OK;
+}
+
+int b200nn_scale_apply(const float* in, const double* ss, uint64_t chain, float* out, long long n, void* stream) {
+    if (n <= 0) return B200NN_OK;
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                   "scale_apply: buffers must be 16-byte aligned");
+    act_bwd_kernel<true><<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(B200NN_ACT_NONE, 0.f, nullptr, in, ss, chain, out, nullptr, n);
+    B200NN_LAUNCH_CHECK("scale_apply");
+    return B200NN_OK;
+}
+
+int b200nn_sumsq(const float* x, long long n, double* ss_out, void* stream) {
+    if (n <= 0) return B200NN_OK;
+    B200NN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sumsq: buffer must be 16-byte aligned");
+    act_bwd_kernel<false><<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(B200NN_ACT_NONE, 0.f, nullptr, x, nullptr, 0, nullptr, ss_out, n);
+    B200NN_LAUNCH_CHECK("sumsq");
+    return B200NN_OK;
+}
+
+int b200nn_softmax_fwd(const float* x, float* p, int rows, int cols, void* stream) {
+    B200NN_REQUIRE(rows >= 0 && cols > 0, "softmax: bad shape %d x %d", rows, cols);
+    if (rows == 0) return B200NN_OK;
+    const int blocks = (rows * 32 + 255) / 256;
+    softmax_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, p, rows, cols);
+    B200NN_LAUNCH_CHECK("softmax");
+    return B200NN_OK;
+}
+
+int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
+                        double* ss_out, int rows, int cols, void* stream) {
+    B200NN_REQUIRE(loss >= 0 && loss <= B200NN_LOSS_CCE, "loss: unknown kind %d", loss);
+    B200NN_REQUIRE(rows > 0 && cols > 0, "loss: bad shape %d x %d", rows, cols);
+    long long threads_needed = cols == 1 ? rows : (long long)rows * 32;
+    int blocks = (int)((threads_needed + 255) / 256);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(loss, fused_pair, p, y, err, loss_acc, ss_out, rows, cols);
+    B200NN_LAUNCH_CHECK("loss");
+    return B200NN_OK;
+}
+
+int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
+                      const long long* step, const int* block_map, int total_blocks, void* stream) {
+    B200NN_REQUIRE(n_params > 0 && total_blocks > 0 && n_layers > 0, "adam_multi: empty parameter list");
+    B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
+    sumsq_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, block_map, gss);
+    B200NN_LAUNCH_CHECK("sumsq_multi");
+    adam_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, gss, hyper, step, block_map);
+    B200NN_LAUNCH_CHECK("adam_multi");
+    return B200NN_OK;
+}
+
+int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
+                     const int* block_map, int total_blocks, void* stream) {
+    B200NN_REQUIRE(n_params > 0 && total_blocks > 0, "sgd_multi: empty parameter list");
+    B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
+    sumsq_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, block_map, gss);
+    B200NN_LAUNCH_CHECK("sumsq_multi");
+    sgd_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, gss, hyper, block_map);
+    B200NN_LAUNCH_CHECK("sgd_multi");
+    return B200NN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,705 @@
+// gemm_simt.cu — fp32 FFMA contraction engine (the rel-1e-5 parity path) for Dense, Conv2D and
+// Conv2DTranspose. One register-tiled kernel C[M,N] = sum_k A(m,k) * B(k,n), parameterised by operand
+// *functors* that gather straight from the NHWC / row-major tensors (implicit GEMM: no im2col buffer is
+// ever materialised, replacing preprocessing.py:34-126), a split-K variant for skinny shapes
+// (deterministic: partials to a workspace, reduced in fixed order), and a shared epilogue that fuses
+// bias + activation (forward), the lazy clip multiplier, the preceding activation's backward and the
+// fp64 sum-of-squares slots (backward).
+//
+// Tile: 64x64x16, 256 threads, 4x4 micro-tile, register prefetch of the next k-slab.
+#include "common.cuh"
+
+namespace b200nn {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
+
+// ------------------------------------------------------------------------------------------------
+// epilogue
+// ------------------------------------------------------------------------------------------------
+struct Epilogue {
+    float* out;                // out[row * ldo + n]
+    long long ldo;
+    const float* bias;         // per n, nullable
+    int act;                   // forward activation applied after bias
+    float alpha;
+    const double* ss;          // lazy clip multiplier applied to the accumulator (linear ops)
+    uint64_t chain;
+    const float* mask_y;       // preceding activation's OUTPUT (same indexing as out), nullable
+    int mask_act;
+    float mask_alpha;
+    double* ss0;               // += sum(v^2) before the mask
+    double* ss1;               // += sum(v^2) after the mask
+    // weight-gradient row handling: GEMM rows are taps in (ky,kx,c) order (+ an optional trailing
+    // "ones" row that carries db); row_mode 1 maps tap rows to the reference's (c,ky,kx) flat order.
+    int row_mode;              // 0 plain, 1 conv-weight permute
+    int kh, kw, C;
+    int n_rows;                // number of real rows (rows >= n_rows go to db)
+    float* db;                 // nullable
+};
+
+struct EpiState {
+    float scale;
+    float a0, a1;
+};
+
+__device__ __forceinline__ void epi_begin(const Epilogue& e, EpiState& st) {
+    st.scale = chain_scale(e.ss, e.chain);
+    st.a0 = 0.0f;
+    st.a1 = 0.0f;
+}
+
+__device__ __forceinline__ void epi_store(const Epilogue& e, EpiState& st, int m, int n, float v) {
+    v *= st.scale;
+    if (m >= e.n_rows) {  // ones row -> db
+        if (e.db != nullptr) e.db[n] = v;
+        return;
+    }
+    long long row = m;
+    if (e.row_mode == 1) {
+        const int c = m % e.C;
+        const int t = m / e.C;
+        const int kx = t % e.kw, ky = t / e.kw;
+        row = ((long long)c * e.kh + ky) * e.kw + kx;
+    }
+    if (e.bias != nullptr) v += e.bias[n];
+    v = act_apply(e.act, v, e.alpha);
+    const long long idx = row * e.ldo + n;
+    st.a0 += v * v;
+    if (e.mask_y != nullptr) {
+        v *= act_grad_from_y(e.mask_act, e.mask_y[idx], e.mask_alpha);
+        st.a1 += v * v;
+    }
+    e.out[idx] = v;
+}
+
+__device__ __forceinline__ void epi_finish(const Epilogue& e, EpiState& st, double* scratch) {
+    if (e.ss0 != nullptr) block_accumulate(st.a0, e.ss0, scratch);
+    if (e.ss1 != nullptr) block_accumulate(st.a1, e.ss1, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand functors. A(m,k): row(m), col(k), fetch(row, col). B(k,n): row(k), col(n), fetch(row, col).
+// Invalid indices (out of range or -1) decode to descriptors that fetch 0.
+// ------------------------------------------------------------------------------------------------
+struct RowMajorA {  // A(m,k) = p[m*ld + k]
+    static constexpr bool kContigK = true;
+    const float* p; long long ld; int M, K;
+    struct Row { const float* base; };
+    struct Col { int k; };
+    __device__ Row row(int m) const { return Row{(m >= 0 && m < M) ? p + (long long)m * ld : nullptr}; }
+    __device__ Col col(int k) const { return Col{(k >= 0 && k < K) ? k : -1}; }
+    __device__ float fetch(const Row& r, const Col& c) const { return (r.base != nullptr && c.k >= 0) ? r.base[c.k] : 0.0f; }
+};
+
+struct ColMajorOnesA {  // A(m,k) = p[k*ld + m] for m < Mreal; A(Mreal,k) = 1 when `ones` (db row)
+    static constexpr bool kContigK = false;
+    const float* p; long long ld; int Mreal, K; int ones;
+    struct Row { int m; };  // -1 invalid, Mreal = ones row
+    struct Col { const float* base; };
+    __device__ Row row(int m) const { return Row{(m >= 0 && m < Mreal + ones) ? m : -1}; }
+    __device__ Col col(int k) const { return Col{(k >= 0 && k < K) ? p + (long long)k * ld : nullptr}; }
+    __device__ float fetch(const Row& r, const Col& c) const {
+        if (r.m < 0 || c.base == nullptr) return 0.0f;
+        return r.m == Mreal ? 1.0f : c.base[r.m];
+    }
+};
+
+struct RowMajorB {  // B(k,n) = p[k*ld + n]
+    static constexpr bool kContigN = true;
+    const float* p; long long ld; int K, N;
+    struct Row { const float* base; };
+    struct Col { int n; };
+    __device__ Row row(int k) const { return Row{(k >= 0 && k < K) ? p + (long long)k * ld : nullptr}; }
+    __device__ Col col(int n) const { return Col{(n >= 0 && n < N) ? n : -1}; }
+    __device__ float fetch(const Row& r, const Col& c) const { return (r.base != nullptr && c.n >= 0) ? r.base[c.n] : 0.0f; }
+};
+
+struct ColMajorB {  // B(k,n) = p[n*ld + k]   (W^T)
+    static constexpr bool kContigN = false;
+    const float* p; long long ld; int K, N;
+    struct Row { int k; };
+    struct Col { const float* base; };
+    __device__ Row row(int k) const { return Row{(k >= 0 && k < K) ? k : -1}; }
+    __device__ Col col(int n) const { return Col{(n >= 0 && n < N) ? p + (long long)n * ld : nullptr}; }
+    __device__ float fetch(const Row& r, const Col& c) const { return (r.k >= 0 && c.base != nullptr) ? c.base[r.k] : 0.0f; }
+};
+
+// im2col window gather: pixel = (n, oy, ox) over an OHxOW grid, tap = (ky, kx, c) with c fastest.
+// value = src[n, oy*sh + ky - ph, ox*sw + kx - pw, c] (0 outside). `skip_truncated`: a window that does not
+// fit entirely inside the source (no padding) yields 0 for every tap (Conv2DTranspose.backward_pass,
+// layers.py:2651).
+struct PatchGather {
+    const float* src; int SH, SW, SC;       // source spatial dims and channels
+    int OH, OW;                             // pixel grid
+    int kh, kw, sh, sw, ph, pw;
+    int n_pix, n_tap;                       // N*OH*OW, kh*kw*SC
+    int skip_truncated;
+    struct Pix { const float* base; int iy0, ix0; };   // base = image n; nullptr invalid
+    struct Tap { int ky, kx, c; };                      // ky = -1 invalid
+    __device__ Pix pix(int m) const {
+        if (m < 0 || m >= n_pix) return Pix{nullptr, 0, 0};
+        const int ox = m % OW; const int t = m / OW; const int oy = t % OH; const int n = t / OH;
+        const int iy0 = oy * sh - ph, ix0 = ox * sw - pw;
+        if (skip_truncated && (iy0 + kh > SH || ix0 + kw > SW)) return Pix{nullptr, 0, 0};
+        return Pix{src + (long long)n * SH * SW * SC, iy0, ix0};
+    }
+    __device__ Tap tap(int k) const {
+        if (k < 0 || k >= n_tap) return Tap{-1, 0, 0};
+        const int c = k % SC; const int t = k / SC;
+        return Tap{t / kw, t % kw, c};
+    }
+    __device__ float get(const Pix& p, const Tap& t) const {
+        if (p.base == nullptr || t.ky < 0) return 0.0f;
+        const int iy = p.iy0 + t.ky, ix = p.ix0 + t.kx;
+        if (iy < 0 || iy >= SH || ix < 0 || ix >= SW) return 0.0f;
+        return p.base[((long long)iy * SW + ix) * SC + t.c];
+    }
+};
+
+struct PatchA {  // A(m = pixel, k = tap)
+    static constexpr bool kContigK = true;
+    PatchGather g;
+    using Row = PatchGather::Pix; using Col = PatchGather::Tap;
+    __device__ Row row(int m) const { return g.pix(m); }
+    __device__ Col col(int k) const { return g.tap(k); }
+    __device__ float fetch(const Row& r, const Col& c) const { return g.get(r, c); }
+};
+
+struct PatchTOnesA {  // A(m = tap (+ ones row), k = pixel)  — weight gradients
+    static constexpr bool kContigK = false;
+    PatchGather g; int ones;
+    struct Row { PatchGather::Tap t; int one; };
+    using Col = PatchGather::Pix;
+    __device__ Row row(int m) const {
+        if (ones && m == g.n_tap) return Row{PatchGather::Tap{-1, 0, 0}, 1};
+        return Row{g.tap(m), 0};
+    }
+    __device__ Col col(int k) const {
+        if (k < 0 || k >= g.n_pix) return Col{nullptr, -1, 0};
+        Col c = g.pix(k);
+        if (c.base == nullptr) { c.iy0 = -2; }  // in-range pixel whose window is skipped: contributes 0 (and 0 to ones)
+        return c;
+    }
+    __device__ float fetch(const Row& r, const Col& c) const {
+        if (r.one) return (c.base != nullptr || c.iy0 == -2) ? 1.0f : 0.0f;
+        return g.get(c, r.t);
+    }
+};
+
+// transposed-window gather (col2im as a gather / Conv2DTranspose forward): pixel = (n, Y, X) over a DHxDW
+// grid, tap = (ky, kx, ch): value = src[n, (Y + py - ky)/sh, (X + px - kx)/sw, ch] when divisible and in range.
+struct StridedGatherA {
+    static constexpr bool kContigK = true;
+    const float* src; int SH, SW, SC;       // source (coarse) dims and channels
+    int DH, DW;                             // destination (fine) grid
+    int kh, kw, sh, sw, py, px;
+    int n_pix, n_tap;
+    struct Row { const float* base; int y, x; };
+    struct Col { int ky, kx, c; };
+    __device__ Row row(int m) const {
+        if (m < 0 || m >= n_pix) return Row{nullptr, 0, 0};
+        const int X = m % DW; const int t = m / DW; const int Y = t % DH; const int n = t / DH;
+        return Row{src + (long long)n * SH * SW * SC, Y + py, X + px};
+    }
+    __device__ Col col(int k) const {
+        if (k < 0 || k >= n_tap) return Col{-1, 0, 0};
+        const int c = k % SC; const int t = k / SC;
+        return Col{t / kw, t % kw, c};
+    }
+    __device__ float fetch(const Row& r, const Col& c) const {
+        if (r.base == nullptr || c.ky < 0) return 0.0f;
+        const int ny = r.y - c.ky, nx = r.x - c.kx;
+        if (ny < 0 || nx < 0) return 0.0f;
+        const int iy = ny / sh, ix = nx / sw;
+        if (iy * sh != ny || ix * sw != nx || iy >= SH || ix >= SW) return 0.0f;
+        return r.base[((long long)iy * SW + ix) * SC + c.c];
+    }
+};
+
+// weights of Conv2D seen from the forward: B(k = (ky,kx,c), f) = w[((c*kh + ky)*kw + kx)*F + f]   (Q1)
+struct ConvWFwdB {
+    static constexpr bool kContigN = true;
+    const float* w; int kh, kw, C, F;
+    struct Row { const float* base; };
+    struct Col { int n; };
+    __device__ Row row(int k) const {
+        if (k < 0 || k >= kh * kw * C) return Row{nullptr};
+        const int c = k % C; const int t = k / C; const int kx = t % kw, ky = t / kw;
+        return Row{w + (((long long)c * kh + ky) * kw + kx) * F};
+    }
+    __device__ Col col(int n) const { return Col{(n >= 0 && n < F) ? n : -1}; }
+    __device__ float fetch(const Row& r, const Col& c) const { return (r.base != nullptr && c.n >= 0) ? r.base[c.n] : 0.0f; }
+};
+
+// weights of Conv2D seen from dgrad: B(k = (ky,kx,f), c) = w[((c*kh + ky)*kw + kx)*F + f]
+struct ConvWDgradB {
+    static constexpr bool kContigN = false;
+    const float* w; int kh, kw, C, F;
+    struct Row { int off; };   // (ky*kw + kx)*F + f ; -1 invalid
+    struct Col { const float* base; };
+    __device__ Row row(int k) const { return Row{(k >= 0 && k < kh * kw * F) ? k : -1}; }
+    __device__ Col col(int n) const { return Col{(n >= 0 && n < C) ? w + (long long)n * kh * kw * F : nullptr}; }
+    __device__ float fetch(const Row& r, const Col& c) const { return (r.off >= 0 && c.base != nullptr) ? c.base[r.off] : 0.0f; }
+};
+
+// weights of Conv2DTranspose seen from the forward: B(k = (ky,kx,c), f) = w[((ky*kw + kx)*F + f)*C + c]
+struct ConvTWFwdB {
+    static constexpr bool kContigN = false;
+    const float* w; int kh, kw, C, F;
+    struct Row { int tap, c; };
+    struct Col { int f; };
+    __device__ Row row(int k) const {
+        if (k < 0 || k >= kh * kw * C) return Row{-1, 0};
+        return Row{k / C, k % C};
+    }
+    __device__ Col col(int n) const { return Col{(n >= 0 && n < F) ? n : -1}; }
+    __device__ float fetch(const Row& r, const Col& c) const {
+        return (r.tap >= 0 && c.f >= 0) ? w[((long long)r.tap * F + c.f) * C + r.c] : 0.0f;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <class AF, class BF>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(AF af, BF bf, Epilogue epi, int M, int N, int K, int k_chunk,
+                                                        float* __restrict__ ws) {
+    __shared__ __align__(16) float As[BK][BM + PADM];
+    __shared__ __align__(16) float Bs[BK][BN + PADM];
+    __shared__ double scratch[32];
+
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // ---- loader thread mapping (hoist the decode of the index that stays fixed across k-slabs)
+    typename AF::Row a_rows[4];
+    typename BF::Col b_cols[4];
+    if constexpr (AF::kContigK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a_rows[i] = af.row(m0 + (tid >> 4) + i * 16);
+    } else {
+        a_rows[0] = af.row(m0 + (tid & 63));
+    }
+    if constexpr (BF::kContigN) {
+        b_cols[0] = bf.col(n0 + (tid & 63));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b_cols[i] = bf.col(n0 + (tid >> 4) + i * 16);
+    }
+
+    float ra[4], rb[4];
+    auto load_tile = [&](int k0) {
+        if constexpr (AF::kContigK) {
+            const int k = k0 + (tid & 15);
+            const typename AF::Col c = af.col(k < k_end ? k : -1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ra[i] = af.fetch(a_rows[i], c);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + (tid >> 6) + i * 4;
+                ra[i] = af.fetch(a_rows[0], af.col(k < k_end ? k : -1));
+            }
+        }
+        if constexpr (BF::kContigN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + (tid >> 6) + i * 4;
+                rb[i] = bf.fetch(bf.row(k < k_end ? k : -1), b_cols[0]);
+            }
+        } else {
+            const int k = k0 + (tid & 15);
+            const typename BF::Row r = bf.row(k < k_end ? k : -1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rb[i] = bf.fetch(r, b_cols[i]);
+        }
+    };
+    auto store_tile = [&]() {
+        if constexpr (AF::kContigK) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[tid & 15][(tid >> 4) + i * 16] = ra[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[(tid >> 6) + i * 4][tid & 63] = ra[i];
+        }
+        if constexpr (BF::kContigN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[(tid >> 6) + i * 4][tid & 63] = rb[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[tid & 15][(tid >> 4) + i * 16] = rb[i];
+        }
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    if (k_begin < k_end) {
+        load_tile(k_begin);
+        store_tile();
+        __syncthreads();
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+            const bool has_next = k0 + BK < k_end;
+            if (has_next) load_tile(k0 + BK);
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+            if (has_next) {
+                store_tile();
+                __syncthreads();
+            }
+        }
+    }
+
+    if (ws != nullptr) {  // split-K: raw partials, reduced by splitk_reduce_kernel
+        float* dst = ws + (long long)blockIdx.z * M * N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < N) dst[(long long)m * N + n] = acc[i][j];
+            }
+        }
+        return;
+    }
+    EpiState st;
+    epi_begin(epi, st);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) epi_store(epi, st, m, n, acc[i][j]);
+        }
+    }
+    epi_finish(epi, st, scratch);
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                            Epilogue epi) {
+    __shared__ double scratch[32];
+    EpiState st;
+    epi_begin(epi, st);
+    const long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        for (int s = 0; s < splits; ++s) v += ws[(long long)s * total + i];
+        epi_store(epi, st, (int)(i / N), (int)(i % N), v);
+    }
+    epi_finish(epi, st, scratch);
+}
+
+// column sums of a [R, F] matrix with the lazy clip multiplier: out[f] = scale * sum_r x[r, f]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, long long R, int F,
+                                                             float* __restrict__ partial) {
+    // block handles rows [blockIdx.x * rows_per_block, ...); thread t handles columns t, t+256, ...
+    const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(R, r0 + rows_per_block);
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float s = 0.0f;
+        for (long long r = r0; r < r1; ++r) s += x[r * F + f];
+        partial[(long long)blockIdx.x * F + f] = s;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int F, const double* ss,
+                                    uint64_t chain, float* __restrict__ out) {
+    const float scale = chain_scale(ss, chain);
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * F + f];
+        out[f] = s * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------------
+static int choose_splits(long long M, long long N, long long K) {
+    const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    if (tiles >= 2LL * kNumSMs || K < 256) return 1;
+    long long want = (2LL * kNumSMs + tiles - 1) / tiles;
+    long long maxs = K / 128;
+    if (maxs < 1) maxs = 1;
+    long long s = want < maxs ? want : maxs;
+    if (s > 1024) s = 1024;
+    return (int)(s < 1 ? 1 : s);
+}
+
+static size_t ws_bytes_for(long long M, long long N, long long K) {
+    const int s = choose_splits(M, N, K);
+    return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+static Epilogue plain_epilogue(float* out, long long ldo, int n_rows) {
+    Epilogue e;
+    e.out = out; e.ldo = ldo; e.bias = nullptr; e.act = B200NN_ACT_NONE; e.alpha = 0.f;
+    e.ss = nullptr; e.chain = 0; e.mask_y = nullptr; e.mask_act = B200NN_ACT_NONE; e.mask_alpha = 0.f;
+    e.ss0 = nullptr; e.ss1 = nullptr; e.row_mode = 0; e.kh = e.kw = e.C = 1; e.n_rows = n_rows; e.db = nullptr;
+    return e;
+}
+
+template <class AF, class BF>
+static int launch_gemm(const char* name, const AF& af, const BF& bf, const Epilogue& epi, int M, int N, int K,
+                       float* ws, cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return B200NN_OK;
+    const int splits = choose_splits(M, N, K);
+    const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    if (splits == 1) {
+        gemm_simt_kernel<AF, BF><<<grid, 256, 0, stream>>>(af, bf, epi, M, N, K, K > 0 ? K : 1, nullptr);
+        B200NN_LAUNCH_CHECK(name);
+        return B200NN_OK;
+    }
+    B200NN_REQUIRE(ws != nullptr, "%s: split-K needs a workspace (M=%d N=%d K=%d)", name, M, N, K);
+    int k_chunk = (K + splits - 1) / splits;
+    k_chunk = (k_chunk + BK - 1) / BK * BK;
+    gemm_simt_kernel<AF, BF><<<grid, 256, 0, stream>>>(af, bf, epi, M, N, K, k_chunk, ws);
+    B200NN_LAUNCH_CHECK(name);
+    const long long total = (long long)M * N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, splits, M, N, epi);
+    B200NN_LAUNCH_CHECK("splitk_reduce");
+    return B200NN_OK;
+}
+
+static int check_act(const char* who, int act, float alpha) {
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "%s: unknown activation %d", who, act);
+    B200NN_REQUIRE(act != B200NN_ACT_LEAKYRELU || alpha > 0.0f, "%s: LeakyReLU needs alpha > 0", who);
+    return B200NN_OK;
+}
+
+static void dx_epilogue(Epilogue& e, const double* ss, uint64_t chain, const float* mask_y, int prev_act,
+                        float prev_alpha, double* ss0, double* ss1) {
+    e.ss = ss; e.chain = chain; e.ss0 = ss0;
+    if (prev_act != B200NN_ACT_NONE) {
+        e.mask_y = mask_y; e.mask_act = prev_act; e.mask_alpha = prev_alpha; e.ss1 = ss1;
+    }
+}
+
+}  // namespace b200nn
+
+using namespace b200nn;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------- Dense
+size_t b200nn_dense_ws_bytes(int M, int N, int K) {
+    size_t a = ws_bytes_for(M, N, K);          // fwd  [M,N] over K
+    size_t b = ws_bytes_for(M, K, N);          // dx   [M,K] over N
+    size_t c = ws_bytes_for((long long)K + 1, N, M);  // dw+db [K+1,N] over M
+    size_t r = a > b ? a : b;
+    return r > c ? r : c;
+}
+
+int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
+                     int act, float alpha, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "dense_fwd: math mode %d is served by the tcgen05 entry points", math);
+    B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_fwd: bad shape M=%d N=%d K=%d", M, N, K);
+    if (int rc = check_act("dense_fwd", act, alpha)) return rc;
+    RowMajorA af{x, K, M, K};
+    RowMajorB bf{w, N, K, N};
+    Epilogue e = plain_epilogue(y, N, M);
+    e.bias = b; e.act = act; e.alpha = alpha;
+    return launch_gemm("dense_fwd", af, bf, e, M, N, K, ws, as_stream(stream));
+}
+
+int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err, const double* ss, uint64_t chain,
+                     float* dx, float* dw, float* db, int M, int N, int K, int prev_act, float prev_alpha,
+                     double* ss_out0, double* ss_out1, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "dense_bwd: math mode %d is served by the tcgen05 entry points", math);
+    B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_bwd: bad shape M=%d N=%d K=%d", M, N, K);
+    if (int rc = check_act("dense_bwd", prev_act, prev_alpha)) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
+        ColMajorOnesA af{x, K, K, M, db != nullptr ? 1 : 0};
+        RowMajorB bf{err, N, M, N};
+        Epilogue e = plain_epilogue(dw, N, K);
+        e.ss = ss; e.chain = chain; e.db = db;
+        if (int rc = launch_gemm("dense_dw", af, bf, e, K + (db != nullptr ? 1 : 0), N, M, ws, st)) return rc;
+    }
+    if (dx != nullptr) {  // dx[M,K] = err[M,N] . w^T
+        RowMajorA af{err, N, M, N};
+        ColMajorB bf{w, N, N, K};
+        Epilogue e = plain_epilogue(dx, K, M);
+        dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+        if (int rc = launch_gemm("dense_dx", af, bf, e, M, K, N, ws, st)) return rc;
+    }
+    return B200NN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Conv2D
+static int check_conv_geom(const char* who, const b200nn_conv_geom* g) {
+    B200NN_REQUIRE(g != nullptr, "%s: null geometry", who);
+    B200NN_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->F > 0 && g->kh > 0 && g->kw > 0 && g->sh > 0 &&
+                       g->sw > 0 && g->ph >= 0 && g->pw >= 0,
+                   "%s: bad geometry", who);
+    B200NN_REQUIRE(g->OH == (g->H + 2 * g->ph - g->kh) / g->sh + 1 && g->OW == (g->W + 2 * g->pw - g->kw) / g->sw + 1 &&
+                       g->OH > 0 && g->OW > 0,
+                   "%s: output size %dx%d inconsistent with input %dx%d k%dx%d s%dx%d p%dx%d", who, g->OH, g->OW, g->H,
+                   g->W, g->kh, g->kw, g->sh, g->sw, g->ph, g->pw);
+    B200NN_REQUIRE((long long)g->N * g->OH * g->OW < (1LL << 31) && (long long)g->N * g->H * g->W < (1LL << 31),
+                   "%s: pixel count overflows int32", who);
+    return B200NN_OK;
+}
+
+size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
+    const long long Mo = (long long)g->N * g->OH * g->OW, Mi = (long long)g->N * g->H * g->W;
+    const long long Kf = (long long)g->kh * g->kw * g->C, Kd = (long long)g->kh * g->kw * g->F;
+    size_t a = ws_bytes_for(Mo, g->F, Kf);
+    size_t b = ws_bytes_for(Kf + 1, g->F, Mo);
+    size_t c = ws_bytes_for(Mi, g->C, Kd);
+    size_t r = a > b ? a : b;
+    return r > c ? r : c;
+}
+
+static PatchGather conv_patches(const b200nn_conv_geom* g, const float* x) {
+    PatchGather p;
+    p.src = x; p.SH = g->H; p.SW = g->W; p.SC = g->C; p.OH = g->OH; p.OW = g->OW;
+    p.kh = g->kh; p.kw = g->kw; p.sh = g->sh; p.sw = g->sw; p.ph = g->ph; p.pw = g->pw;
+    p.n_pix = g->N * g->OH * g->OW; p.n_tap = g->kh * g->kw * g->C; p.skip_truncated = 0;
+    return p;
+}
+
+int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* b, float* y,
+                      int act, float alpha, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "conv2d_fwd: unsupported math mode %d", math);
+    if (int rc = check_conv_geom("conv2d_fwd", g)) return rc;
+    if (int rc = check_act("conv2d_fwd", act, alpha)) return rc;
+    PatchA af{conv_patches(g, x)};
+    ConvWFwdB bf{w, g->kh, g->kw, g->C, g->F};
+    const int M = g->N * g->OH * g->OW, K = g->kh * g->kw * g->C;
+    Epilogue e = plain_epilogue(y, g->F, M);
+    e.bias = b; e.act = act; e.alpha = alpha;
+    return launch_gemm("conv2d_fwd", af, bf, e, M, g->F, K, ws, as_stream(stream));
+}
+
+int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* err,
+                      const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
+                      float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "conv2d_bwd: unsupported math mode %d", math);
+    if (int rc = check_conv_geom("conv2d_bwd", g)) return rc;
+    if (int rc = check_act("conv2d_bwd", prev_act, prev_alpha)) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int Mo = g->N * g->OH * g->OW, Mi = g->N * g->H * g->W;
+    const int Kf = g->kh * g->kw * g->C, Kd = g->kh * g->kw * g->F;
+    if (dw != nullptr) {  // rows = taps (ky,kx,c) + ones row; reduce over output pixels
+        PatchTOnesA af{conv_patches(g, x), db != nullptr ? 1 : 0};
+        RowMajorB bf{err, g->F, Mo, g->F};
+        Epilogue e = plain_epilogue(dw, g->F, Kf);
+        e.ss = ss; e.chain = chain; e.db = db;
+        e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
+        if (int rc = launch_gemm("conv2d_dw", af, bf, e, Kf + (db != nullptr ? 1 : 0), g->F, Mo, ws, st)) return rc;
+    }
+    if (dx != nullptr) {  // gather form of col2im(err . W^T), preprocessing.py:82-126
+        StridedGatherA af;
+        af.src = err; af.SH = g->OH; af.SW = g->OW; af.SC = g->F; af.DH = g->H; af.DW = g->W;
+        af.kh = g->kh; af.kw = g->kw; af.sh = g->sh; af.sw = g->sw; af.py = g->ph; af.px = g->pw;
+        af.n_pix = Mi; af.n_tap = Kd;
+        ConvWDgradB bf{w, g->kh, g->kw, g->C, g->F};
+        Epilogue e = plain_epilogue(dx, g->C, Mi);
+        dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+        if (int rc = launch_gemm("conv2d_dx", af, bf, e, Mi, g->C, Kd, ws, st)) return rc;
+    }
+    return B200NN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Conv2DTranspose
+static int check_convt_geom(const char* who, const b200nn_convt_geom* g) {
+    B200NN_REQUIRE(g != nullptr, "%s: null geometry", who);
+    B200NN_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->F > 0 && g->kh > 0 && g->kw > 0 && g->sh > 0 &&
+                       g->sw > 0 && g->pt >= 0 && g->pl >= 0 && g->OH > 0 && g->OW > 0,
+                   "%s: bad geometry", who);
+    B200NN_REQUIRE((long long)g->N * g->OH * g->OW < (1LL << 31), "%s: pixel count overflows int32", who);
+    return B200NN_OK;
+}
+
+size_t b200nn_convt_ws_bytes(const b200nn_convt_geom* g) {
+    const long long Mo = (long long)g->N * g->OH * g->OW, Mi = (long long)g->N * g->H * g->W;
+    const long long Kf = (long long)g->kh * g->kw * g->C, Kb = (long long)g->kh * g->kw * g->F;
+    size_t a = ws_bytes_for(Mo, g->F, Kf);
+    size_t b = ws_bytes_for(Kb, g->C, Mi);
+    size_t c = ws_bytes_for(Mi, g->C, Kb);
+    size_t d = (size_t)kNumSMs * 2 * g->F * sizeof(float);  // colsum partials for db
+    size_t r = a > b ? a : b;
+    r = r > c ? r : c;
+    return r > d ? r : d;
+}
+
+int b200nn_convt_fwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* b,
+                     float* y, int act, float alpha, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "convt_fwd: unsupported math mode %d", math);
+    if (int rc = check_convt_geom("convt_fwd", g)) return rc;
+    if (int rc = check_act("convt_fwd", act, alpha)) return rc;
+    StridedGatherA af;
+    af.src = x; af.SH = g->H; af.SW = g->W; af.SC = g->C; af.DH = g->OH; af.DW = g->OW;
+    af.kh = g->kh; af.kw = g->kw; af.sh = g->sh; af.sw = g->sw; af.py = g->pt; af.px = g->pl;
+    af.n_pix = g->N * g->OH * g->OW; af.n_tap = g->kh * g->kw * g->C;
+    ConvTWFwdB bf{w, g->kh, g->kw, g->C, g->F};
+    Epilogue e = plain_epilogue(y, g->F, af.n_pix);
+    e.bias = b; e.act = act; e.alpha = alpha;
+    return launch_gemm("convt_fwd", af, bf, e, af.n_pix, g->F, af.n_tap, ws, as_stream(stream));
+}
+
+int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* err,
+                     const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
+                     float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream) {
+    B200NN_REQUIRE(math == B200NN_MATH_FP32, "convt_bwd: unsupported math mode %d", math);
+    if (int rc = check_convt_geom("convt_bwd", g)) return rc;
+    if (int rc = check_act("convt_bwd", prev_act, prev_alpha)) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int Mi = g->N * g->H * g->W;
+    const int Kb = g->kh * g->kw * g->F;
+    // windows over the (cropped) error, stride s, no pad offset, truncated windows skipped (layers.py:2645-2651)
+    PatchGather p;
+    p.src = err; p.SH = g->OH; p.SW = g->OW; p.SC = g->F; p.OH = g->H; p.OW = g->W;
+    p.kh = g->kh; p.kw = g->kw; p.sh = g->sh; p.sw = g->sw; p.ph = 0; p.pw = 0;
+    p.n_pix = Mi; p.n_tap = Kb; p.skip_truncated = 1;
+    if (db != nullptr) {  // layers.py:2641: sum over ALL error pixels
+        B200NN_REQUIRE(ws != nullptr, "convt_bwd: workspace required");
+        const long long R = (long long)g->N * g->OH * g->OW;
+        int nb = (int)((R + 255) / 256);
+        if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+        colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
+        B200NN_LAUNCH_CHECK("convt_db_partial");
+        colsum_final_kernel<<<(g->F + 127) / 128, 128, 0, st>>>(ws, nb, g->F, ss, chain, db);
+        B200NN_LAUNCH_CHECK("convt_db_final");
+    }
+    if (dw != nullptr) {  // dw[(ky,kx,f), c] = sum_pix window(pix, tap) * x[pix, c]
+        PatchTOnesA af{p, 0};
+        RowMajorB bf{x, g->C, Mi, g->C};
+        Epilogue e = plain_epilogue(dw, g->C, Kb);
+        e.ss = ss; e.chain = chain;
+        if (int rc = launch_gemm("convt_dw", af, bf, e, Kb, g->C, Mi, ws, st)) return rc;
+    }
+    if (dx != nullptr) {  // dx[pix, c] = sum_tap window(pix, tap) * w[tap, c]
+        PatchA af{p};
+        RowMajorB bf{w, g->C, Kb, g->C};
+        Epilogue e = plain_epilogue(dx, g->C, Mi);
+        dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+        if (int rc = launch_gemm("convt_dx", af, bf, e, Mi, g->C, Kb, ws, st)) return rc;
+    }
+    return B200NN_OK;
+}
+
+}  // extern "C"

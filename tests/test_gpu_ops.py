@@ -1,0 +1,372 @@
+"""GPU parity, op level: every C-ABI kernel family against (a) the golden vectors produced by executing
+the upstream reference (tests/golden/ops.npz) and (b) the numpy oracle on seeded inputs at larger sizes.
+
+Tolerances (BASELINE.json north_star): fp32 FFMA path within rel 1e-5 (norm-relative: max|a-b| / max|b|),
+max-pool outputs and argmax bit-exact.
+"""
+import numpy as np
+import pytest
+
+import nnl_oracle as O
+from helpers import nrel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    from neuralnetlib_b200 import _backend as B, _ops as ops
+
+    class Ctx:
+        pass
+
+    k = Ctx()
+    k.B, k.ops, k.torch = B, ops, torch
+    k.dev = lambda a: B.to_device(np.asarray(a, dtype=np.float32))
+    k.host = lambda t: (B.synchronize(), t.detach().cpu().numpy().astype(np.float64))[1]
+    k.empty = B.empty
+    k.ss = lambda n=16: B.zeros((n,), dtype=torch.float64)
+    return k
+
+
+def _f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+ACTS = {"linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "leakyrelu": 4}
+
+
+@pytest.mark.parametrize("name", list(ACTS))
+def test_activation_fwd_bwd_golden(K, golden, name):
+    g = golden("ops")
+    alpha = 0.2 if name == "leakyrelu" else 0.0
+    x = K.dev(g["act_x"]); y = K.empty(x.shape)
+    K.ops.act_fwd(ACTS[name], alpha, x, y)
+    assert nrel(K.host(y), g[f"act_{name}_y"]) < TOL
+    err = K.dev(g["act_err"]); dx = K.empty(x.shape); ss = K.ss()
+    K.ops.act_bwd(ACTS[name], alpha, y, err, ss, (), dx, 3)
+    assert nrel(K.host(dx), g[f"act_{name}_dx"]) < TOL
+    assert abs(K.host(ss)[3] - np.sum(g[f"act_{name}_dx"] ** 2)) < 1e-5 * np.sum(g[f"act_{name}_dx"] ** 2)
+
+
+def test_activation_large_unaligned(K):
+    rng = np.random.default_rng(1)
+    n = 1_000_003
+    x = rng.normal(size=n).astype(np.float32) * 4
+    xd = K.dev(x); yd = K.empty((n,))
+    for name in ("relu", "sigmoid", "tanh"):
+        K.ops.act_fwd(ACTS[name], 0.0, xd, yd)
+        assert nrel(K.host(yd), O.act_fwd(name, x.astype(np.float64))) < TOL
+
+
+def test_softmax_and_losses_golden(K, golden):
+    g = golden("ops")
+    x = K.dev(g["act_x"]); p = K.empty(x.shape)
+    K.ops.softmax_fwd(x, p)
+    assert nrel(K.host(p), g["act_softmax_y"]) < TOL
+    for kind, code, pk, yk in (("cce", 2, "loss_p", "loss_y"), ("mse", 0, "loss_p", "loss_y"), ("bce", 1, "loss_pb", "loss_yb")):
+        pd, yd = K.dev(g[pk]), K.dev(g[yk])
+        err = K.empty(pd.shape); acc = K.B.zeros((4,), dtype=K.torch.float64); ss = K.ss()
+        K.ops.loss_fwd_bwd(code, 0, pd, yd, err, acc, ss, 0)
+        rows, cols = g[pk].shape
+        denom = rows if kind == "cce" else rows * cols
+        assert abs(K.host(acc)[0] / denom - float(g[f"loss_{kind}"])) < 1e-5 * abs(float(g[f"loss_{kind}"]))
+        assert nrel(K.host(err), g[f"loss_{kind}_d"]) < TOL
+        # fused pair: err = p - y, not divided by the batch (models.py:200-205)
+        K.ops.zero_f64(ss); K.ops.zero_f64(acc)
+        K.ops.loss_fwd_bwd(code, 1, pd, yd, err, acc, ss, 1)
+        assert nrel(K.host(err), _f32(g[pk]) - _f32(g[yk])) < TOL
+        assert abs(K.host(ss)[1] - np.sum((g[pk] - g[yk]) ** 2)) < 1e-5
+    # argmax count incl. first-index tie break (metrics.py:84-89)
+    p = np.array([[0.5, 0.5, 0.0], [0.1, 0.2, 0.7], [0.3, 0.3, 0.4]], dtype=np.float32)
+    y = np.array([[1, 0, 0], [0, 0, 1], [0, 1, 0]], dtype=np.float32)
+    acc = K.B.zeros((4,), dtype=K.torch.float64)
+    K.ops.loss_fwd_bwd(2, 1, K.dev(p), K.dev(y), K.empty(p.shape), acc, None, None)
+    assert K.host(acc)[1] == np.sum(p.argmax(1) == y.argmax(1)) == 2
+
+
+def test_clip_chain(K, golden):
+    g = golden("ops")
+    x = K.dev(g["clip_in"]); ss = K.ss(); out = K.empty(x.shape)
+    K.ops.sumsq(x, ss, 5)
+    K.ops.scale_apply(x, ss, (5,), out)
+    assert nrel(K.host(out), g["clip_big"]) < TOL
+    xs = K.dev(g["clip_in"] * 1e-2); K.ops.zero_f64(ss)
+    K.ops.sumsq(xs, ss, 2)
+    K.ops.scale_apply(xs, ss, (2,), out)
+    assert nrel(K.host(out), g["clip_small"]) < 1e-7  # norm <= 1: untouched
+    # two-slot chain: acc = s0 * clip(s0^2 * ss1)
+    ss2 = K.B.to_device(np.array([4.0, 9.0, 0.25]), dtype=K.torch.float64)
+    K.ops.scale_apply(x, ss2, (0, 1), out)   # s0 = 1/2; n2 = 1/4*9 -> s1 = 2/3 ; total 1/3
+    assert nrel(K.host(out), _f32(g["clip_in"]) / 3.0) < 1e-6
+    K.ops.scale_apply(x, ss2, (2, 0), out)   # slot2 <= 1: no clip; then 1/2
+    assert nrel(K.host(out), _f32(g["clip_in"]) / 2.0) < 1e-6
+
+
+def test_dense_golden(K, golden):
+    g = golden("ops")
+    x, w, b, err = (K.dev(g[k]) for k in ("dense_x", "dense_w", "dense_b", "dense_err"))
+    y = K.empty((5, 3))
+    K.ops.dense_fwd(0, x, w, b.reshape(-1), y, 0, 0.0, None)
+    assert nrel(K.host(y), g["dense_y"]) < TOL
+    dx, dw, db = K.empty((5, 7)), K.empty((7, 3)), K.empty((3,))
+    K.ops.dense_bwd(0, x, w, err, None, (), dx, dw, db, 0, 0.0, None, None, None)
+    assert nrel(K.host(dx), g["dense_dx"]) < TOL
+    assert nrel(K.host(dw), g["dense_dw"]) < TOL
+    assert nrel(K.host(db), g["dense_db"].reshape(-1)) < TOL
+
+
+@pytest.mark.parametrize("M,N,Kd,act", [(32, 128, 784, "relu"), (256, 64, 6272, "relu"), (256, 10, 64, "linear"),
+                                        (100, 70, 33, "sigmoid"), (1, 5, 3, "tanh"), (300, 300, 300, "leakyrelu")])
+def test_dense_oracle(K, M, N, Kd, act):
+    rng = np.random.default_rng(M * 7 + N)
+    x = rng.normal(size=(M, Kd)).astype(np.float32)
+    w = (rng.normal(size=(Kd, N)) / np.sqrt(Kd)).astype(np.float32)
+    b = rng.normal(size=(N,)).astype(np.float32)
+    err = rng.normal(size=(M, N)).astype(np.float32)
+    alpha = 0.1 if act == "leakyrelu" else 0.0
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    wsb = K.ops.dense_ws_bytes(M, N, Kd)
+    ws = K.empty((max(wsb // 4, 1),))
+    y = K.empty((M, N))
+    K.ops.dense_fwd(0, xd, wd, bd, y, ACTS[act], alpha, ws)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    ref = O.act_fwd(act, O.dense_fwd(x64, w64, b.astype(np.float64)), alpha)
+    assert nrel(K.host(y), ref) < TOL
+    # backward with a clip chain and the fused backward of a preceding activation (mask from x)
+    ss = K.ss()
+    K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty((M, Kd)), K.empty((Kd, N)), K.empty((N,))
+    xpos = np.maximum(x, 0)  # pretend x is a ReLU output
+    xpd = K.dev(xpos)
+    K.ops.dense_bwd(0, xpd, wd, ed, ss, (0,), dx, dw, db, ACTS["relu"], 0.0, 1, 2, ws)
+    e64 = O.clip_l2(err.astype(np.float64))
+    rdx, rdw, rdb = O.dense_bwd(xpos.astype(np.float64), w64, e64)
+    hss = K.host(ss)
+    assert abs(hss[1] - np.sum(rdx ** 2)) < 1e-4 * np.sum(rdx ** 2)
+    masked = rdx * (xpos > 0)
+    assert nrel(K.host(dx), masked) < TOL
+    assert abs(hss[2] - np.sum(masked ** 2)) < 1e-4 * max(np.sum(masked ** 2), 1e-30)
+    assert nrel(K.host(dw), rdw) < TOL
+    assert nrel(K.host(db), rdb.reshape(-1)) < TOL
+    # dx == None is allowed (first parametrised layer in fit)
+    K.ops.dense_bwd(0, xpd, wd, ed, ss, (0,), None, dw, db, 0, 0.0, None, None, ws)
+    assert nrel(K.host(dw), rdw) < TOL
+
+
+def _conv_geom(K, N, H, W, C, F, kh, kw, sh, sw, pad):
+    oh, ow, ph, pw = O.conv2d_geometry(H, W, kh, kw, sh, sw, pad)
+    return K.B.ConvGeom(N, H, W, C, F, kh, kw, sh, sw, ph, pw, oh, ow), oh, ow
+
+
+@pytest.mark.parametrize("gi", range(6))
+def test_conv2d_golden(K, golden, gi):
+    g = golden("ops")
+    H, W, C, F, kh, kw, sh, sw, same = [int(v) for v in g[f"conv{gi}_cfg"]]
+    geom, oh, ow = _conv_geom(K, 3, H, W, C, F, kh, kw, sh, sw, "same" if same else "valid")
+    x, w, b, err = (K.dev(g[f"conv{gi}_{k}"]) for k in ("x", "w", "b", "err"))
+    ws = K.empty((max(K.ops.conv2d_ws_bytes(geom) // 4, 1),))
+    y = K.empty((3, oh, ow, F))
+    K.ops.conv2d_fwd(0, geom, x, w, b.reshape(-1), y, 0, 0.0, ws)
+    assert nrel(K.host(y), g[f"conv{gi}_y"]) < TOL
+    dx, dw, db = K.empty((3, H, W, C)), K.empty((kh, kw, C, F)), K.empty((F,))
+    K.ops.conv2d_bwd(0, geom, x, w, err, None, (), dx, dw, db, 0, 0.0, None, None, ws)
+    assert nrel(K.host(dx), g[f"conv{gi}_dx"]) < TOL
+    assert nrel(K.host(dw), g[f"conv{gi}_dw"]) < TOL
+    assert nrel(K.host(db), g[f"conv{gi}_db"]) < TOL
+
+
+@pytest.mark.parametrize("N,H,W,C,F,k,s,pad", [(16, 28, 28, 1, 32, 3, 1, "same"), (8, 32, 32, 3, 64, 3, 1, "same"),
+                                               (4, 16, 16, 64, 128, 3, 1, "same"), (8, 28, 28, 1, 32, 3, 2, "same"),
+                                               (8, 13, 13, 32, 64, 3, 2, "same"), (4, 28, 28, 32, 1, 3, 1, "same")])
+def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
+    rng = np.random.default_rng(H * 31 + C)
+    x = rng.normal(size=(N, H, W, C)).astype(np.float32)
+    w = (rng.normal(size=(k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    geom, oh, ow = _conv_geom(K, N, H, W, C, F, k, k, s, s, pad)
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    ws = K.empty((max(K.ops.conv2d_ws_bytes(geom) // 4, 1),))
+    y = K.empty((N, oh, ow, F))
+    K.ops.conv2d_fwd(0, geom, xd, wd, bd, y, 1, 0.0, ws)
+    ref = np.maximum(O.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), pad), 0)
+    assert nrel(K.host(y), ref) < TOL
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty(x.shape), K.empty(w.shape), K.empty((F,))
+    K.ops.conv2d_bwd(0, geom, xd, wd, ed, ss, (0,), dx, dw, db, 0, 0.0, 1, None, ws)
+    rdx, rdw, rdb = O.conv2d_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (s, s), pad)
+    assert nrel(K.host(dx), rdx) < TOL
+    assert nrel(K.host(dw), rdw) < TOL
+    assert nrel(K.host(db), rdb) < TOL
+    assert abs(K.host(ss)[1] - np.sum(rdx ** 2)) < 1e-4 * np.sum(rdx ** 2)
+
+
+def _convt_geom(K, N, H, W, C, F, kh, kw, sh, sw, pad):
+    oh, ow, pt, pb, pl, pr = O.convT_geometry(H, W, kh, kw, sh, sw, pad)
+    return K.B.ConvTGeom(N, H, W, C, F, kh, kw, sh, sw, pt, pl, oh, ow), oh, ow
+
+
+@pytest.mark.parametrize("gi", range(6))
+def test_convt_golden(K, golden, gi):
+    g = golden("ops")
+    H, W, C, F, kh, kw, sh, sw, same = [int(v) for v in g[f"convT{gi}_cfg"]]
+    geom, oh, ow = _convt_geom(K, 3, H, W, C, F, kh, kw, sh, sw, "same" if same else "valid")
+    x, w, b, err = (K.dev(g[f"convT{gi}_{k}"]) for k in ("x", "w", "b", "err"))
+    ws = K.empty((max(K.ops.convt_ws_bytes(geom) // 4, 1),))
+    y = K.empty((3, oh, ow, F))
+    K.ops.convt_fwd(0, geom, x, w, b.reshape(-1), y, 0, 0.0, ws)
+    assert nrel(K.host(y), g[f"convT{gi}_y"]) < TOL
+    dx, dw, db = K.empty((3, H, W, C)), K.empty((kh, kw, F, C)), K.empty((F,))
+    K.ops.convt_bwd(0, geom, x, w, err, None, (), dx, dw, db, 0, 0.0, None, None, ws)
+    assert nrel(K.host(dx), g[f"convT{gi}_dx"]) < TOL
+    assert nrel(K.host(dw), g[f"convT{gi}_dw"]) < TOL
+    assert nrel(K.host(db), g[f"convT{gi}_db"].reshape(-1)) < TOL
+
+
+@pytest.mark.parametrize("N,H,W,C,F", [(8, 7, 7, 128, 64), (8, 14, 14, 64, 32)])
+def test_convt_oracle(K, N, H, W, C, F):
+    rng = np.random.default_rng(H + C)
+    x = np.maximum(rng.normal(size=(N, H, W, C)), 0).astype(np.float32)
+    w = (rng.normal(size=(3, 3, F, C)) / np.sqrt(9 * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    geom, oh, ow = _convt_geom(K, N, H, W, C, F, 3, 3, 2, 2, "same")
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    ws = K.empty((max(K.ops.convt_ws_bytes(geom) // 4, 1),))
+    y = K.empty((N, oh, ow, F))
+    K.ops.convt_fwd(0, geom, xd, wd, bd, y, 1, 0.0, ws)
+    ref = np.maximum(O.convT_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (2, 2), "same"), 0)
+    assert nrel(K.host(y), ref) < TOL
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty(x.shape), K.empty(w.shape), K.empty((F,))
+    K.ops.convt_bwd(0, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    rdx, rdw, rdb = O.convT_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (2, 2))
+    assert nrel(K.host(dx), rdx * (x > 0)) < TOL
+    assert nrel(K.host(dw), rdw) < TOL
+    assert nrel(K.host(db), rdb.reshape(-1)) < TOL
+    assert np.all(K.host(dx)[:, -1] == 0) and np.all(K.host(dx)[:, :, -1] == 0)  # Q12 edge skip
+
+
+def test_batchnorm_golden(K, golden):
+    g = golden("ops")
+    x1 = K.dev(g["bn_x1"]); shp = g["bn_x1"].shape[1:]
+    P = int(np.prod(shp))
+    gamma, beta = K.B.to_device(np.ones(P)), K.B.zeros((P,))
+    rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
+    sm, si, y = K.empty((P,)), K.empty((P,)), K.empty(x1.shape)
+    K.ops.bn_fwd_train(x1, gamma, beta, rm, rv, sm, si, y, 0.9, 1e-5)
+    assert nrel(K.host(y), g["bn_y1"]) < TOL
+    assert nrel(K.host(rm).reshape(shp), g["bn_rm1"]) < TOL and nrel(K.host(rv).reshape(shp), g["bn_rv1"]) < TOL
+    e1 = K.dev(g["bn_e1"]); dx, dg, dbt = K.empty(x1.shape), K.empty((P,)), K.empty((P,))
+    K.ops.bn_bwd(x1, e1, None, (), gamma, sm, si, dx, dg, dbt, 0, 0.0, None, None)
+    assert nrel(K.host(dx), g["bn_dx1"]) < 2e-5
+    assert nrel(K.host(dg).reshape(shp), g["bn_dgamma1"]) < TOL and nrel(K.host(dbt).reshape(shp), g["bn_dbeta1"]) < TOL
+    x2 = K.dev(g["bn_x2"])
+    K.ops.bn_fwd_train(x2, gamma, beta, rm, rv, sm, si, y, 0.9, 1e-5)
+    assert nrel(K.host(y), g["bn_y2"]) < TOL
+    assert nrel(K.host(rm).reshape(shp), g["bn_rm2"]) < TOL and nrel(K.host(rv).reshape(shp), g["bn_rv2"]) < TOL
+    K.ops.bn_fwd_infer(x1, gamma, beta, rm, rv, y, 1e-5)
+    assert nrel(K.host(y), g["bn_yinf"]) < TOL
+
+
+@pytest.mark.parametrize("Bn,shape", [(256, (28, 28, 32)), (64, (8, 8, 5)), (7, (33,))])
+def test_batchnorm_oracle(K, Bn, shape):
+    rng = np.random.default_rng(Bn)
+    x = np.maximum(rng.normal(size=(Bn,) + shape) * 0.05, 0).astype(np.float32)  # post-ReLU conv-like input
+    e = rng.normal(size=x.shape).astype(np.float32)
+    P = int(np.prod(shape))
+    gamma = (1 + 0.1 * rng.normal(size=P)).astype(np.float32); beta = (0.1 * rng.normal(size=P)).astype(np.float32)
+    xd, ed, gd, bd = K.dev(x), K.dev(e), K.dev(gamma), K.dev(beta)
+    rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
+    sm, si, y = K.empty((P,)), K.empty((P,)), K.empty(x.shape)
+    K.ops.bn_fwd_train(xd, gd, bd, rm, rv, sm, si, y, 0.9, 1e-5)
+    g64, b64 = gamma.astype(np.float64).reshape(shape), beta.astype(np.float64).reshape(shape)
+    ry, rrm, rrv, cache = O.bn_fwd(x.astype(np.float64), g64, b64, np.zeros(shape), np.ones(shape), 0.9, 1e-5, True)
+    assert nrel(K.host(y), ry) < TOL
+    assert nrel(K.host(rv).reshape(shape), rrv) < TOL
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dg, dbt = K.empty(x.shape), K.empty((P,)), K.empty((P,))
+    K.ops.bn_bwd(xd, ed, ss, (0,), gd, sm, si, dx, dg, dbt, 1, 0.0, 1, 2)
+    rdx, rdg, rdb = O.bn_bwd(O.clip_l2(e.astype(np.float64)), g64, cache, 1e-5)
+    assert nrel(K.host(dx), rdx * (x > 0)) < 2e-5
+    assert nrel(K.host(dg).reshape(shape), rdg) < 2e-5
+    h = K.host(ss)
+    assert abs(h[1] - np.sum(rdx ** 2)) < 1e-4 * np.sum(rdx ** 2)
+    assert abs(h[2] - np.sum((rdx * (x > 0)) ** 2)) < 1e-4 * np.sum(rdx ** 2)
+
+
+@pytest.mark.parametrize("gi", range(4))
+def test_maxpool_golden(K, golden, gi):
+    g = golden("ops")
+    H, W, C, ph, pw, sh, sw = [int(v) for v in g[f"pool{gi}_cfg"]]
+    oh, ow = (H - ph) // sh + 1, (W - pw) // sw + 1
+    geom = K.B.PoolGeom(3, H, W, C, ph, pw, sh, sw, 0, 0, oh, ow)
+    x, err = K.dev(g[f"pool{gi}_x"]), K.dev(g[f"pool{gi}_err"])
+    y = K.empty((3, oh, ow, C)); dx = K.empty(x.shape)
+    K.ops.maxpool_fwd(geom, x, y)
+    assert np.array_equal(K.host(y), _f32(g[f"pool{gi}_y"]))  # bit-exact selection
+    K.ops.maxpool_bwd(geom, x, y, err, None, (), dx, None)
+    assert nrel(K.host(dx), g[f"pool{gi}_dx"]) < TOL
+
+
+def test_maxpool_ties_all_zero(K):
+    geom = K.B.PoolGeom(1, 2, 2, 1, 2, 2, 2, 2, 0, 0, 1, 1)
+    x = K.B.zeros((1, 2, 2, 1)); y = K.empty((1, 1, 1, 1)); dx = K.empty((1, 2, 2, 1))
+    K.ops.maxpool_fwd(geom, x, y)
+    K.ops.maxpool_bwd(geom, x, y, K.dev(np.ones((1, 1, 1, 1))), None, (), dx, None)
+    assert np.array_equal(K.host(dx).ravel(), [1, 1, 1, 1])  # Q6: every tied maximum receives the gradient
+
+
+def test_adam_sgd_golden(K, golden):
+    g = golden("ops")
+    torch = K.torch
+    p = [K.dev(g[f"adam_p{i}_init"]) for i in range(4)]
+    gs = [K.dev(g[f"adam_g{i}"]) for i in range(6)]
+    m = [K.B.zeros(t.shape) for t in p]; v = [K.B.zeros(t.shape) for t in p]
+    hyper = K.B.to_device(np.array([1e-3, 0.9, 0.999, 1e-8]), dtype=torch.float64)
+    t = K.B.zeros((1,), dtype=torch.int64)
+    # reference: opt.update(5, w0, g0, b0, g1); update(3, w1, g2, b1, g3); update(5, w0, g4, b0, g5) -> t = 1, 2, 3
+    for (pi, gi) in (((0, 1), (0, 1)), ((2, 3), (2, 3)), ((0, 1), (4, 5))):
+        plan = K.ops.OptPlan([(p[pi[0]], gs[gi[0]], m[pi[0]], v[pi[0]], 1, 0), (p[pi[1]], gs[gi[1]], m[pi[1]], v[pi[1]], 1, 0)], 1)
+        K.ops.step_begin(None, None, t, 1)
+        K.ops.adam_multi(plan, hyper, t)
+    for i in range(4):
+        assert nrel(K.host(p[i]), g[f"adam_p{i}_final"]) < TOL
+    assert nrel(K.host(m[0]), g["adam_m_w5"]) < TOL and nrel(K.host(v[0]), g["adam_v_w5"]) < TOL
+    assert int(K.host(t.double())[0]) == int(g["adam_t"])
+    w = K.dev(g["sgd_w_init"]); gg = K.dev(g["sgd_g"])
+    plan = K.ops.OptPlan([(w, gg, None, None, 1, 0)], 1)
+    K.ops.sgd_multi(plan, K.B.to_device(np.array([0.05, 0, 0, 0]), dtype=torch.float64))
+    assert nrel(K.host(w), g["sgd_w_final"]) < TOL
+
+
+def test_adam_clip_and_large(K):
+    rng = np.random.default_rng(3)
+    n = 100_003
+    p0 = rng.normal(size=n).astype(np.float32); g0 = rng.normal(size=n).astype(np.float32)
+    pd, gd = K.dev(p0), K.dev(g0)
+    md, vd = K.B.zeros((n,)), K.B.zeros((n,))
+    hyper = K.B.to_device(np.array([1e-3, 0.9, 0.999, 1e-8]), dtype=K.torch.float64)
+    t = K.B.zeros((1,), dtype=K.torch.int64)
+    plan = K.ops.OptPlan([(pd, gd, md, vd, 2, 1)], 3)
+    ref = O.OracleAdam(); ref.t = 0
+    p64 = p0.astype(np.float64)
+    for step in range(2):
+        K.ops.step_begin(None, None, t, 3)
+        K.ops.adam_multi(plan, hyper, t)
+        ref.t = step * 3 + 1  # oracle increments to t = step*3 + 2 inside update
+        ref.update(0, p64, O.clip_l2(g0.astype(np.float64)))
+    assert nrel(K.host(pd), p64) < TOL
+    assert nrel(K.host(md), ref.m_w[0]) < TOL and nrel(K.host(vd), ref.v_w[0]) < TOL
+
+
+def test_gather_rows(K):
+    rng = np.random.default_rng(0)
+    src = rng.normal(size=(50, 7, 9)).astype(np.float32)
+    idx = rng.permutation(50)[:20]
+    d = K.empty((20, 7, 9))
+    K.ops.gather_rows(K.dev(src), K.B.to_device(idx, dtype=K.torch.int64), d)
+    assert np.array_equal(K.host(d), src[idx].astype(np.float64))
