@@ -1,0 +1,334 @@
+"""Resident execution plan of a `Sequential` for one (batch shape, training flag).
+
+Replaces the per-layer NumPy loop of models.py:159-264 by a static program over pre-allocated HBM buffers:
+  * forward: [Dense|Conv2D|Conv2DTranspose]+Activation pairs run as one kernel (bias + activation epilogue);
+    Input/Flatten/Reshape are views;
+  * backward: the reference's clip of every error tensor to L2 norm <= 1 (models.py:214) is carried lazily as a
+    chain of float64 sum-of-squares slots (include/b200nn.h), so no extra pass over any tensor is needed; the
+    backward of an Activation is folded into the dx epilogue of the layer that consumes its output; the dx of the
+    first parametrised layer is skipped inside fit (nothing observes it);
+  * update: per-tensor gradient clip (models.py:240-242) + Adam/SGD for every parameter tensor in one fused
+    multi-tensor launch, Adam's per-layer `t` advanced on the device;
+  * the whole step (step_begin, forward, loss, backward, update) is captured into one CUDA graph on its second
+    execution and replayed afterwards: one host call per step, no allocation, no host<->device traffic except the
+    batch upload and (when asked for) the loss read-back.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _backend as B
+from . import _ops as ops
+from .layers import Activation, BatchNormalization, Input, _Err
+from .losses import BinaryCrossentropy, CategoricalCrossentropy
+
+MAX_SLOTS = 256
+
+
+class _Program:
+    """A list of kernel launches that is run eagerly once and replayed as a CUDA graph afterwards."""
+
+    def __init__(self, name):
+        self.name = name
+        self.ops = []
+        self.graph = None
+        self.runs = 0
+
+    def run(self, use_graph=True):
+        if self.graph is not None:
+            ops.graph_launch(self.graph)
+        elif use_graph and self.runs >= 1:
+            ops.graph_begin()
+            try:
+                for fn in self.ops:
+                    fn()
+            finally:
+                self.graph = ops.graph_end()
+            ops.graph_launch(self.graph)
+        else:
+            for fn in self.ops:
+                fn()
+        self.runs += 1
+
+    def destroy(self):
+        if self.graph is not None:
+            ops.graph_destroy(self.graph)
+            self.graph = None
+
+
+class Plan:
+    def __init__(self, model, batch_shape, training: bool):
+        self.model = model
+        self.layers = list(model.layers)
+        self.batch_shape = tuple(int(s) for s in batch_shape)
+        self.B = self.batch_shape[0]
+        self.training = bool(training)
+        self.ss = B.zeros((MAX_SLOTS,), dtype=torch.float64)
+        self.acc = B.zeros((4,), dtype=torch.float64)
+        self.n_slots = 0
+        self._ws = None
+        self._ws_bytes = 0
+        self._emit_to = None
+        self.x_in = B.empty(self.batch_shape)
+        self.x_stage = None
+        self.y_in = None
+        self.y_stage = None
+        self.state = [dict() for _ in self.layers]
+        self.outs = [None] * len(self.layers)
+        self.fwd_fused = [False] * len(self.layers)   # Activation i applied inside layer i-1's kernel
+        self.programs = {}
+        self._build_forward()
+
+    # ---- allocation context used by the layers' plan hooks ---------------------------------------------------
+    def buf(self, shape):
+        return B.empty(tuple(int(s) for s in shape))
+
+    def slot(self):
+        if self.n_slots >= MAX_SLOTS:
+            raise RuntimeError("too many clip slots in one plan")
+        s = self.n_slots
+        self.n_slots += 1
+        return s
+
+    def need_ws(self, nbytes):
+        self._ws_bytes = max(self._ws_bytes, int(nbytes))
+
+    @property
+    def ws(self):
+        if self._ws is None or self._ws.numel() * 4 < self._ws_bytes:
+            self._ws_keep = getattr(self, "_ws_keep", []) + [self._ws]   # captured graphs may still point at it
+            self._ws = B.empty((max(self._ws_bytes // 4, 1),))
+        return self._ws
+
+    def emit(self, fn):
+        self._emit_to.append(fn)
+
+    # ---- forward ------------------------------------------------------------------------------------------------
+    def _build_forward(self):
+        prog = _Program("forward")
+        self._emit_to = prog.ops
+        layers = self.layers
+        x = self.x_in
+        i, n = 0, len(layers)
+        while i < n:
+            L = layers[i]
+            if L._is_view:
+                shp = L._out_shape(tuple(x.shape))
+                if isinstance(L, Input):
+                    if tuple(L.input_shape) != tuple(x.shape[1:]) and int(np.prod(L.input_shape)) != int(np.prod(x.shape[1:])):
+                        raise ValueError(f"Input layer expects {tuple(L.input_shape)}, got {tuple(x.shape[1:])}")
+                else:
+                    L.input_shape = tuple(x.shape)
+                y = x.reshape(shp)
+                self.state[i].update(in_shape=tuple(x.shape))
+                self.outs[i] = y
+                x = y
+                i += 1
+                continue
+            nxt = layers[i + 1] if i + 1 < n else None
+            fuse = L._fuses_act and isinstance(nxt, Activation) and nxt._fusable
+            self.state[i].update(in_shape=tuple(x.shape))
+            y = L._plan_forward(self, self.state[i], x, nxt if fuse else None, self.training)
+            self.outs[i] = y
+            if fuse:
+                self.outs[i + 1] = y
+                self.state[i + 1].update(y=y, in_shape=tuple(y.shape))
+                self.fwd_fused[i + 1] = True
+                i += 2
+            else:
+                i += 1
+            x = y
+        self.pred = x
+        self.programs["forward"] = prog
+        self._emit_to = None
+
+    # ---- backward -----------------------------------------------------------------------------------------------
+    def _has_weights(self, L):
+        return hasattr(L, "weights")
+
+    def _build_backward(self, err: _Err, gan: bool, compute_only: bool, want_input_error: bool):
+        """Emits the backward kernels into self._emit_to; returns (updates, input_error or None)."""
+        layers = self.layers
+        n = len(layers)
+        updates = []
+        cur = err
+        i = n - 1
+        if isinstance(layers[i], Activation):
+            if gan:   # models.py:211-212: the real derivative of the last activation, no clip before it
+                cur = layers[i]._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
+            # not gan: p - y (recognised pairs) or the raw loss derivative with the activation's derivative
+            # skipped (models.py:198-210, Q7) -- both already sit in `err`
+            i -= 1
+        while i >= 0 and cur is not None:
+            L = layers[i]
+            if L._is_view:
+                cur = _Err(cur.t.reshape(self.state[i]["in_shape"]), cur.chain)
+                i -= 1
+                continue
+            need_dx = want_input_error or any(self._has_weights(layers[k]) for k in range(i))
+            if not need_dx and not self._has_weights(L):
+                cur = None   # nothing upstream is trainable and nobody observes the input error
+                break
+            if isinstance(L, Activation):
+                cur = L._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
+                i -= 1
+                continue
+            mask, j = None, i - 1
+            if L._supports_mask and need_dx:
+                while j >= 0 and layers[j]._is_view and not isinstance(layers[j], Input):
+                    j -= 1
+                if j >= 1 and isinstance(layers[j], Activation) and layers[j]._fusable:
+                    mask = layers[j]
+            et = cur.t.reshape(self.outs[i].shape)
+            cur = L._plan_backward(self, self.state[i], _Err(et, cur.chain), mask, need_dx)
+            if self._has_weights(L) and not compute_only:
+                updates.append(i)
+            if mask is not None and cur is not None:
+                cur = _Err(cur.t.reshape(self.outs[j].shape), cur.chain)
+                i = j - 1
+            else:
+                i -= 1
+        return updates, cur
+
+    def _loss_kind(self):
+        lf = self.model.loss_function
+        if lf is None or lf._kind is None:
+            raise ValueError("the model must be compiled with a supported loss before training")
+        last = self.layers[-1]
+        fused = False
+        if isinstance(last, Activation):
+            name = type(last.activation_function).__name__
+            fused = (name == "Softmax" and isinstance(lf, CategoricalCrossentropy)) or \
+                    (name == "Sigmoid" and isinstance(lf, BinaryCrossentropy))
+        return lf._kind, fused
+
+    def _ensure_targets(self):
+        if self.y_in is None:
+            self.y_in = B.empty(tuple(self.pred.shape))
+
+    def program(self, kind: str):
+        """kind: 'forward' | 'train' (fwd+loss+bwd+update) | 'loss' (loss value only, evaluate) |
+        'backward' / 'backward_gan' / 'backward_compute_only' (public backward_pass on an external error)."""
+        if kind in self.programs:
+            return self.programs[kind]
+        prog = _Program(kind)
+        self._emit_to = prog.ops
+        model = self.model
+        if kind == "train":
+            self._ensure_targets()
+            opt = model.optimizer
+            lk, fused = self._loss_kind()
+            counter = opt._t_counter()
+            begin_at = len(prog.ops)
+            prog.ops.append(None)  # placeholder for step_begin (needs the number of updated layers)
+            prog.ops.extend(self.programs["forward"].ops)
+            err0 = self.buf(self.pred.shape)
+            s0 = self.slot()
+            pred, y_in, acc, ss = self.pred, self.y_in, self.acc, self.ss
+            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0))
+            updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
+            ups = []
+            for li in updates:
+                L = self.layers[li]
+                ups.append((li, L._weights, L._d_weights, L._bias, L._d_bias))
+            n_upd = len(ups)
+            if n_upd:
+                oplan = opt._make_plan(ups)
+                self.emit(lambda: opt._run_plan(oplan))
+            prog.ops[begin_at] = lambda: ops.step_begin(ss, acc, counter, n_upd)
+            self.train_err0 = err0
+        elif kind == "loss":
+            self._ensure_targets()
+            lk, fused = self._loss_kind()
+            pred, y_in, acc = self.pred, self.y_in, self.acc
+            self.emit(lambda: ops.step_begin(None, acc, None, 0))
+            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, None, acc, None, None))
+        elif kind in ("backward", "backward_gan", "backward_compute_only"):
+            gan, compute_only = kind == "backward_gan", kind == "backward_compute_only"
+            opt = model.optimizer
+            counter = opt._t_counter() if (opt is not None and not compute_only) else None
+            ss, acc = self.ss, self.acc
+            begin_at = len(prog.ops)
+            prog.ops.append(None)
+            self.err_in = self.buf(self.pred.shape)
+            last_is_act = isinstance(self.layers[-1], Activation)
+            if last_is_act and not gan:
+                # models.py:198-210: for the recognised pairs the incoming error is REPLACED by predictions - y_true
+                lk, fused = self._loss_kind() if model.loss_function is not None else (None, False)
+                if fused:
+                    self._ensure_targets()
+                    pred, y_in, err_in = self.pred, self.y_in, self.err_in
+                    self.emit(lambda: ops.loss_fwd_bwd(lk, 1, pred, y_in, err_in, None, None, None))
+                s0 = self.slot()
+                err_in = self.err_in
+                self.emit(lambda: ops.sumsq(err_in, ss, s0))
+                start = _Err(self.err_in, (s0,))
+            elif last_is_act and gan:
+                start = _Err(self.err_in, ())
+            else:
+                s0 = self.slot()
+                err_in = self.err_in
+                self.emit(lambda: ops.sumsq(err_in, ss, s0))
+                start = _Err(self.err_in, (s0,))
+            updates, in_err = self._build_backward(start, gan, compute_only, True)
+            # materialise the returned input error: clip folded in (the reference clips before Input too)
+            self.in_err_out = self.buf(in_err.t.shape)
+            iet, chain, out = in_err.t, in_err.chain, self.in_err_out
+            self.emit(lambda: ops.scale_apply(iet, ss, chain, out))
+            ups = [(li, self.layers[li]._weights, self.layers[li]._d_weights, self.layers[li]._bias, self.layers[li]._d_bias)
+                   for li in updates]
+            n_upd = len(ups)
+            if n_upd:
+                oplan = opt._make_plan(ups)
+                self.emit(lambda: opt._run_plan(oplan))
+            prog.ops[begin_at] = lambda: ops.step_begin(ss, None, counter, n_upd)
+        else:
+            raise KeyError(kind)
+        self._emit_to = None
+        _ = self.ws  # allocate the workspace before any capture
+        self.programs[kind] = prog
+        return prog
+
+    # ---- host <-> device staging -----------------------------------------------------------------------------------
+    @staticmethod
+    def _upload(dst: torch.Tensor, stage_attr, owner, src):
+        """Copy a host array (any float dtype) or a device tensor into the static input buffer `dst`.
+        float32 C-contiguous arrays are copied straight from their own memory (asynchronously when it is pinned);
+        anything else is converted into a pinned staging buffer first."""
+        if isinstance(src, torch.Tensor):
+            if src.is_cuda:
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src.reshape(dst.shape))
+                return
+            src_t = src
+        else:
+            a = np.asarray(src)
+            if a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable:
+                src_t = torch.from_numpy(a)
+            else:
+                stage = getattr(owner, stage_attr, None)
+                if stage is None:
+                    stage = torch.empty(tuple(dst.shape), dtype=torch.float32, pin_memory=True)
+                    setattr(owner, stage_attr, stage)
+                evt = getattr(owner, stage_attr + "_evt", None)
+                if evt is not None:
+                    evt.synchronize()   # the previous async copy out of this staging buffer must have finished
+                np.copyto(stage.numpy(), a.reshape(tuple(stage.shape)), casting="unsafe")
+                dst.copy_(stage, non_blocking=True)
+                evt = torch.cuda.Event()
+                evt.record(B.stream_obj())
+                setattr(owner, stage_attr + "_evt", evt)
+                return
+        dst.copy_(src_t.reshape(dst.shape), non_blocking=True)
+
+    def set_input(self, x):
+        self._upload(self.x_in, "x_stage", self, x)
+
+    def set_target(self, y):
+        self._ensure_targets()
+        self._upload(self.y_in, "y_stage", self, y)
+
+    def destroy(self):
+        for p in self.programs.values():
+            p.destroy()

@@ -1,0 +1,808 @@
+"""Mirror of the hot-path layers of neuralnetlib/layers.py on the device:
+Layer :14-36, Input :39-64, Dense :67-218, Activation :221-261, Conv2D :345-530, MaxPooling2D :533-643,
+Flatten :646-664, BatchNormalization :1205-1304, Reshape :1563-1588, Conv2DTranspose :2536-2692.
+
+Same constructor signatures, attributes (`weights`, `bias`, `d_weights`, `d_bias`, `gamma`, ... read as float64
+NumPy arrays, assignable), `get_config`/`from_config` and error behaviour. Parameters, gradients and caches live
+in HBM as float32; weights are initialised on the host with the reference's own NumPy generator calls so that
+seeds reproduce. `forward_pass` / `backward_pass` accept NumPy arrays (returning float64 arrays,
+Q10) or device tensors. Inside `Sequential`, layers are compiled into a fused, graph-captured plan
+(`engine.py`) through the `_plan_forward` / `_plan_backward` hooks.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import _backend as B
+from . import _ops as ops
+from . import get_math
+from .activations import ActivationFunction, Softmax
+
+
+def _math_code():
+    return ops.MATH_TF32 if get_math() == "tf32" else ops.MATH_FP32
+
+
+def _is_dev(x):
+    return isinstance(x, torch.Tensor)
+
+
+def _in(x):
+    """-> (device float32 tensor, was_host)."""
+    if _is_dev(x):
+        return x.contiguous(), False
+    return B.to_device(np.asarray(x)), True
+
+
+def _out(t, was_host):
+    return B.to_host(t) if was_host else t
+
+
+class _Err:
+    """An error tensor together with the clip slots still pending on it (see include/b200nn.h)."""
+    __slots__ = ("t", "chain")
+
+    def __init__(self, t, chain=()):
+        self.t, self.chain = t, tuple(chain)
+
+
+class _EagerCtx:
+    """Allocation context of the layer-by-layer (non-plan) API: fresh buffers per call, no clip slots."""
+    ss = None
+
+    def buf(self, shape):
+        return B.empty(tuple(int(s) for s in shape))
+
+    def slot(self):
+        return None
+
+    def need_ws(self, nbytes):
+        self._ws = B.empty((max(int(nbytes) // 4, 1),))
+
+    @property
+    def ws(self):
+        return getattr(self, "_ws", None)
+
+    def emit(self, fn):
+        fn()
+
+
+def _act_of(layer):
+    """(kind, alpha) of a fusable Activation layer, else (ACT_NONE, 0)."""
+    if layer is None:
+        return ops.ACT_NONE, 0.0
+    f = layer.activation_function
+    return f._kind, float(f._alpha)
+
+
+class Layer:
+    def __init__(self):
+        self.input = None
+        self.output = None
+
+    def forward_pass(self, input_data):
+        raise NotImplementedError
+
+    def backward_pass(self, output_error):
+        raise NotImplementedError
+
+    def get_config(self) -> dict:
+        raise NotImplementedError
+
+    @staticmethod
+    def from_config(config: dict) -> "Layer":
+        name = config["name"]
+        cls = globals().get(name)
+        if cls is None or not isinstance(cls, type) or not issubclass(cls, Layer):
+            raise ValueError(f"Invalid layer name: {name}. Make sure the class {name} is defined.")
+        return cls.from_config(config)
+
+    # ---- plan protocol ----------------------------------------------------------------------------------
+    _is_view = False         # Input / Flatten / Reshape: no kernel, no clip slot
+    _fuses_act = False       # forward can apply a following Activation in its epilogue
+    _supports_mask = False   # backward can fold the preceding Activation's backward into its dx epilogue
+
+    def _out_shape(self, in_shape):
+        return in_shape
+
+
+class _ParamMixin:
+    """Device-resident parameters with the reference's NumPy attribute surface."""
+
+    def _param_get(self, name):
+        t = getattr(self, "_" + name, None)
+        if t is None:
+            return None
+        return B.to_host(t).reshape(self._shapes[name])
+
+    def _param_set(self, name, value):
+        if value is None:
+            setattr(self, "_" + name, None)
+            return
+        arr = np.asarray(value, dtype=np.float64)
+        cur = getattr(self, "_" + name, None)
+        if not hasattr(self, "_shapes"):
+            self._shapes = {}
+        if cur is not None and cur.numel() == arr.size:
+            cur.copy_(B.to_device(arr).reshape(cur.shape))   # keep the pointer: captured graphs stay valid
+        else:
+            setattr(self, "_" + name, B.to_device(arr))
+        self._shapes[name] = arr.shape
+
+
+def _param_property(name):
+    return property(lambda self: self._param_get(name), lambda self, v: self._param_set(name, v))
+
+
+# =======================================================================================================
+class Input(Layer):
+    _is_view = True
+
+    def __init__(self, input_shape):
+        if isinstance(input_shape, int):
+            input_shape = (input_shape,)
+        self.input_shape = input_shape
+        self.input_dim = np.prod(input_shape)
+
+    def __str__(self) -> str:
+        return f"Input(input_shape={self.input_shape})"
+
+    def forward_pass(self, input_data):
+        return input_data
+
+    def backward_pass(self, output_error):
+        return output_error
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "input_shape": self.input_shape, "input_dim": self.input_dim}
+
+    @staticmethod
+    def from_config(config: dict):
+        return Input(config["input_shape"])
+
+
+# =======================================================================================================
+class Dense(Layer, _ParamMixin):
+    _fuses_act = True
+    _supports_mask = True
+    weights = _param_property("weights")
+    bias = _param_property("bias")
+    d_weights = _param_property("d_weights")
+    d_bias = _param_property("d_bias")
+
+    def __init__(self, units: int, weights_init: str = "glorot_uniform", bias_init: str = "zeros",
+                 random_state: int = None, init_scale: float = 1.0, input_dim: int = None, **kwargs):
+        super().__init__()
+        self.units = units
+        self._weights = self._bias = self._d_weights = self._d_bias = None
+        self._shapes = {}
+        self.weights_init = weights_init
+        self.bias_init = bias_init
+        self.random_state = random_state
+        self.init_scale = init_scale
+        self.input_dim = input_dim
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def __str__(self) -> str:
+        return f"Dense(units={self.units})"
+
+    def initialize_weights(self, input_size: int):
+        """Host-side, same generator calls as layers.py:89-150 so that seeds reproduce."""
+        self.rng = np.random.default_rng(self.random_state if self.random_state is not None else int(time.time_ns()))
+        fan_in, fan_out = input_size, self.units
+        shape = (input_size, self.units)
+        uniform = {"glorot_uniform": 6 / (fan_in + fan_out), "xavier_uniform": 6 / (fan_in + fan_out),
+                   "he_uniform": 6 / fan_in, "lecun_uniform": 3 / fan_in}
+        normal = {"glorot_normal": 2 / (fan_in + fan_out), "xavier_normal": 2 / (fan_in + fan_out),
+                  "he_normal": 2 / fan_in, "lecun_normal": 1 / fan_in}
+        if self.weights_init == "scaled_normal":
+            w = self.rng.normal(0, self.init_scale / np.sqrt(fan_in), shape)
+        elif self.weights_init in uniform:
+            lim = np.sqrt(uniform[self.weights_init])
+            w = self.rng.uniform(-lim, lim, shape)
+        elif self.weights_init in normal:
+            w = self.rng.normal(0, np.sqrt(normal[self.weights_init]), shape)
+        elif self.weights_init == "orthogonal":
+            q, r = np.linalg.qr(self.rng.normal(0, 1, shape))
+            w = q * np.sign(np.diag(r))
+        else:
+            raise ValueError(
+                "Invalid weights_init value. Possible values are 'scaled_normal', 'glorot_uniform', 'glorot_normal', "
+                "'he_uniform', 'he_normal', 'lecun_uniform', 'lecun_normal', 'orthogonal'")
+        if self.bias_init == "zeros":
+            b = np.zeros((1, self.units))
+        elif self.bias_init == "ones":
+            b = np.ones((1, self.units))
+        elif self.bias_init == "normal":
+            b = self.rng.normal(0, 0.05, (1, self.units))
+        elif self.bias_init == "uniform":
+            b = self.rng.uniform(-0.05, 0.05, (1, self.units))
+        else:
+            raise ValueError("Invalid bias_init value. Possible values are 'zeros', 'ones', 'normal', 'uniform'")
+        self.weights, self.bias = w, b
+        self.d_weights, self.d_bias = np.zeros_like(w), np.zeros_like(b)
+
+    def _ensure_grads(self):
+        if self._d_weights is None:
+            self.d_weights = np.zeros(self._shapes["weights"])
+            self.d_bias = np.zeros(self._shapes["bias"])
+
+    # -- plan hooks
+    def _out_shape(self, in_shape):
+        return in_shape[:-1] + (self.units,)
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        feat = x.shape[-1]
+        if self._weights is None:
+            self.initialize_weights(feat)
+        self._ensure_grads()
+        if self._weights.shape[0] != feat:
+            raise ValueError(f"shapes {tuple(x.shape)} and {tuple(self._weights.shape)} not aligned")
+        M = x.numel() // feat
+        ctx.need_ws(ops.dense_ws_bytes(M, self.units, feat))
+        y = ctx.buf(tuple(x.shape[:-1]) + (self.units,))
+        kind, alpha = _act_of(act_layer)
+        math = _math_code()
+        st.update(x=x, math=math)
+        w, b = self._weights, self._bias
+        ctx.emit(lambda: ops.dense_fwd(math, x, w, b, y, kind, alpha, ctx.ws))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x = st["x"]
+        dx = ctx.buf(x.shape) if need_dx else None
+        kind, alpha = _act_of(mask_layer)
+        s0 = ctx.slot() if need_dx else None
+        s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
+        w, dw, db, ss, chain, math = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"]
+        et = err.t
+        ctx.emit(lambda: ops.dense_bwd(math, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        if not need_dx:
+            return None
+        return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    # -- reference API (layers.py:152-198)
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input_shape = tuple(x.shape)
+        if x.dim() == 1:
+            x = x.reshape(1, -1)
+        self.input = input_data
+        ctx = _EagerCtx()
+        self._st = {}
+        return _out(self._plan_forward(ctx, self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        dx = self._plan_backward(_EagerCtx(), self._st, _Err(e.reshape(-1, self.units)), None, True)
+        return _out(dx.t.reshape(self._st["x"].shape), host)
+
+    def get_config(self) -> dict:
+        w, b = self.weights, self.bias
+        return {"name": self.__class__.__name__, "weights": w.tolist() if w is not None else None,
+                "bias": b.tolist() if b is not None else None, "units": self.units, "weights_init": self.weights_init,
+                "bias_init": self.bias_init, "random_state": self.random_state}
+
+    @staticmethod
+    def from_config(config: dict):
+        layer = Dense(config["units"], config["weights_init"], config["bias_init"], config["random_state"])
+        if config["weights"] is not None:
+            layer.weights = np.array(config["weights"])
+            layer.bias = np.array(config["bias"])
+        return layer
+
+
+# =======================================================================================================
+class Activation(Layer):
+    def __init__(self, activation_function):
+        super().__init__()
+        self.activation_function = activation_function if isinstance(activation_function, ActivationFunction) \
+            else ActivationFunction.from_name(activation_function)
+
+    def __str__(self) -> str:
+        return f"Activation({type(self.activation_function).__name__})"
+
+    @property
+    def _fusable(self):
+        f = self.activation_function
+        return f._kind is not None and not (f._kind == ops.ACT_LEAKYRELU and f._alpha <= 0)
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        y = ctx.buf(x.shape)
+        f = self.activation_function
+        if isinstance(f, Softmax):
+            if x.dim() != 2:
+                raise ValueError("Softmax expects a 2-D (batch, classes) input")
+            ctx.emit(lambda: ops.softmax_fwd(x, y))
+        else:
+            kind, alpha = f._kind, float(f._alpha)
+            ctx.emit(lambda: ops.act_fwd(kind, alpha, x, y))
+        st.update(y=y)
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx, y=None):
+        f = self.activation_function
+        if f._kind is None:
+            raise NotImplementedError("Derivative of Softmax is not implemented. It is not needed for backpropagation.")
+        y = st["y"] if y is None else y
+        dx = ctx.buf(y.shape)
+        s = ctx.slot()
+        kind, alpha, ss, chain, et = f._kind, float(f._alpha), ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.act_bwd(kind, alpha, y, et, ss, chain, dx, s))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        y = self._plan_forward(_EagerCtx(), self._st, x, None, True)
+        self.output = _out(y, host)
+        return self.output
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e.reshape(self._st["y"].shape)), None, True).t, host)
+
+    def get_config(self) -> dict:
+        f = self.activation_function
+        return {"name": self.__class__.__name__,
+                "activation_function": {"name": f.__class__.__name__, "config": f.get_config() if hasattr(f, "get_config") else {}}}
+
+    @staticmethod
+    def from_config(config: dict):
+        return Activation(ActivationFunction.from_config(config["activation_function"]))
+
+    @staticmethod
+    def from_name(name: str) -> "Activation":
+        key = name.lower().replace("_", "")
+        for sub in _all_subclasses(ActivationFunction):
+            if sub.__name__.lower() == key:
+                return Activation(sub())
+        raise ValueError(f"No activation function found for the name: {name}")
+
+
+def _all_subclasses(cls):
+    out = []
+    for s in cls.__subclasses__():
+        if not s.__name__.startswith("_"):
+            out.append(s)
+        out.extend(_all_subclasses(s))
+    return out
+
+
+# =======================================================================================================
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class Conv2D(Layer, _ParamMixin):
+    _fuses_act = True
+    _supports_mask = True
+    weights = _param_property("weights")
+    bias = _param_property("bias")
+    d_weights = _param_property("d_weights")
+    d_bias = _param_property("d_bias")
+
+    def __init__(self, filters: int, kernel_size, strides=1, padding: str = "valid", weights_init: str = "default",
+                 bias_init: str = "default", random_state: int = None, **kwargs):
+        self.filters = filters
+        self.kernel_size = _pair(kernel_size)
+        self.strides = _pair(strides)
+        self.padding = padding
+        self._weights = self._bias = self._d_weights = self._d_bias = None
+        self._shapes = {}
+        self.weights_init = weights_init
+        self.bias_init = bias_init
+        self.random_state = random_state
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def initialize_weights(self, input_shape: tuple):
+        """layers.py:367-398 (same generator calls)."""
+        in_channels = input_shape[3]
+        fan_in = np.prod(self.kernel_size) * in_channels
+        fan_out = np.prod(self.kernel_size) * self.filters
+        self.rng = np.random.default_rng(self.random_state if self.random_state is not None else int(time.time_ns()))
+        shape = (*self.kernel_size, in_channels, self.filters)
+        if self.weights_init in ("glorot_uniform", "xavier"):
+            lim = np.sqrt(6 / (fan_in + fan_out))
+            w = self.rng.uniform(-lim, lim, shape)
+        elif self.weights_init == "he":
+            w = self.rng.normal(0, np.sqrt(2 / fan_in), shape)
+        elif self.weights_init == "default":
+            w = self.rng.normal(0, 0.01, shape)
+        else:
+            raise ValueError("Invalid weights_init value. Possible values are 'xavier', 'he', and 'default'.")
+        if self.bias_init == "default":
+            b = np.zeros((1, self.filters))
+        elif self.bias_init == "normal":
+            b = self.rng.normal(0, 0.01, (1, self.filters))
+        elif self.bias_init == "uniform":
+            b = self.rng.uniform(-0.1, 0.1, (1, self.filters))
+        elif self.bias_init == "small":
+            b = np.full((1, self.filters), 0.01)
+        else:
+            raise ValueError("Invalid bias_init value. Possible values are 'normal', 'uniform', 'small' and 'default'.")
+        self.weights, self.bias = w, b
+        self.d_weights, self.d_bias = np.zeros_like(w), np.zeros((self.filters,))  # d_bias is (F,) after backward (Q9)
+
+    def __str__(self) -> str:
+        return (f"Conv2D(num_filters={self.filters}, kernel_size={self.kernel_size}, strides={self.strides}, "
+                f"padding={self.padding})")
+
+    def _geometry(self, shape):
+        """layers.py:450-469."""
+        N, H, W, Cin = (int(s) for s in shape)
+        kh, kw = self.kernel_size
+        sh, sw = self.strides
+        if self.padding == "same":
+            oh, ow = -(-H // sh), -(-W // sw)
+            ph = max(0, (oh - 1) * sh + kh - H) // 2
+            pw = max(0, (ow - 1) * sw + kw - W) // 2
+        else:
+            ph = pw = 0
+        oh = (H + 2 * ph - kh) // sh + 1
+        ow = (W + 2 * pw - kw) // sw + 1
+        return B.ConvGeom(N, H, W, Cin, self.filters, kh, kw, sh, sw, ph, pw, oh, ow)
+
+    def _out_shape(self, in_shape):
+        g = self._geometry(in_shape)
+        return (in_shape[0], g.OH, g.OW, self.filters)
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, f"Conv2D input must be 4D (batch_size, height, width, channels), got {tuple(x.shape)}"
+        if self._weights is None:
+            self.initialize_weights(tuple(x.shape))
+        if self._d_weights is None:
+            self.d_weights = np.zeros(self._shapes["weights"]); self.d_bias = np.zeros((self.filters,))
+        assert x.shape[3] == self._weights.shape[2], "Number of input channels must match"
+        g = self._geometry(x.shape)
+        if g.OH <= 0 or g.OW <= 0:
+            raise ValueError(f"Size mismatch: Conv2D output would be {g.OH}x{g.OW}")
+        ctx.need_ws(ops.conv2d_ws_bytes(g))
+        y = ctx.buf((x.shape[0], g.OH, g.OW, self.filters))
+        kind, alpha = _act_of(act_layer)
+        math = ops.MATH_FP32
+        st.update(x=x, g=g, math=math)
+        w, b = self._weights, self._bias
+        ctx.emit(lambda: ops.conv2d_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, g = st["x"], st["g"]
+        dx = ctx.buf(x.shape) if need_dx else None
+        kind, alpha = _act_of(mask_layer)
+        s0 = ctx.slot() if need_dx else None
+        s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
+        w, dw, db, ss, chain, math, et = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"], err.t
+        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        if not need_dx:
+            return None
+        return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        w, b = self.weights, self.bias
+        return {"name": self.__class__.__name__, "weights": w.tolist() if w is not None else None,
+                "bias": b.tolist() if b is not None else None, "filters": self.filters, "kernel_size": self.kernel_size,
+                "strides": self.strides, "padding": self.padding, "weights_init": self.weights_init,
+                "bias_init": self.bias_init, "random_state": self.random_state}
+
+    @classmethod
+    def from_config(cls, config: dict):
+        layer = cls(config["filters"], config["kernel_size"], config["strides"], config["padding"], config["weights_init"],
+                    config["bias_init"], config["random_state"])
+        if config["weights"] is not None:
+            layer.weights = np.array(config["weights"])
+            layer.bias = np.array(config["bias"])
+        return layer
+
+
+# =======================================================================================================
+class Conv2DTranspose(Conv2D):
+    """layers.py:2536-2692. weights (kh, kw, F, C_in); bias and d_bias (1, 1, 1, F)."""
+
+    def initialize_weights(self, input_shape: tuple):
+        in_channels = input_shape[3]
+        self.rng = np.random.default_rng(self.random_state if self.random_state is not None else int(time.time_ns()))
+        shape = (*self.kernel_size, self.filters, in_channels)
+        if self.weights_init == "xavier":
+            w = self.rng.normal(0, np.sqrt(2 / (np.prod(self.kernel_size) * self.filters)), shape)
+        elif self.weights_init == "he":
+            w = self.rng.normal(0, np.sqrt(2 / (in_channels * np.prod(self.kernel_size))), shape)
+        elif self.weights_init == "default":
+            w = self.rng.normal(0, 0.01, shape)
+        else:
+            raise ValueError("Invalid weights_init value. Possible values are 'xavier', 'he', and 'default'.")
+        bshape = (1, 1, 1, self.filters)
+        if self.bias_init == "default":
+            b = np.zeros(bshape)
+        elif self.bias_init == "normal":
+            b = self.rng.normal(0, 0.01, bshape)
+        elif self.bias_init == "uniform":
+            b = self.rng.uniform(-0.1, 0.1, bshape)
+        elif self.bias_init == "small":
+            b = np.full(bshape, 0.01)
+        else:
+            raise ValueError("Invalid bias_init value.")
+        self.weights, self.bias = w, b
+        self.d_weights, self.d_bias = np.zeros_like(w), np.zeros_like(b)
+
+    def __str__(self) -> str:
+        return (f"Conv2DTranspose(filters={self.filters}, kernel_size={self.kernel_size}, strides={self.strides}, "
+                f"padding={self.padding})")
+
+    def _geometry(self, shape):
+        """layers.py:2597-2609."""
+        N, H, W, Cin = (int(s) for s in shape)
+        kh, kw = self.kernel_size
+        sh, sw = self.strides
+        if self.padding == "same":
+            oh, ow = H * sh, W * sw
+            pt = max((H - 1) * sh + kh - oh, 0) // 2
+            pl = max((W - 1) * sw + kw - ow, 0) // 2
+        else:
+            oh, ow = (H - 1) * sh + kh, (W - 1) * sw + kw
+            pt = pl = 0
+        return B.ConvTGeom(N, H, W, Cin, self.filters, kh, kw, sh, sw, pt, pl, oh, ow)
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, "Conv2DTranspose input must be 4D (batch_size, height, width, channels)"
+        if self._weights is None:
+            self.initialize_weights(tuple(x.shape))
+        if self._d_weights is None:
+            self.d_weights = np.zeros(self._shapes["weights"]); self.d_bias = np.zeros((1, 1, 1, self.filters))
+        assert x.shape[3] == self._weights.shape[3], "Number of input channels must match"
+        g = self._geometry(x.shape)
+        ctx.need_ws(ops.convt_ws_bytes(g))
+        y = ctx.buf((x.shape[0], g.OH, g.OW, self.filters))
+        kind, alpha = _act_of(act_layer)
+        math = ops.MATH_FP32
+        st.update(x=x, g=g, math=math)
+        w, b = self._weights, self._bias
+        ctx.emit(lambda: ops.convt_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, g = st["x"], st["g"]
+        dx = ctx.buf(x.shape) if need_dx else None
+        kind, alpha = _act_of(mask_layer)
+        s0 = ctx.slot() if need_dx else None
+        s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
+        w, dw, db, ss, chain, math, et = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"], err.t
+        ctx.emit(lambda: ops.convt_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        if not need_dx:
+            return None
+        return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+
+# =======================================================================================================
+class MaxPooling2D(Layer):
+    def __init__(self, pool_size, strides=None, padding: str = "valid"):
+        self.pool_size = _pair(pool_size)
+        self.strides = _pair(strides) if strides is not None else self.pool_size
+        self.padding = padding
+
+    def __str__(self) -> str:
+        return f"MaxPooling2D(pool_size={self.pool_size}, strides={self.strides}, padding={self.padding})"
+
+    def _geometry(self, shape):
+        """layers.py:574-589."""
+        N, H, W, Cc = (int(s) for s in shape)
+        (ph, pw), (sh, sw) = self.pool_size, self.strides
+        if self.padding == "same":
+            pad_h = ((H - 1) * sh + ph - H) // 2
+            pad_w = ((W - 1) * sw + pw - W) // 2
+            if pad_h <= 0 or pad_w <= 0:
+                # the reference crops d_input[pad:-pad], which is empty for pad == 0 (layers.py:639-641)
+                raise ValueError("MaxPooling2D(padding='same') needs a positive pad; the reference backward breaks otherwise")
+        else:
+            pad_h = pad_w = 0
+        oh = (H + 2 * pad_h - ph) // sh + 1
+        ow = (W + 2 * pad_w - pw) // sw + 1
+        return B.PoolGeom(N, H, W, Cc, ph, pw, sh, sw, pad_h, pad_w, oh, ow)
+
+    def _out_shape(self, in_shape):
+        g = self._geometry(in_shape)
+        return (in_shape[0], g.OH, g.OW, in_shape[3])
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, f"MaxPooling2D input must be 4D (batch_size, channels, height, width), got {tuple(x.shape)}"
+        g = self._geometry(x.shape)
+        y = ctx.buf((x.shape[0], g.OH, g.OW, x.shape[3]))
+        st.update(x=x, y=y, g=g)
+        ctx.emit(lambda: ops.maxpool_fwd(g, x, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, y, g = st["x"], st["y"], st["g"]
+        dx = ctx.buf(x.shape)
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.maxpool_bwd(g, x, y, et, ss, chain, dx, s))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "pool_size": self.pool_size, "strides": self.strides, "padding": self.padding}
+
+    @staticmethod
+    def from_config(config: dict):
+        return MaxPooling2D(config["pool_size"], config["strides"], config["padding"])
+
+
+# =======================================================================================================
+class Flatten(Layer):
+    _is_view = True
+
+    def __init__(self):
+        pass
+
+    def __str__(self) -> str:
+        return "Flatten"
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0], int(np.prod(in_shape[1:])))
+
+    def forward_pass(self, input_data):
+        assert len(input_data.shape) >= 2, f"Flatten input must be at least 2D, got {input_data.shape}"
+        self.input_shape = tuple(input_data.shape)
+        return input_data.reshape(input_data.shape[0], -1)
+
+    def backward_pass(self, output_error):
+        return output_error.reshape(self.input_shape)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__}
+
+    @staticmethod
+    def from_config(config: dict):
+        return Flatten()
+
+
+class Reshape(Layer):
+    _is_view = True
+
+    def __init__(self, target_shape: tuple, input_shape: tuple | None = None):
+        super().__init__()
+        self.target_shape = tuple(target_shape)
+        self.input_shape = None
+
+    def __str__(self) -> str:
+        return f"Reshape(target_shape={self.target_shape}, input_shape={self.input_shape})"
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0],) + self.target_shape
+
+    def forward_pass(self, input_data):
+        self.input_shape = tuple(input_data.shape)
+        return input_data.reshape((input_data.shape[0],) + self.target_shape)
+
+    def backward_pass(self, output_error):
+        return output_error.reshape(self.input_shape)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "target_shape": self.target_shape, "input_shape": self.input_shape}
+
+    @staticmethod
+    def from_config(config: dict):
+        return Reshape(config["target_shape"], config["input_shape"])
+
+
+# =======================================================================================================
+class BatchNormalization(Layer, _ParamMixin):
+    """layers.py:1205-1304. Statistics are per POSITION (gamma/beta/running_* have the shape of one sample);
+    has no `weights` attribute, so `Sequential` never updates gamma/beta."""
+    _supports_mask = True
+    gamma = _param_property("gamma")
+    beta = _param_property("beta")
+    d_gamma = _param_property("d_gamma")
+    d_beta = _param_property("d_beta")
+    running_mean = _param_property("running_mean")
+    running_var = _param_property("running_var")
+
+    def __init__(self, momentum: float = 0.9, epsilon: float = 1e-5, **kwargs):
+        self._gamma = self._beta = self._d_gamma = self._d_beta = self._running_mean = self._running_var = None
+        self._shapes = {}
+        self.momentum = momentum
+        self.epsilon = epsilon
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def initialize_weights(self, input_shape: tuple):
+        self.gamma, self.beta = np.ones(input_shape), np.zeros(input_shape)
+        self.d_gamma, self.d_beta = np.zeros(input_shape), np.zeros(input_shape)
+        self.running_mean, self.running_var = np.zeros(input_shape), np.ones(input_shape)
+
+    def __str__(self) -> str:
+        return f"BatchNormalization(momentum={self.momentum}, epsilon={self.epsilon})"
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        shp = tuple(int(s) for s in x.shape[1:])
+        if self._gamma is None or self._running_mean is None or self._running_var is None:
+            self.initialize_weights(shp)
+        if self._d_gamma is None:
+            self.d_gamma, self.d_beta = np.zeros(shp), np.zeros(shp)
+        if int(np.prod(shp)) != self._gamma.numel():
+            raise ValueError(f"BatchNormalization was initialised for {tuple(self._shapes['gamma'])}, got {shp}")
+        y = ctx.buf(x.shape)
+        P = self._gamma.numel()
+        gm, bt, rm, rv = self._gamma, self._beta, self._running_mean, self._running_var
+        mom, eps = float(self.momentum), float(self.epsilon)
+        if training:
+            sm, si = ctx.buf((P,)), ctx.buf((P,))
+            st.update(x=x, save_mean=sm, save_invstd=si, trained=True)
+            ctx.emit(lambda: ops.bn_fwd_train(x, gm, bt, rm, rv, sm, si, y, mom, eps))
+        else:
+            st.update(x=x, trained=False)
+            ctx.emit(lambda: ops.bn_fwd_infer(x, gm, bt, rm, rv, y, eps))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        if not st.get("trained"):
+            raise NotImplementedError("BatchNormalization.backward_pass after an inference-mode forward relies on stale "
+                                      "training caches in the reference (layers.py:1258-1276); not supported")
+        x = st["x"]
+        dx = ctx.buf(x.shape)
+        kind, alpha = _act_of(mask_layer)
+        s0 = ctx.slot()
+        s1 = ctx.slot() if mask_layer is not None else None
+        gm, sm, si, dg, dbt, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], self._d_gamma, self._d_beta, ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.bn_bwd(x, et, ss, chain, gm, sm, si, dx, dg, dbt, kind, alpha, s0, s1))
+        return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    def forward_pass(self, input_data, training: bool = True):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, training), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        g = self.gamma
+        tl = lambda a: a.tolist() if a is not None else None  # noqa: E731
+        return {"name": self.__class__.__name__, "gamma": tl(g), "beta": tl(self.beta), "momentum": self.momentum,
+                "epsilon": self.epsilon, "running_mean": tl(self.running_mean), "running_var": tl(self.running_var),
+                "input_shape": g.shape if g is not None else None}
+
+    @staticmethod
+    def from_config(config: dict):
+        layer = BatchNormalization(config["momentum"], config["epsilon"])
+        if config["gamma"] is not None:
+            layer.gamma, layer.beta = np.array(config["gamma"]), np.array(config["beta"])
+            layer.running_mean, layer.running_var = np.array(config["running_mean"]), np.array(config["running_var"])
+            layer.d_gamma, layer.d_beta = np.zeros_like(layer.gamma), np.zeros_like(layer.beta)
+        return layer
+
+
+# =======================================================================================================
+# layer-ordering validation used by Sequential.add (layers.py:3916-3980, restricted to the layers that exist here)
+incompatibility_dict = {
+    Input: [], Dense: [Conv2D, Conv2DTranspose], Activation: [], Conv2D: [], Conv2DTranspose: [], MaxPooling2D: [],
+    Flatten: [], BatchNormalization: [], Reshape: [],
+}

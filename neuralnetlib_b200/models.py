@@ -1,0 +1,529 @@
+"""Mirror of neuralnetlib/models.py on the device: Sequential (:81-721) and GAN.train_on_batch/fit core (:2366-2936).
+
+The Python surface is the reference's (add/compile/fit/train_on_batch/forward_pass/backward_pass/evaluate/predict/
+save/load; same arguments, defaults, exceptions); the per-batch work runs as one captured CUDA graph over
+HBM-resident buffers (engine.Plan). NumPy appears only at the entry points and when an attribute is read.
+"""
+from __future__ import annotations
+
+import json
+import time
+
+import numpy as np
+import torch
+
+from . import _backend as B
+from . import _ops as ops
+from .activations import ActivationFunction
+from .engine import Plan
+from .layers import *  # noqa: F401,F403  (the reference re-exports the layers from models)
+from .layers import Activation, Dense, Input, Layer, incompatibility_dict
+from .losses import BinaryCrossentropy, CategoricalCrossentropy, LossFunction  # noqa: F401
+from .metrics import Metric
+from .optimizers import Optimizer
+from .utils import History, format_number, progress_bar, shuffle_indices, train_test_split
+
+_RESIDENT_DATASET_BYTES = 8 << 30   # datasets up to 8 GiB are kept in HBM for the whole fit()
+
+
+class BaseModel:
+    def __init__(self, gradient_clip_threshold: float = 5.0, enable_padding: bool = False, padding_size: int = 32,
+                 random_state: int | None = None):
+        self.gradient_clip_threshold = gradient_clip_threshold   # unused by Sequential in the reference too
+        self.enable_padding = enable_padding
+        self.padding_size = padding_size
+        self.random_state = random_state if random_state is not None else time.time_ns()
+
+
+class Sequential(BaseModel):
+    def __init__(self, gradient_clip_threshold: float = 5.0, enable_padding: bool = False, padding_size: int = 32,
+                 random_state: int | None = None, n_classes: int | None = None):
+        super().__init__(gradient_clip_threshold, enable_padding, padding_size, random_state)
+        self.layers = []
+        self.loss_function = None
+        self.optimizer = None
+        self.y_true = None
+        self._initialized = False
+        self.n_classes = n_classes
+        self.metrics = None
+        self._plans = {}
+        self._last_plan = None
+        self._pred_host = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def __str__(self) -> str:
+        s = (f"Sequential(gradient_clip_threshold={self.gradient_clip_threshold}, enable_padding={self.enable_padding}, "
+             f"padding_size={self.padding_size}, random_state={self.random_state})\n")
+        s += "-------------------------------------------------\n"
+        for i, layer in enumerate(self.layers):
+            s += f"Layer {i + 1}: {str(layer)}\n"
+        s += "-------------------------------------------------\n"
+        s += f"Loss function: {str(self.loss_function)}\nOptimizer: {str(self.optimizer)}\n"
+        s += "-------------------------------------------------\n"
+        return s
+
+    def summary(self):
+        print(str(self))
+
+    def add(self, layer: Layer):
+        """models.py:111-148."""
+        if not self.layers:
+            if not isinstance(layer, Input):
+                raise ValueError("The first layer must be an Input layer.")
+        else:
+            if self.random_state and hasattr(layer, "random_state"):
+                layer.random_state = self.random_state
+            if isinstance(layer, Dense) and isinstance(self.layers[0], Input):
+                layer.input_dim = self.layers[0].input_dim
+            prev_t, cur_t = type(self.layers[-1]), type(layer)
+            if cur_t in incompatibility_dict.get(prev_t, []):
+                raise ValueError(f"{cur_t.__name__} layer cannot follow {prev_t.__name__} layer.")
+        self.layers.append(layer)
+        act = getattr(layer, "activation", getattr(layer, "activation_function", None))
+        if act and not isinstance(layer, Activation):
+            if isinstance(act, str):
+                self.layers.append(Activation.from_name(act))
+            elif isinstance(act, ActivationFunction):
+                self.layers.append(Activation(act))
+            elif isinstance(act, Activation):
+                self.layers.append(act)
+            else:
+                raise ValueError(f"Invalid activation function: {act}")
+        self._drop_plans()
+
+    def compile(self, loss_function, optimizer, verbose: bool = False, metrics: list | None = None):
+        self.loss_function = loss_function if isinstance(loss_function, LossFunction) else LossFunction.from_name(loss_function)
+        self.optimizer = optimizer if isinstance(optimizer, Optimizer) else Optimizer.from_name(optimizer)
+        self.metrics = metrics
+        self._drop_plans()
+        if verbose:
+            print(str(self))
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _drop_plans(self):
+        for p in self._plans.values():
+            p.destroy()
+        self._plans = {}
+        self._last_plan = None
+
+    def _plan(self, batch_shape, training: bool) -> Plan:
+        key = (tuple(int(s) for s in batch_shape), bool(training))
+        p = self._plans.get(key)
+        if p is None:
+            p = Plan(self, key[0], key[1])
+            self._plans[key] = p
+        return p
+
+    @property
+    def predictions(self):
+        """Output of the last forward pass as a float64 array (device->host copy on first read)."""
+        if self._pred_host is None and self._last_plan is not None:
+            self._pred_host = B.to_host(self._last_plan.pred)[:self._last_rows]
+        return self._pred_host
+
+    @predictions.setter
+    def predictions(self, v):
+        self._pred_host = v
+
+    def _prepare_input(self, X, labels):
+        if self.n_classes is not None and labels is not None:
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError("Input shape must be (batch_size, features) for conditional models")
+            labels = np.asarray(labels)
+            if labels.ndim == 1:
+                labels = np.eye(self.n_classes)[labels]
+            elif labels.shape[1] != self.n_classes:
+                raise ValueError(f"Labels must have {self.n_classes} classes")
+            X = np.concatenate([X, labels], axis=1)
+        rows = X.shape[0]
+        if self.enable_padding and rows % self.padding_size:
+            X = np.asarray(X) if not isinstance(X, torch.Tensor) else X.cpu().numpy()
+            padded = np.zeros(((rows + self.padding_size - 1) // self.padding_size * self.padding_size,) + X.shape[1:], dtype=X.dtype)
+            padded[:rows] = X
+            X = padded
+        return X, rows
+
+    def _forward_dev(self, X, training: bool = True, labels=None) -> torch.Tensor:
+        X, rows = self._prepare_input(X, labels)
+        shape = tuple(X.shape) if len(X.shape) > 1 else (1, int(X.shape[0]))
+        plan = self._plan(shape, training)
+        plan.set_input(X)
+        plan.program("forward").run()
+        self._last_plan, self._last_rows, self._pred_host = plan, rows, None
+        return plan.pred[:rows]
+
+    def forward_pass(self, X, training: bool = True, labels=None):
+        """models.py:159-193. NumPy in -> float64 NumPy out; device tensor in -> device tensor out."""
+        out = self._forward_dev(X, training, labels)
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            return out
+        return self.predictions
+
+    def backward_pass(self, error, gan: bool = False, compute_only: bool = False):
+        """models.py:195-249 on the plan of the last forward pass. Returns the error w.r.t. the model input."""
+        plan = self._last_plan
+        if plan is None:
+            raise RuntimeError("backward_pass requires a preceding forward_pass")
+        dev_in = isinstance(error, torch.Tensor) and error.is_cuda
+        kind = "backward_gan" if gan else ("backward_compute_only" if compute_only else "backward")
+        if gan and compute_only:
+            raise NotImplementedError("gan=True together with compute_only=True is not used by the reference")
+        prog = plan.program(kind)
+        Plan._upload(plan.err_in, "_err_stage", plan, error if dev_in else np.asarray(error).reshape(tuple(plan.err_in.shape)))
+        if self.y_true is not None and plan.y_in is not None:
+            plan.set_target(self.y_true if isinstance(self.y_true, torch.Tensor) else np.asarray(self.y_true).reshape(tuple(plan.y_in.shape)))
+        prog.run()
+        return plan.in_err_out if dev_in else B.to_host(plan.in_err_out)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _loss_denominator(self, plan):
+        rows = plan.pred.shape[0]
+        cols = plan.pred.numel() // rows
+        return rows if isinstance(self.loss_function, CategoricalCrossentropy) else rows * cols
+
+    def _train_step(self, x_batch, y_batch) -> Plan:
+        """One fused step on the device; does not synchronise (the loss numerator stays in plan.acc[0])."""
+        shape = tuple(x_batch.shape)
+        plan = self._plan(shape, True)
+        prog = plan.program("train")
+        plan.set_input(x_batch)
+        plan.set_target(y_batch if isinstance(y_batch, torch.Tensor) else np.asarray(y_batch).reshape(tuple(plan.y_in.shape)))
+        prog.run()
+        self._last_plan, self._last_rows, self._pred_host = plan, shape[0], None
+        return plan
+
+    def train_on_batch(self, x_batch, y_batch) -> float:
+        """models.py:251-264: forward, loss, backward with clips, optimizer updates; returns the loss as a float
+        (the only device->host transfer of the step)."""
+        if self.loss_function is None or self.optimizer is None:
+            raise ValueError("The model must be compiled before training")
+        self.y_true = y_batch
+        plan = self._train_step(x_batch, y_batch)
+        return float(plan.acc[0].item()) / self._loss_denominator(plan)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def fit(self, x_train, y_train, epochs: int, batch_size: int | None = None, verbose: bool = True,
+            metrics: list | None = None, random_state: int | None = None, validation_data: tuple | None = None,
+            validation_split: float | None = None, callbacks: list = [], plot_decision_boundary: bool = False) -> dict:
+        """models.py:266-563 with the dataset resident in HBM: the epoch permutation (same generator as utils.shuffle)
+        is uploaded once per epoch and every mini-batch is gathered on the device; losses and predictions are
+        accumulated on the device and read back once per epoch unless a callback / verbose output needs them."""
+        if plot_decision_boundary:
+            raise NotImplementedError("plot_decision_boundary is outside the B200 hot path")
+        if getattr(self, "metrics", None) is not None:
+            metrics = self.metrics
+        history = History({"loss": [], "val_loss": []})
+        if validation_split is not None and validation_data is not None:
+            raise ValueError("Cannot specify both validation_data and validation_split")
+        seed = random_state if random_state is not None else self.random_state
+        if validation_split is not None:
+            x_train, x_val, y_train, y_val = train_test_split(x_train, y_train, test_size=validation_split, random_state=seed)
+            validation_data = (x_val, y_val)
+        x_train = np.asarray(x_train)
+        y_train = np.asarray(y_train)
+        for layer in self.layers:
+            if hasattr(layer, "random_state"):
+                layer.random_state = seed
+        if validation_data is not None:
+            x_val, y_val = np.asarray(validation_data[0]), np.asarray(validation_data[1])
+        mobjs = None
+        if metrics is not None:
+            mobjs = []
+            for m in metrics:
+                if m == "val_loss":
+                    continue
+                try:
+                    mo = Metric(m)
+                except ValueError as e:
+                    raise ValueError(f"Invalid metric: {m}") from e
+                mobjs.append(mo)
+                history[mo.name] = []
+                if validation_data is not None:
+                    history[f"val_{mo.name}"] = []
+        callbacks = callbacks if callbacks is not None else []
+        logs = {"model": self, "params": {"epochs": epochs, "batch_size": batch_size, "verbose": verbose,
+                                          "metrics": [m.name for m in (mobjs or [])], "validation": validation_data is not None}}
+        for cb in callbacks:
+            cb.on_train_begin(logs)
+
+        N = x_train.shape[0]
+        bs = int(batch_size) if batch_size is not None else N
+        y2 = y_train.reshape(N, -1) if y_train.ndim > 1 else y_train.reshape(N, 1)
+        resident = (x_train.size + y2.size) * 4 <= _RESIDENT_DATASET_BYTES
+        if resident:
+            x_dev, y_dev = B.to_device(x_train), B.to_device(y2)
+        num_batches = (N + bs - 1) // bs
+        sync_each_batch = bool(callbacks) or verbose
+        loss_hist = B.zeros((num_batches,), dtype=torch.float64)
+        keep_pred = mobjs is not None
+        try:
+            for epoch in range(epochs):
+                epoch_logs = {"model": self}
+                for cb in callbacks:
+                    cb.on_epoch_begin(epoch, epoch_logs)
+                start = time.time()
+                perm = shuffle_indices(N, seed)                      # models.py:386-389: same seed => same permutation
+                y_shuf = y2[perm] if keep_pred else None
+                perm_dev = B.to_device(perm, dtype=torch.int64) if resident else None
+                pred_all = None
+                running = 0.0
+                denoms = []
+                for bi, j in enumerate(range(0, N, bs)):
+                    rows = min(bs, N - j)
+                    batch_logs = {"batch": bi, "size": rows, "model": self}
+                    for cb in callbacks:
+                        cb.on_batch_begin(bi, batch_logs)
+                    plan = self._plan((rows,) + x_train.shape[1:], True)
+                    prog = plan.program("train")
+                    if resident:
+                        ops.gather_rows(x_dev, perm_dev[j:j + rows], plan.x_in)
+                        ops.gather_rows(y_dev, perm_dev[j:j + rows], plan.y_in)
+                    else:
+                        plan.set_input(x_train[perm[j:j + rows]])
+                        plan.set_target(y2[perm[j:j + rows]].reshape(tuple(plan.y_in.shape)))
+                    prog.run()
+                    self._last_plan, self._last_rows, self._pred_host = plan, rows, None
+                    loss_hist[bi:bi + 1].copy_(plan.acc[0:1], non_blocking=True)
+                    denoms.append(self._loss_denominator(plan))
+                    if keep_pred:
+                        if pred_all is None:
+                            pred_all = B.empty((N, plan.pred.numel() // rows))
+                        pred_all[j:j + rows].copy_(plan.pred.reshape(rows, -1), non_blocking=True)
+                    if sync_each_batch:
+                        batch_loss = float(plan.acc[0].item()) / denoms[-1]
+                        running += batch_loss
+                        batch_logs["loss"] = batch_loss
+                        if mobjs is not None:
+                            pb = B.to_host(plan.pred.reshape(rows, -1))
+                            for mo in mobjs:
+                                batch_logs[mo.name] = mo(pb, y_shuf[j:j + rows])
+                        for cb in callbacks:
+                            cb.on_batch_end(bi, batch_logs)
+                        if verbose:
+                            msg = f"Epoch {epoch + 1}/{epochs} - {time.time() - start:.2f}s - loss: {format_number(running / (bi + 1))}"
+                            progress_bar(bi + 1, num_batches, message=msg)
+                losses = loss_hist.cpu().numpy() / np.asarray(denoms, dtype=np.float64)   # one read-back per epoch
+                error = float(np.sum(losses) / num_batches)
+                history["loss"].append(error)
+                epoch_logs.update({"loss": error, "time": time.time() - start})
+                if mobjs is not None:
+                    preds = B.to_host(pred_all)
+                    for mo in mobjs:
+                        v = mo(preds, y_shuf)
+                        history[mo.name].append(v)
+                        epoch_logs[mo.name] = v
+                if validation_data is not None:
+                    val_loss, val_pred = self.evaluate(x_val, y_val, bs)
+                    history["val_loss"].append(val_loss)
+                    epoch_logs["val_loss"] = val_loss
+                    if mobjs is not None:
+                        for mo in mobjs:
+                            v = mo(val_pred, y_val)
+                            history[f"val_{mo.name}"].append(v)
+                            epoch_logs[f"val_{mo.name}"] = v
+                if verbose:
+                    extra = "".join(f" - {k}: {format_number(v)}" for k, v in epoch_logs.items() if k not in ("model", "time"))
+                    progress_bar(num_batches, num_batches, message=f"Epoch {epoch + 1}/{epochs} - {epoch_logs['time']:.2f}s{extra}")
+                    print()
+                stop = False
+                for cb in callbacks:
+                    if cb.on_epoch_end(epoch, epoch_logs):
+                        stop = True
+                        break
+                if stop:
+                    break
+        finally:
+            for cb in callbacks:
+                cb.on_train_end({"model": self, "history": history})
+            if verbose:
+                print()
+        return history
+
+    # ------------------------------------------------------------------------------------------------------------
+    def evaluate(self, x_test, y_test, batch_size: int = 32) -> tuple:
+        """models.py:565-601: inference-mode forward + loss per batch; (mean of batch losses, all predictions)."""
+        x_test, y_test = np.asarray(x_test), np.asarray(y_test)
+        n = len(x_test)
+        batch_size = int(batch_size) if batch_size else n
+        total, preds, nb = 0.0, [], 0
+        for i in range(0, n, batch_size):
+            xb, yb = x_test[i:i + batch_size], y_test[i:i + batch_size]
+            out = self._forward_dev(xb, training=False)
+            plan = self._last_plan
+            plan.set_target(yb.reshape(tuple(plan.pred.shape)))
+            plan.program("loss").run()
+            total += float(plan.acc[0].item()) / self._loss_denominator(plan)
+            preds.append(B.to_host(out))
+            nb += 1
+        return total / max(nb, 1), np.vstack(preds)
+
+    def predict(self, X, temperature: float = 1.0) -> np.ndarray:
+        """models.py:603-615."""
+        X = np.array(X)
+        self._forward_dev(X, training=False)
+        predictions = self.predictions
+        if not np.isclose(temperature, 1.0, rtol=1e-09, atol=1e-09):
+            predictions = np.exp(np.log(np.clip(predictions, 1e-7, 1.0)) / temperature)
+            predictions /= np.sum(predictions, axis=-1, keepdims=True)
+        return predictions
+
+    # ------------------------------------------------------------------------------------------------------------
+    def save(self, filename: str):
+        """models.py:674-696 — same JSON layout (weights as nested lists, optimizer state incl. Adam t/m/v)."""
+        state = {"type": "Sequential", "layers": [layer.get_config() for layer in self.layers],
+                 "gradient_clip_threshold": self.gradient_clip_threshold, "enable_padding": self.enable_padding,
+                 "padding_size": self.padding_size, "random_state": self.random_state, "n_classes": self.n_classes}
+        if self.loss_function:
+            state["loss_function"] = self.loss_function.get_config()
+        if self.optimizer:
+            state["optimizer"] = self.optimizer.get_config()
+        with open(filename, "w") as f:
+            json.dump(state, f, indent=4, default=_json_default)
+        return state
+
+    @classmethod
+    def load(cls, filename: str) -> "Sequential":
+        with open(filename, "r") as f:
+            state = json.load(f)
+        model = cls()
+        for k in ("gradient_clip_threshold", "enable_padding", "padding_size", "random_state", "n_classes"):
+            if k in state:
+                setattr(model, k, state[k])
+        model.layers = [Layer.from_config(c) for c in state.get("layers", [])]
+        if "loss_function" in state:
+            model.loss_function = LossFunction.from_config(state["loss_function"])
+        if "optimizer" in state:
+            model.optimizer = Optimizer.from_config(state["optimizer"])
+        return model
+
+
+def _json_default(o):
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    raise TypeError(f"not JSON serialisable: {type(o)}")
+
+
+# ================================================================================================================
+class GAN(BaseModel):
+    """models.py:2366-2936, hot path only: compile, train_on_batch (D step on real+fake, G step through the frozen D
+    with compute_only / gan=True) and the fit loop around it. Plotting, metrics on generated samples and
+    save/load are out of scope. Both networks stay on the device for the whole step."""
+
+    def __init__(self, latent_dim: int = 100, n_classes: int | None = None, gradient_clip_threshold: float = 0.1,
+                 enable_padding: bool = False, padding_size: int = 32, random_state: int | None = None,
+                 use_spectral_norm: bool = True, use_gradient_penalty: bool = True, gp_weight: float = 10.0,
+                 image_height: int | None = None, image_width: int | None = None, label_smoothing: float = 0.9):
+        super().__init__(gradient_clip_threshold, enable_padding, padding_size, random_state)
+        if n_classes is not None:
+            raise NotImplementedError("conditional GANs are outside the B200 hot path")
+        self.latent_dim, self.n_classes = latent_dim, n_classes
+        self.generator = self.discriminator = None
+        self.generator_optimizer = self.discriminator_optimizer = None
+        self.generator_loss = self.discriminator_loss = None
+        # spectral norm / gradient penalty are never applied by the reference's train_on_batch
+        self.use_spectral_norm, self.use_gradient_penalty, self.gp_weight = use_spectral_norm, use_gradient_penalty, gp_weight
+        self._image_height, self._image_width = image_height, image_width
+        self.label_smoothing = label_smoothing
+        self._train_step = 0
+
+    def compile(self, generator: Sequential, discriminator: Sequential, generator_optimizer, discriminator_optimizer,
+                loss_function="bce", verbose: bool = False, metrics: list | None = None):
+        self.generator, self.discriminator = generator, discriminator
+        if not any(isinstance(layer, Dense) for layer in generator.layers):
+            raise ValueError("The generator must contain at least one Dense layer.")
+        as_opt = lambda o: o if isinstance(o, Optimizer) else Optimizer.from_name(o)  # noqa: E731
+        as_loss = lambda l: l if isinstance(l, LossFunction) else LossFunction.from_name(l)  # noqa: E731
+        self.generator_optimizer, self.discriminator_optimizer = as_opt(generator_optimizer), as_opt(discriminator_optimizer)
+        self.generator_loss, self.discriminator_loss = as_loss(loss_function), as_loss(loss_function)
+        generator.loss_function, generator.optimizer = self.generator_loss, self.generator_optimizer
+        discriminator.loss_function, discriminator.optimizer = self.discriminator_loss, self.discriminator_optimizer
+        generator._drop_plans()
+        discriminator._drop_plans()
+        self.metrics = metrics
+        self.last_activation = generator.layers[-1].activation_function.get_config()["name"].lower()
+        if verbose:
+            print(f"GAN(latent_dim={self.latent_dim})")
+
+    def forward_pass(self, latent_vectors, training: bool = True):
+        if self.generator is None:
+            raise ValueError("Model must be compiled before forward pass")
+        return self.generator.forward_pass(latent_vectors, training)
+
+    def _generate_latent_points(self, n_samples: int, labels=None):
+        """models.py:2522-2565: re-seeded identically on every call."""
+        rng = np.random.default_rng(self.random_state)
+        return rng.normal(0, 1, (n_samples, self.latent_dim)), None
+
+    def _loss_value(self, net: Sequential, plan) -> float:
+        return float(plan.acc[0].item()) / net._loss_denominator(plan)
+
+    def train_on_batch(self, real_samples, labels=None, batch_size: int = 32, n_critic: int = 1) -> tuple[float, float]:
+        """models.py:2609-2667."""
+        G, D = self.generator, self.discriminator
+        real_samples = np.asarray(real_samples)
+        rng = np.random.default_rng(self.random_state)
+        d_loss_total = 0.0
+        comb_labels = np.zeros((2 * batch_size, 1), dtype=np.float32)
+        comb_labels[:batch_size] = self.label_smoothing
+        comb_labels[batch_size:] = 1 - self.label_smoothing
+        for _ in range(n_critic):
+            idx = rng.choice(len(real_samples), batch_size, replace=False)
+            z, _ = self._generate_latent_points(batch_size)
+            fake = G._forward_dev(z, training=False)
+            d_in_shape = (2 * batch_size,) + tuple(real_samples.shape[1:])
+            d_plan = D._plan(d_in_shape, True)
+            d_prog = d_plan.program("train")
+            d_plan.x_in[:batch_size].copy_(B.to_device(real_samples[idx]).reshape(d_plan.x_in[:batch_size].shape))
+            d_plan.x_in[batch_size:].copy_(fake.reshape(d_plan.x_in[batch_size:].shape))
+            d_plan.set_target(comb_labels)
+            D.y_true = comb_labels
+            d_prog.run()
+            D._last_plan, D._last_rows, D._pred_host = d_plan, 2 * batch_size, None
+            d_loss_total += self._loss_value(D, d_plan)
+        d_loss_avg = d_loss_total / n_critic
+
+        z, _ = self._generate_latent_points(batch_size)
+        fake = G._forward_dev(z, training=True)
+        D._forward_dev(fake.reshape((batch_size,) + tuple(real_samples.shape[1:])), training=False)
+        ones = np.ones((batch_size, 1), dtype=np.float32)
+        D.y_true = ones
+        dp = D._last_plan
+        dp.set_target(ones)
+        dp.program("loss").run()
+        g_loss = self._loss_value(D, dp)
+        # models.py:2661-2664: g_grad = loss.derivative(ones, predictions); with a Sigmoid+BCE discriminator the
+        # shortcut in Sequential.backward_pass replaces it by predictions - ones
+        g_grad = B.empty(tuple(dp.pred.shape))
+        ops.loss_fwd_bwd(self.generator_loss._kind, 0, dp.pred, dp.y_in, g_grad, None, None, None)
+        d_grad = D.backward_pass(g_grad, compute_only=True)
+        G.backward_pass(d_grad, gan=True)
+        self._train_step += 1
+        return d_loss_avg, g_loss
+
+    def fit(self, x_train, y_train=None, epochs: int = 100, batch_size: int | None = None, n_critic: int = 5,
+            verbose: bool = True, random_state: int | None = None, callbacks: list = [], **unused) -> dict:
+        """Core of models.py:2669-2936: per epoch, shuffle, then one train_on_batch per mini-batch."""
+        history = History({"discriminator_loss": [], "generator_loss": []})
+        x_train = np.asarray(x_train)
+        bs = batch_size or len(x_train)
+        seed = random_state if random_state is not None else self.random_state
+        for epoch in range(epochs):
+            start = time.time()
+            xs = x_train[shuffle_indices(len(x_train), seed)]
+            dl, gl, nb = 0.0, 0.0, 0
+            for j in range(0, len(xs) - bs + 1, bs):
+                d, g = self.train_on_batch(xs[j:j + bs], None, min(bs, len(xs[j:j + bs])), n_critic)
+                dl, gl, nb = dl + d, gl + g, nb + 1
+                if verbose:
+                    progress_bar(nb, max(len(xs) // bs, 1), message=f"Epoch {epoch + 1}/{epochs} - {time.time() - start:.2f}s - "
+                                 f"d_loss: {format_number(dl / nb)} - g_loss: {format_number(gl / nb)}")
+            history["discriminator_loss"].append(dl / max(nb, 1))
+            history["generator_loss"].append(gl / max(nb, 1))
+            if verbose:
+                print()
+        return history

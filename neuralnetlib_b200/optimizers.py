@@ -1,0 +1,256 @@
+"""Mirror of neuralnetlib/optimizers.py (Optimizer, SGD :40-60, Adam :167-283) with device-resident state.
+
+`update(layer_index, weights, weights_grad, bias, bias_grad)` keeps the reference contract: it mutates
+`weights` / `bias` IN PLACE (NumPy arrays are uploaded, updated by the fused multi-tensor kernel and written
+back; device tensors are updated where they live). Inside a compiled Sequential plan the same kernel updates
+every parameter tensor of the model in one launch, with Adam's per-layer `t` (optimizers.py:236) and the
+per-tensor gradient clip (models.py:240-242) computed on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _backend as B
+from . import _ops as ops
+
+
+class Optimizer:
+    def __init__(self, learning_rate: float = 0.01):
+        self._hyper = None
+        self.learning_rate = learning_rate
+
+    def update(self, layer_index: int, weights, weights_grad, bias=None, bias_grad=None):
+        raise NotImplementedError
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__}
+
+    @staticmethod
+    def from_config(config: dict):
+        for cls in Optimizer.__subclasses__():
+            if cls.__name__ == config["name"]:
+                return cls.from_config(config) if "from_config" in cls.__dict__ else cls(
+                    **{k: v for k, v in config.items() if k != "name"})
+        raise ValueError(f"No optimizer found for the name: {config['name']}")
+
+    @staticmethod
+    def from_name(name: str) -> "Optimizer":
+        key = name.lower().replace("_", "")
+        for cls in Optimizer.__subclasses__():
+            if cls.__name__.lower() == key:
+                return cls()
+        raise ValueError(f"No optimizer found for the name: {name}")
+
+    # -- learning_rate is read by the kernels from device memory so that callbacks.LearningRateScheduler
+    #    (callbacks.py:346-354) can change it without re-capturing the step graph
+    @property
+    def learning_rate(self):
+        return self._lr
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self._lr = v
+        if getattr(self, "_hyper", None) is not None:
+            self._upload_hyper()
+
+    def _hyper_values(self):
+        return [float(self._lr), 0.0, 0.0, 0.0]
+
+    def _upload_hyper(self):
+        vals = torch.tensor(self._hyper_values(), dtype=torch.float64)
+        if self._hyper is None:
+            self._hyper = vals.to(B.device())
+        else:
+            self._hyper.copy_(vals)
+
+    def _ensure_device(self):
+        if self._hyper is None:
+            B.stream_obj()
+            self._upload_hyper()
+
+    # plan interface -------------------------------------------------------------------------------
+    def _t_counter(self):
+        return None
+
+    def _make_plan(self, updates):
+        """updates: list of (layer_index, w, dw, b, db) device tensors in update order (last layer first)."""
+        raise NotImplementedError
+
+    def _run_plan(self, plan):
+        raise NotImplementedError
+
+    @staticmethod
+    def _as_pairs(weights, weights_grad, bias, bias_grad):
+        pairs = [(weights, weights_grad)]
+        if bias is not None and bias_grad is not None:
+            pairs.append((bias, bias_grad))
+        return pairs
+
+
+def _stage(param, grad):
+    """-> (device param, device grad, writeback or None)."""
+    if isinstance(param, torch.Tensor):
+        g = grad if isinstance(grad, torch.Tensor) else B.to_device(grad)
+        return param, g.reshape(-1) if g.dim() == 0 else g, None
+    if not isinstance(param, np.ndarray):
+        raise TypeError("parameters must be numpy arrays or device tensors")
+    pd = B.to_device(param)
+    gd = B.to_device(np.broadcast_to(np.asarray(grad, dtype=np.float64), param.shape))
+    return pd, gd, param
+
+
+class SGD(Optimizer):
+    def __init__(self, learning_rate: float = 0.01, **kwargs):
+        super().__init__(learning_rate)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def update(self, layer_index, weights, weights_grad, bias=None, bias_grad=None):
+        self._ensure_device()
+        staged = [_stage(p, g) for p, g in self._as_pairs(weights, weights_grad, bias, bias_grad)]
+        plan = ops.OptPlan([(p, g.contiguous(), None, None, 1, 0) for p, g, _ in staged], 1)
+        ops.sgd_multi(plan, self._hyper)
+        for p, _, host in staged:
+            if host is not None:
+                host[...] = B.to_host(p).reshape(host.shape)
+
+    def _make_plan(self, updates):
+        self._ensure_device()
+        entries = []
+        for j, (idx, w, dw, b, db) in enumerate(updates, start=1):
+            entries.append((w, dw, None, None, j, 1))
+            if b is not None:
+                entries.append((b, db, None, None, j, 1))
+        return ops.OptPlan(entries, max(len(updates), 1))
+
+    def _run_plan(self, plan):
+        ops.sgd_multi(plan, self._hyper)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "learning_rate": self.learning_rate}
+
+    def __str__(self):
+        return f"{self.__class__.__name__}(learning_rate={self.learning_rate})"
+
+    @staticmethod
+    def from_config(config: dict):
+        return SGD(config["learning_rate"])
+
+
+class Adam(Optimizer):
+    def __init__(self, learning_rate: float = 0.001, beta_1: float = 0.9, beta_2: float = 0.999,
+                 epsilon: float = 1e-8, clip_norm: float = None, clip_value: float = None, **kwargs) -> None:
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        super().__init__(learning_rate)
+        if clip_norm is not None or clip_value is not None:
+            raise NotImplementedError("Adam(clip_norm/clip_value) (optimizers.py:190-202) is not on the B200 hot path; "
+                                      "Sequential's own gradient clip (models.py:240-242) is built in")
+        self.clip_norm, self.clip_value = clip_norm, clip_value
+        self._t_host = 0
+        self._t_dev = None
+        self._state = {}    # (kind, layer_index) -> (m, v) device tensors, kind in {"w", "b"}
+        self._shapes = {}   # (kind, layer_index) -> reference shape of the parameter
+        self._min_denom = 1e-16
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def _hyper_values(self):
+        return [float(self._lr), float(self.beta_1), float(self.beta_2), float(self.epsilon)]
+
+    def _ensure_device(self):
+        super()._ensure_device()
+        if self._t_dev is None:
+            self._t_dev = torch.tensor([self._t_host], dtype=torch.int64).to(B.device())
+
+    # `t` counts update() calls, i.e. LAYERS, not steps (optimizers.py:236). It lives on the device.
+    @property
+    def t(self):
+        if self._t_dev is None:
+            return self._t_host
+        return int(self._t_dev.cpu()[0].item())
+
+    @t.setter
+    def t(self, v):
+        self._t_host = int(v)
+        if self._t_dev is not None:
+            self._t_dev.fill_(int(v))
+
+    def _t_counter(self):
+        self._ensure_device()
+        return self._t_dev
+
+    def _moments(self, kind, layer_index, like: torch.Tensor, shape=None):
+        key = (kind, layer_index)
+        if key not in self._state:
+            self._state[key] = (B.zeros(like.shape), B.zeros(like.shape))
+            self._shapes[key] = tuple(shape if shape is not None else like.shape)
+        return self._state[key]
+
+    def update(self, layer_index, weights, weights_grad, bias=None, bias_grad=None) -> None:
+        self._ensure_device()
+        staged = []
+        for kind, (p, g) in zip(("w", "b"), self._as_pairs(weights, weights_grad, bias, bias_grad)):
+            pd, gd, host = _stage(p, g)
+            m, v = self._moments(kind, layer_index, pd, None if host is None else host.shape)
+            staged.append((pd, gd.contiguous(), m, v, host))
+        plan = ops.OptPlan([(pd, gd, m, v, 1, 0) for pd, gd, m, v, _ in staged], 1)
+        ops.step_begin(None, None, self._t_dev, 1)   # self.t += 1
+        ops.adam_multi(plan, self._hyper, self._t_dev)
+        for pd, _, _, _, host in staged:
+            if host is not None:
+                host[...] = B.to_host(pd).reshape(host.shape)
+
+    def _make_plan(self, updates):
+        self._ensure_device()
+        entries = []
+        for j, (idx, w, dw, b, db) in enumerate(updates, start=1):
+            m, v = self._moments("w", idx, w)
+            entries.append((w, dw, m, v, j, 1))
+            if b is not None:
+                m, v = self._moments("b", idx, b)
+                entries.append((b, db, m, v, j, 1))
+        return ops.OptPlan(entries, max(len(updates), 1))
+
+    def _run_plan(self, plan):
+        ops.adam_multi(plan, self._hyper, self._t_dev)
+
+    # reference-shaped views of the state (optimizers.py:247-261) --------------------------------------
+    def _host_state(self, kind, which):
+        return {idx: B.to_host(mv[which]).reshape(self._shapes[(k, idx)])
+                for (k, idx), mv in self._state.items() if k == kind}
+
+    def _set_state(self, kind, which, d):
+        self._ensure_device()
+        for idx, arr in d.items():
+            arr = np.asarray(arr, dtype=np.float64)
+            key = (kind, int(idx))
+            if key not in self._state:
+                self._state[key] = (B.zeros(arr.shape), B.zeros(arr.shape))
+                self._shapes[key] = arr.shape
+            self._state[key][which].copy_(B.to_device(arr).reshape(self._state[key][which].shape))
+
+    m_w = property(lambda self: self._host_state("w", 0), lambda self, d: self._set_state("w", 0, d))
+    v_w = property(lambda self: self._host_state("w", 1), lambda self, d: self._set_state("w", 1, d))
+    m_b = property(lambda self: self._host_state("b", 0), lambda self, d: self._set_state("b", 0, d))
+    v_b = property(lambda self: self._host_state("b", 1), lambda self, d: self._set_state("b", 1, d))
+
+    def get_config(self) -> dict:
+        tolist = lambda d: {k: v.tolist() for k, v in d.items()}  # noqa: E731
+        return {"name": self.__class__.__name__, "learning_rate": self.learning_rate, "beta_1": self.beta_1,
+                "beta_2": self.beta_2, "epsilon": self.epsilon, "clip_norm": self.clip_norm, "clip_value": self.clip_value,
+                "t": self.t, "m_w": tolist(self.m_w), "v_w": tolist(self.v_w), "m_b": tolist(self.m_b),
+                "v_b": tolist(self.v_b)}
+
+    @staticmethod
+    def from_config(config: dict):
+        adam = Adam(learning_rate=config["learning_rate"], beta_1=config["beta_1"], beta_2=config["beta_2"],
+                    epsilon=config["epsilon"], clip_norm=config.get("clip_norm"), clip_value=config.get("clip_value"))
+        adam.t = config["t"]
+        for name in ("m_w", "v_w", "m_b", "v_b"):
+            setattr(adam, name, {int(k): np.array(v) for k, v in config[name].items()})
+        return adam
+
+    def __str__(self):
+        return (f"{self.__class__.__name__}(learning_rate={self.learning_rate}, beta_1={self.beta_1}, "
+                f"beta_2={self.beta_2}, epsilon={self.epsilon}, clip_norm={self.clip_norm}, clip_value={self.clip_value})")

@@ -1,0 +1,276 @@
+"""GPU parity, model level: Sequential.train_on_batch / fit / forward+backward and GAN.train_on_batch through the
+public drop-in API against (a) golden traces recorded from the unmodified reference and (b) the oracle at
+larger batch sizes.
+
+Tolerances: losses, predictions, gradients within rel 1e-5 (norm-relative) on the FFMA path. Post-Adam weights use
+the criterion SURVEY.md §7 derives from Adam's conditioning at |g| ~ eps: >= 99.9 % of the elements within
+1e-5 * max|w| and every element within 2 * lr of the reference.
+"""
+import numpy as np
+import pytest
+
+import nnl_oracle as O
+from helpers import check_packed, nrel
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def _nn():
+    from neuralnetlib_b200 import layers, models, optimizers
+    return layers, models, optimizers
+
+
+def build_cfg(cfg, width=None, seed=42):
+    L, M, Opt = _nn()
+    m = M.Sequential(random_state=seed)
+    if cfg == 1:
+        m.add(L.Input(784)); m.add(L.Dense(128, activation="relu")); m.add(L.Dense(64, activation="relu"))
+        m.add(L.Dense(10, activation="softmax"))
+    elif cfg == 2:
+        m.add(L.Input((28, 28, 1))); m.add(L.Conv2D(32, 3, padding="same", activation="relu")); m.add(L.BatchNormalization())
+        m.add(L.MaxPooling2D(2)); m.add(L.Flatten()); m.add(L.Dense(64, activation="relu")); m.add(L.Dense(10, activation="softmax"))
+    elif cfg == 3:
+        m.add(L.Input((32, 32, 3)))
+        for f in (64, 128, 256):
+            m.add(L.Conv2D(f, 3, padding="same", activation="relu")); m.add(L.BatchNormalization()); m.add(L.MaxPooling2D(2))
+        m.add(L.Flatten()); m.add(L.Dense(10, activation="softmax"))
+    elif cfg == 4:
+        w = width or 4096
+        m.add(L.Input(w))
+        for _ in range(4):
+            m.add(L.Dense(w, activation="relu"))
+        m.add(L.Dense(10, activation="softmax"))
+    m.compile(loss_function="categorical_crossentropy", optimizer=Opt.Adam())
+    return m
+
+
+def weights_close(w, ref_full_or_none, g, name, lr=1e-3):
+    """Quantile criterion for post-Adam weights (see module docstring)."""
+    w = np.asarray(w, dtype=np.float64)
+    if name in g:
+        ref, sub = g[name], w
+    else:
+        ref, sub = g[name + "__sub"], w.ravel()[::int(g[name + "__stride"])]
+    assert sub.shape == ref.shape or sub.size == ref.size
+    d = np.abs(sub.ravel() - ref.ravel())
+    scale = max(np.abs(ref).max(), 1e-30)
+    outliers = int(np.sum(d > 1e-5 * scale + 1e-9))
+    # at most 0.1 % of the elements (2 for tiny tensors such as a 64-element bias) may sit at |g| ~ eps
+    assert outliers <= max(2, int(1e-3 * d.size)), f"{name}: {outliers} of {d.size} elements beyond 1e-5*max|w|"
+    assert d.max() <= 2 * lr, f"{name}: max |dw| {d.max():.3e} exceeds 2*lr"
+
+
+@pytest.mark.parametrize("name,cfg,width", [("cfg1_b32", 1, None), ("cfg2_b8", 2, None), ("cfg3_b4", 3, None),
+                                            ("cfg4w256_b16", 4, 256)])
+def test_train_on_batch_golden(golden, name, cfg, width):
+    L, M, Opt = _nn()
+    g = golden(name)
+    # config 3 at batch 4 is ill-conditioned by construction: three stacked BatchNorms whose per-position statistics
+    # come from 4 samples (many positions have ~zero variance => 1/std up to 223, which amplifies fp32 rounding of the
+    # conv outputs). Gradients reach 6.5e-5 there; at batch 32 the same model is within 5e-5 (oracle test below).
+    TOL = 1e-4 if cfg == 3 else globals()["TOL"]
+    m = build_cfg(cfg, width)
+    x, y = g["x"].astype(np.float32), g["y"].astype(np.float32)
+    for s in range(int(g["steps"])):
+        loss = m.train_on_batch(x, y)
+        assert isinstance(loss, float)
+        ref = float(g[f"s{s}_loss"])
+        assert abs(loss - ref) <= 1e-5 * max(1.0, abs(ref)), (s, loss, ref)
+        check_packed(g, f"s{s}_pred", m.predictions, 5e-5, what=f"step{s} ")
+        for li, layer in enumerate(m.layers):
+            if hasattr(layer, "weights"):
+                check_packed(g, f"s{s}_L{li}_dw", layer.d_weights, TOL, what=f"step{s} ")
+                key = f"s{s}_L{li}_db"
+                shp = g[key].shape if key in g else tuple(g[key + "__shape"])
+                assert layer.d_bias.shape == shp   # Q9: Conv2D d_bias is (F,), Dense (1, units)
+                check_packed(g, key, layer.d_bias, TOL, what=f"step{s} ")
+                weights_close(layer.weights, None, g, f"s{s}_L{li}_w")
+                weights_close(layer.bias, None, g, f"s{s}_L{li}_b")
+            if isinstance(layer, L.BatchNormalization):
+                check_packed(g, f"s{s}_L{li}_rm", layer.running_mean, TOL)
+                check_packed(g, f"s{s}_L{li}_rv", layer.running_var, TOL)
+                assert not hasattr(layer, "weights")   # Q5: gamma/beta are never updated by Sequential
+                assert np.all(layer.gamma == 1.0)
+    opt = m.optimizer
+    assert opt.t == int(g["adam_t"])                                      # Q3: t counts layers, not steps
+    assert sorted(opt.m_w.keys()) == [int(k) for k in g["adam_keys"]]
+    for k in opt.m_w:
+        check_packed(g, f"adam_m_w{k}", opt.m_w[k], 1e-4)
+        check_packed(g, f"adam_v_w{k}", opt.v_w[k], 1e-4)
+    pe = m.forward_pass(x, training=False)
+    check_packed(g, "final_pred_eval", pe, 1e-3)
+
+
+@pytest.mark.parametrize("name,cfg", [("cfg1_b32", 1), ("cfg2_b8", 2), ("cfg3_b4", 3)])
+def test_public_forward_backward_trace(golden, name, cfg):
+    """forward_pass + backward_pass through the public API reproduce the reference's returned input error
+    (every clip on the way included) and the per-layer gradients of step 0."""
+    g = golden(name)
+    m = build_cfg(cfg)
+    x, y = g["x"].astype(np.float32), g["y"].astype(np.float32)
+    p = m.forward_pass(x)
+    check_packed(g, "s0_pred", p, 5e-5)
+    m.y_true = y
+    err = O.loss_derivative("cce", y.astype(np.float64), p)
+    in_err = m.backward_pass(err)
+    check_packed(g, "s0_L0_inerr", in_err, 1e-4 if cfg == 3 else 5e-5)
+    for li, layer in enumerate(m.layers):
+        if hasattr(layer, "weights"):
+            check_packed(g, f"s0_L{li}_dw", layer.d_weights, 1e-4 if cfg == 3 else TOL)
+
+
+@pytest.mark.parametrize("cfg,batch,steps,tol", [(1, 32, 4, TOL), (2, 64, 3, TOL), (2, 256, 3, TOL), (3, 32, 2, 5e-5),
+                                                 (4, 64, 2, TOL)])
+def test_train_on_batch_oracle_full_size(cfg, batch, steps, tol):
+    width = 512 if cfg == 4 else None   # config 4 at reduced width keeps the fp64 oracle to seconds
+    m = build_cfg(cfg, width)
+    specs, shp = O.config_specs(cfg)
+    if width:
+        for sp in specs:
+            if sp.get("units") == 4096:
+                sp["units"] = width
+        rng = np.random.default_rng(0)
+        x = rng.random((batch, width)).astype(np.float32)
+        y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+    else:
+        x, y = O.synthetic_batch(cfg, batch)
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    mine = [(i, l) for i, l in enumerate(m.layers) if hasattr(l, "weights")]
+    theirs = [r for r in ref.layers if "w" in r]
+    for s in range(steps):
+        loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+        assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss)), (s, loss, rloss)
+        for (li, layer), rl in zip(mine, theirs):
+            assert nrel(layer.d_weights, rl["dw"]) < tol, (s, li)
+            assert nrel(layer.d_bias.reshape(-1), rl["db"].reshape(-1)) < tol, (s, li)
+            d = np.abs(layer.weights - rl["w"])
+            assert np.mean(d <= 1e-5 * np.abs(rl["w"]).max() + 1e-9) >= 0.999 and d.max() <= 2e-3, (s, li)
+        assert m.optimizer.t == ref.optimizer.t
+        # Teacher forcing: Adam amplifies fp32-vs-fp64 rounding on elements with |g| ~ eps into weight differences
+        # of up to lr, which would make later steps incomparable. Every step therefore starts
+        # from the device's state: one-step parity from identical states is what is asserted.
+        mw, vw, mb, vb = m.optimizer.m_w, m.optimizer.v_w, m.optimizer.m_b, m.optimizer.v_b
+        for (li, layer), rl in zip(mine, theirs):
+            rl["w"], rl["b"] = layer.weights, layer.bias
+            ref.optimizer.m_w[li], ref.optimizer.v_w[li] = mw[li], vw[li]
+            ref.optimizer.m_b[li], ref.optimizer.v_b[li] = mb[li], vb[li]
+        for layer, rl in zip(m.layers, ref.layers):
+            if rl["type"] == "bn":
+                rl["running_mean"], rl["running_var"] = layer.running_mean, layer.running_var
+
+
+def test_argmax_and_pool_selection_bit_exact():
+    """Dyadic-rational inputs (multiples of 2^-6) make every product and sum exact in fp32 and fp64 alike, so the
+    max-pool selection and the prediction argmax must agree bit for bit."""
+    L, M, Opt = _nn()
+    rng = np.random.default_rng(5)
+    x = (rng.integers(-32, 32, size=(16, 8, 8, 2)) / 64.0).astype(np.float32)
+    pool = L.MaxPooling2D(2)
+    out = pool.forward_pass(x)
+    ref = O.maxpool_fwd(x.astype(np.float64), (2, 2), (2, 2))
+    assert np.array_equal(out, ref)
+    e = (rng.integers(-8, 8, size=ref.shape) / 8.0)
+    assert np.array_equal(pool.backward_pass(e), O.maxpool_bwd(x.astype(np.float64), e, (2, 2), (2, 2)))
+    d = L.Dense(10, random_state=3)
+    xd = (rng.integers(-32, 32, size=(64, 12)) / 64.0).astype(np.float32)
+    d.initialize_weights(12)
+    d.weights = np.round(d.weights * 64) / 64
+    logits = d.forward_pass(xd)
+    ref_logits = xd.astype(np.float64) @ d.weights + d.bias
+    assert np.array_equal(logits, ref_logits)
+    assert np.array_equal(np.argmax(logits, 1), np.argmax(ref_logits, 1))
+
+
+def test_fit_golden(golden):
+    g = golden("fit_cfg1")
+    m = build_cfg(1)
+    h = m.fit(g["x"].astype(np.float32), g["y"].astype(np.float32), epochs=2, batch_size=16, verbose=False,
+              metrics=["accuracy"], random_state=42, validation_data=(g["xv"].astype(np.float32), g["yv"].astype(np.float32)))
+    for k in ("loss", "val_loss", "accuracy", "val_accuracy"):
+        ref = g["hist_" + k]
+        got = np.asarray(h[k], dtype=np.float64)
+        assert got.shape == ref.shape, k
+        assert np.allclose(got, ref, rtol=2e-5, atol=1e-6), (k, got, ref)
+    assert m.optimizer.t == int(g["adam_t"])
+    for li, layer in enumerate(m.layers):
+        if hasattr(layer, "weights"):
+            weights_close(layer.weights, None, g, f"L{li}_w")
+    check_packed(g, "pred", m.predict(g["xv"].astype(np.float32)), 1e-3)
+
+
+def test_sgd_sigmoid_cce_reference_smoke_model():
+    """The reference's only integration test (tests/test_models.py:12-39): Input(10)-Dense(20)-Sigmoid, CCE, SGD.
+    Last-layer rule Q7: Sigmoid + CCE is not a recognised pair, so the raw loss derivative flows on."""
+    L, M, Opt = _nn()
+    from neuralnetlib_b200.activations import Sigmoid
+    from neuralnetlib_b200.losses import CategoricalCrossentropy
+    m = M.Sequential(random_state=11)
+    m.add(L.Input(10)); m.add(L.Dense(20)); m.add(L.Activation(Sigmoid()))
+    m.compile(loss_function=CategoricalCrossentropy(), optimizer=Opt.SGD())
+    rng = np.random.default_rng(0)
+    x, y = rng.random((100, 10)), rng.random((100, 20))
+    ref = O.OracleSequential([{"type": "input"}, {"type": "dense", "units": 20}, {"type": "act", "fn": "sigmoid"}], "cce",
+                             O.OracleSGD(), seed=11)
+    for s in range(3):
+        loss, rloss = m.train_on_batch(x[:10], y[:10]), ref.train_on_batch(x[:10], y[:10])
+        assert isinstance(loss, float) and abs(loss - rloss) < 1e-5 * abs(rloss)
+    assert nrel(m.layers[1].weights, ref.layers[1]["w"]) < 1e-5
+    m.fit(x, y, epochs=1, batch_size=10, verbose=False)
+    loss, preds = m.evaluate(rng.random((10, 10)), rng.random((10, 20)))
+    assert isinstance(loss, float) and preds.shape == (10, 20)
+    assert m.predict(rng.random((10, 10))).shape == (10, 20)
+
+
+def test_gan_golden(golden):
+    L, M, Opt = _nn()
+    g = golden("gan_b4")
+    G = M.Sequential(random_state=7)
+    G.add(L.Input(32)); G.add(L.Dense(7 * 7 * 128)); G.add(L.Reshape((7, 7, 128)))
+    G.add(L.Conv2DTranspose(64, kernel_size=3, strides=2, padding="same", activation="relu"))
+    G.add(L.Conv2DTranspose(32, kernel_size=3, strides=2, padding="same", activation="relu"))
+    G.add(L.Conv2D(1, kernel_size=3, padding="same", activation="sigmoid"))
+    D = M.Sequential(random_state=7)
+    D.add(L.Input((28, 28, 1)))
+    D.add(L.Conv2D(32, kernel_size=3, strides=2, padding="same", activation="relu"))
+    D.add(L.Conv2D(64, kernel_size=3, strides=2, padding="same", activation="relu"))
+    D.add(L.Flatten()); D.add(L.Dense(128, activation="relu")); D.add(L.Dense(1, activation="sigmoid"))
+    gan = M.GAN(latent_dim=32, random_state=7)
+    gan.compile(G, D, generator_optimizer="adam", discriminator_optimizer="adam", loss_function="bce")
+    B = int(g["batch"])
+    for s in range(int(g["steps"])):
+        dl, gl = gan.train_on_batch(g["real"].astype(np.float32), batch_size=B, n_critic=1)
+        assert abs(dl - float(g[f"s{s}_d_loss"])) < 1e-5 and abs(gl - float(g[f"s{s}_g_loss"])) < 1e-5, (s, dl, gl)
+        for nm, net in (("G", G), ("D", D)):
+            for li, layer in enumerate(net.layers):
+                if hasattr(layer, "weights"):
+                    check_packed(g, f"s{s}_{nm}{li}_dw", layer.d_weights, 5e-5, what=f"step{s} ")
+                    weights_close(layer.weights, None, g, f"s{s}_{nm}{li}_w")
+    assert G.optimizer.t == int(g["G_t"]) and D.optimizer.t == int(g["D_t"])
+
+
+def test_save_load_roundtrip(tmp_path):
+    L, M, Opt = _nn()
+    m = build_cfg(2)
+    x, y = O.synthetic_batch(2, 8)
+    m.train_on_batch(x, y)
+    path = str(tmp_path / "m.json")
+    m.save(path)
+    m2 = M.Sequential.load(path)
+    assert nrel(m2.predict(x), m.predict(x)) < 1e-6
+    assert m2.optimizer.t == m.optimizer.t
+    assert nrel(m2.optimizer.m_w[6], m.optimizer.m_w[6]) < 1e-7
+    l1, l2 = m.train_on_batch(x, y), m2.train_on_batch(x, y)   # resumed training continues identically
+    assert abs(l1 - l2) < 1e-6
+
+
+def test_early_stopping_and_lr_scheduler_touch_device_state():
+    L, M, Opt = _nn()
+    from neuralnetlib_b200.callbacks import EarlyStopping, LearningRateScheduler
+    m = build_cfg(1)
+    x, y = O.synthetic_batch(1, 64)
+    es = EarlyStopping(patience=2, min_delta=10.0, restore_best_weights=True)   # never "improves": stops after epoch 2
+    lrs = LearningRateScheduler(schedule=lambda epoch, lr: lr * 0.5 ** epoch)
+    h = m.fit(x, y, epochs=5, batch_size=32, verbose=False, callbacks=[es, lrs], random_state=1)
+    assert len(h["loss"]) == 2 and es.stop_training
+    assert abs(m.optimizer.learning_rate - 0.5e-3) < 1e-12
