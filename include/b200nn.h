@@ -59,6 +59,8 @@ int b200nn_version(void);
 size_t b200nn_last_error(char* buf, size_t cap);
 /* 1 when tcgen05 GEMM kernels are compiled in */
 int b200nn_has_tcgen05(void);
+/* number of kernels this library has launched (or recorded into a graph being captured) in this process */
+long long b200nn_launch_count(void);
 
 /* ---- step bookkeeping --------------------------------------------------------------------- */
 /* Zero `n_slots` float64 sum-of-squares slots and `n_acc` float64 accumulators (loss, counters)
@@ -186,6 +188,22 @@ int b200nn_maxpool_fwd(const b200nn_pool_geom* g, const float* x, float* y, void
  * EVERY tied maximum receives the gradient (layers.py:631-637). y is the forward output. */
 int b200nn_maxpool_bwd(const b200nn_pool_geom* g, const float* x, const float* y, const float* err,
                        const double* ss, uint64_t chain, float* dx, double* ss_out, void* stream);
+
+/* ---- fused [BatchNorm -> MaxPool 2x2/s2] forward and [MaxPool -> BatchNorm -> Activation] backward
+ *      (the conv block of BASELINE configs 2 and 3; one pass over the conv output each way) ----- */
+/* Largest batch the register-resident fused kernels accept (callers fall back to the unfused ops beyond it). */
+int b200nn_fused_block_max_batch(void);
+/* x [B,H,W,C] (H, W even) -> y_pool [B,H/2,W/2,C]; also updates the running stats and saves mean / invstd. */
+int b200nn_bn_pool_fwd_train(const float* x, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float* save_mean, float* save_invstd, float* y_pool, int B, int H,
+                             int W, int C, float momentum, float eps, void* stream);
+/* err is the error w.r.t. the pooled output. Emits r0 = BNbwd(poolbwd(chain(err))) * f'(x) and the three
+ * sums of squares of the reference's three clip points (pool-bwd output, BN-bwd output, act-bwd output)
+ * in ss_out0/1/2, plus dgamma/dbeta. The caller chains {slot0, slot1, slot2}. */
+int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                           const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                           float* dgamma, float* dbeta, int B, int H, int W, int C, int prev_act, float prev_alpha,
+                           double* ss_out0, double* ss_out1, double* ss_out2, void* stream);
 
 /* ---- optimizers (optimizers.py:47-50, 167-245) and gradient clip (models.py:240-242) -------- */
 typedef struct {

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "b200nn_version": (c_int, []),
     "b200nn_last_error": (c_size_t, [C.c_char_p, c_size_t]),
     "b200nn_has_tcgen05": (c_int, []),
+    "b200nn_launch_count": (c_ll, []),
     "b200nn_step_begin": (c_int, [_P, c_int, _P, c_int, _P, c_ll, _P]),
     "b200nn_zero_f64": (c_int, [_P, c_int, _P]),
     "b200nn_gather_rows": (c_int, [_P, _P, _P, c_ll, c_ll, _P]),
@@ -75,6 +76,10 @@ _SIGNATURES = {
     "b200nn_bn_bwd": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_int, c_float, _P, _P, _P]),
     "b200nn_maxpool_fwd": (c_int, [C.POINTER(PoolGeom), _P, _P, _P]),
     "b200nn_maxpool_bwd": (c_int, [C.POINTER(PoolGeom), _P, _P, _P, _P, c_u64, _P, _P, _P]),
+    "b200nn_fused_block_max_batch": (c_int, []),
+    "b200nn_bn_pool_fwd_train": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
+    "b200nn_pool_bn_act_bwd": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                        c_float, _P, _P, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
 }

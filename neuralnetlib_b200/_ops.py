@@ -188,6 +188,26 @@ def bn_bwd(x, err, ss, chain, gamma, save_mean, save_invstd, dx, dgamma, dbeta, 
                               _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), stream()))
 
 
+def fused_block_max_batch():
+    return int(lib().b200nn_fused_block_max_batch())
+
+
+def bn_pool_fwd_train(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y_pool, momentum, eps):
+    _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y_pool)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    check(lib().b200nn_bn_pool_fwd_train(ptr(x), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(save_mean),
+                                         ptr(save_invstd), ptr(y_pool), Bn, H, W, Cc, momentum, eps, stream()))
+
+
+def pool_bn_act_bwd(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, dgamma, dbeta, prev_act, prev_alpha, slot0,
+                    slot1, slot2):
+    _f32(x, err, gamma, beta, save_mean, save_invstd, r0, dgamma, dbeta)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    check(lib().b200nn_pool_bn_act_bwd(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(beta), ptr(save_mean),
+                                       ptr(save_invstd), ptr(r0), ptr(dgamma), ptr(dbeta), Bn, H, W, Cc, prev_act, prev_alpha,
+                                       _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), _slot_ptr(ss, slot2), stream()))
+
+
 def maxpool_fwd(g: PoolGeom, x, y):
     _f32(x, y)
     check(lib().b200nn_maxpool_fwd(C.byref(g), ptr(x), ptr(y), stream()))

@@ -181,6 +181,289 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(b200nn_pool_geom g, co
     if (ss_out != nullptr) block_accumulate(acc, ss_out, scratch);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused conv-block kernels (BASELINE configs 2/3: Conv+ReLU -> BatchNorm -> MaxPool 2x2/s2):
+//   forward : BatchNorm(train) + MaxPool in ONE pass over the conv output (read S once, write P + stats)
+//   backward: MaxPool-bwd + BatchNorm-bwd + Activation-bwd in ONE pass (read S and the pooled error once, write R)
+// Tiling: one pool-window position x 32 channels x the WHOLE batch belongs to one thread-block CLUSTER; each CTA of
+// the cluster stages <= 128 batch rows of the window (4 x 128-byte NHWC lines per row, cp.async 16 B) in shared
+// memory, reduces its rows, and the per-position batch statistics are completed across the cluster through
+// distributed shared memory (one 128-float exchange per reduction). Cluster size = ceil(B / 128) <= 8, so batches
+// up to 1024 stay single-pass. All global traffic is full 128-byte lines; the 2x2 max is thread-local.
+// ------------------------------------------------------------------------------------------------
+constexpr int FB_ROWS = 128;     // batch rows staged per CTA
+constexpr int FB_THREADS = 256;  // 32 channel lanes x 8 row groups
+constexpr int FB_RG = FB_THREADS / 32;
+constexpr int FB_MAX_CLUSTER = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, unsigned rank) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(local_smem_ptr));
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(a), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// Sum `v[nq]` (per thread: column (q, lane), partial over this thread's rows) over the row groups of the CTA and
+// over the CTAs of the cluster; every thread gets the totals. `red` is [FB_RG][8][32], `part` is [2][8][32]
+// (double-buffered by `phase` so that a CTA may start the next reduction while peers still read the previous one).
+template <int NQ>
+__device__ __forceinline__ void cluster_colsum(float (&v)[NQ], float (*red)[8][32], float (*part)[8][32], int phase,
+                                               int lane, int rg, unsigned csize) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) red[rg][q][lane] = v[q];
+    __syncthreads();
+    if (rg == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < FB_RG; ++r) s += red[r][q][lane];
+            part[phase][q][lane] = s;
+        }
+    }
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float s = 0.0f;
+        if (csize > 1) {
+            for (unsigned r = 0; r < csize; ++r) s += ld_dsmem(&part[phase][q][lane], r);
+        } else {
+            s = part[phase][q][lane];
+        }
+        v[q] = s;
+    }
+}
+
+struct FbGeom {
+    int B, H, W, C;
+};
+
+// stage rows [row0, row0+nrows) of the 2x2 window at (oy, ox), channels [c0, c0+32) into tile[row][q][32]
+__device__ __forceinline__ void fb_stage_window(float* tile, const float* __restrict__ x, const FbGeom& g, int row0,
+                                                int nrows, int oy, int ox, int c0) {
+    const long long HWC = (long long)g.H * g.W * g.C;
+    const int n4 = nrows * 32;   // float4 chunks: nrows x 4 positions x 8
+    for (int i = threadIdx.x; i < n4; i += FB_THREADS) {
+        const int j = i & 7, q = (i >> 3) & 3, r = i >> 5;
+        const long long src = (long long)(row0 + r) * HWC + ((long long)(2 * oy + (q >> 1)) * g.W + 2 * ox + (q & 1)) * g.C + c0 + j * 4;
+        cp_async16(tile + (r * 4 + q) * 32 + j * 4, x + src);
+    }
+}
+
+__global__ void __launch_bounds__(FB_THREADS) bn_pool_fwd_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 float* __restrict__ rmean, float* __restrict__ rvar,
+                                                                 float* __restrict__ save_mean,
+                                                                 float* __restrict__ save_invstd,
+                                                                 float* __restrict__ y, FbGeom g, float momentum,
+                                                                 float eps) {
+    extern __shared__ __align__(16) float tile[];   // [FB_ROWS][4][32]
+    __shared__ float red[FB_RG][8][32];
+    __shared__ float part[2][8][32];
+    const unsigned csize = cluster_size(), crank = cluster_rank();
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + lane;
+    const int rows_per = (g.B + csize - 1) / csize;
+    const int row0 = crank * rows_per;
+    const int nrows = max(0, min(rows_per, g.B - row0));
+    fb_stage_window(tile, x, g, row0, nrows, oy, ox, c0);
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = rg; r < nrows; r += FB_RG) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += clip10(tile[(r * 4 + q) * 32 + lane]);   // layers.py:1234
+    }
+    cluster_colsum<4>(acc, red, part, 0, lane, rg, csize);
+    float mean[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { mean[q] = acc[q] / (float)g.B; acc[q] = 0.0f; }   // layers.py:1237
+    for (int r = rg; r < nrows; r += FB_RG) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float d = clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q];
+            acc[q] += d * d;
+        }
+    }
+    cluster_colsum<4>(acc, red, part, 1, lane, rg, csize);
+    float gq[4], bq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long p = ((long long)(2 * oy + (q >> 1)) * g.W + 2 * ox + (q & 1)) * g.C + c;
+        const float batch_var = acc[q] / (float)g.B + eps;   // layers.py:1238
+        const float invstd = rsqrtf(batch_var + eps);        // layers.py:1252
+        if (crank == 0 && rg == 0) {
+            rmean[p] = momentum * rmean[p] + (1.0f - momentum) * mean[q];    // layers.py:1240-1243
+            rvar[p] = momentum * rvar[p] + (1.0f - momentum) * batch_var;
+            save_mean[p] = mean[q];
+            save_invstd[p] = invstd;
+        }
+        gq[q] = gamma[p] * invstd;
+        bq[q] = beta[p];
+    }
+    const int OW = g.W >> 1;
+    const long long OHWC = (long long)(g.H >> 1) * OW * g.C, obase = ((long long)oy * OW + ox) * g.C + c;
+    for (int r = rg; r < nrows; r += FB_RG) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m = fmaxf(m, gq[q] * (clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q]) + bq[q]);
+        y[(long long)(row0 + r) * OHWC + obase] = m;   // layers.py:1256 then :599-600
+    }
+    if (csize > 1) cluster_sync_all();   // peers may still be reading this CTA's `part`
+}
+
+__global__ void __launch_bounds__(FB_THREADS) pool_bn_act_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, float* __restrict__ r0, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, FbGeom g, int prev_act, float prev_alpha, double* ss0, double* ss1, double* ss2) {
+    extern __shared__ __align__(16) float tile[];   // [FB_ROWS][4][32] window values, then [FB_ROWS][32] pooled error
+    __shared__ float red[FB_RG][8][32];
+    __shared__ float part[2][8][32];
+    __shared__ double scratch[32];
+    const float scale = chain_scale(ss, chain);
+    const unsigned csize = cluster_size(), crank = cluster_rank();
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + lane;
+    const int rows_per = (g.B + csize - 1) / csize;
+    const int row0 = crank * rows_per;
+    const int nrows = max(0, min(rows_per, g.B - row0));
+    float* etile = tile + FB_ROWS * 128;
+    const int OW = g.W >> 1;
+    const long long OHWC = (long long)(g.H >> 1) * OW * g.C, obase = ((long long)oy * OW + ox) * g.C + c0;
+    fb_stage_window(tile, x, g, row0, nrows, oy, ox, c0);
+    for (int i = threadIdx.x; i < nrows * 8; i += FB_THREADS)
+        cp_async16(etile + (i >> 3) * 32 + (i & 7) * 4, err + (long long)(row0 + (i >> 3)) * OHWC + obase + (i & 7) * 4);
+    float mean[4], invstd[4], gq[4], bq[4];
+    long long pos[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        pos[q] = ((long long)(2 * oy + (q >> 1)) * g.W + 2 * ox + (q & 1)) * g.C + c;
+        mean[q] = save_mean[pos[q]];
+        invstd[q] = save_invstd[pos[q]];
+        gq[q] = gamma[pos[q]] * invstd[q];
+        bq[q] = beta[pos[q]];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // pass 1: U = pool-bwd(e): EVERY tied maximum of the BN output receives e (layers.py:631-637); column sums
+    float sums[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0..3] sum U (d_beta), [4..7] sum U*xhat (d_gamma)
+    float a0 = 0.0f;
+    for (int r = rg; r < nrows; r += FB_RG) {
+        const float e = scale * etile[r * 32 + lane];
+        float yq[4], xh[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float d = clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q];
+            yq[q] = gq[q] * d + bq[q];
+            xh[q] = d * invstd[q];
+        }
+        const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float u = (yq[q] == m) ? e : 0.0f;
+            sums[q] += u;
+            sums[4 + q] += u * xh[q];
+            a0 += u * u;
+        }
+    }
+    cluster_colsum<8>(sums, red, part, 0, lane, rg, csize);
+    if (crank == 0 && rg == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (dbeta != nullptr) dbeta[pos[q]] = sums[q];          // layers.py:1262
+            if (dgamma != nullptr) dgamma[pos[q]] = sums[4 + q];    // layers.py:1261
+        }
+    }
+    const float invB = 1.0f / (float)g.B;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sums[q] *= invB;
+    float a1 = 0.0f, a2 = 0.0f;
+    const long long HWC = (long long)g.H * g.W * g.C;
+    for (int r = rg; r < nrows; r += FB_RG) {
+        const float e = scale * etile[r * 32 + lane];
+        float yq[4], xh[4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            xv[q] = tile[(r * 4 + q) * 32 + lane];
+            const float d = clip10(xv[q]) - mean[q];
+            yq[q] = gq[q] * d + bq[q];
+            xh[q] = d * invstd[q];
+        }
+        const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+        float* rb = r0 + (long long)(row0 + r) * HWC;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float u = (yq[q] == m) ? e : 0.0f;
+            float d = gq[q] * (u - xh[q] * sums[4 + q] - sums[q]);       // BN backward, layers.py:1264-1274
+            a1 += d * d;
+            if (prev_act != B200NN_ACT_NONE) {
+                d *= act_grad_from_y(prev_act, xv[q], prev_alpha);       // Activation backward, layers.py:237
+                a2 += d * d;
+            }
+            rb[pos[q]] = d;
+        }
+    }
+    if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+    if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+    if (prev_act != B200NN_ACT_NONE && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+    if (csize > 1) cluster_sync_all();
+}
+
+static int check_fused_block(const char* who, int B, int H, int W, int C) {
+    B200NN_REQUIRE(B > 0 && B <= FB_ROWS * FB_MAX_CLUSTER, "%s: batch %d outside the single-pass range (1..%d)", who, B,
+                   FB_ROWS * FB_MAX_CLUSTER);
+    B200NN_REQUIRE(H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 32 == 0,
+                   "%s: needs even H, W and C %% 32 == 0 (got %dx%dx%d)", who, H, W, C);
+    B200NN_REQUIRE((long long)(W / 2) * FB_MAX_CLUSTER < (1LL << 31) && H / 2 <= 65535 && C / 32 <= 65535, "%s: grid too large", who);
+    return B200NN_OK;
+}
+
+template <class Kern, class... Args>
+static int launch_fused_block(const char* name, Kern kern, size_t smem, int B, int H, int W, int C, cudaStream_t st,
+                              Args... args) {
+    const int cl = (B + FB_ROWS - 1) / FB_ROWS;
+    static thread_local const void* configured[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool seen = false;
+    for (auto p : configured) seen = seen || p == (const void*)kern;
+    if (!seen) {
+        B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (auto& p : configured) if (p == nullptr) { p = (const void*)kern; break; }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((W / 2) * cl, H / 2, C / 32);
+    cfg.blockDim = dim3(FB_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200NN_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    B200NN_LAUNCH_CHECK(name);
+    return B200NN_OK;
+}
+
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -252,6 +535,34 @@ int b200nn_maxpool_bwd(const b200nn_pool_geom* g, const float* x, const float* y
     maxpool_bwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(*g, x, y, err, ss, chain, dx, ss_out, total);
     B200NN_LAUNCH_CHECK("maxpool_bwd");
     return B200NN_OK;
+}
+
+
+int b200nn_fused_block_max_batch(void) { return FB_ROWS * FB_MAX_CLUSTER; }
+
+int b200nn_bn_pool_fwd_train(const float* x, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float* save_mean, float* save_invstd, float* y_pool, int B, int H,
+                             int W, int C, float momentum, float eps, void* stream) {
+    if (int rc = check_fused_block("bn_pool_fwd_train", B, H, W, C)) return rc;
+    B200NN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "bn_pool_fwd_train: x must be 16-byte aligned");
+    const FbGeom g{B, H, W, C};
+    return launch_fused_block("bn_pool_fwd_train", bn_pool_fwd_kernel, (size_t)FB_ROWS * 128 * sizeof(float), B, H, W, C,
+                              as_stream(stream), x, gamma, beta, running_mean, running_var, save_mean, save_invstd, y_pool, g,
+                              momentum, eps);
+}
+
+int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                           const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                           float* dgamma, float* dbeta, int B, int H, int W, int C, int prev_act, float prev_alpha,
+                           double* ss_out0, double* ss_out1, double* ss_out2, void* stream) {
+    if (int rc = check_fused_block("pool_bn_act_bwd", B, H, W, C)) return rc;
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd: unknown activation %d", prev_act);
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
+                   "pool_bn_act_bwd: x and err must be 16-byte aligned");
+    const FbGeom g{B, H, W, C};
+    return launch_fused_block("pool_bn_act_bwd", pool_bn_act_bwd_kernel, (size_t)FB_ROWS * 160 * sizeof(float), B, H, W, C,
+                              as_stream(stream), x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, dgamma, dbeta, g,
+                              prev_act, prev_alpha, ss_out0, ss_out1, ss_out2);
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 namespace b200nn {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // bumps the process-wide kernel-launch counter (b200nn_launch_count)
 
 #define B200NN_REQUIRE(cond, ...)                 \
     do {                                          \
@@ -30,6 +31,7 @@ void set_error(const char* fmt, ...);
 
 #define B200NN_LAUNCH_CHECK(name)                                                               \
     do {                                                                                       \
+        ::b200nn::count_launch();                                                              \
         cudaError_t _e = cudaPeekAtLastError();                                                \
         if (_e != cudaSuccess) {                                                               \
             cudaGetLastError();                                                                \

@@ -9,6 +9,9 @@
 namespace b200nn {
 
 static thread_local char g_last_error[512] = {0};
+static long long g_launches = 0;
+
+void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -305,6 +308,8 @@ int b200nn_version(void) { return 100; }
 #define B200NN_HAS_TCGEN05 0
 #endif
 int b200nn_has_tcgen05(void) { return B200NN_HAS_TCGEN05; }
+
+long long b200nn_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 size_t b200nn_last_error(char* buf, size_t cap) {
     const size_t n = strlen(g_last_error);

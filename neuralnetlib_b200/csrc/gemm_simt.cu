@@ -409,6 +409,47 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     epi_finish(epi, st, scratch);
 }
 
+
+// Same reduction for FEW outputs and MANY splits (weight gradients of small-K convolutions: a few hundred
+// outputs, hundreds of per-CTA partials): 32 outputs per CTA, the 8 warps stride over the splits with coalesced
+// 128-byte reads, shared-memory combine, warp 0 applies the epilogue.
+__global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                                 Epilogue epi) {
+    __shared__ float sm[8][32];
+    __shared__ double scratch[32];
+    EpiState st;
+    epi_begin(epi, st);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long total = (long long)M * N;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    float v = 0.0f;
+    if (i < total)
+        for (int s = w; s < splits; s += 8) v += ws[(long long)s * total + i];
+    sm[w][lane] = v;
+    __syncthreads();
+    if (w == 0 && i < total) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][lane];
+        epi_store(epi, st, (int)(i / N), (int)(i % N), t);
+    }
+    epi_finish(epi, st, scratch);
+}
+
+static int launch_splitk_reduce(const float* ws, int splits, int M, int N, const Epilogue& epi, cudaStream_t st) {
+    const long long total = (long long)M * N;
+    if (total <= 32768 && splits >= 16) {
+        splitk_reduce_wide_kernel<<<(int)((total + 31) / 32), 256, 0, st>>>(ws, splits, M, N, epi);
+        B200NN_LAUNCH_CHECK("splitk_reduce_wide");
+        return B200NN_OK;
+    }
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, M, N, epi);
+    B200NN_LAUNCH_CHECK("splitk_reduce");
+    return B200NN_OK;
+}
+
 // column sums of a [R, F] matrix with the lazy clip multiplier: out[f] = scale * sum_r x[r, f]
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, long long R, int F,
                                                              float* __restrict__ partial) {
@@ -430,6 +471,170 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nbloc
         for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * F + f];
         out[f] = s * scale;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// small-K convolution fast paths (K = C*kh*kw <= 32: first layers on 1- or 3-channel images).
+// With so few taps the contraction is HBM-bound, so instead of the 64x64 GEMM tile
+// (which wastes >80 % of its FMAs on padding) these kernels stream the big tensor exactly once with
+// 128-bit coalesced accesses and keep the tiny operand on chip.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALLK_MAX = 32;
+
+// y[pix, :] = act(b + sum_tap x[pix, tap] * w[tap, :]).  One thread per output pixel computes ALL F filters: the
+// K input taps are loaded once per pixel (not once per filter group), the weights come from shared memory as
+// warp-broadcast 128-bit reads, and the F outputs leave as F/4 float4 stores. ~2 instructions per FMA instead of ~8.
+template <int FV>   // F / 4
+__global__ void __launch_bounds__(128) conv2d_smallk_fwd_kernel(b200nn_conv_geom g, const float* __restrict__ x,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ y,
+                                                                int act, float alpha, int n_pix) {
+    constexpr int F = FV * 4;
+    __shared__ __align__(16) float ws[SMALLK_MAX * F];  // [tap (ky,kx,c)][F]
+    __shared__ __align__(16) float bs[F];
+    const int K = g.kh * g.kw * g.C;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) {
+        const int f = i % F, k = i / F;
+        const int c = k % g.C, t = k / g.C, kx = t % g.kw, ky = t / g.kw;
+        ws[i] = w[(((long long)c * g.kh + ky) * g.kw + kx) * F + f];   // reference K order (c,ky,kx), Q1
+    }
+    for (int i = threadIdx.x; i < F; i += blockDim.x) bs[i] = bias != nullptr ? bias[i] : 0.0f;
+    __syncthreads();
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
+        const int ox = pix % g.OW; const int t = pix / g.OW; const int oy = t % g.OH; const int n = t / g.OH;
+        const float* xi = x + (long long)n * g.H * g.W * g.C;
+        float4 acc[FV];
+#pragma unroll
+        for (int j = 0; j < FV; ++j) acc[j] = *reinterpret_cast<const float4*>(&bs[j * 4]);
+        int k = 0;
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int iy = oy * g.sh + ky - g.ph;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int ix = ox * g.sw + kx - g.pw;
+                const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+                const float* xp = xi + ((long long)iy * g.W + ix) * g.C;
+                for (int c = 0; c < g.C; ++c, ++k) {
+                    const float xv = ok ? xp[c] : 0.0f;
+                    const float4* wk = reinterpret_cast<const float4*>(&ws[k * F]);
+#pragma unroll
+                    for (int j = 0; j < FV; ++j) {
+                        const float4 wv = wk[j];
+                        acc[j].x = fmaf(xv, wv.x, acc[j].x); acc[j].y = fmaf(xv, wv.y, acc[j].y);
+                        acc[j].z = fmaf(xv, wv.z, acc[j].z); acc[j].w = fmaf(xv, wv.w, acc[j].w);
+                    }
+                }
+            }
+        }
+        float4* yo = reinterpret_cast<float4*>(y + (long long)pix * F);
+#pragma unroll
+        for (int j = 0; j < FV; ++j) {
+            float4 v = acc[j];
+            v.x = act_apply(act, v.x, alpha); v.y = act_apply(act, v.y, alpha);
+            v.z = act_apply(act, v.z, alpha); v.w = act_apply(act, v.w, alpha);
+            yo[j] = v;
+        }
+    }
+}
+
+// Weight gradient of a small-K convolution as a shared-memory mini-GEMM:  dW[tap, f] = sum_pix X[tap, pix] * R[pix, f]
+// (+ a "ones" tap that yields db). A CTA walks a contiguous range of output pixels in tiles: the error tile
+// R[TP][F] is staged with coalesced float4 loads (read from HBM exactly once), the im2col patch tile X[K+1][TP] is
+// gathered once per pixel, and thread (tap group, f) accumulates its few (tap, f) outputs from shared memory
+// (1 conflict-free + 1 broadcast LDS per FMA). Per-CTA partials go to `partial[block][K+1][F]`.
+constexpr int WG_TILE_FLOATS = 8192;   // error tile: TP * F floats = 32 KB
+template <int NACC>
+__global__ void __launch_bounds__(256) conv2d_smallk_wgrad_kernel(b200nn_conv_geom g, const float* __restrict__ x,
+                                                                  const float* __restrict__ err,
+                                                                  float* __restrict__ partial, int n_pix, int TP) {
+    extern __shared__ __align__(16) float smem[];   // Rs[TP][F] | Xs[K+1][TP]
+    __shared__ int tap_off[SMALLK_MAX], tap_dy[SMALLK_MAX], tap_dx[SMALLK_MAX];
+    const int K = g.kh * g.kw * g.C, F = g.F;
+    float* Rs = smem;
+    float* Xs = smem + TP * F;
+    if (threadIdx.x < K) {
+        const int k = threadIdx.x;
+        const int c = k % g.C, tt = k / g.C;
+        tap_dy[k] = tt / g.kw; tap_dx[k] = tt % g.kw;
+        tap_off[k] = (tap_dy[k] * g.W + tap_dx[k]) * g.C + c;
+    }
+    const int TG = blockDim.x / F;            // tap groups
+    const int f = threadIdx.x % F, tg = threadIdx.x / F;
+    float acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
+    int chunk = (n_pix + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + TP - 1) / TP * TP;
+    const int p_begin = blockIdx.x * chunk, p_end = min(n_pix, p_begin + chunk);
+    for (int p0 = p_begin; p0 < p_end; p0 += TP) {
+        __syncthreads();   // previous tile fully consumed (also orders the tap table on the first pass)
+        const int np = min(TP, p_end - p0);
+        // error tile, float4
+        const float4* src = reinterpret_cast<const float4*>(err + (long long)p0 * F);
+        const int n4 = np * F / 4, t4 = TP * F / 4;
+        for (int i = threadIdx.x; i < t4; i += blockDim.x)
+            reinterpret_cast<float4*>(Rs)[i] = i < n4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // patch tile: TP divides the block size, so a thread owns ONE pixel of the tile (decoded once) and a
+        // strided subset of its taps
+        {
+            const int pp = threadIdx.x % TP, kstep = blockDim.x / TP;
+            const int pix = p0 + pp;
+            const bool pok = pp < np;
+            const int ox = pix % g.OW, t = pix / g.OW, oy = t % g.OH, n = t / g.OH;
+            const int iy0 = oy * g.sh - g.ph, ix0 = ox * g.sw - g.pw;
+            const float* xb = x + ((long long)n * g.H + iy0) * g.W * g.C + (long long)ix0 * g.C;
+            for (int k = threadIdx.x / TP; k <= K; k += kstep) {
+                float v = 0.0f;
+                if (pok) {
+                    if (k == K) {
+                        v = 1.0f;
+                    } else {
+                        const int iy = iy0 + tap_dy[k], ix = ix0 + tap_dx[k];
+                        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = xb[tap_off[k]];
+                    }
+                }
+                Xs[k * TP + pp] = v;
+            }
+        }
+        __syncthreads();
+        for (int pp = 0; pp < TP; pp += 4) {
+            const float r0 = Rs[(pp + 0) * F + f], r1 = Rs[(pp + 1) * F + f], r2 = Rs[(pp + 2) * F + f], r3 = Rs[(pp + 3) * F + f];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                const int t = tg + a * TG;
+                if (t <= K) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&Xs[t * TP + pp]);   // warp-broadcast
+                    acc[a] = fmaf(xv.x, r0, acc[a]); acc[a] = fmaf(xv.y, r1, acc[a]);
+                    acc[a] = fmaf(xv.z, r2, acc[a]); acc[a] = fmaf(xv.w, r3, acc[a]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        const int t = tg + a * TG;
+        if (t <= K) partial[((long long)blockIdx.x * (K + 1) + t) * F + f] = acc[a];
+    }
+}
+
+static bool smallk_fwd_ok(const b200nn_conv_geom* g) {
+    const int K = g->kh * g->kw * g->C;
+    return K <= SMALLK_MAX && (g->F == 32 || g->F == 64 || g->F == 16);
+}
+static bool smallk_wgrad_ok(const b200nn_conv_geom* g) {
+    const int K = g->kh * g->kw * g->C;
+    return K <= SMALLK_MAX && g->F >= 4 && g->F <= 256 && 256 % g->F == 0;
+}
+static int smallk_wgrad_tile(const b200nn_conv_geom* g) {   // pixels per tile: divides 256, multiple of 4
+    const int tp = WG_TILE_FLOATS / g->F;
+    return tp > 256 ? 256 : tp;
+}
+static int smallk_wgrad_blocks(const b200nn_conv_geom* g) {
+    const long long n_pix = (long long)g->N * g->OH * g->OW;
+    const int TP = smallk_wgrad_tile(g);
+    long long blocks = (n_pix + TP - 1) / TP;       // at least one tile per CTA
+    if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+    return (int)(blocks < 1 ? 1 : blocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -475,12 +680,7 @@ static int launch_gemm(const char* name, const AF& af, const BF& bf, const Epilo
     k_chunk = (k_chunk + BK - 1) / BK * BK;
     gemm_simt_kernel<AF, BF><<<grid, 256, 0, stream>>>(af, bf, epi, M, N, K, k_chunk, ws);
     B200NN_LAUNCH_CHECK(name);
-    const long long total = (long long)M * N;
-    long long blocks = (total + 255) / 256;
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    splitk_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, splits, M, N, epi);
-    B200NN_LAUNCH_CHECK("splitk_reduce");
-    return B200NN_OK;
+    return launch_splitk_reduce(ws, splits, M, N, epi, stream);
 }
 
 static int check_act(const char* who, int act, float alpha) {
@@ -570,7 +770,12 @@ size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
     size_t b = ws_bytes_for(Kf + 1, g->F, Mo);
     size_t c = ws_bytes_for(Mi, g->C, Kd);
     size_t r = a > b ? a : b;
-    return r > c ? r : c;
+    r = r > c ? r : c;
+    if (smallk_wgrad_ok(g)) {
+        const size_t d = (size_t)smallk_wgrad_blocks(g) * (Kf + 1) * g->F * sizeof(float);
+        r = r > d ? r : d;
+    }
+    return r;
 }
 
 static PatchGather conv_patches(const b200nn_conv_geom* g, const float* x) {
@@ -586,9 +791,19 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
     B200NN_REQUIRE(math == B200NN_MATH_FP32, "conv2d_fwd: unsupported math mode %d", math);
     if (int rc = check_conv_geom("conv2d_fwd", g)) return rc;
     if (int rc = check_act("conv2d_fwd", act, alpha)) return rc;
+    const int M = g->N * g->OH * g->OW, K = g->kh * g->kw * g->C;
+    if (smallk_fwd_ok(g) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+        long long blocks = ((long long)M + 127) / 128;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        cudaStream_t st = as_stream(stream);
+        if (g->F == 32) conv2d_smallk_fwd_kernel<8><<<(int)blocks, 128, 0, st>>>(*g, x, w, b, y, act, alpha, M);
+        else if (g->F == 64) conv2d_smallk_fwd_kernel<16><<<(int)blocks, 128, 0, st>>>(*g, x, w, b, y, act, alpha, M);
+        else conv2d_smallk_fwd_kernel<4><<<(int)blocks, 128, 0, st>>>(*g, x, w, b, y, act, alpha, M);
+        B200NN_LAUNCH_CHECK("conv2d_smallk_fwd");
+        return B200NN_OK;
+    }
     PatchA af{conv_patches(g, x)};
     ConvWFwdB bf{w, g->kh, g->kw, g->C, g->F};
-    const int M = g->N * g->OH * g->OW, K = g->kh * g->kw * g->C;
     Epilogue e = plain_epilogue(y, g->F, M);
     e.bias = b; e.act = act; e.alpha = alpha;
     return launch_gemm("conv2d_fwd", af, bf, e, M, g->F, K, ws, as_stream(stream));
@@ -603,7 +818,29 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
     cudaStream_t st = as_stream(stream);
     const int Mo = g->N * g->OH * g->OW, Mi = g->N * g->H * g->W;
     const int Kf = g->kh * g->kw * g->C, Kd = g->kh * g->kw * g->F;
-    if (dw != nullptr) {  // rows = taps (ky,kx,c) + ones row; reduce over output pixels
+    if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
+        const int nb = smallk_wgrad_blocks(g), TP = smallk_wgrad_tile(g);
+        Epilogue e = plain_epilogue(dw, g->F, Kf);
+        e.ss = ss; e.chain = chain; e.db = db;
+        e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
+        const int TG = 256 / g->F;
+        const int nacc = (Kf + 1 + TG - 1) / TG;
+        const size_t smem = ((size_t)TP * g->F + (size_t)(Kf + 1) * TP) * sizeof(float);
+        static thread_local bool configured = false;
+        if (!configured) {
+            B200NN_CUDA(cudaFuncSetAttribute(conv2d_smallk_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B200NN_CUDA(cudaFuncSetAttribute(conv2d_smallk_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B200NN_CUDA(cudaFuncSetAttribute(conv2d_smallk_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B200NN_CUDA(cudaFuncSetAttribute(conv2d_smallk_wgrad_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured = true;
+        }
+        if (nacc <= 2) conv2d_smallk_wgrad_kernel<2><<<nb, 256, smem, st>>>(*g, x, err, ws, Mo, TP);
+        else if (nacc <= 4) conv2d_smallk_wgrad_kernel<4><<<nb, 256, smem, st>>>(*g, x, err, ws, Mo, TP);
+        else if (nacc <= 8) conv2d_smallk_wgrad_kernel<8><<<nb, 256, smem, st>>>(*g, x, err, ws, Mo, TP);
+        else conv2d_smallk_wgrad_kernel<33><<<nb, 256, smem, st>>>(*g, x, err, ws, Mo, TP);
+        B200NN_LAUNCH_CHECK("conv2d_smallk_wgrad");
+        if (int rc = launch_splitk_reduce(ws, nb, Kf + 1, g->F, e, st)) return rc;
+    } else if (dw != nullptr) {  // rows = taps (ky,kx,c) + ones row; reduce over output pixels
         PatchTOnesA af{conv_patches(g, x), db != nullptr ? 1 : 0};
         RowMajorB bf{err, g->F, Mo, g->F};
         Epilogue e = plain_epilogue(dw, g->F, Kf);

@@ -15,6 +15,8 @@ Replaces the per-layer NumPy loop of models.py:159-264 by a static program over 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -32,6 +34,7 @@ class _Program:
     def __init__(self, name):
         self.name = name
         self.ops = []
+        self.meta = []      # (kernel family name, algorithmic bytes) per op, parallel to ops
         self.graph = None
         self.runs = 0
 
@@ -78,6 +81,7 @@ class Plan:
         self.outs = [None] * len(self.layers)
         self.fwd_fused = [False] * len(self.layers)   # Activation i applied inside layer i-1's kernel
         self.programs = {}
+        self.fuse_blocks = os.environ.get("B200NN_FUSE_BLOCKS", "1") != "0"
         self._build_forward()
 
     # ---- allocation context used by the layers' plan hooks ---------------------------------------------------
@@ -101,13 +105,20 @@ class Plan:
             self._ws = B.empty((max(self._ws_bytes // 4, 1),))
         return self._ws
 
-    def emit(self, fn):
-        self._emit_to.append(fn)
+    def emit(self, fn, name=None, io=()):
+        """Record one launch; `io` lists the tensors it must read or write once each (algorithmic bytes)."""
+        self._emit_to.ops.append(fn)
+        seen, nbytes = set(), 0
+        for t in io:
+            if t is not None and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                nbytes += t.numel() * t.element_size()
+        self._emit_to.meta.append((name or "op", nbytes))
 
     # ---- forward ------------------------------------------------------------------------------------------------
     def _build_forward(self):
         prog = _Program("forward")
-        self._emit_to = prog.ops
+        self._emit_to = prog
         layers = self.layers
         x = self.x_in
         i, n = 0, len(layers)
@@ -129,6 +140,14 @@ class Plan:
             nxt = layers[i + 1] if i + 1 < n else None
             fuse = L._fuses_act and isinstance(nxt, Activation) and nxt._fusable
             self.state[i].update(in_shape=tuple(x.shape))
+            if isinstance(L, BatchNormalization) and self.fuse_blocks and L._can_fuse_pool(x, nxt, self.training):
+                y = L._plan_forward(self, self.state[i], x, None, self.training, pool=nxt)   # BN + MaxPool: one kernel
+                self.outs[i] = None                      # the BatchNorm output is never materialised
+                self.outs[i + 1] = y
+                self.state[i + 1].update(in_shape=tuple(x.shape), fused_into_bn=True)
+                i += 2
+                x = y
+                continue
             y = L._plan_forward(self, self.state[i], x, nxt if fuse else None, self.training)
             self.outs[i] = y
             if fuse:
@@ -174,6 +193,17 @@ class Plan:
                 cur = L._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
                 i -= 1
                 continue
+            if self.state[i].get("fused_into_bn"):
+                # MaxPool whose forward ran inside the preceding BatchNorm kernel: pool-bwd + BN-bwd (+ the backward of
+                # the Activation feeding the BatchNorm) as one kernel
+                bn_i = i - 1
+                mask, j = None, bn_i - 1
+                if j >= 1 and isinstance(layers[j], Activation) and layers[j]._fusable:
+                    mask = layers[j]
+                et = cur.t.reshape(self.outs[i].shape)
+                cur = layers[bn_i]._plan_backward_fused_pool(self, self.state[bn_i], _Err(et, cur.chain), mask)
+                i = j - 1 if mask is not None else bn_i - 1
+                continue
             mask, j = None, i - 1
             if L._supports_mask and need_dx:
                 while j >= 0 and layers[j]._is_view and not isinstance(layers[j], Input):
@@ -213,7 +243,7 @@ class Plan:
         if kind in self.programs:
             return self.programs[kind]
         prog = _Program(kind)
-        self._emit_to = prog.ops
+        self._emit_to = prog
         model = self.model
         if kind == "train":
             self._ensure_targets()
@@ -222,11 +252,13 @@ class Plan:
             counter = opt._t_counter()
             begin_at = len(prog.ops)
             prog.ops.append(None)  # placeholder for step_begin (needs the number of updated layers)
+            prog.meta.append(("step_begin", 0))
             prog.ops.extend(self.programs["forward"].ops)
+            prog.meta.extend(self.programs["forward"].meta)
             err0 = self.buf(self.pred.shape)
             s0 = self.slot()
             pred, y_in, acc, ss = self.pred, self.y_in, self.acc, self.ss
-            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0))
+            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
             ups = []
             for li in updates:
@@ -235,15 +267,15 @@ class Plan:
             n_upd = len(ups)
             if n_upd:
                 oplan = opt._make_plan(ups)
-                self.emit(lambda: opt._run_plan(oplan))
+                self.emit(lambda: opt._run_plan(oplan), "optimizer_multi", opt._plan_io(oplan))
             prog.ops[begin_at] = lambda: ops.step_begin(ss, acc, counter, n_upd)
             self.train_err0 = err0
         elif kind == "loss":
             self._ensure_targets()
             lk, fused = self._loss_kind()
             pred, y_in, acc = self.pred, self.y_in, self.acc
-            self.emit(lambda: ops.step_begin(None, acc, None, 0))
-            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, None, acc, None, None))
+            self.emit(lambda: ops.step_begin(None, acc, None, 0), "step_begin")
+            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, None, acc, None, None), "loss_fwd_bwd", (pred, y_in))
         elif kind in ("backward", "backward_gan", "backward_compute_only"):
             gan, compute_only = kind == "backward_gan", kind == "backward_compute_only"
             opt = model.optimizer
@@ -251,6 +283,7 @@ class Plan:
             ss, acc = self.ss, self.acc
             begin_at = len(prog.ops)
             prog.ops.append(None)
+            prog.meta.append(("step_begin", 0))
             self.err_in = self.buf(self.pred.shape)
             last_is_act = isinstance(self.layers[-1], Activation)
             if last_is_act and not gan:
@@ -259,29 +292,29 @@ class Plan:
                 if fused:
                     self._ensure_targets()
                     pred, y_in, err_in = self.pred, self.y_in, self.err_in
-                    self.emit(lambda: ops.loss_fwd_bwd(lk, 1, pred, y_in, err_in, None, None, None))
+                    self.emit(lambda: ops.loss_fwd_bwd(lk, 1, pred, y_in, err_in, None, None, None), "loss_fwd_bwd", (pred, y_in, err_in))
                 s0 = self.slot()
                 err_in = self.err_in
-                self.emit(lambda: ops.sumsq(err_in, ss, s0))
+                self.emit(lambda: ops.sumsq(err_in, ss, s0), "sumsq", (err_in,))
                 start = _Err(self.err_in, (s0,))
             elif last_is_act and gan:
                 start = _Err(self.err_in, ())
             else:
                 s0 = self.slot()
                 err_in = self.err_in
-                self.emit(lambda: ops.sumsq(err_in, ss, s0))
+                self.emit(lambda: ops.sumsq(err_in, ss, s0), "sumsq", (err_in,))
                 start = _Err(self.err_in, (s0,))
             updates, in_err = self._build_backward(start, gan, compute_only, True)
             # materialise the returned input error: clip folded in (the reference clips before Input too)
             self.in_err_out = self.buf(in_err.t.shape)
             iet, chain, out = in_err.t, in_err.chain, self.in_err_out
-            self.emit(lambda: ops.scale_apply(iet, ss, chain, out))
+            self.emit(lambda: ops.scale_apply(iet, ss, chain, out), "scale_apply", (iet, out))
             ups = [(li, self.layers[li]._weights, self.layers[li]._d_weights, self.layers[li]._bias, self.layers[li]._d_bias)
                    for li in updates]
             n_upd = len(ups)
             if n_upd:
                 oplan = opt._make_plan(ups)
-                self.emit(lambda: opt._run_plan(oplan))
+                self.emit(lambda: opt._run_plan(oplan), "optimizer_multi", opt._plan_io(oplan))
             prog.ops[begin_at] = lambda: ops.step_begin(ss, None, counter, n_upd)
         else:
             raise KeyError(kind)

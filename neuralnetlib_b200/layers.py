@@ -66,7 +66,7 @@ class _EagerCtx:
     def ws(self):
         return getattr(self, "_ws", None)
 
-    def emit(self, fn):
+    def emit(self, fn, name=None, io=()):
         fn()
 
 
@@ -249,7 +249,7 @@ class Dense(Layer, _ParamMixin):
         math = _math_code()
         st.update(x=x, math=math)
         w, b = self._weights, self._bias
-        ctx.emit(lambda: ops.dense_fwd(math, x, w, b, y, kind, alpha, ctx.ws))
+        ctx.emit(lambda: ops.dense_fwd(math, x, w, b, y, kind, alpha, ctx.ws), "dense_fwd", (x, w, b, y))
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
@@ -260,7 +260,8 @@ class Dense(Layer, _ParamMixin):
         s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
         w, dw, db, ss, chain, math = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"]
         et = err.t
-        ctx.emit(lambda: ops.dense_bwd(math, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        ctx.emit(lambda: ops.dense_bwd(math, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws), "dense_bwd",
+                 (x, et, dw, db) + ((w, dx) if need_dx else ()))
         if not need_dx:
             return None
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
@@ -317,10 +318,10 @@ class Activation(Layer):
         if isinstance(f, Softmax):
             if x.dim() != 2:
                 raise ValueError("Softmax expects a 2-D (batch, classes) input")
-            ctx.emit(lambda: ops.softmax_fwd(x, y))
+            ctx.emit(lambda: ops.softmax_fwd(x, y), "softmax_fwd", (x, y))
         else:
             kind, alpha = f._kind, float(f._alpha)
-            ctx.emit(lambda: ops.act_fwd(kind, alpha, x, y))
+            ctx.emit(lambda: ops.act_fwd(kind, alpha, x, y), "act_fwd", (x, y))
         st.update(y=y)
         return y
 
@@ -332,7 +333,7 @@ class Activation(Layer):
         dx = ctx.buf(y.shape)
         s = ctx.slot()
         kind, alpha, ss, chain, et = f._kind, float(f._alpha), ctx.ss, err.chain, err.t
-        ctx.emit(lambda: ops.act_bwd(kind, alpha, y, et, ss, chain, dx, s))
+        ctx.emit(lambda: ops.act_bwd(kind, alpha, y, et, ss, chain, dx, s), "act_bwd", (y, et, dx))
         return _Err(dx, () if s is None else (s,))
 
     def forward_pass(self, input_data):
@@ -469,7 +470,7 @@ class Conv2D(Layer, _ParamMixin):
         math = ops.MATH_FP32
         st.update(x=x, g=g, math=math)
         w, b = self._weights, self._bias
-        ctx.emit(lambda: ops.conv2d_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws))
+        ctx.emit(lambda: ops.conv2d_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws), "conv2d_fwd", (x, w, b, y))
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
@@ -479,7 +480,8 @@ class Conv2D(Layer, _ParamMixin):
         s0 = ctx.slot() if need_dx else None
         s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
         w, dw, db, ss, chain, math, et = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"], err.t
-        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws), "conv2d_bwd",
+                 (x, et, dw, db) + ((w, dx) if need_dx else ()))
         if not need_dx:
             return None
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
@@ -573,7 +575,7 @@ class Conv2DTranspose(Conv2D):
         math = ops.MATH_FP32
         st.update(x=x, g=g, math=math)
         w, b = self._weights, self._bias
-        ctx.emit(lambda: ops.convt_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws))
+        ctx.emit(lambda: ops.convt_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws), "convt_fwd", (x, w, b, y))
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
@@ -583,7 +585,8 @@ class Conv2DTranspose(Conv2D):
         s0 = ctx.slot() if need_dx else None
         s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
         w, dw, db, ss, chain, math, et = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"], err.t
-        ctx.emit(lambda: ops.convt_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws))
+        ctx.emit(lambda: ops.convt_bwd(math, g, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws), "convt_bwd",
+                 (x, et, dw, db) + ((w, dx) if need_dx else ()))
         if not need_dx:
             return None
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
@@ -624,7 +627,7 @@ class MaxPooling2D(Layer):
         g = self._geometry(x.shape)
         y = ctx.buf((x.shape[0], g.OH, g.OW, x.shape[3]))
         st.update(x=x, y=y, g=g)
-        ctx.emit(lambda: ops.maxpool_fwd(g, x, y))
+        ctx.emit(lambda: ops.maxpool_fwd(g, x, y), "maxpool_fwd", (x, y))
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
@@ -632,7 +635,7 @@ class MaxPooling2D(Layer):
         dx = ctx.buf(x.shape)
         s = ctx.slot()
         ss, chain, et = ctx.ss, err.chain, err.t
-        ctx.emit(lambda: ops.maxpool_bwd(g, x, y, et, ss, chain, dx, s))
+        ctx.emit(lambda: ops.maxpool_bwd(g, x, y, et, ss, chain, dx, s), "maxpool_bwd", (x, y, et, dx))
         return _Err(dx, () if s is None else (s,))
 
     def forward_pass(self, input_data):
@@ -739,7 +742,13 @@ class BatchNormalization(Layer, _ParamMixin):
     def __str__(self) -> str:
         return f"BatchNormalization(momentum={self.momentum}, epsilon={self.epsilon})"
 
-    def _plan_forward(self, ctx, st, x, act_layer, training):
+    def _can_fuse_pool(self, x, pool, training):
+        """BatchNorm(train) -> MaxPool 2x2/s2 'valid' on an even, 32-channel-aligned NHWC tensor runs as one kernel."""
+        return (training and isinstance(pool, MaxPooling2D) and x.dim() == 4 and pool.pool_size == (2, 2)
+                and pool.strides == (2, 2) and pool.padding == "valid" and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0
+                and x.shape[3] % 32 == 0 and x.shape[0] <= ops.fused_block_max_batch())
+
+    def _plan_forward(self, ctx, st, x, act_layer, training, pool=None):
         shp = tuple(int(s) for s in x.shape[1:])
         if self._gamma is None or self._running_mean is None or self._running_var is None:
             self.initialize_weights(shp)
@@ -747,17 +756,23 @@ class BatchNormalization(Layer, _ParamMixin):
             self.d_gamma, self.d_beta = np.zeros(shp), np.zeros(shp)
         if int(np.prod(shp)) != self._gamma.numel():
             raise ValueError(f"BatchNormalization was initialised for {tuple(self._shapes['gamma'])}, got {shp}")
-        y = ctx.buf(x.shape)
         P = self._gamma.numel()
         gm, bt, rm, rv = self._gamma, self._beta, self._running_mean, self._running_var
         mom, eps = float(self.momentum), float(self.epsilon)
+        if pool is not None:
+            yp = ctx.buf((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
+            sm, si = ctx.buf((P,)), ctx.buf((P,))
+            st.update(x=x, save_mean=sm, save_invstd=si, trained=True, fused_pool=True)
+            ctx.emit(lambda: ops.bn_pool_fwd_train(x, gm, bt, rm, rv, sm, si, yp, mom, eps), "bn_pool_fwd_train", (x, yp))
+            return yp
+        y = ctx.buf(x.shape)
         if training:
             sm, si = ctx.buf((P,)), ctx.buf((P,))
             st.update(x=x, save_mean=sm, save_invstd=si, trained=True)
-            ctx.emit(lambda: ops.bn_fwd_train(x, gm, bt, rm, rv, sm, si, y, mom, eps))
+            ctx.emit(lambda: ops.bn_fwd_train(x, gm, bt, rm, rv, sm, si, y, mom, eps), "bn_fwd_train", (x, y))
         else:
             st.update(x=x, trained=False)
-            ctx.emit(lambda: ops.bn_fwd_infer(x, gm, bt, rm, rv, y, eps))
+            ctx.emit(lambda: ops.bn_fwd_infer(x, gm, bt, rm, rv, y, eps), "bn_fwd_infer", (x, y))
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
@@ -770,8 +785,23 @@ class BatchNormalization(Layer, _ParamMixin):
         s0 = ctx.slot()
         s1 = ctx.slot() if mask_layer is not None else None
         gm, sm, si, dg, dbt, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], self._d_gamma, self._d_beta, ctx.ss, err.chain, err.t
-        ctx.emit(lambda: ops.bn_bwd(x, et, ss, chain, gm, sm, si, dx, dg, dbt, kind, alpha, s0, s1))
+        ctx.emit(lambda: ops.bn_bwd(x, et, ss, chain, gm, sm, si, dx, dg, dbt, kind, alpha, s0, s1), "bn_bwd", (x, et, dx))
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    def _plan_backward_fused_pool(self, ctx, st, err, mask_layer):
+        """err is the error w.r.t. the POOLED output; emits MaxPool-bwd + BatchNorm-bwd (+ Activation-bwd) as one
+        kernel and returns the error w.r.t. the BatchNorm input with the 2 (or 3) clip slots the reference applies
+        between those layers (models.py:214)."""
+        x = st["x"]
+        r0 = ctx.buf(x.shape)
+        kind, alpha = _act_of(mask_layer)
+        s0, s1 = ctx.slot(), ctx.slot()
+        s2 = ctx.slot() if mask_layer is not None else None
+        gm, bt, sm, si, dg, dbt, ss, chain, et = (self._gamma, self._beta, st["save_mean"], st["save_invstd"], self._d_gamma,
+                                                  self._d_beta, ctx.ss, err.chain, err.t)
+        ctx.emit(lambda: ops.pool_bn_act_bwd(x, et, ss, chain, gm, bt, sm, si, r0, dg, dbt, kind, alpha, s0, s1, s2),
+                 "pool_bn_act_bwd", (x, et, r0))
+        return _Err(r0, tuple(s for s in (s0, s1, s2) if s is not None))
 
     def forward_pass(self, input_data, training: bool = True):
         x, host = _in(input_data)

@@ -81,6 +81,14 @@ class Optimizer:
         raise NotImplementedError
 
     @staticmethod
+    def _plan_io(plan):
+        """Tensors one optimizer launch reads/writes once each: p, g (+ m, v); the clip norm re-reads g."""
+        io = []
+        for p, g, m, v, _, _ in plan.keep:
+            io.extend([p, g, m, v])
+        return tuple(io)
+
+    @staticmethod
     def _as_pairs(weights, weights_grad, bias, bias_grad):
         pairs = [(weights, weights_grad)]
         if bias is not None and bias_grad is not None:

@@ -370,3 +370,48 @@ def test_gather_rows(K):
     d = K.empty((20, 7, 9))
     K.ops.gather_rows(K.dev(src), K.B.to_device(idx, dtype=K.torch.int64), d)
     assert np.array_equal(K.host(d), src[idx].astype(np.float64))
+
+
+@pytest.mark.parametrize("Bn,H,W,C", [(256, 28, 28, 32), (64, 8, 8, 64), (130, 4, 6, 32), (300, 4, 4, 32), (1024, 4, 4, 32), (5, 2, 2, 32)])
+def test_fused_bn_pool_block(K, Bn, H, W, C):
+    """BatchNorm(train)+MaxPool forward and MaxPool+BatchNorm+ReLU backward as single kernels (cluster/DSMEM batch
+    reduction for B > 128) against the unfused oracle chain incl. the three clip points between the layers."""
+    rng = np.random.default_rng(Bn + H)
+    x = np.maximum(rng.normal(size=(Bn, H, W, C)) * 0.05 - 0.01, 0).astype(np.float32)
+    x[:, 0, 0, 0] = 0.0  # an all-dead window column: 4-way ties in the pool (Q6)
+    x[:, 0, 1, 0] = 0.0; x[:, 1, 0, 0] = 0.0; x[:, 1, 1, 0] = 0.0
+    P = H * W * C
+    gamma = (1 + 0.1 * rng.normal(size=P)).astype(np.float32); beta = (0.1 * rng.normal(size=P)).astype(np.float32)
+    beta.reshape(H, W, C)[:2, :2, 0] = 0.25; gamma.reshape(H, W, C)[:2, :2, 0] = 1.0
+    xd, gd, bd = K.dev(x), K.dev(gamma), K.dev(beta)
+    rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
+    sm, si = K.empty((P,)), K.empty((P,))
+    yp = K.empty((Bn, H // 2, W // 2, C))
+    K.ops.bn_pool_fwd_train(xd, gd, bd, rm, rv, sm, si, yp, 0.9, 1e-5)
+    shp = (H, W, C)
+    g64, b64 = gamma.astype(np.float64).reshape(shp), beta.astype(np.float64).reshape(shp)
+    x64 = x.astype(np.float64)
+    ybn, rrm, rrv, cache = O.bn_fwd(x64, g64, b64, np.zeros(shp), np.ones(shp), 0.9, 1e-5, True)
+    ryp = O.maxpool_fwd(ybn, (2, 2), (2, 2))
+    assert nrel(K.host(yp), ryp) < TOL
+    assert nrel(K.host(rm).reshape(shp), rrm) < TOL and nrel(K.host(rv).reshape(shp), rrv) < TOL
+    e = rng.normal(size=ryp.shape).astype(np.float32)
+    ed = K.dev(e); ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    r0, dg, dbt = K.empty(x.shape), K.empty((P,)), K.empty((P,))
+    K.ops.pool_bn_act_bwd(xd, ed, ss, (0,), gd, bd, sm, si, r0, dg, dbt, 1, 0.0, 1, 2, 3)
+    # reference chain: clip -> pool bwd -> clip -> bn bwd -> clip -> relu' ; the kernel emits the unclipped
+    # intermediates plus their sums of squares, the chain (1, 2, 3) reproduces the clips
+    U = O.maxpool_bwd(ybn, O.clip_l2(e.astype(np.float64)), (2, 2), (2, 2))
+    D, rdg, rdb = O.bn_bwd(U, g64, cache, 1e-5)             # bn_bwd is linear: D(clip(U)) = s_U * D(U)
+    R = D * (x64 > 0)
+    h = K.host(ss)
+    assert abs(h[1] - np.sum(U ** 2)) < 1e-4 * np.sum(U ** 2)
+    assert abs(h[2] - np.sum(D ** 2)) < 1e-4 * np.sum(D ** 2)
+    assert abs(h[3] - np.sum(R ** 2)) < 1e-4 * np.sum(R ** 2)
+    assert nrel(K.host(r0), R) < 2e-5
+    assert nrel(K.host(dg).reshape(shp), rdg) < 2e-5 and nrel(K.host(dbt).reshape(shp), rdb) < 2e-5
+    out = K.empty(x.shape)
+    K.ops.scale_apply(r0, ss, (1, 2, 3), out)
+    ref = O.clip_l2(O.bn_bwd(O.clip_l2(U), g64, cache, 1e-5)[0]) * (x64 > 0)
+    assert nrel(K.host(out), O.clip_l2(ref)) < 2e-5
+    assert np.all(U[:, :2, :2, 0] == O.clip_l2(e.astype(np.float64))[:, :1, :1, 0][:, :, :, None].reshape(Bn, 1, 1))  # 4-way tie
