@@ -159,9 +159,11 @@ def run_b200(args):
     if world != args.gpus and rank == 0:
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
+    import neuralnetlib_b200 as nn
     from neuralnetlib_b200 import _backend as B
     import nnl_oracle as O  # synthetic data recipe only; the oracle is never on the timed path
 
+    nn.set_math(args.math)
     lib = B.load_library()
     stream = B.stream_obj()
     model = build_model()
@@ -258,7 +260,9 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": total_batch, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB device write outside the timed events)",
-                   "math": "fp32 FFMA (parity path, rel 1e-5)", "step": "one captured CUDA graph per step"},
+                   "math": ("tf32: Dense GEMMs on tcgen05 kind::tf32 (rel 2e-3), conv/BN/pool/Adam fp32" if args.math == "tf32"
+                            else "fp32 FFMA everywhere (parity path, rel 1e-5)"),
+                   "step": "one captured CUDA graph per step"},
         "e2e": {"value": total_batch / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(x.nbytes + y.nbytes), "d2h_bytes_per_step": 8, "last_loss": loss},
         "gpu_launches": int(launches_eager_step * K),
@@ -290,6 +294,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--math", default=os.environ.get("B200NN_MATH", "tf32"), choices=["fp32", "tf32"],
+                    help="Dense contractions: fp32 = FFMA parity path (rel 1e-5); tf32 = tcgen05 tensor cores (rel 2e-3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -218,33 +218,42 @@ __device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, unsigned 
     return v;
 }
 
-// Sum `v[nq]` (per thread: column (q, lane), partial over this thread's rows) over the row groups of the CTA and
-// over the CTAs of the cluster; every thread gets the totals. `red` is [FB_RG][8][32], `part` is [2][8][32]
-// (double-buffered by `phase` so that a CTA may start the next reduction while peers still read the previous one).
+// Thread mapping of the fused kernels: thread = (channel quad cq = tid % 8 -> channels 4cq..4cq+3 as one float4,
+// row group rg = tid / 8 in 0..31). Every shared-memory access is a conflict-free 128-bit LDS, every statistic is
+// kept per channel quad, and the 2x2 max is thread-local.
+constexpr int FB_RGV = FB_THREADS / 8;   // 32 row groups
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_clip10(float4 a) { return make_float4(clip10(a.x), clip10(a.y), clip10(a.z), clip10(a.w)); }
+
+// Sum v[NQ] (float4 per window position / statistic; partial over this thread's rows) over the 32 row groups of the
+// CTA and over the CTAs of the cluster (distributed shared memory); every thread gets the totals.
+// `red` is [FB_RGV][NQ][8] float4, `part` is [2][NQ][8] float4 (double-buffered by `phase`).
 template <int NQ>
-__device__ __forceinline__ void cluster_colsum(float (&v)[NQ], float (*red)[8][32], float (*part)[8][32], int phase,
-                                               int lane, int rg, unsigned csize) {
+__device__ __forceinline__ void cluster_colsum4(float4 (&v)[NQ], float4* red, float4* part, int phase, int cq, int rg,
+                                                unsigned csize) {
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) red[rg][q][lane] = v[q];
+    for (int q = 0; q < NQ; ++q) red[(rg * NQ + q) * 8 + cq] = v[q];
     __syncthreads();
-    if (rg == 0) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            float s = 0.0f;
-#pragma unroll
-            for (int r = 0; r < FB_RG; ++r) s += red[r][q][lane];
-            part[phase][q][lane] = s;
-        }
+    // 8 * NQ float4 totals per CTA: thread t < 8*NQ sums column t over the 32 row groups
+    if (threadIdx.x < 8 * NQ) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < FB_RGV; ++r) s = f4_add(s, red[r * NQ * 8 + threadIdx.x]);
+        part[phase * NQ * 8 + threadIdx.x] = s;
     }
     if (csize > 1) cluster_sync_all(); else __syncthreads();
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-        float s = 0.0f;
+        const float* src = reinterpret_cast<const float*>(&part[phase * NQ * 8 + q * 8 + cq]);
+        float4 s;
         if (csize > 1) {
-            for (unsigned r = 0; r < csize; ++r) s += ld_dsmem(&part[phase][q][lane], r);
+            s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (unsigned r = 0; r < csize; ++r)
+                s = f4_add(s, make_float4(ld_dsmem(src, r), ld_dsmem(src + 1, r), ld_dsmem(src + 2, r), ld_dsmem(src + 3, r)));
         } else {
-            s = part[phase][q][lane];
+            s = part[phase * NQ * 8 + q * 8 + cq];
         }
         v[q] = s;
     }
@@ -266,6 +275,9 @@ __device__ __forceinline__ void fb_stage_window(float* tile, const float* __rest
     }
 }
 
+#define FB_FOR4(...) _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_) { __VA_ARGS__ }
+__device__ __forceinline__ float& f4_at(float4& a, int k) { return reinterpret_cast<float*>(&a)[k]; }
+
 __global__ void __launch_bounds__(FB_THREADS) bn_pool_fwd_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
@@ -275,73 +287,91 @@ __global__ void __launch_bounds__(FB_THREADS) bn_pool_fwd_kernel(const float* __
                                                                  float* __restrict__ y, FbGeom g, float momentum,
                                                                  float eps) {
     extern __shared__ __align__(16) float tile[];   // [FB_ROWS][4][32]
-    __shared__ float red[FB_RG][8][32];
-    __shared__ float part[2][8][32];
+    __shared__ float4 red[FB_RGV * 4 * 8];
+    __shared__ float4 part[2 * 4 * 8];
     const unsigned csize = cluster_size(), crank = cluster_rank();
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + lane;
+    const int cq = threadIdx.x & 7, rg = threadIdx.x >> 3;
+    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + cq * 4;
     const int rows_per = (g.B + csize - 1) / csize;
     const int row0 = crank * rows_per;
     const int nrows = max(0, min(rows_per, g.B - row0));
     fb_stage_window(tile, x, g, row0, nrows, oy, ox, c0);
     cp_async_wait_all();
     __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = rg; r < nrows; r += FB_RG) {
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    float4 acc[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += clip10(tile[(r * 4 + q) * 32 + lane]);   // layers.py:1234
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = rg; r < nrows; r += FB_RGV) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = f4_add(acc[q], f4_clip10(t4[(r * 4 + q) * 8 + cq]));   // layers.py:1234
     }
-    cluster_colsum<4>(acc, red, part, 0, lane, rg, csize);
-    float mean[4];
+    cluster_colsum4<4>(acc, red, part, 0, cq, rg, csize);
+    float4 mean[4];
+    const float invB = 1.0f / (float)g.B;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { mean[q] = acc[q] / (float)g.B; acc[q] = 0.0f; }   // layers.py:1237
-    for (int r = rg; r < nrows; r += FB_RG) {
+    for (int q = 0; q < 4; ++q) {   // layers.py:1237
+        mean[q] = make_float4(acc[q].x * invB, acc[q].y * invB, acc[q].z * invB, acc[q].w * invB);
+        acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int r = rg; r < nrows; r += FB_RGV) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float d = clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q];
-            acc[q] += d * d;
+            const float4 v = f4_clip10(t4[(r * 4 + q) * 8 + cq]);
+            const float dx_ = v.x - mean[q].x, dy_ = v.y - mean[q].y, dz_ = v.z - mean[q].z, dw_ = v.w - mean[q].w;
+            acc[q].x = fmaf(dx_, dx_, acc[q].x); acc[q].y = fmaf(dy_, dy_, acc[q].y);
+            acc[q].z = fmaf(dz_, dz_, acc[q].z); acc[q].w = fmaf(dw_, dw_, acc[q].w);
         }
     }
-    cluster_colsum<4>(acc, red, part, 1, lane, rg, csize);
-    float gq[4], bq[4];
+    cluster_colsum4<4>(acc, red, part, 1, cq, rg, csize);
+    float4 gq[4], bq[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const long long p = ((long long)(2 * oy + (q >> 1)) * g.W + 2 * ox + (q & 1)) * g.C + c;
-        const float batch_var = acc[q] / (float)g.B + eps;   // layers.py:1238
-        const float invstd = rsqrtf(batch_var + eps);        // layers.py:1252
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + p);
+        bq[q] = *reinterpret_cast<const float4*>(beta + p);
+        float4 bv, is;
+        FB_FOR4(f4_at(bv, k_) = f4_at(acc[q], k_) * invB + eps;            /* layers.py:1238 */
+                f4_at(is, k_) = rsqrtf(f4_at(bv, k_) + eps);               /* layers.py:1252 */
+                f4_at(gq[q], k_) = f4_at(const_cast<float4&>(gm), k_) * f4_at(is, k_);)
         if (crank == 0 && rg == 0) {
-            rmean[p] = momentum * rmean[p] + (1.0f - momentum) * mean[q];    // layers.py:1240-1243
-            rvar[p] = momentum * rvar[p] + (1.0f - momentum) * batch_var;
-            save_mean[p] = mean[q];
-            save_invstd[p] = invstd;
+            float4 rm = *reinterpret_cast<const float4*>(rmean + p), rv = *reinterpret_cast<const float4*>(rvar + p);
+            FB_FOR4(f4_at(rm, k_) = momentum * f4_at(rm, k_) + (1.0f - momentum) * f4_at(mean[q], k_);   /* layers.py:1240-1243 */
+                    f4_at(rv, k_) = momentum * f4_at(rv, k_) + (1.0f - momentum) * f4_at(bv, k_);)
+            *reinterpret_cast<float4*>(rmean + p) = rm;
+            *reinterpret_cast<float4*>(rvar + p) = rv;
+            *reinterpret_cast<float4*>(save_mean + p) = mean[q];
+            *reinterpret_cast<float4*>(save_invstd + p) = is;
         }
-        gq[q] = gamma[p] * invstd;
-        bq[q] = beta[p];
     }
     const int OW = g.W >> 1;
     const long long OHWC = (long long)(g.H >> 1) * OW * g.C, obase = ((long long)oy * OW + ox) * g.C + c;
-    for (int r = rg; r < nrows; r += FB_RG) {
-        float m = -INFINITY;
+    for (int r = rg; r < nrows; r += FB_RGV) {
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) m = fmaxf(m, gq[q] * (clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q]) + bq[q]);
-        y[(long long)(row0 + r) * OHWC + obase] = m;   // layers.py:1256 then :599-600
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = f4_clip10(t4[(r * 4 + q) * 8 + cq]);
+            m.x = fmaxf(m.x, fmaf(gq[q].x, v.x - mean[q].x, bq[q].x)); m.y = fmaxf(m.y, fmaf(gq[q].y, v.y - mean[q].y, bq[q].y));
+            m.z = fmaxf(m.z, fmaf(gq[q].z, v.z - mean[q].z, bq[q].z)); m.w = fmaxf(m.w, fmaf(gq[q].w, v.w - mean[q].w, bq[q].w));
+        }
+        *reinterpret_cast<float4*>(y + (long long)(row0 + r) * OHWC + obase) = m;   // layers.py:1256 then :599-600
     }
     if (csize > 1) cluster_sync_all();   // peers may still be reading this CTA's `part`
 }
 
-__global__ void __launch_bounds__(FB_THREADS) pool_bn_act_bwd_kernel(
+__global__ void __launch_bounds__(FB_THREADS, 2) pool_bn_act_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
     const float* __restrict__ save_invstd, float* __restrict__ r0, float* __restrict__ dgamma,
     float* __restrict__ dbeta, FbGeom g, int prev_act, float prev_alpha, double* ss0, double* ss1, double* ss2) {
     extern __shared__ __align__(16) float tile[];   // [FB_ROWS][4][32] window values, then [FB_ROWS][32] pooled error
-    __shared__ float red[FB_RG][8][32];
-    __shared__ float part[2][8][32];
+    __shared__ float4 red[FB_RGV * 8 * 8];
+    __shared__ float4 part[2 * 8 * 8];
     __shared__ double scratch[32];
     const float scale = chain_scale(ss, chain);
     const unsigned csize = cluster_size(), crank = cluster_rank();
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + lane;
+    const int cq = threadIdx.x & 7, rg = threadIdx.x >> 3;
+    const int ox = blockIdx.x / csize, oy = blockIdx.y, c0 = blockIdx.z * 32, c = c0 + cq * 4;
     const int rows_per = (g.B + csize - 1) / csize;
     const int row0 = crank * rows_per;
     const int nrows = max(0, min(rows_per, g.B - row0));
@@ -351,75 +381,87 @@ __global__ void __launch_bounds__(FB_THREADS) pool_bn_act_bwd_kernel(
     fb_stage_window(tile, x, g, row0, nrows, oy, ox, c0);
     for (int i = threadIdx.x; i < nrows * 8; i += FB_THREADS)
         cp_async16(etile + (i >> 3) * 32 + (i & 7) * 4, err + (long long)(row0 + (i >> 3)) * OHWC + obase + (i & 7) * 4);
-    float mean[4], invstd[4], gq[4], bq[4];
+    float4 mean[4], invstd[4], gq[4], bq[4];
     long long pos[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         pos[q] = ((long long)(2 * oy + (q >> 1)) * g.W + 2 * ox + (q & 1)) * g.C + c;
-        mean[q] = save_mean[pos[q]];
-        invstd[q] = save_invstd[pos[q]];
-        gq[q] = gamma[pos[q]] * invstd[q];
-        bq[q] = beta[pos[q]];
+        mean[q] = *reinterpret_cast<const float4*>(save_mean + pos[q]);
+        invstd[q] = *reinterpret_cast<const float4*>(save_invstd + pos[q]);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + pos[q]);
+        gq[q] = make_float4(gm.x * invstd[q].x, gm.y * invstd[q].y, gm.z * invstd[q].z, gm.w * invstd[q].w);
+        bq[q] = *reinterpret_cast<const float4*>(beta + pos[q]);
     }
     cp_async_wait_all();
     __syncthreads();
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    const float4* e4 = reinterpret_cast<const float4*>(etile);
     // pass 1: U = pool-bwd(e): EVERY tied maximum of the BN output receives e (layers.py:631-637); column sums
-    float sums[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [0..3] sum U (d_beta), [4..7] sum U*xhat (d_gamma)
+    float4 sums[8];   // [0..3] sum U (d_beta), [4..7] sum U*xhat (d_gamma)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sums[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float a0 = 0.0f;
-    for (int r = rg; r < nrows; r += FB_RG) {
-        const float e = scale * etile[r * 32 + lane];
-        float yq[4], xh[4];
+    for (int r = rg; r < nrows; r += FB_RGV) {
+        float4 e = e4[r * 8 + cq];
+        e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
+        float4 xv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float d = clip10(tile[(r * 4 + q) * 32 + lane]) - mean[q];
-            yq[q] = gq[q] * d + bq[q];
-            xh[q] = d * invstd[q];
-        }
-        const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float u = (yq[q] == m) ? e : 0.0f;
-            sums[q] += u;
-            sums[4 + q] += u * xh[q];
-            a0 += u * u;
-        }
+        for (int q = 0; q < 4; ++q) xv[q] = f4_clip10(t4[(r * 4 + q) * 8 + cq]);
+        FB_FOR4(
+            float yq[4], xh[4];
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                const float d = f4_at(xv[q], k_) - f4_at(mean[q], k_);
+                yq[q] = fmaf(f4_at(gq[q], k_), d, f4_at(bq[q], k_));
+                xh[q] = d * f4_at(invstd[q], k_);
+            }
+            const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;
+                f4_at(sums[q], k_) += u;
+                f4_at(sums[4 + q], k_) = fmaf(u, xh[q], f4_at(sums[4 + q], k_));
+                a0 = fmaf(u, u, a0);
+            })
     }
-    cluster_colsum<8>(sums, red, part, 0, lane, rg, csize);
+    cluster_colsum4<8>(sums, red, part, 0, cq, rg, csize);
     if (crank == 0 && rg == 0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (dbeta != nullptr) dbeta[pos[q]] = sums[q];          // layers.py:1262
-            if (dgamma != nullptr) dgamma[pos[q]] = sums[4 + q];    // layers.py:1261
+            if (dbeta != nullptr) *reinterpret_cast<float4*>(dbeta + pos[q]) = sums[q];          // layers.py:1262
+            if (dgamma != nullptr) *reinterpret_cast<float4*>(dgamma + pos[q]) = sums[4 + q];    // layers.py:1261
         }
     }
     const float invB = 1.0f / (float)g.B;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) sums[q] *= invB;
+    for (int q = 0; q < 8; ++q) sums[q] = make_float4(sums[q].x * invB, sums[q].y * invB, sums[q].z * invB, sums[q].w * invB);
     float a1 = 0.0f, a2 = 0.0f;
     const long long HWC = (long long)g.H * g.W * g.C;
-    for (int r = rg; r < nrows; r += FB_RG) {
-        const float e = scale * etile[r * 32 + lane];
-        float yq[4], xh[4], xv[4];
+    for (int r = rg; r < nrows; r += FB_RGV) {
+        float4 e = e4[r * 8 + cq];
+        e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
+        float4 xraw[4], out[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            xv[q] = tile[(r * 4 + q) * 32 + lane];
-            const float d = clip10(xv[q]) - mean[q];
-            yq[q] = gq[q] * d + bq[q];
-            xh[q] = d * invstd[q];
-        }
-        const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+        for (int q = 0; q < 4; ++q) xraw[q] = t4[(r * 4 + q) * 8 + cq];
+        FB_FOR4(
+            float yq[4], xh[4];
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                const float d = clip10(f4_at(xraw[q], k_)) - f4_at(mean[q], k_);
+                yq[q] = fmaf(f4_at(gq[q], k_), d, f4_at(bq[q], k_));
+                xh[q] = d * f4_at(invstd[q], k_);
+            }
+            const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;
+                float d = f4_at(gq[q], k_) * (u - xh[q] * f4_at(sums[4 + q], k_) - f4_at(sums[q], k_));   /* layers.py:1264-1274 */
+                a1 = fmaf(d, d, a1);
+                if (prev_act != B200NN_ACT_NONE) {
+                    d *= act_grad_from_y(prev_act, f4_at(xraw[q], k_), prev_alpha);                    /* layers.py:237 */
+                    a2 = fmaf(d, d, a2);
+                }
+                f4_at(out[q], k_) = d;
+            })
         float* rb = r0 + (long long)(row0 + r) * HWC;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float u = (yq[q] == m) ? e : 0.0f;
-            float d = gq[q] * (u - xh[q] * sums[4 + q] - sums[q]);       // BN backward, layers.py:1264-1274
-            a1 += d * d;
-            if (prev_act != B200NN_ACT_NONE) {
-                d *= act_grad_from_y(prev_act, xv[q], prev_alpha);       // Activation backward, layers.py:237
-                a2 += d * d;
-            }
-            rb[pos[q]] = d;
-        }
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(rb + pos[q]) = out[q];
     }
     if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
     if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);

@@ -305,7 +305,7 @@ extern "C" {
 int b200nn_version(void) { return 100; }
 
 #ifndef B200NN_HAS_TCGEN05
-#define B200NN_HAS_TCGEN05 0
+#define B200NN_HAS_TCGEN05 1   /* gemm_tcgen05.cuh: kind::tf32 GEMM behind B200NN_MATH_TF32 */
 #endif
 int b200nn_has_tcgen05(void) { return B200NN_HAS_TCGEN05; }
 

@@ -72,6 +72,20 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, EpiState& st, int m
     e.out[idx] = v;
 }
 
+// same as epi_store for the plain row mode, with the activation-backward mask value already loaded by the caller
+// (lets the caller batch the mask loads of several rows ahead of their use)
+__device__ __forceinline__ void epi_store_premask(const Epilogue& e, EpiState& st, int m, int n, float v, float mask_val) {
+    v *= st.scale;
+    if (e.bias != nullptr) v += e.bias[n];
+    v = act_apply(e.act, v, e.alpha);
+    st.a0 += v * v;
+    if (e.mask_y != nullptr) {
+        v *= act_grad_from_y(e.mask_act, mask_val, e.mask_alpha);
+        st.a1 += v * v;
+    }
+    e.out[(long long)m * e.ldo + n] = v;
+}
+
 __device__ __forceinline__ void epi_finish(const Epilogue& e, EpiState& st, double* scratch) {
     if (e.ss0 != nullptr) block_accumulate(st.a0, e.ss0, scratch);
     if (e.ss1 != nullptr) block_accumulate(st.a1, e.ss1, scratch);
@@ -637,6 +651,111 @@ static int smallk_wgrad_blocks(const b200nn_conv_geom* g) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Small-N Dense (classifier heads: Dense(10), Dense(1)).  With N <= 32 a 64x64 / 128xN MMA tile is almost all
+// padding and the layer is pure latency, so these kernels map threads to the long dimensions instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALLN_MAX = 32;
+
+// y[m, :] = act(b + x[m, :] . w)   — one warp per row, lanes stride over k, N accumulators per lane, shuffle-reduce
+__global__ void __launch_bounds__(256) dense_smalln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ y, int M,
+                                                               int N, int K, int act, float alpha) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        float acc[SMALLN_MAX];
+#pragma unroll
+        for (int n = 0; n < SMALLN_MAX; ++n) acc[n] = 0.0f;
+        const float* xr = x + (long long)m * K;
+        for (int k = lane; k < K; k += 32) {
+            const float xv = xr[k];
+            const float* wr = w + (long long)k * N;
+#pragma unroll
+            for (int n = 0; n < SMALLN_MAX; ++n)
+                if (n < N) acc[n] = fmaf(xv, wr[n], acc[n]);
+        }
+        float mine = 0.0f;
+#pragma unroll
+        for (int n = 0; n < SMALLN_MAX; ++n) {
+            if (n < N) {
+                const float t = warp_sum(acc[n]);
+                if (lane == n) mine = t;
+            }
+        }
+        if (lane < N) y[(long long)m * N + lane] = act_apply(act, mine + (b != nullptr ? b[lane] : 0.0f), alpha);
+    }
+}
+
+// dx[m, k] = scale * sum_n e[m, n] * w[k, n]  (+ fused activation backward and the two sums of squares)
+__global__ void __launch_bounds__(256) dense_smalln_dx_kernel(const float* __restrict__ e, const float* __restrict__ w,
+                                                              Epilogue epi, int M, int N, int K) {
+    __shared__ double scratch[32];
+    EpiState st;
+    epi_begin(epi, st);
+    const long long total = (long long)M * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / K), k = (int)(i % K);
+        const float* er = e + (long long)m * N;
+        const float* wr = w + (long long)k * N;
+        float v = 0.0f;
+        for (int n = 0; n < N; ++n) v = fmaf(er[n], wr[n], v);
+        const float mk = epi.mask_y != nullptr ? epi.mask_y[i] : 0.0f;
+        epi_store_premask(epi, st, m, k, v, mk);
+    }
+    epi_finish(epi, st, scratch);
+}
+
+// partial[chunk][k (+ ones row K)][n] = sum over the chunk's rows of x[m, k] * e[m, n]
+__global__ void __launch_bounds__(256) dense_smalln_dw_kernel(const float* __restrict__ x, const float* __restrict__ e,
+                                                              float* __restrict__ partial, int M, int N, int K,
+                                                              int rows_per_chunk) {
+    __shared__ float es[64 * SMALLN_MAX];   // the chunk's error rows, staged 64 rows at a time
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;    // 0..K (K = ones row -> db)
+    const int m_begin = blockIdx.y * rows_per_chunk, m_end = min(M, m_begin + rows_per_chunk);
+    float acc[SMALLN_MAX];
+#pragma unroll
+    for (int n = 0; n < SMALLN_MAX; ++n) acc[n] = 0.0f;
+    for (int mb = m_begin; mb < m_end; mb += 64) {
+        const int nr = min(64, m_end - mb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * N; i += blockDim.x) es[i] = e[(long long)mb * N + i];
+        __syncthreads();
+        if (k <= K) {
+            for (int r0 = 0; r0 < nr; r0 += 8) {
+                float xv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)   // 8 independent loads in flight
+                    xv[j] = (r0 + j < nr) ? (k < K ? x[(long long)(mb + r0 + j) * K + k] : 1.0f) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float* er = &es[min(r0 + j, nr - 1) * N];
+#pragma unroll
+                    for (int n = 0; n < SMALLN_MAX; ++n)
+                        if (n < N) acc[n] = fmaf(xv[j], er[n], acc[n]);
+                }
+            }
+        }
+    }
+    if (k <= K) {
+        float* dst = partial + ((long long)blockIdx.y * (K + 1) + k) * N;
+#pragma unroll
+        for (int n = 0; n < SMALLN_MAX; ++n)
+            if (n < N) dst[n] = acc[n];
+    }
+}
+
+static int smalln_chunks(int M) {
+    int c = (M + 7) / 8;                // >= 8 rows per chunk
+    return c > 64 ? 64 : (c < 1 ? 1 : c);
+}
+static size_t smalln_ws_bytes(int M, int N, int K) { return (size_t)smalln_chunks(M) * (K + 1) * N * sizeof(float); }
+
+}  // namespace b200nn
+#include "gemm_tcgen05.cuh"   // needs Epilogue / launch_splitk_reduce; lives in b200nn::tc
+namespace b200nn {
+
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -705,33 +824,87 @@ extern "C" {
 
 // ---------------------------------------------------------------------------------------------- Dense
 size_t b200nn_dense_ws_bytes(int M, int N, int K) {
-    size_t a = ws_bytes_for(M, N, K);          // fwd  [M,N] over K
-    size_t b = ws_bytes_for(M, K, N);          // dx   [M,K] over N
-    size_t c = ws_bytes_for((long long)K + 1, N, M);  // dw+db [K+1,N] over M
-    size_t r = a > b ? a : b;
-    return r > c ? r : c;
+    size_t r = 0;
+    auto mx = [&](size_t v) { if (v > r) r = v; };
+    mx(ws_bytes_for(M, N, K));                    // fwd  [M,N] over K
+    mx(ws_bytes_for(M, K, N));                    // dx   [M,K] over N
+    mx(ws_bytes_for((long long)K + 1, N, M));     // dw+db [K+1,N] over M
+    mx(tc::tc_ws_bytes(M, N, K));                 // the same three on the tcgen05 path
+    mx(tc::tc_ws_bytes(M, K, N));
+    mx(tc::tc_ws_bytes(K, N, M));
+    mx((size_t)kNumSMs * 2 * N * sizeof(float));  // column-sum partials for db on the tcgen05 path
+    if (N <= SMALLN_MAX) mx(smalln_ws_bytes(M, N, K));
+    return r;
+}
+
+static bool dense_tc_ok(const float* x, const float* w, const float* other, int M, int N, int K) {
+    // TMA needs 16-byte aligned bases and row pitches; tiny problems stay on the FFMA kernel
+    return tc::tma_ok(x, K) && tc::tma_ok(w, N) && tc::tma_ok(other, N) && (long long)M * N * K >= (1LL << 18);
 }
 
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                      int act, float alpha, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "dense_fwd: math mode %d is served by the tcgen05 entry points", math);
+    B200NN_REQUIRE(math == B200NN_MATH_FP32 || math == B200NN_MATH_TF32, "dense_fwd: unknown math mode %d", math);
     B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_fwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (int rc = check_act("dense_fwd", act, alpha)) return rc;
-    RowMajorA af{x, K, M, K};
-    RowMajorB bf{w, N, K, N};
+    if (N <= SMALLN_MAX) {
+        int blocks = (M + 7) / 8;
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        dense_smalln_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y, M, N, K, act, alpha);
+        B200NN_LAUNCH_CHECK("dense_smalln_fwd");
+        return B200NN_OK;
+    }
     Epilogue e = plain_epilogue(y, N, M);
     e.bias = b; e.act = act; e.alpha = alpha;
+    if (math == B200NN_MATH_TF32 && dense_tc_ok(x, w, y, M, N, K))
+        return tc::tc_gemm(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream));
+    RowMajorA af{x, K, M, K};
+    RowMajorB bf{w, N, K, N};
     return launch_gemm("dense_fwd", af, bf, e, M, N, K, ws, as_stream(stream));
 }
 
 int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err, const double* ss, uint64_t chain,
                      float* dx, float* dw, float* db, int M, int N, int K, int prev_act, float prev_alpha,
                      double* ss_out0, double* ss_out1, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "dense_bwd: math mode %d is served by the tcgen05 entry points", math);
+    B200NN_REQUIRE(math == B200NN_MATH_FP32 || math == B200NN_MATH_TF32, "dense_bwd: unknown math mode %d", math);
     B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_bwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (int rc = check_act("dense_bwd", prev_act, prev_alpha)) return rc;
     cudaStream_t st = as_stream(stream);
-    if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
+    if (N <= SMALLN_MAX && ws != nullptr) {
+        if (dw != nullptr) {
+            const int chunks = smalln_chunks(M);
+            const int rpc = (M + chunks - 1) / chunks;
+            const dim3 grid((K + 1 + 255) / 256, chunks);
+            dense_smalln_dw_kernel<<<grid, 256, 0, st>>>(x, err, ws, M, N, K, rpc);
+            B200NN_LAUNCH_CHECK("dense_smalln_dw");
+            Epilogue e = plain_epilogue(dw, N, K);
+            e.ss = ss; e.chain = chain; e.db = db;
+            if (int rc = launch_splitk_reduce(ws, chunks, K + 1, N, e, st)) return rc;
+        }
+        if (dx != nullptr) {
+            Epilogue e = plain_epilogue(dx, K, M);
+            dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+            long long blocks = ((long long)M * K + 255) / 256;
+            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            dense_smalln_dx_kernel<<<(int)blocks, 256, 0, st>>>(err, w, e, M, N, K);
+            B200NN_LAUNCH_CHECK("dense_smalln_dx");
+        }
+        return B200NN_OK;
+    }
+    const bool use_tc = math == B200NN_MATH_TF32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;
+    if (dw != nullptr && use_tc) {
+        if (db != nullptr) {   // layers.py:197
+            int nb = (M + 7) / 8;   // >= 8 rows per CTA; threads run over the columns
+            if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+            colsum_partial_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
+            B200NN_LAUNCH_CHECK("dense_db_partial");
+            colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(ws, nb, N, ss, chain, db);
+            B200NN_LAUNCH_CHECK("dense_db_final");
+        }
+        Epilogue e = plain_epilogue(dw, N, K);   // dw[K,N] = x^T . err : both operands MN-major, no transposed copies
+        e.ss = ss; e.chain = chain;
+        if (int rc = tc::tc_gemm(x, K, true, err, N, true, e, K, N, M, ws, st)) return rc;
+    } else if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
         ColMajorOnesA af{x, K, K, M, db != nullptr ? 1 : 0};
         RowMajorB bf{err, N, M, N};
         Epilogue e = plain_epilogue(dw, N, K);
@@ -739,11 +912,15 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         if (int rc = launch_gemm("dense_dw", af, bf, e, K + (db != nullptr ? 1 : 0), N, M, ws, st)) return rc;
     }
     if (dx != nullptr) {  // dx[M,K] = err[M,N] . w^T
-        RowMajorA af{err, N, M, N};
-        ColMajorB bf{w, N, N, K};
         Epilogue e = plain_epilogue(dx, K, M);
         dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
-        if (int rc = launch_gemm("dense_dx", af, bf, e, M, K, N, ws, st)) return rc;
+        if (use_tc) {
+            if (int rc = tc::tc_gemm(err, N, false, w, N, false, e, M, K, N, ws, st)) return rc;
+        } else {
+            RowMajorA af{err, N, M, N};
+            ColMajorB bf{w, N, N, K};
+            if (int rc = launch_gemm("dense_dx", af, bf, e, M, K, N, ws, st)) return rc;
+        }
     }
     return B200NN_OK;
 }
@@ -915,7 +1092,7 @@ int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const
     if (db != nullptr) {  // layers.py:2641: sum over ALL error pixels
         B200NN_REQUIRE(ws != nullptr, "convt_bwd: workspace required");
         const long long R = (long long)g->N * g->OH * g->OW;
-        int nb = (int)((R + 255) / 256);
+        int nb = (int)((R + 63) / 64);
         if (nb > kNumSMs * 2) nb = kNumSMs * 2;
         colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
         B200NN_LAUNCH_CHECK("convt_db_partial");

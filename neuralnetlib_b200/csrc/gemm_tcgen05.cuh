@@ -1,0 +1,377 @@
+// gemm_tcgen05.cuh — Blackwell tensor-core contraction for Dense layers (math mode TF32, rel 2e-3):
+//   D[M,N] (fp32) = A[M,K] . B[K,N]  with fp32 operands read as TF32 by tcgen05.mma.kind::tf32,
+//   fp32 accumulation in TMEM, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a
+//   multi-stage mbarrier pipeline. Warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+//   allocator + single-thread MMA issuer, warps 2..5 = epilogue (tcgen05.ld 32x32b -> registers -> the shared
+//   Epilogue: bias / activation / lazy clip multiplier / fused activation backward / fp64 sum-of-squares slots).
+//
+// Both operand majors are supported WITHOUT transposed copies (the three GEMMs of a Dense layer need all of them):
+//   K-major  : element (mn, k) at  base[mn * ld + k]   -> TMA box {32 k, rows mn}, smem tile [mn][128 B], SW128,
+//              UMMA descriptor SBO = 1024 B, one MMA k-step (8 tf32) advances the start address by 32 B;
+//   MN-major : element (mn, k) at  base[k * ld + mn]   -> BLOCK_MN/32 TMA boxes {32 mn, BLOCK_K k}, each a
+//              [k][128 B] slab of 4 KB. 32-bit MN-major operands must use the 32-byte-atom swizzle
+//              (UMMA LayoutType SWIZZLE_128B_BASE32B = Swizzle<2,5,2>, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+//              plain SWIZZLE_128B silently yields zeros, see scripts/tc_probe.cu): atom = 128 B x 4 k rows, so
+//              LBO = 4096 B (next 32 mn), SBO = 512 B (next 4 k), one MMA k-step advances the start by 1024 B.
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
+// Tails in M, N and K are handled by TMA zero fill + guarded stores. Skinny shapes use split-K over blockIdx.z
+// (partials to a workspace, reduced in fixed order by splitk_reduce_*).
+#pragma once
+#include <cuda.h>
+
+namespace b200nn {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;          // tf32 elements = 128 bytes = one swizzle span
+constexpr int UMMA_K = 8;            // tf32 elements per tcgen05.mma
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SLAB_BYTES = BLOCK_K * 128;   // one 32-wide MN slab of an MN-major operand
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"   // same asm block: the registers are only defined after the wait
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout [61,64): SWIZZLE_128B = 2 (K-major), SWIZZLE_128B_BASE32B = 1 (MN-major 32-bit)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) { return make_desc(tile + kstep * 32, 16, 1024, 2); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep) { return make_desc(tile + kstep * 1024, SLAB_BYTES, 512, 1); }
+// instruction descriptor (InstrDescriptor): c_format F32 = 1 [4,6) | a/b format TF32 = 2 [7,10) [10,13) | a_major [15] |
+// b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue epi, int M,
+                 int N, int K, int kb_per_split, float* __restrict__ ws) {
+    constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 (BLOCK_N in {32,64,128,256})
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ double scratch[32];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+    const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_begin = blockIdx.z * kb_per_split;
+    const int kb_end = min(kb_total, kb_begin + kb_per_split);
+    const int num_kb = kb_end - kb_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&full_bar[s]), 1);
+                mbar_init(smem_u32(&empty_bar[s]), 1);
+            }
+            mbar_init(smem_u32(&tmem_full_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t round = i / STAGES;
+                mbar_wait(smem_u32(&empty_bar[s]), (round & 1) ^ 1);   // first pass over the ring returns immediately
+                const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint32_t bar = smem_u32(&full_bar[s]);
+                mbar_expect_tx(bar, STAGE_BYTES);
+                const int k0 = (kb_begin + i) * BLOCK_K;
+                if constexpr (A_MN) {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * SLAB_BYTES, &tmA, bar, m0 + j * 32, k0);
+                } else {
+                    tma_load_2d(sa, &tmA, bar, k0, m0);
+                }
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
+                } else {
+                    tma_load_2d(sb, &tmB, bar, k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single elected thread) =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t round = i / STAGES;
+                mbar_wait(smem_u32(&full_bar[s]), round & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                    const uint64_t ad = A_MN ? desc_mnmajor(sa, j) : desc_kmajor(sa, j);
+                    const uint64_t bd = B_MN ? desc_mnmajor(sb, j) : desc_kmajor(sb, j);
+                    tc_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&empty_bar[s]));          // frees the smem stage once these MMAs have read it
+            }
+            tc_commit(smem_u32(&tmem_full_bar));             // accumulator complete
+        }
+    }
+
+    // ===== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====
+    // tcgen05.ld hands thread t the 32 columns of accumulator ROW t; a 32x32 shared-memory transpose turns that into
+    // lane = column, so every global access of the epilogue (output, bias, activation-backward mask) is a coalesced
+    // 128-byte line instead of 32 rows x 4 bytes.
+    __shared__ float xpose[4][32][33];
+    EpiState st;
+    epi_begin(epi, st);
+    if (warp >= 2) {
+        const int q = warp & 3;
+        float (*tile)[33] = xpose[warp - 2];
+        if (num_kb > 0) {
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            if (n0 + c >= N) break;
+            float v[32];
+            if (num_kb > 0) {
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tile[lane][i] = v[i];   // row = lane
+            __syncwarp();
+            const int n = n0 + c + lane;
+            if (n < N) {
+                const bool plain = ws == nullptr && epi.row_mode == 0 && epi.n_rows >= M;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    const int mb = m0 + q * 32 + r0;
+                    if (mb >= M) break;
+                    float val[8], msk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {   // 8 independent smem + global loads in flight before any use
+                        val[j] = tile[r0 + j][lane];
+                        msk[j] = (plain && epi.mask_y != nullptr && mb + j < M) ? epi.mask_y[(long long)(mb + j) * epi.ldo + n] : 0.0f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int m = mb + j;
+                        if (m < M) {
+                            if (ws != nullptr) ws[((long long)blockIdx.z * M + m) * N + n] = val[j];
+                            else if (plain) epi_store_premask(epi, st, m, n, val[j], msk[j]);
+                            else epi_store(epi, st, m, n, val[j]);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (ws == nullptr) epi_finish(epi, st, scratch);
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; box = {32, box_rows};
+// K-major operands use SWIZZLE_128B, MN-major operands the 32-byte-atom variant (see the header comment)
+static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows,
+                    bool mn_major) {
+    EncodeTiledFn fn = encode_fn();
+    B200NN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200NN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (inner=%lld outer=%lld ld=%lld)", (int)r, inner, outer, ld);
+    return B200NN_OK;
+}
+
+// can this operand be described by a TMA map? (16-byte aligned base and row pitch)
+static bool tma_ok(const float* base, long long ld) {
+    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * sizeof(float)) % 16 == 0 && ld > 0;
+}
+
+static int tc_block_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
+
+struct TcPlan {
+    int block_n, splits, kb_per_split;
+};
+
+static TcPlan tc_plan(long long M, long long N, long long K) {
+    TcPlan p;
+    p.block_n = tc_block_n((int)N);
+    // if the tile grid cannot fill the 148 SMs anyway, narrower tiles spread the (epilogue-heavy) work over more SMs
+    while (p.block_n > 32 && ((M + BLOCK_M - 1) / BLOCK_M) * ((N + p.block_n - 1) / p.block_n) < kNumSMs) p.block_n >>= 1;
+    const long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + p.block_n - 1) / p.block_n);
+    const long long kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+    long long splits = 1;
+    if (tiles < kNumSMs && kb_total >= 8) {
+        splits = (kNumSMs + tiles - 1) / tiles;
+        const long long maxs = kb_total / 4;       // at least 4 k-blocks (128 k) per split
+        if (splits > maxs) splits = maxs;
+        if (splits < 1) splits = 1;
+    }
+    long long per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;           // every split non-empty
+    p.splits = (int)splits;
+    p.kb_per_split = (int)per;
+    return p;
+}
+
+static size_t tc_ws_bytes(long long M, long long N, long long K) {
+    const TcPlan p = tc_plan(M, N, K);
+    return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
+                            const TcPlan& p, float* ws, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BN * 128) + 1024;
+    auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, p.splits);
+    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr);
+    B200NN_LAUNCH_CHECK("gemm_tf32");
+    if (p.splits > 1) return launch_splitk_reduce(ws, p.splits, M, N, epi, st);
+    return B200NN_OK;
+}
+
+// short reductions (<= 2 k-blocks per CTA) are epilogue-bound: a 2-stage ring keeps the shared-memory footprint small
+// so that several CTAs (and their epilogue warps) share an SM; long reductions get a deep ring
+template <int BN, bool A_MN, bool B_MN>
+static int tc_launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
+                             const TcPlan& p, float* ws, cudaStream_t st) {
+    if (p.kb_per_split <= 2) return tc_launch_stages<BN, 2, A_MN, B_MN>(ta, tb, epi, M, N, K, p, ws, st);
+    return tc_launch_stages<BN, (BN >= 256 ? 4 : 6), A_MN, B_MN>(ta, tb, epi, M, N, K, p, ws, st);
+}
+
+// D[M,N] = A.B ; a_mn: A stored [K][M] (ld = lda) else [M][K]; b_mn: B stored [K][N] else [N][K]
+static int tc_gemm(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi,
+                   int M, int N, int K, float* ws, cudaStream_t st) {
+    const TcPlan p = tc_plan(M, N, K);
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "gemm_tf32: split-K needs a workspace");
+    CUtensorMap ta, tb;
+    if (a_mn) { if (int rc = make_map(&ta, A, M, K, lda, BLOCK_K, true)) return rc; }
+    else      { if (int rc = make_map(&ta, A, K, M, lda, BLOCK_M, false)) return rc; }
+    if (b_mn) { if (int rc = make_map(&tb, B, N, K, ldb, BLOCK_K, true)) return rc; }
+    else      { if (int rc = make_map(&tb, B, K, N, ldb, p.block_n, false)) return rc; }
+    B200NN_REQUIRE(!(a_mn && !b_mn), "gemm_tf32: (A MN-major, B K-major) is not instantiated");
+#define TC_DISPATCH(BN)                                                                              \
+    if (a_mn) return tc_launch_variant<BN, true, true>(ta, tb, epi, M, N, K, p, ws, st);             \
+    if (b_mn) return tc_launch_variant<BN, false, true>(ta, tb, epi, M, N, K, p, ws, st);            \
+    return tc_launch_variant<BN, false, false>(ta, tb, epi, M, N, K, p, ws, st);
+    switch (p.block_n) {
+        case 32: TC_DISPATCH(32)
+        case 64: TC_DISPATCH(64)
+        case 128: TC_DISPATCH(128)
+        default: TC_DISPATCH(256)
+    }
+#undef TC_DISPATCH
+}
+
+}  // namespace tc
+}  // namespace b200nn

@@ -274,3 +274,32 @@ def test_early_stopping_and_lr_scheduler_touch_device_state():
     h = m.fit(x, y, epochs=5, batch_size=32, verbose=False, callbacks=[es, lrs], random_state=1)
     assert len(h["loss"]) == 2 and es.stop_training
     assert abs(m.optimizer.learning_rate - 0.5e-3) < 1e-12
+
+
+@pytest.mark.parametrize("cfg,batch,width", [(2, 256, None), (1, 32, None), (4, 256, 1024)])
+def test_tf32_tensor_core_mode_within_2e3(cfg, batch, width):
+    """Math mode 'tf32' (Dense GEMMs on tcgen05 kind::tf32, fp32 accumulate in TMEM): one step from identical state
+    stays within the north star's rel 2e-3 of the fp64 oracle."""
+    import neuralnetlib_b200 as nn
+    nn.set_math("tf32")
+    try:
+        m = build_cfg(cfg, width)
+        specs, shp = O.config_specs(cfg)
+        if width:
+            for sp in specs:
+                if sp.get("units") == 4096:
+                    sp["units"] = width
+            rng = np.random.default_rng(0)
+            x = rng.random((batch, width)).astype(np.float32)
+            y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+        else:
+            x, y = O.synthetic_batch(cfg, batch)
+        ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+        loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+        assert abs(loss - rloss) <= 2e-3 * max(1.0, abs(rloss))
+        assert nrel(m.predictions, ref.predictions) < 2e-3
+        for layer, rl in zip([l for l in m.layers if hasattr(l, "weights")], [r for r in ref.layers if "w" in r]):
+            assert nrel(layer.d_weights, rl["dw"]) < 2e-3
+            assert nrel(layer.d_bias.reshape(-1), rl["db"].reshape(-1)) < 2e-3
+    finally:
+        nn.set_math("fp32")

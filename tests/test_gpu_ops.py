@@ -415,3 +415,33 @@ def test_fused_bn_pool_block(K, Bn, H, W, C):
     ref = O.clip_l2(O.bn_bwd(O.clip_l2(U), g64, cache, 1e-5)[0]) * (x64 > 0)
     assert nrel(K.host(out), O.clip_l2(ref)) < 2e-5
     assert np.all(U[:, :2, :2, 0] == O.clip_l2(e.astype(np.float64))[:, :1, :1, 0][:, :, :, None].reshape(Bn, 1, 1))  # 4-way tie
+
+
+@pytest.mark.parametrize("M,N,Kd", [(256, 64, 6272), (512, 512, 512), (300, 260, 200), (128, 32, 64), (64, 4096, 512),
+                                    (1000, 128, 96), (256, 256, 2048)])
+def test_dense_tf32_tcgen05(K, M, N, Kd):
+    """tcgen05 kind::tf32 path (TMA + TMEM): all three GEMMs of a Dense layer (K-major x MN-major, K x K, MN x MN),
+    split-K and M/N/K tails, within the north star's rel 2e-3 of the fp64 oracle."""
+    assert K.B.lib().b200nn_has_tcgen05() == 1
+    rng = np.random.default_rng(M + N + Kd)
+    x = np.maximum(rng.normal(size=(M, Kd)), 0).astype(np.float32)
+    w = (rng.normal(size=(Kd, N)) / np.sqrt(Kd)).astype(np.float32)
+    b = rng.normal(size=(N,)).astype(np.float32)
+    err = rng.normal(size=(M, N)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    ws = K.empty((max(K.ops.dense_ws_bytes(M, N, Kd) // 4, 1),))
+    y = K.empty((M, N))
+    K.ops.dense_fwd(1, xd, wd, bd, y, 1, 0.0, ws)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    ref = np.maximum(x64 @ w64 + b, 0)
+    assert nrel(K.host(y), ref) < 2e-3
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty((M, Kd)), K.empty((Kd, N)), K.empty((N,))
+    K.ops.dense_bwd(1, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    e64 = O.clip_l2(err.astype(np.float64))
+    rdx, rdw, rdb = O.dense_bwd(x64, w64, e64)
+    assert nrel(K.host(dx), rdx * (x > 0)) < 2e-3
+    assert nrel(K.host(dw), rdw) < 2e-3
+    assert nrel(K.host(db), rdb.reshape(-1)) < 1e-5
+    h = K.host(ss)
+    assert abs(h[1] - np.sum(rdx ** 2)) < 5e-3 * np.sum(rdx ** 2)
