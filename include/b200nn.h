@@ -229,6 +229,64 @@ int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, do
 int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
                      const int* block_map, int total_blocks, void* stream);
 
+/* ---- data parallelism: one process per GPU on one NVLink/NVSwitch box -----------------------
+ * The reference is single-process; under a batch shard per GPU its batch-global quantities become sums over ranks:
+ * gradients (models.py:200-205 — never divided by the batch, so SUM not mean), the L2 norms behind every clip
+ * (models.py:214, 240-242), BatchNormalization's per-position statistics (layers.py:1237-1238) and the reductions of its
+ * backward (layers.py:1261-1270). One primitive serves them all: an in-place sum-allreduce of a device buffer, either
+ * through NCCL (bandwidth-bound gradient buckets) or through a one-shot exchange over CUDA-IPC-mapped peer memory
+ * (latency-bound scalars and statistic vectors; every rank sums the contributions in rank order, so all ranks obtain
+ * bit-identical results). Both are asynchronous on `stream` and capturable into the step graph. */
+typedef struct b200nn_comm b200nn_comm;
+/* dlopen libnccl (NULL: the copy already loaded into the process, e.g. PyTorch's) */
+int b200nn_comm_load_nccl(const char* path);
+int b200nn_comm_nccl_version(void);
+/* rank 0 creates the 128-byte NCCL id; the host side broadcasts it (torch.distributed) */
+int b200nn_comm_unique_id(void* out128);
+int b200nn_comm_create(const void* unique_id128, int rank, int world, b200nn_comm** out);
+int b200nn_comm_destroy(b200nn_comm* comm);
+/* symmetric peer buffer: allocate `bytes` (zeroed) and return its CUDA IPC handle; after an all-gather of the
+ * handles on the host side, map every peer. Optional: without it every allreduce goes through NCCL. */
+size_t b200nn_comm_ipc_handle_bytes(void);
+int b200nn_comm_peer_alloc(b200nn_comm* comm, size_t bytes, void* handle_out);
+int b200nn_comm_peer_open(b200nn_comm* comm, const void* all_handles);
+int b200nn_comm_has_peer(const b200nn_comm* comm);
+/* peer waits that gave up after 10 s because a rank never arrived (synchronises the device); non-zero = results invalid */
+int b200nn_comm_timeouts(const b200nn_comm* comm);
+/* reserve an exchange site (double-buffered inbox of world x payload_bytes) in the symmetric buffer; every rank
+ * must create the same sites in the same order */
+int b200nn_comm_site_create(b200nn_comm* comm, size_t payload_bytes, int* site_out);
+/* buf[0..n) <- sum over ranks, in place. dtype 0 = float32, 1 = float64. site >= 0: one-shot peer-memory exchange
+ * through that site; site < 0: ncclAllReduce. */
+int b200nn_comm_allreduce_sum(b200nn_comm* comm, int site, void* buf, long long n, int dtype, void* stream);
+
+/* ---- BatchNormalization under data parallelism: each batch-coupled kernel splits at its reduction ---------------
+ * forward:  b200nn_bn_stats_partial  ->  sum `stats` over ranks (fp64)  ->  b200nn_bn_fwd_apply | b200nn_bn_pool_fwd_apply
+ * backward: *_bwd_partial            ->  sum dgamma / dbeta over ranks  ->  *_bwd_apply
+ * `stats` is [2][P] float64: sum clip(x) and sum clip(x)^2 over the LOCAL batch rows (the second moment is formed from
+ * an exact two-pass local M2). B_total is the global batch (layers.py:1237-1238 take mean / var over all of it). */
+int b200nn_bn_stats_partial(const float* x, double* stats, int B, long long P, void* stream);
+int b200nn_bn_fwd_apply(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        float* save_mean, float* save_invstd, const double* stats, float* y, int B, long long P,
+                        long long B_total, float momentum, float eps, void* stream);
+int b200nn_bn_pool_fwd_apply(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             float* save_mean, float* save_invstd, const double* stats, float* y_pool, int B, int H, int W,
+                             int C, long long B_total, float momentum, float eps, void* stream);
+/* dgamma / dbeta receive the LOCAL sums (layers.py:1261-1262); after the sum over ranks the apply half reads them. */
+int b200nn_bn_bwd_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* save_mean,
+                          const float* save_invstd, float* dgamma, float* dbeta, int B, long long P, void* stream);
+int b200nn_bn_bwd_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                        const float* save_mean, const float* save_invstd, float* dx, const float* dgamma, const float* dbeta,
+                        int B, long long P, long long B_total, int prev_act, float prev_alpha, double* ss_out0,
+                        double* ss_out1, void* stream);
+int b200nn_pool_bn_bwd_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd, float* dgamma,
+                               float* dbeta, int B, int H, int W, int C, double* ss_out0, void* stream);
+int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                 const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                                 const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
+                                 int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

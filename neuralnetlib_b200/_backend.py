@@ -82,6 +82,27 @@ _SIGNATURES = {
                                         c_float, _P, _P, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
+    # data parallelism (csrc/comm.cu) and the split BatchNorm kernels
+    "b200nn_comm_load_nccl": (c_int, [C.c_char_p]),
+    "b200nn_comm_nccl_version": (c_int, []),
+    "b200nn_comm_unique_id": (c_int, [_P]),
+    "b200nn_comm_create": (c_int, [_P, c_int, c_int, C.POINTER(c_void_p)]),
+    "b200nn_comm_destroy": (c_int, [_P]),
+    "b200nn_comm_ipc_handle_bytes": (c_size_t, []),
+    "b200nn_comm_peer_alloc": (c_int, [_P, c_size_t, _P]),
+    "b200nn_comm_peer_open": (c_int, [_P, _P]),
+    "b200nn_comm_has_peer": (c_int, [_P]),
+    "b200nn_comm_timeouts": (c_int, [_P]),
+    "b200nn_comm_site_create": (c_int, [_P, c_size_t, C.POINTER(c_int)]),
+    "b200nn_comm_allreduce_sum": (c_int, [_P, c_int, _P, c_ll, c_int, _P]),
+    "b200nn_bn_stats_partial": (c_int, [_P, _P, c_int, c_ll, _P]),
+    "b200nn_bn_fwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_float, c_float, _P]),
+    "b200nn_bn_pool_fwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_ll, c_float, c_float, _P]),
+    "b200nn_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, c_int, c_ll, _P]),
+    "b200nn_bn_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_int, c_float, _P, _P, _P]),
+    "b200nn_pool_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "b200nn_pool_bn_act_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_ll,
+                                              c_int, c_float, _P, _P, _P]),
 }
 
 

@@ -208,6 +208,66 @@ def pool_bn_act_bwd(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, 
                                        _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), _slot_ptr(ss, slot2), stream()))
 
 
+# data-parallel halves of the BatchNorm kernels (include/b200nn.h); `stats` is float64 [2P], `sums` float32 [2P] = dbeta | dgamma
+def bn_stats_partial(x, stats):
+    _f32(x)
+    Bn = x.shape[0]
+    assert stats.dtype == torch.float64 and stats.numel() == 2 * (x.numel() // Bn)
+    check(lib().b200nn_bn_stats_partial(ptr(x), ptr(stats), Bn, x.numel() // Bn, stream()))
+
+
+def bn_fwd_apply(x, gamma, beta, rmean, rvar, save_mean, save_invstd, stats, y, b_total, momentum, eps):
+    _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y)
+    Bn = x.shape[0]
+    check(lib().b200nn_bn_fwd_apply(ptr(x), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(save_mean), ptr(save_invstd),
+                                    ptr(stats), ptr(y), Bn, x.numel() // Bn, int(b_total), momentum, eps, stream()))
+
+
+def bn_pool_fwd_apply(x, gamma, beta, rmean, rvar, save_mean, save_invstd, stats, y_pool, b_total, momentum, eps):
+    _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y_pool)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    check(lib().b200nn_bn_pool_fwd_apply(ptr(x), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(save_mean),
+                                         ptr(save_invstd), ptr(stats), ptr(y_pool), Bn, H, W, Cc, int(b_total), momentum, eps,
+                                         stream()))
+
+
+def bn_bwd_partial(x, err, ss, chain, save_mean, save_invstd, sums):
+    _f32(x, err, save_mean, save_invstd, sums)
+    Bn = x.shape[0]
+    P = x.numel() // Bn
+    check(lib().b200nn_bn_bwd_partial(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(save_mean), ptr(save_invstd),
+                                      sums.data_ptr() + 4 * P, sums.data_ptr(), Bn, P, stream()))
+
+
+def bn_bwd_apply(x, err, ss, chain, gamma, save_mean, save_invstd, dx, sums, b_total, prev_act, prev_alpha, slot0, slot1):
+    _f32(x, err, gamma, save_mean, save_invstd, dx, sums)
+    Bn = x.shape[0]
+    P = x.numel() // Bn
+    check(lib().b200nn_bn_bwd_apply(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(save_mean), ptr(save_invstd),
+                                    ptr(dx), sums.data_ptr() + 4 * P, sums.data_ptr(), Bn, P, int(b_total), prev_act, prev_alpha,
+                                    _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), stream()))
+
+
+def pool_bn_bwd_partial(x, err, ss, chain, gamma, beta, save_mean, save_invstd, sums, slot0):
+    _f32(x, err, gamma, beta, save_mean, save_invstd, sums)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    P = H * W * Cc
+    check(lib().b200nn_pool_bn_bwd_partial(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(beta), ptr(save_mean),
+                                           ptr(save_invstd), sums.data_ptr() + 4 * P, sums.data_ptr(), Bn, H, W, Cc,
+                                           _slot_ptr(ss, slot0), stream()))
+
+
+def pool_bn_act_bwd_apply(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, sums, b_total, prev_act, prev_alpha,
+                          slot1, slot2):
+    _f32(x, err, gamma, beta, save_mean, save_invstd, r0, sums)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    P = H * W * Cc
+    check(lib().b200nn_pool_bn_act_bwd_apply(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(beta),
+                                             ptr(save_mean), ptr(save_invstd), ptr(r0), sums.data_ptr() + 4 * P, sums.data_ptr(),
+                                             Bn, H, W, Cc, int(b_total), prev_act, prev_alpha, _slot_ptr(ss, slot1),
+                                             _slot_ptr(ss, slot2), stream()))
+
+
 def maxpool_fwd(g: PoolGeom, x, y):
     _f32(x, y)
     check(lib().b200nn_maxpool_fwd(C.byref(g), ptr(x), ptr(y), stream()))

@@ -73,14 +73,142 @@ __global__ void __launch_bounds__(256) bn_fwd_infer_kernel(const float* __restri
     }
 }
 
+// ---- data-parallel split of the forward (comm.cu): local partial sums -> sum over ranks -> apply -------------------
+// stats[col] = sum_rows clip(x), stats[P + col] = sum_rows clip(x)^2, both fp64. The second moment is formed from the
+// exact two-pass local M2 (M2 + S^2/B in fp64), so the only cancellation left is the fp64 one in the combine.
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float* __restrict__ x, double* __restrict__ stats, int B,
+                                                               long long P) {
+    __shared__ float sm[BN_ROWG][BN_COLS];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const long long col = (long long)blockIdx.x * BN_COLS + cx;
+    const bool ok = col < P;
+    const float* xc = x + col;
+    float s = 0.0f;
+    if (ok) {
+#pragma unroll 4
+        for (int r = ry; r < B; r += BN_ROWG) s += clip10(xc[(long long)r * P]);
+    }
+    const float sum = colgroup_sum(s, sm, cx, ry);
+    const float mean = sum / (float)B;
+    float q = 0.0f;
+    if (ok) {
+#pragma unroll 4
+        for (int r = ry; r < B; r += BN_ROWG) {
+            const float d = clip10(xc[(long long)r * P]) - mean;
+            q += d * d;
+        }
+    }
+    const float m2 = colgroup_sum(q, sm, cx, ry);
+    if (ok && ry == 0) {
+        const double S = (double)mean * (double)B;
+        stats[col] = S;
+        stats[P + col] = (double)m2 + S * S / (double)B;
+    }
+}
+
+// mean / batch_var / invstd of one position from the rank-summed moments (layers.py:1237-1238, :1252)
+__device__ __forceinline__ void bn_finalize(double S1, double S2, double n_total, float eps, float& mean, float& batch_var,
+                                            float& invstd) {
+    const double m = S1 / n_total;
+    double var = S2 / n_total - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    batch_var = (float)var + eps;
+    invstd = rsqrtf(batch_var + eps);
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ rmean,
+                                                           float* __restrict__ rvar, float* __restrict__ save_mean,
+                                                           float* __restrict__ save_invstd, const double* __restrict__ stats,
+                                                           float* __restrict__ y, int B, long long P, double n_total,
+                                                           float momentum, float eps) {
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const long long col = (long long)blockIdx.x * BN_COLS + cx;
+    if (col >= P) return;
+    float mean, batch_var, invstd;
+    bn_finalize(stats[col], stats[P + col], n_total, eps, mean, batch_var, invstd);
+    if (ry == 0) {
+        rmean[col] = momentum * rmean[col] + (1.0f - momentum) * mean;
+        rvar[col] = momentum * rvar[col] + (1.0f - momentum) * batch_var;
+        save_mean[col] = mean;
+        save_invstd[col] = invstd;
+    }
+    const float g = gamma[col] * invstd, b = beta[col];
+    const float* xc = x + col;
+    float* yc = y + col;
+#pragma unroll 4
+    for (int r = ry; r < B; r += BN_ROWG) yc[(long long)r * P] = g * (clip10(xc[(long long)r * P]) - mean) + b;
+}
+
+// BatchNorm apply + MaxPool 2x2/s2 from rank-summed moments: a thread owns (window, channel quad) and FB_APPLY_ROWS batch rows
+constexpr int FB_APPLY_ROWS = 8;
+__global__ void __launch_bounds__(256) bn_pool_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ rmean,
+                                                            float* __restrict__ rvar, float* __restrict__ save_mean,
+                                                            float* __restrict__ save_invstd, const double* __restrict__ stats,
+                                                            float* __restrict__ y, int B, int H, int W, int C, double n_total,
+                                                            float momentum, float eps, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int CQ = C >> 2, OW = W >> 1, OH = H >> 1;
+    const int cq = (int)(idx % CQ); long long t = idx / CQ;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH); const int chunk = (int)(t / OH);
+    const int c = cq * 4;
+    const long long P = (long long)H * W * C;
+    float4 mean[4], gq[4], bq[4];
+    long long pos[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        pos[q] = ((long long)(2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * C + c;
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + pos[q]);
+        bq[q] = *reinterpret_cast<const float4*>(beta + pos[q]);
+        float mv[4], bv[4], is[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bn_finalize(stats[pos[q] + k], stats[P + pos[q] + k], n_total, eps, mv[k], bv[k], is[k]);
+        mean[q] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        gq[q] = make_float4(gm.x * is[0], gm.y * is[1], gm.z * is[2], gm.w * is[3]);
+        if (chunk == 0) {
+            float4 rm = *reinterpret_cast<const float4*>(rmean + pos[q]), rv = *reinterpret_cast<const float4*>(rvar + pos[q]);
+            rm = make_float4(momentum * rm.x + (1.0f - momentum) * mv[0], momentum * rm.y + (1.0f - momentum) * mv[1],
+                             momentum * rm.z + (1.0f - momentum) * mv[2], momentum * rm.w + (1.0f - momentum) * mv[3]);
+            rv = make_float4(momentum * rv.x + (1.0f - momentum) * bv[0], momentum * rv.y + (1.0f - momentum) * bv[1],
+                             momentum * rv.z + (1.0f - momentum) * bv[2], momentum * rv.w + (1.0f - momentum) * bv[3]);
+            *reinterpret_cast<float4*>(rmean + pos[q]) = rm;
+            *reinterpret_cast<float4*>(rvar + pos[q]) = rv;
+            *reinterpret_cast<float4*>(save_mean + pos[q]) = mean[q];
+            *reinterpret_cast<float4*>(save_invstd + pos[q]) = make_float4(is[0], is[1], is[2], is[3]);
+        }
+    }
+    const long long OP = (long long)OH * OW * C, obase = ((long long)oy * OW + ox) * C + c;
+    const int r0 = chunk * FB_APPLY_ROWS, r1 = min(B, r0 + FB_APPLY_ROWS);
+#pragma unroll 2
+    for (int r = r0; r < r1; ++r) {
+        const float* xr = x + (long long)r * P;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = *reinterpret_cast<const float4*>(xr + pos[q]);
+            v = make_float4(clip10(v.x), clip10(v.y), clip10(v.z), clip10(v.w));
+            m.x = fmaxf(m.x, fmaf(gq[q].x, v.x - mean[q].x, bq[q].x)); m.y = fmaxf(m.y, fmaf(gq[q].y, v.y - mean[q].y, bq[q].y));
+            m.z = fmaxf(m.z, fmaf(gq[q].z, v.z - mean[q].z, bq[q].z)); m.w = fmaxf(m.w, fmaf(gq[q].w, v.w - mean[q].w, bq[q].w));
+        }
+        *reinterpret_cast<float4*>(y + (long long)r * OP + obase) = m;
+    }
+}
+
+// MODE 0: single GPU. MODE 1 (data parallel, first half): only the two batch reductions, written as LOCAL partial sums to
+// dbeta / dgamma. MODE 2 (second half): dbeta / dgamma hold the rank-summed reductions; B_total is the global batch.
+template <int MODE>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ err,
                                                      const double* __restrict__ ss, uint64_t chain,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ save_mean,
                                                      const float* __restrict__ save_invstd, float* __restrict__ dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int B,
-                                                     long long P, int prev_act, float prev_alpha, double* ss_out0,
-                                                     double* ss_out1) {
+                                                     long long P, int B_total, int prev_act, float prev_alpha,
+                                                     double* ss_out0, double* ss_out1) {
     __shared__ float sm[BN_ROWG][BN_COLS];
     __shared__ double scratch[32];
     const float scale = chain_scale(ss, chain);
@@ -90,26 +218,33 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ x
     const float mean = ok ? save_mean[col] : 0.0f, invstd = ok ? save_invstd[col] : 0.0f;
     const float* xc = x + col;
     const float* ec = err + col;
-    float se = 0.0f, sex = 0.0f;
-    if (ok) {
+    float sum_e, sum_ex;
+    if (MODE != 2) {
+        float se = 0.0f, sex = 0.0f;
+        if (ok) {
 #pragma unroll 4
-        for (int r = ry; r < B; r += BN_ROWG) {
-            const float e = scale * ec[(long long)r * P];
-            const float xh = (clip10(xc[(long long)r * P]) - mean) * invstd;
-            se += e;
-            sex += e * xh;
+            for (int r = ry; r < B; r += BN_ROWG) {
+                const float e = scale * ec[(long long)r * P];
+                const float xh = (clip10(xc[(long long)r * P]) - mean) * invstd;
+                se += e;
+                sex += e * xh;
+            }
         }
-    }
-    const float sum_e = colgroup_sum(se, sm, cx, ry);       // d_beta   (layers.py:1262)
-    const float sum_ex = colgroup_sum(sex, sm, cx, ry);     // d_gamma  (layers.py:1261)
-    float a0 = 0.0f, a1 = 0.0f;
-    if (ok) {
-        if (ry == 0) {
+        sum_e = colgroup_sum(se, sm, cx, ry);       // d_beta   (layers.py:1262)
+        sum_ex = colgroup_sum(sex, sm, cx, ry);     // d_gamma  (layers.py:1261)
+        if (ok && ry == 0) {
             if (dgamma != nullptr) dgamma[col] = sum_ex;
             if (dbeta != nullptr) dbeta[col] = sum_e;
         }
+        if (MODE == 1) return;
+    } else {
+        sum_e = ok ? dbeta[col] : 0.0f;
+        sum_ex = ok ? dgamma[col] : 0.0f;
+    }
+    float a0 = 0.0f, a1 = 0.0f;
+    if (ok) {
         // layers.py:1264-1274 in closed form: dx = gamma*invstd*(e - xhat*sum(e*xhat)/B - sum(e)/B)
-        const float gi = gamma[col] * invstd, invB = 1.0f / (float)B;
+        const float gi = gamma[col] * invstd, invB = 1.0f / (float)B_total;
         float* dc = dx + col;
 #pragma unroll 4
         for (int r = ry; r < B; r += BN_ROWG) {
@@ -359,11 +494,14 @@ __global__ void __launch_bounds__(FB_THREADS) bn_pool_fwd_kernel(const float* __
     if (csize > 1) cluster_sync_all();   // peers may still be reading this CTA's `part`
 }
 
+// MODE 0: single GPU. MODE 1 (data parallel, first half): pass 1 only -- LOCAL partial sums to dbeta / dgamma and ss0.
+// MODE 2 (second half): dbeta / dgamma hold the rank-summed reductions; pass 2 only (ss1, ss2). B_total = global batch.
+template <int MODE>
 __global__ void __launch_bounds__(FB_THREADS, 2) pool_bn_act_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
     const float* __restrict__ save_invstd, float* __restrict__ r0, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, FbGeom g, int prev_act, float prev_alpha, double* ss0, double* ss1, double* ss2) {
+    float* __restrict__ dbeta, FbGeom g, int B_total, int prev_act, float prev_alpha, double* ss0, double* ss1, double* ss2) {
     extern __shared__ __align__(16) float tile[];   // [FB_ROWS][4][32] window values, then [FB_ROWS][32] pooled error
     __shared__ float4 red[FB_RGV * 8 * 8];
     __shared__ float4 part[2 * 8 * 8];
@@ -401,36 +539,49 @@ __global__ void __launch_bounds__(FB_THREADS, 2) pool_bn_act_bwd_kernel(
 #pragma unroll
     for (int q = 0; q < 8; ++q) sums[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float a0 = 0.0f;
-    for (int r = rg; r < nrows; r += FB_RGV) {
-        float4 e = e4[r * 8 + cq];
-        e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
-        float4 xv[4];
+    if (MODE != 2) {
+        for (int r = rg; r < nrows; r += FB_RGV) {
+            float4 e = e4[r * 8 + cq];
+            e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
+            float4 xv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xv[q] = f4_clip10(t4[(r * 4 + q) * 8 + cq]);
-        FB_FOR4(
-            float yq[4], xh[4];
-            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
-                const float d = f4_at(xv[q], k_) - f4_at(mean[q], k_);
-                yq[q] = fmaf(f4_at(gq[q], k_), d, f4_at(bq[q], k_));
-                xh[q] = d * f4_at(invstd[q], k_);
+            for (int q = 0; q < 4; ++q) xv[q] = f4_clip10(t4[(r * 4 + q) * 8 + cq]);
+            FB_FOR4(
+                float yq[4], xh[4];
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    const float d = f4_at(xv[q], k_) - f4_at(mean[q], k_);
+                    yq[q] = fmaf(f4_at(gq[q], k_), d, f4_at(bq[q], k_));
+                    xh[q] = d * f4_at(invstd[q], k_);
+                }
+                const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;
+                    f4_at(sums[q], k_) += u;
+                    f4_at(sums[4 + q], k_) = fmaf(u, xh[q], f4_at(sums[4 + q], k_));
+                    a0 = fmaf(u, u, a0);
+                })
+        }
+        cluster_colsum4<8>(sums, red, part, 0, cq, rg, csize);
+        if (crank == 0 && rg == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (dbeta != nullptr) *reinterpret_cast<float4*>(dbeta + pos[q]) = sums[q];          // layers.py:1262
+                if (dgamma != nullptr) *reinterpret_cast<float4*>(dgamma + pos[q]) = sums[4 + q];    // layers.py:1261
             }
-            const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
-            _Pragma("unroll") for (int q = 0; q < 4; ++q) {
-                const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;
-                f4_at(sums[q], k_) += u;
-                f4_at(sums[4 + q], k_) = fmaf(u, xh[q], f4_at(sums[4 + q], k_));
-                a0 = fmaf(u, u, a0);
-            })
-    }
-    cluster_colsum4<8>(sums, red, part, 0, cq, rg, csize);
-    if (crank == 0 && rg == 0) {
+        }
+        if (MODE == 1) {
+            if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+            if (csize > 1) cluster_sync_all();
+            return;
+        }
+    } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (dbeta != nullptr) *reinterpret_cast<float4*>(dbeta + pos[q]) = sums[q];          // layers.py:1262
-            if (dgamma != nullptr) *reinterpret_cast<float4*>(dgamma + pos[q]) = sums[4 + q];    // layers.py:1261
+            sums[q] = *reinterpret_cast<const float4*>(dbeta + pos[q]);
+            sums[4 + q] = *reinterpret_cast<const float4*>(dgamma + pos[q]);
         }
     }
-    const float invB = 1.0f / (float)g.B;
+    const float invB = 1.0f / (float)B_total;
 #pragma unroll
     for (int q = 0; q < 8; ++q) sums[q] = make_float4(sums[q].x * invB, sums[q].y * invB, sums[q].z * invB, sums[q].w * invB);
     float a1 = 0.0f, a2 = 0.0f;
@@ -463,10 +614,10 @@ __global__ void __launch_bounds__(FB_THREADS, 2) pool_bn_act_bwd_kernel(
 #pragma unroll
         for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(rb + pos[q]) = out[q];
     }
-    if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+    if (MODE == 0 && ss0 != nullptr) block_accumulate(a0, ss0, scratch);
     if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
     if (prev_act != B200NN_ACT_NONE && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
-    if (csize > 1) cluster_sync_all();
+    if (MODE == 0 && csize > 1) cluster_sync_all();
 }
 
 static int check_fused_block(const char* who, int B, int H, int W, int C) {
@@ -482,7 +633,7 @@ template <class Kern, class... Args>
 static int launch_fused_block(const char* name, Kern kern, size_t smem, int B, int H, int W, int C, cudaStream_t st,
                               Args... args) {
     const int cl = (B + FB_ROWS - 1) / FB_ROWS;
-    static thread_local const void* configured[4] = {nullptr, nullptr, nullptr, nullptr};
+    static thread_local const void* configured[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool seen = false;
     for (auto p : configured) seen = seen || p == (const void*)kern;
     if (!seen) {
@@ -541,9 +692,54 @@ int b200nn_bn_bwd(const float* x, const float* err, const double* ss, uint64_t c
     B200NN_REQUIRE(B > 0 && P > 0, "bn_bwd: bad shape B=%d P=%lld", B, P);
     B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "bn_bwd: unknown activation %d", prev_act);
     const long long blocks = (P + BN_COLS - 1) / BN_COLS;
-    bn_bwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, save_mean, save_invstd, dx, dgamma,
-                                                            dbeta, B, P, prev_act, prev_alpha, ss_out0, ss_out1);
+    bn_bwd_kernel<0><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, save_mean, save_invstd, dx, dgamma,
+                                                               dbeta, B, P, B, prev_act, prev_alpha, ss_out0, ss_out1);
     B200NN_LAUNCH_CHECK("bn_bwd");
+    return B200NN_OK;
+}
+
+// ---- data-parallel halves (see b200nn.h) ------------------------------------------------------------------------
+int b200nn_bn_stats_partial(const float* x, double* stats, int B, long long P, void* stream) {
+    B200NN_REQUIRE(B > 0 && P > 0 && stats != nullptr, "bn_stats_partial: bad argument B=%d P=%lld", B, P);
+    const long long blocks = (P + BN_COLS - 1) / BN_COLS;
+    B200NN_REQUIRE(blocks < (1LL << 31), "bn_stats_partial: too many positions");
+    bn_stats_partial_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, stats, B, P);
+    B200NN_LAUNCH_CHECK("bn_stats_partial");
+    return B200NN_OK;
+}
+
+int b200nn_bn_fwd_apply(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        float* save_mean, float* save_invstd, const double* stats, float* y, int B, long long P,
+                        long long B_total, float momentum, float eps, void* stream) {
+    B200NN_REQUIRE(B > 0 && P > 0 && B_total >= B && stats != nullptr, "bn_fwd_apply: bad argument");
+    const long long blocks = (P + BN_COLS - 1) / BN_COLS;
+    bn_fwd_apply_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, gamma, beta, running_mean, running_var, save_mean,
+                                                                  save_invstd, stats, y, B, P, (double)B_total, momentum, eps);
+    B200NN_LAUNCH_CHECK("bn_fwd_apply");
+    return B200NN_OK;
+}
+
+int b200nn_bn_bwd_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* save_mean,
+                          const float* save_invstd, float* dgamma, float* dbeta, int B, long long P, void* stream) {
+    B200NN_REQUIRE(B > 0 && P > 0 && dgamma != nullptr && dbeta != nullptr, "bn_bwd_partial: bad argument");
+    const long long blocks = (P + BN_COLS - 1) / BN_COLS;
+    bn_bwd_kernel<1><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, nullptr, save_mean, save_invstd, nullptr, dgamma,
+                                                               dbeta, B, P, B, 0, 0.f, nullptr, nullptr);
+    B200NN_LAUNCH_CHECK("bn_bwd_partial");
+    return B200NN_OK;
+}
+
+int b200nn_bn_bwd_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                        const float* save_mean, const float* save_invstd, float* dx, const float* dgamma, const float* dbeta,
+                        int B, long long P, long long B_total, int prev_act, float prev_alpha, double* ss_out0,
+                        double* ss_out1, void* stream) {
+    B200NN_REQUIRE(B > 0 && P > 0 && B_total >= B && dgamma != nullptr && dbeta != nullptr, "bn_bwd_apply: bad argument");
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "bn_bwd_apply: unknown activation %d", prev_act);
+    const long long blocks = (P + BN_COLS - 1) / BN_COLS;
+    bn_bwd_kernel<2><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, save_mean, save_invstd, dx,
+                                                               const_cast<float*>(dgamma), const_cast<float*>(dbeta), B, P,
+                                                               (int)B_total, prev_act, prev_alpha, ss_out0, ss_out1);
+    B200NN_LAUNCH_CHECK("bn_bwd_apply");
     return B200NN_OK;
 }
 
@@ -602,9 +798,56 @@ int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, u
     B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
                    "pool_bn_act_bwd: x and err must be 16-byte aligned");
     const FbGeom g{B, H, W, C};
-    return launch_fused_block("pool_bn_act_bwd", pool_bn_act_bwd_kernel, (size_t)FB_ROWS * 160 * sizeof(float), B, H, W, C,
+    return launch_fused_block("pool_bn_act_bwd", pool_bn_act_bwd_kernel<0>, (size_t)FB_ROWS * 160 * sizeof(float), B, H, W, C,
                               as_stream(stream), x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, dgamma, dbeta, g,
-                              prev_act, prev_alpha, ss_out0, ss_out1, ss_out2);
+                              B, prev_act, prev_alpha, ss_out0, ss_out1, ss_out2);
+}
+
+int b200nn_bn_pool_fwd_apply(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             float* save_mean, float* save_invstd, const double* stats, float* y_pool, int B, int H, int W,
+                             int C, long long B_total, float momentum, float eps, void* stream) {
+    B200NN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && B_total >= B && stats != nullptr,
+                   "bn_pool_fwd_apply: needs even H, W and C %% 4 == 0 (got %dx%dx%d)", H, W, C);
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_pool)) & 15) == 0,
+                   "bn_pool_fwd_apply: x and y must be 16-byte aligned");
+    const long long chunks = (B + FB_APPLY_ROWS - 1) / FB_APPLY_ROWS;
+    const long long total = chunks * (H / 2) * (W / 2) * (C / 4);
+    const long long blocks = (total + 255) / 256;
+    B200NN_REQUIRE(blocks < (1LL << 31), "bn_pool_fwd_apply: grid too large");
+    bn_pool_apply_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, gamma, beta, running_mean, running_var, save_mean,
+                                                                   save_invstd, stats, y_pool, B, H, W, C, (double)B_total,
+                                                                   momentum, eps, total);
+    B200NN_LAUNCH_CHECK("bn_pool_fwd_apply");
+    return B200NN_OK;
+}
+
+int b200nn_pool_bn_bwd_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd, float* dgamma,
+                               float* dbeta, int B, int H, int W, int C, double* ss_out0, void* stream) {
+    if (int rc = check_fused_block("pool_bn_bwd_partial", B, H, W, C)) return rc;
+    B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr, "pool_bn_bwd_partial: dgamma / dbeta are required");
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
+                   "pool_bn_bwd_partial: x and err must be 16-byte aligned");
+    const FbGeom g{B, H, W, C};
+    return launch_fused_block("pool_bn_bwd_partial", pool_bn_act_bwd_kernel<1>, (size_t)FB_ROWS * 160 * sizeof(float), B, H, W, C,
+                              as_stream(stream), x, err, ss, chain, gamma, beta, save_mean, save_invstd, (float*)nullptr, dgamma,
+                              dbeta, g, B, 0, 0.f, ss_out0, (double*)nullptr, (double*)nullptr);
+}
+
+int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                 const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                                 const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
+                                 int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream) {
+    if (int rc = check_fused_block("pool_bn_act_bwd_apply", B, H, W, C)) return rc;
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd_apply: unknown activation %d", prev_act);
+    B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && B_total >= B, "pool_bn_act_bwd_apply: bad argument");
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
+                   "pool_bn_act_bwd_apply: x and err must be 16-byte aligned");
+    const FbGeom g{B, H, W, C};
+    return launch_fused_block("pool_bn_act_bwd_apply", pool_bn_act_bwd_kernel<2>, (size_t)FB_ROWS * 160 * sizeof(float), B, H, W,
+                              C, as_stream(stream), x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0,
+                              const_cast<float*>(dgamma), const_cast<float*>(dbeta), g, (int)B_total, prev_act, prev_alpha,
+                              (double*)nullptr, ss_out1, ss_out2);
 }
 
 }  // extern "C"

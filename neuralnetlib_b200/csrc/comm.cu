@@ -1,0 +1,322 @@
+// comm.cu — data-parallel exchanges for one-process-per-GPU training on one NVLink/NVSwitch box.
+//
+// The reference has no distributed code; what must cross GPUs follows from its batch-global semantics: gradient SUMS
+// (models.py:200-205 never divides by the batch), the whole-tensor L2 norms behind every clip (models.py:214,
+// preprocessing.py:220-224), BatchNormalization's per-position batch statistics (layers.py:1237-1238) and the two batch
+// reductions of its backward (layers.py:1261-1270). All of them are sums, so one primitive serves: an in-place
+// sum-allreduce of a device buffer, in two implementations:
+//
+//   * NCCL (ncclAllReduce over NVLink 5 / NVSwitch) for the gradient buckets — bandwidth-bound payloads. libnccl is
+//     resolved at run time from the copy the process already loaded (PyTorch bundles it); nothing links against it.
+//   * a ONE-SHOT peer-memory exchange for the latency-bound payloads (1-5 fp64 clip norms, BatchNorm statistic
+//     vectors): every rank owns a "symmetric" buffer mapped into every peer with CUDA IPC; a rank STORES its
+//     contribution straight into each peer's inbox over NVLink, raises a per-(site, rank, CTA) flag with a
+//     system-scope release, spins on its own flags with system-scope acquires and then sums the inbox in RANK
+//     ORDER — so every rank computes bit-identical sums (the clip multipliers derived from them must agree exactly
+//     or the replicas drift apart). One kernel per exchange, no host involvement, capturable into the step graph;
+//     inboxes are double-buffered on the parity of a device-resident round counter so that a fast rank can never
+//     overwrite data a slow rank is still summing.
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only; every call goes through dlsym'd pointers
+#include <stddef.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200nn {
+
+constexpr int MAX_WORLD = 8;
+constexpr int MAX_SITES = 96;
+constexpr int MAX_XCTAS = 64;
+
+struct SymHeader {                                       // offset 0 of every rank's symmetric buffer
+    unsigned int flags[MAX_SITES][2][MAX_WORLD][MAX_XCTAS];
+    unsigned int seq[MAX_SITES];                          // completed rounds per site (local)
+    unsigned int done[MAX_SITES];                         // CTAs that finished the current round (local)
+    unsigned int timeouts;                                // waits that gave up (a peer never arrived): results are invalid
+};
+constexpr unsigned long long WAIT_TIMEOUT_NS = 10ull * 1000ull * 1000ull * 1000ull;   // a lost peer must not hang the GPU
+
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    void* handle = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl(const char* path) {
+    if (g_nccl.AllReduce != nullptr) return B200NN_OK;
+    const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* c : cands) {
+        if (c == nullptr || c[0] == 0) continue;
+        h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (h != nullptr) break;
+    }
+    if (h == nullptr) {
+        set_error("libnccl.so.2 could not be loaded: %s", dlerror());
+        return B200NN_ENOTSUP;
+    }
+    g_nccl.handle = h;
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    g_nccl.GetVersion = reinterpret_cast<decltype(g_nccl.GetVersion)>(dlsym(h, "ncclGetVersion"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("libnccl does not export the expected entry points");
+        g_nccl = NcclApi();
+        return B200NN_ENOTSUP;
+    }
+    return B200NN_OK;
+}
+
+#define B200NN_NCCL(expr)                                                                                  \
+    do {                                                                                                   \
+        ncclResult_t _r = (expr);                                                                          \
+        if (_r != ncclSuccess) {                                                                           \
+            ::b200nn::set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+            return B200NN_ECUDA;                                                                           \
+        }                                                                                                  \
+    } while (0)
+
+struct PeerPtrs {
+    char* p[MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_inbox(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_inbox(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// In-place sum of buf[0..n) over the ranks. Grid <= MAX_XCTAS CTAs (all resident: a CTA only ever waits for the
+// CTA with the same index on the other GPUs, which pushes before it waits).
+template <class T>
+__global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int rank, int world, int site, size_t data_off,
+                                                           size_t rank_stride, T* __restrict__ buf, long long n) {
+    SymHeader* me = reinterpret_cast<SymHeader*>(peers.p[rank]);
+    const unsigned seq = *reinterpret_cast<volatile unsigned*>(&me->seq[site]) + 1u;
+    const unsigned par = seq & 1u;
+    long long per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + 3) & ~3LL;
+    const long long lo = min(n, (long long)blockIdx.x * per), hi = min(n, lo + per);
+    // push this CTA's slice into every rank's inbox (own rank included: the reduction below then reads one layout)
+    for (int p = 0; p < world; ++p) {
+        T* dst = reinterpret_cast<T*>(peers.p[p] + data_off + ((size_t)par * world + rank) * rank_stride);
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = buf[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        SymHeader* peer = reinterpret_cast<SymHeader*>(peers.p[threadIdx.x]);
+        st_release_sys(&peer->flags[site][par][rank][blockIdx.x], seq);
+        const unsigned* mine = &me->flags[site][par][threadIdx.x][blockIdx.x];
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ld_acquire_sys(mine) != seq) {
+            if ((++spins & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WAIT_TIMEOUT_NS) {
+                    atomicAdd(&me->timeouts, 1u);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const T* src = reinterpret_cast<const T*>(peers.p[rank] + data_off + (size_t)par * world * rank_stride);
+    const size_t stride_elems = rank_stride / sizeof(T);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        T s = ld_inbox(src + i);
+        for (int p = 1; p < world; ++p) s += ld_inbox(src + (size_t)p * stride_elems + i);   // fixed rank order
+        buf[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&me->done[site], 1u) == gridDim.x - 1) {
+            me->done[site] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&me->seq[site]) = seq;
+        }
+    }
+}
+
+}  // namespace b200nn
+
+using namespace b200nn;
+
+struct b200nn_comm {
+    int rank, world, device;
+    ncclComm_t nccl;
+    char* sym_local;
+    size_t sym_bytes;
+    char* peer[MAX_WORLD];
+    bool peer_ready;
+    size_t bump;
+    int n_sites;
+    size_t site_off[MAX_SITES], site_stride[MAX_SITES];
+};
+
+extern "C" {
+
+int b200nn_comm_load_nccl(const char* path) { return load_nccl(path); }
+
+int b200nn_comm_nccl_version(void) {
+    int v = 0;
+    if (g_nccl.GetVersion != nullptr) g_nccl.GetVersion(&v);
+    return v;
+}
+
+int b200nn_comm_unique_id(void* out128) {
+    B200NN_REQUIRE(out128 != nullptr, "comm_unique_id: null buffer");
+    if (int rc = load_nccl(nullptr)) return rc;
+    ncclUniqueId id;
+    B200NN_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return B200NN_OK;
+}
+
+int b200nn_comm_create(const void* unique_id128, int rank, int world, b200nn_comm** out) {
+    B200NN_REQUIRE(out != nullptr && unique_id128 != nullptr, "comm_create: null argument");
+    B200NN_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "comm_create: bad rank %d / world %d (max %d)",
+                   rank, world, MAX_WORLD);
+    if (int rc = load_nccl(nullptr)) return rc;
+    b200nn_comm* c = new b200nn_comm();
+    memset(c, 0, sizeof(*c));
+    c->rank = rank;
+    c->world = world;
+    B200NN_CUDA(cudaGetDevice(&c->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    B200NN_NCCL(g_nccl.CommInitRank(&c->nccl, world, id, rank));
+    *out = c;
+    return B200NN_OK;
+}
+
+int b200nn_comm_destroy(b200nn_comm* c) {
+    if (c == nullptr) return B200NN_OK;
+    for (int p = 0; p < c->world; ++p)
+        if (c->peer_ready && p != c->rank && c->peer[p] != nullptr) cudaIpcCloseMemHandle(c->peer[p]);
+    if (c->sym_local != nullptr) cudaFree(c->sym_local);
+    if (c->nccl != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(c->nccl);
+    delete c;
+    return B200NN_OK;
+}
+
+size_t b200nn_comm_ipc_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+int b200nn_comm_peer_alloc(b200nn_comm* c, size_t bytes, void* handle_out) {
+    B200NN_REQUIRE(c != nullptr && handle_out != nullptr, "comm_peer_alloc: null argument");
+    B200NN_REQUIRE(c->sym_local == nullptr, "comm_peer_alloc: already allocated");
+    B200NN_REQUIRE(bytes >= sizeof(SymHeader) + (1u << 20), "comm_peer_alloc: need at least %zu bytes", sizeof(SymHeader) + (1u << 20));
+    void* p = nullptr;
+    B200NN_CUDA(cudaMalloc(&p, bytes));
+    B200NN_CUDA(cudaMemset(p, 0, bytes));
+    B200NN_CUDA(cudaDeviceSynchronize());
+    c->sym_local = static_cast<char*>(p);
+    c->sym_bytes = bytes;
+    c->bump = (sizeof(SymHeader) + 255) & ~size_t(255);
+    cudaIpcMemHandle_t h;
+    B200NN_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle_out, &h, sizeof(h));
+    return B200NN_OK;
+}
+
+int b200nn_comm_peer_open(b200nn_comm* c, const void* all_handles) {
+    B200NN_REQUIRE(c != nullptr && all_handles != nullptr && c->sym_local != nullptr, "comm_peer_open: allocate first");
+    const char* hs = static_cast<const char*>(all_handles);
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) {
+            c->peer[p] = c->sym_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)p * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        B200NN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer[p] = static_cast<char*>(ptr);
+    }
+    c->peer_ready = true;
+    return B200NN_OK;
+}
+
+int b200nn_comm_has_peer(const b200nn_comm* c) { return (c != nullptr && c->peer_ready) ? 1 : 0; }
+
+// number of peer waits that timed out so far (synchronises the device); non-zero means an exchange produced garbage
+int b200nn_comm_timeouts(const b200nn_comm* c) {
+    if (c == nullptr || c->sym_local == nullptr) return 0;
+    unsigned v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, c->sym_local + offsetof(SymHeader, timeouts), sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)v;
+}
+
+int b200nn_comm_site_create(b200nn_comm* c, size_t payload_bytes, int* site_out) {
+    B200NN_REQUIRE(c != nullptr && site_out != nullptr, "comm_site_create: null argument");
+    B200NN_REQUIRE(c->peer_ready, "comm_site_create: peer memory is not mapped");
+    B200NN_REQUIRE(c->n_sites < MAX_SITES, "comm_site_create: more than %d exchange sites", MAX_SITES);
+    const size_t stride = (payload_bytes + 255) & ~size_t(255);
+    const size_t need = 2 * (size_t)c->world * stride;
+    B200NN_REQUIRE(c->bump + need <= c->sym_bytes, "comm_site_create: symmetric buffer exhausted (%zu + %zu > %zu bytes)", c->bump, need,
+                   c->sym_bytes);
+    const int s = c->n_sites++;
+    c->site_off[s] = c->bump;
+    c->site_stride[s] = stride;
+    c->bump += need;
+    *site_out = s;
+    return B200NN_OK;
+}
+
+// dtype: 0 = float32, 1 = float64. site >= 0 selects the one-shot peer-memory exchange (the payload must fit the
+// site); site < 0 uses NCCL.
+int b200nn_comm_allreduce_sum(b200nn_comm* c, int site, void* buf, long long n, int dtype, void* stream) {
+    B200NN_REQUIRE(c != nullptr && buf != nullptr && n > 0, "comm_allreduce_sum: bad argument");
+    B200NN_REQUIRE(dtype == 0 || dtype == 1, "comm_allreduce_sum: dtype %d", dtype);
+    if (c->world == 1) return B200NN_OK;
+    const size_t esz = dtype == 0 ? 4 : 8;
+    if (site < 0) {
+        B200NN_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, dtype == 0 ? ncclFloat32 : ncclFloat64, ncclSum, c->nccl, as_stream(stream)));
+        count_launch();
+        return B200NN_OK;
+    }
+    B200NN_REQUIRE(c->peer_ready && site < c->n_sites, "comm_allreduce_sum: unknown site %d", site);
+    B200NN_REQUIRE((size_t)n * esz <= c->site_stride[site], "comm_allreduce_sum: payload %lld x %zu exceeds site %d (%zu bytes)", n, esz,
+                   site, c->site_stride[site]);
+    PeerPtrs pp;
+    for (int p = 0; p < MAX_WORLD; ++p) pp.p[p] = p < c->world ? c->peer[p] : nullptr;
+    long long ctas = (n + 1023) / 1024;
+    if (ctas > MAX_XCTAS) ctas = MAX_XCTAS;
+    if (ctas < 1) ctas = 1;
+    const int threads = n <= 32 ? 32 : 256;
+    if (dtype == 0)
+        exchange_sum_kernel<float><<<(int)ctas, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site],
+                                                                                c->site_stride[site], static_cast<float*>(buf), n);
+    else
+        exchange_sum_kernel<double><<<(int)ctas, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site],
+                                                                                 c->site_stride[site], static_cast<double*>(buf), n);
+    B200NN_LAUNCH_CHECK("exchange_sum");
+    return B200NN_OK;
+}
+
+}  // extern "C"

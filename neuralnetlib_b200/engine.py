@@ -67,9 +67,14 @@ class Plan:
         self.batch_shape = tuple(int(s) for s in batch_shape)
         self.B = self.batch_shape[0]
         self.training = bool(training)
-        self.ss = B.zeros((MAX_SLOTS,), dtype=torch.float64)
-        self.acc = B.zeros((4,), dtype=torch.float64)
+        # accumulators (loss numerator, correct count) directly in front of the clip slots: under data parallelism the
+        # loss kernel's outputs {acc, slot 0} then travel in ONE exchange
+        self._ssacc = B.zeros((4 + MAX_SLOTS,), dtype=torch.float64)
+        self.acc = self._ssacc[0:4]
+        self.ss = self._ssacc[4:]
         self.n_slots = 0
+        self.dp = getattr(model, "_dp", None)
+        self.world = self.dp.world if self.dp is not None else 1
         self._ws = None
         self._ws_bytes = 0
         self._emit_to = None
@@ -97,6 +102,24 @@ class Plan:
 
     def need_ws(self, nbytes):
         self._ws_bytes = max(self._ws_bytes, int(nbytes))
+
+    def buf64(self, shape):
+        return B.empty(tuple(int(s) for s in shape), dtype=torch.float64)
+
+    # ---- data parallelism (parallel.py, csrc/comm.cu) ------------------------------------------------------------------
+    def allreduce(self, t, name="allreduce"):
+        """Emit an in-place sum of `t` over the ranks (no-op on one GPU). Small payloads get a one-shot exchange site."""
+        if self.dp is None:
+            return
+        comm = self.dp.comm
+        site = comm.site(t.numel() * t.element_size())
+        self.emit(lambda: comm.allreduce(t, site), name, ())
+
+    def _sync_slots(self, first):
+        """Sum the clip slots [first, n_slots) produced by the op(s) just emitted over the ranks: the reference's clips
+        act on whole-batch tensors (models.py:214), so their norms are global."""
+        if self.dp is not None and self.n_slots > first:
+            self.allreduce(self.ss[first:self.n_slots], "slot_exchange")
 
     @property
     def ws(self):
@@ -175,11 +198,16 @@ class Plan:
         i = n - 1
         if isinstance(layers[i], Activation):
             if gan:   # models.py:211-212: the real derivative of the last activation, no clip before it
+                first = self.n_slots
                 cur = layers[i]._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
+                self._sync_slots(first)
             # not gan: p - y (recognised pairs) or the raw loss derivative with the activation's derivative
             # skipped (models.py:198-210, Q7) -- both already sit in `err`
             i -= 1
+        first = self.n_slots
         while i >= 0 and cur is not None:
+            self._sync_slots(first)   # slots of the previous op (no-op on one GPU)
+            first = self.n_slots
             L = layers[i]
             if L._is_view:
                 cur = _Err(cur.t.reshape(self.state[i]["in_shape"]), cur.chain)
@@ -219,7 +247,17 @@ class Plan:
                 i = j - 1
             else:
                 i -= 1
+        self._sync_slots(first)
         return updates, cur
+
+    def _grad_exchange(self, updates):
+        """Sum the gradients of the layers about to be updated over the ranks (NCCL, bucketed; parallel.py)."""
+        if self.dp is None or not updates:
+            return
+        dp = self.dp
+        for lo, hi, _ in dp.buckets:
+            t = dp.flat[lo:hi]
+            self.emit(lambda t=t: dp.comm.allreduce(t, -1), "grad_allreduce", (t,))
 
     def _loss_kind(self):
         lf = self.model.loss_function
@@ -259,7 +297,15 @@ class Plan:
             s0 = self.slot()
             pred, y_in, acc, ss = self.pred, self.y_in, self.acc, self.ss
             self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
+            if self.dp is not None:
+                self.dp.flatten_grads(self.layers)
+                if s0 == 0:
+                    self.allreduce(self._ssacc[0:5], "loss_exchange")      # loss numerator, correct count, ||err||^2
+                else:
+                    self.allreduce(self.acc, "loss_exchange")
+                    self.allreduce(self.ss[s0:s0 + 1], "slot_exchange")
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
+            self._grad_exchange(updates)
             ups = []
             for li in updates:
                 L = self.layers[li]
@@ -285,7 +331,10 @@ class Plan:
             prog.ops.append(None)
             prog.meta.append(("step_begin", 0))
             self.err_in = self.buf(self.pred.shape)
+            if self.dp is not None:
+                self.dp.flatten_grads(self.layers)
             last_is_act = isinstance(self.layers[-1], Activation)
+            first = self.n_slots
             if last_is_act and not gan:
                 # models.py:198-210: for the recognised pairs the incoming error is REPLACED by predictions - y_true
                 lk, fused = self._loss_kind() if model.loss_function is not None else (None, False)
@@ -304,7 +353,9 @@ class Plan:
                 err_in = self.err_in
                 self.emit(lambda: ops.sumsq(err_in, ss, s0), "sumsq", (err_in,))
                 start = _Err(self.err_in, (s0,))
+            self._sync_slots(first)
             updates, in_err = self._build_backward(start, gan, compute_only, True)
+            self._grad_exchange(updates)
             # materialise the returned input error: clip folded in (the reference clips before Input too)
             self.in_err_out = self.buf(in_err.t.shape)
             iet, chain, out = in_err.t, in_err.chain, self.in_err_out

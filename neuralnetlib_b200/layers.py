@@ -52,6 +52,8 @@ class _Err:
 class _EagerCtx:
     """Allocation context of the layer-by-layer (non-plan) API: fresh buffers per call, no clip slots."""
     ss = None
+    dp = None
+    world = 1
 
     def buf(self, shape):
         return B.empty(tuple(int(s) for s in shape))
@@ -759,6 +761,23 @@ class BatchNormalization(Layer, _ParamMixin):
         P = self._gamma.numel()
         gm, bt, rm, rv = self._gamma, self._beta, self._running_mean, self._running_var
         mom, eps = float(self.momentum), float(self.epsilon)
+        if training and ctx.dp is not None:
+            # data parallel (parallel.py): local moments -> sum over ranks -> apply, so that mean / var are those of the
+            # GLOBAL batch (layers.py:1237-1238)
+            b_total = x.shape[0] * ctx.world
+            stats = ctx.buf64((2 * P,))
+            sm, si = ctx.buf((P,)), ctx.buf((P,))
+            st.update(x=x, save_mean=sm, save_invstd=si, trained=True, fused_pool=pool is not None)
+            ctx.emit(lambda: ops.bn_stats_partial(x, stats), "bn_stats_partial", (x,))
+            ctx.allreduce(stats, "bn_stats_exchange")
+            if pool is not None:
+                yp = ctx.buf((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
+                ctx.emit(lambda: ops.bn_pool_fwd_apply(x, gm, bt, rm, rv, sm, si, stats, yp, b_total, mom, eps),
+                         "bn_pool_fwd_apply", (x, yp))
+                return yp
+            y = ctx.buf(x.shape)
+            ctx.emit(lambda: ops.bn_fwd_apply(x, gm, bt, rm, rv, sm, si, stats, y, b_total, mom, eps), "bn_fwd_apply", (x, y))
+            return y
         if pool is not None:
             yp = ctx.buf((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
             sm, si = ctx.buf((P,)), ctx.buf((P,))
@@ -784,9 +803,27 @@ class BatchNormalization(Layer, _ParamMixin):
         kind, alpha = _act_of(mask_layer)
         s0 = ctx.slot()
         s1 = ctx.slot() if mask_layer is not None else None
-        gm, sm, si, dg, dbt, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], self._d_gamma, self._d_beta, ctx.ss, err.chain, err.t
+        gm, sm, si, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
+        if ctx.dp is not None:
+            sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
+            ctx.emit(lambda: ops.bn_bwd_partial(x, et, ss, chain, sm, si, sums), "bn_bwd_partial", (x, et))
+            ctx.allreduce(sums, "bn_sums_exchange")
+            ctx.emit(lambda: ops.bn_bwd_apply(x, et, ss, chain, gm, sm, si, dx, sums, b_total, kind, alpha, s0, s1), "bn_bwd_apply",
+                     (x, et, dx))
+            return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+        dg, dbt = self._d_gamma, self._d_beta
         ctx.emit(lambda: ops.bn_bwd(x, et, ss, chain, gm, sm, si, dx, dg, dbt, kind, alpha, s0, s1), "bn_bwd", (x, et, dx))
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    def _dp_sums(self, ctx):
+        """[d_beta | d_gamma] as ONE float32 buffer (a single exchange sums both over the ranks); d_beta / d_gamma become
+        views of it."""
+        P = self._gamma.numel()
+        sums = getattr(self, "_dp_sums_buf", None)
+        if sums is None or sums.numel() != 2 * P:
+            sums = self._dp_sums_buf = B.zeros((2 * P,))
+            self._d_beta, self._d_gamma = sums[:P], sums[P:]
+        return sums
 
     def _plan_backward_fused_pool(self, ctx, st, err, mask_layer):
         """err is the error w.r.t. the POOLED output; emits MaxPool-bwd + BatchNorm-bwd (+ Activation-bwd) as one
@@ -797,8 +834,15 @@ class BatchNormalization(Layer, _ParamMixin):
         kind, alpha = _act_of(mask_layer)
         s0, s1 = ctx.slot(), ctx.slot()
         s2 = ctx.slot() if mask_layer is not None else None
-        gm, bt, sm, si, dg, dbt, ss, chain, et = (self._gamma, self._beta, st["save_mean"], st["save_invstd"], self._d_gamma,
-                                                  self._d_beta, ctx.ss, err.chain, err.t)
+        gm, bt, sm, si, ss, chain, et = self._gamma, self._beta, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
+        if ctx.dp is not None:
+            sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
+            ctx.emit(lambda: ops.pool_bn_bwd_partial(x, et, ss, chain, gm, bt, sm, si, sums, s0), "pool_bn_bwd_partial", (x, et))
+            ctx.allreduce(sums, "bn_sums_exchange")
+            ctx.emit(lambda: ops.pool_bn_act_bwd_apply(x, et, ss, chain, gm, bt, sm, si, r0, sums, b_total, kind, alpha, s1, s2),
+                     "pool_bn_act_bwd_apply", (x, et, r0))
+            return _Err(r0, tuple(s for s in (s0, s1, s2) if s is not None))
+        dg, dbt = self._d_gamma, self._d_beta
         ctx.emit(lambda: ops.pool_bn_act_bwd(x, et, ss, chain, gm, bt, sm, si, r0, dg, dbt, kind, alpha, s0, s1, s2),
                  "pool_bn_act_bwd", (x, et, r0))
         return _Err(r0, tuple(s for s in (s0, s1, s2) if s is not None))

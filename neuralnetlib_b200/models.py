@@ -49,6 +49,7 @@ class Sequential(BaseModel):
         self._plans = {}
         self._last_plan = None
         self._pred_host = None
+        self._dp = None   # parallel.DataParallel once make_data_parallel() has been called
 
     # ------------------------------------------------------------------------------------------------------------
     def __str__(self) -> str:
@@ -177,9 +178,11 @@ class Sequential(BaseModel):
         return plan.in_err_out if dev_in else B.to_host(plan.in_err_out)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _loss_denominator(self, plan):
+    def _loss_denominator(self, plan, after_train: bool = False):
         rows = plan.pred.shape[0]
         cols = plan.pred.numel() // rows
+        if after_train:
+            rows *= plan.world   # data parallel: a train step leaves the RANK SUM of the numerators in plan.acc
         return rows if isinstance(self.loss_function, CategoricalCrossentropy) else rows * cols
 
     def _train_step(self, x_batch, y_batch) -> Plan:
@@ -200,7 +203,7 @@ class Sequential(BaseModel):
             raise ValueError("The model must be compiled before training")
         self.y_true = y_batch
         plan = self._train_step(x_batch, y_batch)
-        return float(plan.acc[0].item()) / self._loss_denominator(plan)
+        return float(plan.acc[0].item()) / self._loss_denominator(plan, True)
 
     # ------------------------------------------------------------------------------------------------------------
     def fit(self, x_train, y_train, epochs: int, batch_size: int | None = None, verbose: bool = True,
@@ -249,6 +252,9 @@ class Sequential(BaseModel):
 
         N = x_train.shape[0]
         bs = int(batch_size) if batch_size is not None else N
+        dp = self._dp
+        if dp is not None:
+            from .parallel import shard_rows   # every rank holds the full dataset and trains on its rows of each batch
         y2 = y_train.reshape(N, -1) if y_train.ndim > 1 else y_train.reshape(N, 1)
         resident = (x_train.size + y2.size) * 4 <= _RESIDENT_DATASET_BYTES
         if resident:
@@ -269,27 +275,34 @@ class Sequential(BaseModel):
                 pred_all = None
                 running = 0.0
                 denoms = []
+                seen = []   # rows (of the permuted dataset) whose predictions this rank holds
                 for bi, j in enumerate(range(0, N, bs)):
                     rows = min(bs, N - j)
                     batch_logs = {"batch": bi, "size": rows, "model": self}
                     for cb in callbacks:
                         cb.on_batch_begin(bi, batch_logs)
+                    j0 = j
+                    if dp is not None:
+                        lo, hi = shard_rows(rows, dp.world, dp.rank)
+                        j0, rows = j + lo, hi - lo
                     plan = self._plan((rows,) + x_train.shape[1:], True)
                     prog = plan.program("train")
                     if resident:
-                        ops.gather_rows(x_dev, perm_dev[j:j + rows], plan.x_in)
-                        ops.gather_rows(y_dev, perm_dev[j:j + rows], plan.y_in)
+                        ops.gather_rows(x_dev, perm_dev[j0:j0 + rows], plan.x_in)
+                        ops.gather_rows(y_dev, perm_dev[j0:j0 + rows], plan.y_in)
                     else:
-                        plan.set_input(x_train[perm[j:j + rows]])
-                        plan.set_target(y2[perm[j:j + rows]].reshape(tuple(plan.y_in.shape)))
+                        plan.set_input(x_train[perm[j0:j0 + rows]])
+                        plan.set_target(y2[perm[j0:j0 + rows]].reshape(tuple(plan.y_in.shape)))
                     prog.run()
                     self._last_plan, self._last_rows, self._pred_host = plan, rows, None
+                    j = j0   # predictions / metrics below are those of this rank's rows
                     loss_hist[bi:bi + 1].copy_(plan.acc[0:1], non_blocking=True)
-                    denoms.append(self._loss_denominator(plan))
+                    denoms.append(self._loss_denominator(plan, True))
                     if keep_pred:
                         if pred_all is None:
                             pred_all = B.empty((N, plan.pred.numel() // rows))
                         pred_all[j:j + rows].copy_(plan.pred.reshape(rows, -1), non_blocking=True)
+                        seen.append((j, j + rows))
                     if sync_each_batch:
                         batch_loss = float(plan.acc[0].item()) / denoms[-1]
                         running += batch_loss
@@ -308,9 +321,12 @@ class Sequential(BaseModel):
                 history["loss"].append(error)
                 epoch_logs.update({"loss": error, "time": time.time() - start})
                 if mobjs is not None:
-                    preds = B.to_host(pred_all)
+                    preds, y_seen = B.to_host(pred_all), y_shuf
+                    if dp is not None:   # metrics over this rank's rows only (the loss above is global)
+                        sel = np.concatenate([np.arange(a, b) for a, b in seen])
+                        preds, y_seen = preds[sel], y_shuf[sel]
                     for mo in mobjs:
-                        v = mo(preds, y_shuf)
+                        v = mo(preds, y_seen)
                         history[mo.name].append(v)
                         epoch_logs[mo.name] = v
                 if validation_data is not None:
@@ -459,8 +475,8 @@ class GAN(BaseModel):
         rng = np.random.default_rng(self.random_state)
         return rng.normal(0, 1, (n_samples, self.latent_dim)), None
 
-    def _loss_value(self, net: Sequential, plan) -> float:
-        return float(plan.acc[0].item()) / net._loss_denominator(plan)
+    def _loss_value(self, net: Sequential, plan, after_train: bool = False) -> float:
+        return float(plan.acc[0].item()) / net._loss_denominator(plan, after_train)
 
     def train_on_batch(self, real_samples, labels=None, batch_size: int = 32, n_critic: int = 1) -> tuple[float, float]:
         """models.py:2609-2667."""
@@ -484,7 +500,7 @@ class GAN(BaseModel):
             D.y_true = comb_labels
             d_prog.run()
             D._last_plan, D._last_rows, D._pred_host = d_plan, 2 * batch_size, None
-            d_loss_total += self._loss_value(D, d_plan)
+            d_loss_total += self._loss_value(D, d_plan, True)
         d_loss_avg = d_loss_total / n_critic
 
         z, _ = self._generate_latent_points(batch_size)

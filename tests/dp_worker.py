@@ -1,0 +1,137 @@
+"""Worker of tests/test_gpu_dp.py — run as  python -m torch.distributed.run --nproc-per-node N tests/dp_worker.py
+One process per GPU. Each rank trains on ITS ROWS of a global batch through the public API with `make_data_parallel`,
+and the result is compared with the single-process fp64 oracle on the GLOBAL batch (the reference's semantics):
+loss, gradients (already rank-summed), post-Adam weights, BatchNorm running statistics. Exercised: Dense-only (config 1),
+Conv+BN+MaxPool fused block (config 2), an un-pooled BatchNorm (generic split kernels), both exchange transports
+(B200NN_PEER=1 one-shot peer memory, B200NN_PEER=0 NCCL only), CUDA-graph replay (3 steps) and `fit` sharding."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import nnl_oracle as O
+
+
+def nrel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a.reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def build(kind):
+    from neuralnetlib_b200 import layers as L, models as M, optimizers as Opt
+    m = M.Sequential(random_state=42)
+    if kind == "cfg1":
+        m.add(L.Input(784)); m.add(L.Dense(128, activation="relu")); m.add(L.Dense(64, activation="relu"))
+        m.add(L.Dense(10, activation="softmax"))
+        specs, shp = O.config_specs(1)
+    elif kind == "cfg2":
+        m.add(L.Input((28, 28, 1))); m.add(L.Conv2D(32, 3, padding="same", activation="relu")); m.add(L.BatchNormalization())
+        m.add(L.MaxPooling2D(2)); m.add(L.Flatten()); m.add(L.Dense(64, activation="relu")); m.add(L.Dense(10, activation="softmax"))
+        specs, shp = O.config_specs(2)
+    else:   # Dense -> BatchNorm (2-D, generic kernels) -> Dense
+        m.add(L.Input(40)); m.add(L.Dense(48, activation="relu")); m.add(L.BatchNormalization()); m.add(L.Dense(10, activation="softmax"))
+        specs = [{"type": "input"}, {"type": "dense", "units": 48}, {"type": "act", "fn": "relu"}, {"type": "bn"},
+                 {"type": "dense", "units": 10}, {"type": "act", "fn": "softmax"}]
+        shp = (40,)
+    m.compile(loss_function="categorical_crossentropy", optimizer=Opt.Adam())
+    return m, specs, shp
+
+
+def run_case(kind, batch, steps, rank, world, comm):
+    from neuralnetlib_b200 import parallel as P
+    m, specs, shp = build(kind)
+    P.make_data_parallel(m, comm)
+    rng = np.random.default_rng(0)
+    x = rng.random((batch,) + tuple(shp)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+    lo, hi = P.shard_rows(batch, world, rank)
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    mine = [(i, l) for i, l in enumerate(m.layers) if hasattr(l, "weights")]
+    worst = 0.0
+    for s in range(steps):
+        loss, rloss = m.train_on_batch(x[lo:hi], y[lo:hi]), ref.train_on_batch(x, y)
+        assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss)), (kind, s, loss, rloss)
+        theirs = [r for r in ref.layers if "w" in r]
+        for (li, layer), rl in zip(mine, theirs):
+            for got, want, nm in ((layer.d_weights, rl["dw"], "dw"), (layer.d_bias.reshape(-1), rl["db"].reshape(-1), "db")):
+                d = np.abs(np.asarray(got, np.float64).reshape(want.shape) - want)
+                scale = np.abs(want).max()
+                frac = float(np.mean(d <= 3e-5 * scale))
+                assert frac >= 0.9 and d.max() <= 1e-2 * scale, (kind, s, li, nm, frac, d.max() / scale)
+                worst = max(worst, float(np.median(d) / scale))
+            d = np.abs(layer.weights - rl["w"])
+            assert np.mean(d <= 1e-5 * np.abs(rl["w"]).max() + 1e-9) >= 0.999 and d.max() <= 2e-3, (kind, s, li)
+        for layer, rl in zip(m.layers, ref.layers):
+            if rl["type"] == "bn":
+                assert nrel(layer.running_mean, rl["running_mean"]) < 2e-5 and nrel(layer.running_var, rl["running_var"]) < 2e-5
+                assert nrel(layer.d_gamma, rl["dgamma"]) < 1e-3 and nrel(layer.d_beta, rl["dbeta"]) < 1e-3, (kind, s)
+        assert m.optimizer.t == ref.optimizer.t
+        # teacher forcing (see tests/test_gpu_models.py): the next step starts from the device's state
+        mw, vw, mb, vb = m.optimizer.m_w, m.optimizer.v_w, m.optimizer.m_b, m.optimizer.v_b
+        for (li, layer), rl in zip(mine, theirs):
+            rl["w"], rl["b"] = layer.weights, layer.bias
+            ref.optimizer.m_w[li], ref.optimizer.v_w[li] = mw[li], vw[li]
+            ref.optimizer.m_b[li], ref.optimizer.v_b[li] = mb[li], vb[li]
+        for layer, rl in zip(m.layers, ref.layers):
+            if rl["type"] == "bn":
+                rl["running_mean"], rl["running_var"] = layer.running_mean, layer.running_var
+    # replicas must be bit-identical: same weights on every rank
+    w = torch.from_numpy(np.concatenate([l.weights.ravel() for _, l in mine])).to(torch.float64)
+    ws = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert all(torch.equal(ws[0], t) for t in ws), f"{kind}: replicas diverged"
+    assert m._last_plan.program("train").graph is not None or steps < 2
+    return worst
+
+
+def run_fit(rank, world, comm):
+    from neuralnetlib_b200 import parallel as P
+    m, specs, shp = build("cfg1")
+    P.make_data_parallel(m, comm)
+    rng = np.random.default_rng(1)
+    x = rng.random((256, 784)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, 256)]
+    h = m.fit(x, y, epochs=2, batch_size=64, verbose=False, random_state=3)
+    t = torch.tensor(h["loss"], dtype=torch.float64)
+    ts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(ts, t)
+    assert all(torch.equal(ts[0], tt) for tt in ts), "fit: loss history differs between ranks"
+    assert h["loss"][1] < h["loss"][0]
+    # single-process oracle fit on the global batches: same permutation, same batches
+    from neuralnetlib_b200.utils import shuffle_indices
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=3)
+    perm = shuffle_indices(256, 3)
+    losses = [ref.train_on_batch(x[perm[j:j + 64]], y[perm[j:j + 64]]) for j in range(0, 256, 64)]
+    assert abs(h["loss"][0] - float(np.mean(losses))) <= 2e-4 * abs(np.mean(losses)), (h["loss"][0], np.mean(losses))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")     # bootstrap only: the data path is libb200nn's own NCCL communicator / peer memory
+    from neuralnetlib_b200 import parallel as P
+    comm = P.Communicator()
+    want_peer = os.environ.get("B200NN_PEER", "1") != "0"
+    if want_peer:
+        assert comm.peer, "CUDA IPC peer mapping failed"
+    out = {}
+    for kind, batch, steps in (("cfg1", 32 * world, 3), ("cfg2", 32 * world, 3), ("bn2d", 16 * world, 3)):
+        out[kind] = run_case(kind, batch, steps, rank, world, comm)
+    run_fit(rank, world, comm)
+    assert comm.timeouts() == 0, "a peer exchange timed out"
+    dist.barrier()
+    if rank == 0:
+        print(f"DP_OK world={world} peer={comm.peer} nccl={comm.nccl_version} median-errs={out}")
+    comm.destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
