@@ -248,10 +248,11 @@ def run_b200(args):
     step_bytes = sum(b for _, b in prog.meta)
     breakdown = sorted(((names[i], round(per_op[i] * 1e3, 2), prog.meta[i][1]) for i in range(len(per_op))), key=lambda t: -t[1])
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        sys.stdout.flush()
+        os._exit(0)   # the captured step graphs still hold the NCCL communicator: let process exit reclaim it
 
     total_batch = BATCH_PER_GPU * world
     line = {
@@ -262,7 +263,10 @@ def run_b200(args):
                    "l2": "flushed between steps (256 MiB device write outside the timed events)",
                    "math": ("tf32: Dense GEMMs on tcgen05 kind::tf32 (rel 2e-3), conv/BN/pool/Adam fp32" if args.math == "tf32"
                             else "fp32 FFMA everywhere (parity path, rel 1e-5)"),
-                   "step": "one captured CUDA graph per step"},
+                   "step": "one captured CUDA graph per step",
+                   **({"data_parallel": "exact global-batch semantics: NCCL gradient sum + "
+                       + ("one-shot NVLink peer-memory exchanges" if model._dp.comm.peer else "NCCL")
+                       + " for clip norms / BatchNorm moments, all inside the step graph"} if world > 1 else {})},
         "e2e": {"value": total_batch / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(x.nbytes + y.nbytes), "d2h_bytes_per_step": 8, "last_loss": loss},
         "gpu_launches": int(launches_eager_step * K),
@@ -282,8 +286,9 @@ def run_b200(args):
                                 "sample": f"{budget_steps} train_on_batch steps of the same workload at batch {BATCH_PER_GPU} "
                                           f"after 1 warm-up ({dt:.1f} s of CPU work; numpy fp64 oracle port of the reference path)"}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
     return 0
 
 

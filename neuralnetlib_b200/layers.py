@@ -723,8 +723,21 @@ class BatchNormalization(Layer, _ParamMixin):
     _supports_mask = True
     gamma = _param_property("gamma")
     beta = _param_property("beta")
-    d_gamma = _param_property("d_gamma")
-    d_beta = _param_property("d_beta")
+
+    def _dgrad_get(self, name):
+        """d_gamma / d_beta as the reference leaves them. The fused pool+BN backward kernel accumulates them BEFORE the clip
+        the reference applies between MaxPooling2D.backward_pass and BatchNormalization.backward_pass (models.py:214; the
+        kernel carries that clip lazily as a slot), so the pending multiplier is applied when the attribute is read."""
+        v = self._param_get(name)
+        pend = getattr(self, "_dgrad_pending", None)
+        if v is not None and pend is not None:
+            n2 = float(pend[0][pend[1]].item())
+            if n2 > 1.0:
+                v = v / np.sqrt(n2)
+        return v
+
+    d_gamma = property(lambda self: self._dgrad_get("d_gamma"), lambda self, v: self._param_set("d_gamma", v))
+    d_beta = property(lambda self: self._dgrad_get("d_beta"), lambda self, v: self._param_set("d_beta", v))
     running_mean = _param_property("running_mean")
     running_var = _param_property("running_var")
 
@@ -804,6 +817,7 @@ class BatchNormalization(Layer, _ParamMixin):
         s0 = ctx.slot()
         s1 = ctx.slot() if mask_layer is not None else None
         gm, sm, si, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
+        self._dgrad_pending = None
         if ctx.dp is not None:
             sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.bn_bwd_partial(x, et, ss, chain, sm, si, sums), "bn_bwd_partial", (x, et))
@@ -835,6 +849,7 @@ class BatchNormalization(Layer, _ParamMixin):
         s0, s1 = ctx.slot(), ctx.slot()
         s2 = ctx.slot() if mask_layer is not None else None
         gm, bt, sm, si, ss, chain, et = self._gamma, self._beta, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
+        self._dgrad_pending = (ctx.ss, s0) if ctx.ss is not None else None
         if ctx.dp is not None:
             sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.pool_bn_bwd_partial(x, et, ss, chain, gm, bt, sm, si, sums, s0), "pool_bn_bwd_partial", (x, et))

@@ -56,6 +56,7 @@ def run_case(kind, batch, steps, rank, world, comm):
     mine = [(i, l) for i, l in enumerate(m.layers) if hasattr(l, "weights")]
     worst = 0.0
     for s in range(steps):
+        print(f"[rank {rank}] {kind} step {s}", flush=True)
         loss, rloss = m.train_on_batch(x[lo:hi], y[lo:hi]), ref.train_on_batch(x, y)
         assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss)), (kind, s, loss, rloss)
         theirs = [r for r in ref.layers if "w" in r]
@@ -67,11 +68,13 @@ def run_case(kind, batch, steps, rank, world, comm):
                 assert frac >= 0.9 and d.max() <= 1e-2 * scale, (kind, s, li, nm, frac, d.max() / scale)
                 worst = max(worst, float(np.median(d) / scale))
             d = np.abs(layer.weights - rl["w"])
-            assert np.mean(d <= 1e-5 * np.abs(rl["w"]).max() + 1e-9) >= 0.999 and d.max() <= 2e-3, (kind, s, li)
+            need = 0.9 if type(layer).__name__ == "Conv2D" else 0.999   # below a max-pool: see tests/test_gpu_models.py
+            assert np.mean(d <= 1e-5 * np.abs(rl["w"]).max() + 1e-9) >= need and d.max() <= 2e-3, (kind, s, li)
         for layer, rl in zip(m.layers, ref.layers):
             if rl["type"] == "bn":
                 assert nrel(layer.running_mean, rl["running_mean"]) < 2e-5 and nrel(layer.running_var, rl["running_var"]) < 2e-5
-                assert nrel(layer.d_gamma, rl["dgamma"]) < 1e-3 and nrel(layer.d_beta, rl["dbeta"]) < 1e-3, (kind, s)
+                eg, eb = nrel(layer.d_gamma, rl["dgamma"]), nrel(layer.d_beta, rl["dbeta"])
+                assert eg < 1e-3 and eb < 1e-3, (kind, s, eg, eb)
         assert m.optimizer.t == ref.optimizer.t
         # teacher forcing (see tests/test_gpu_models.py): the next step starts from the device's state
         mw, vw, mb, vb = m.optimizer.m_w, m.optimizer.v_w, m.optimizer.m_b, m.optimizer.v_b
@@ -124,13 +127,17 @@ def main():
     out = {}
     for kind, batch, steps in (("cfg1", 32 * world, 3), ("cfg2", 32 * world, 3), ("bn2d", 16 * world, 3)):
         out[kind] = run_case(kind, batch, steps, rank, world, comm)
+        print(f"[rank {rank}] {kind} ok, timeouts so far {comm.timeouts()}", flush=True)
     run_fit(rank, world, comm)
+    print(f"[rank {rank}] fit ok", flush=True)
     assert comm.timeouts() == 0, "a peer exchange timed out"
     dist.barrier()
     if rank == 0:
         print(f"DP_OK world={world} peer={comm.peer} nccl={comm.nccl_version} median-errs={out}")
-    comm.destroy()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    # no ncclCommDestroy here: the captured step graphs still reference the communicator, and NCCL's destroy waits for them;
+    # process exit reclaims everything
+    os._exit(0)
 
 
 if __name__ == "__main__":
