@@ -28,6 +28,9 @@ import sys
 import threading
 import time
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner to STDOUT; rank 0 must print exactly one JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:

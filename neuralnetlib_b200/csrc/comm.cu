@@ -108,21 +108,45 @@ __device__ __forceinline__ double ld_inbox(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ uint4 ld_inbox16(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+template <class T>
+__device__ __forceinline__ void add16(uint4& acc, const uint4& v) {
+    constexpr int N = 16 / sizeof(T);
+    T* a = reinterpret_cast<T*>(&acc);
+    const T* b = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] += b[i];
+}
+
 // In-place sum of buf[0..n) over the ranks. Grid <= MAX_XCTAS CTAs (all resident: a CTA only ever waits for the
-// CTA with the same index on the other GPUs, which pushes before it waits).
+// CTA with the same index on the other GPUs, which pushes before it waits). The payload moves as 16-byte vectors
+// (one NVLink store per peer per vector); `buf` must be 16-byte aligned, a tail shorter than 16 bytes goes scalar in CTA 0.
 template <class T>
 __global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int rank, int world, int site, size_t data_off,
-                                                           size_t rank_stride, T* __restrict__ buf, long long n) {
+                                                           size_t rank_stride, T* __restrict__ buf, long long n, int vec_ok) {
+    constexpr int EPV = 16 / sizeof(T);
     SymHeader* me = reinterpret_cast<SymHeader*>(peers.p[rank]);
     const unsigned seq = *reinterpret_cast<volatile unsigned*>(&me->seq[site]) + 1u;
     const unsigned par = seq & 1u;
-    long long per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + 3) & ~3LL;
-    const long long lo = min(n, (long long)blockIdx.x * per), hi = min(n, lo + per);
+    const long long nvec = vec_ok ? n / EPV : 0;   // an unaligned (small) buffer goes scalar through CTA 0
+    const long long per = (nvec + gridDim.x - 1) / gridDim.x;
+    const long long lo = min(nvec, (long long)blockIdx.x * per), hi = min(nvec, lo + per);
+    const size_t my_off = data_off + ((size_t)par * world + rank) * rank_stride;
     // push this CTA's slice into every rank's inbox (own rank included: the reduction below then reads one layout)
-    for (int p = 0; p < world; ++p) {
-        T* dst = reinterpret_cast<T*>(peers.p[p] + data_off + ((size_t)par * world + rank) * rank_stride);
-        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = buf[i];
+    const uint4* src4 = reinterpret_cast<const uint4*>(buf);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint4 v = src4[i];
+        for (int p = 0; p < world; ++p) reinterpret_cast<uint4*>(peers.p[p] + my_off)[i] = v;
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * EPV + threadIdx.x; i < n; i += blockDim.x) {
+            const T v = buf[i];
+            for (int p = 0; p < world; ++p) reinterpret_cast<T*>(peers.p[p] + my_off)[i] = v;
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -145,12 +169,19 @@ __global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int r
         }
     }
     __syncthreads();
-    const T* src = reinterpret_cast<const T*>(peers.p[rank] + data_off + (size_t)par * world * rank_stride);
-    const size_t stride_elems = rank_stride / sizeof(T);
+    const char* inbox = peers.p[rank] + data_off + (size_t)par * world * rank_stride;
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        T s = ld_inbox(src + i);
-        for (int p = 1; p < world; ++p) s += ld_inbox(src + (size_t)p * stride_elems + i);   // fixed rank order
-        buf[i] = s;
+        uint4 acc = ld_inbox16(reinterpret_cast<const uint4*>(inbox) + i);
+        for (int p = 1; p < world; ++p)                                                   // fixed rank order
+            add16<T>(acc, ld_inbox16(reinterpret_cast<const uint4*>(inbox + (size_t)p * rank_stride) + i));
+        reinterpret_cast<uint4*>(buf)[i] = acc;
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * EPV + threadIdx.x; i < n; i += blockDim.x) {
+            T s2 = ld_inbox(reinterpret_cast<const T*>(inbox) + i);
+            for (int p = 1; p < world; ++p) s2 += ld_inbox(reinterpret_cast<const T*>(inbox + (size_t)p * rank_stride) + i);
+            buf[i] = s2;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -305,16 +336,19 @@ int b200nn_comm_allreduce_sum(b200nn_comm* c, int site, void* buf, long long n, 
                    site, c->site_stride[site]);
     PeerPtrs pp;
     for (int p = 0; p < MAX_WORLD; ++p) pp.p[p] = p < c->world ? c->peer[p] : nullptr;
-    long long ctas = (n + 1023) / 1024;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(buf) & 15) == 0 ? 1 : 0;
+    B200NN_REQUIRE(vec_ok || n <= 4096, "comm_allreduce_sum: large payloads must be 16-byte aligned");
+    const long long nvec = vec_ok ? (long long)((size_t)n * esz / 16) : 0;
+    long long ctas = (nvec + 255) / 256;      // one 16-byte vector per thread when it fits
     if (ctas > MAX_XCTAS) ctas = MAX_XCTAS;
     if (ctas < 1) ctas = 1;
-    const int threads = n <= 32 ? 32 : 256;
+    const int threads = nvec <= 32 ? 32 : 256;
     if (dtype == 0)
         exchange_sum_kernel<float><<<(int)ctas, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site],
-                                                                                c->site_stride[site], static_cast<float*>(buf), n);
+                                                                                c->site_stride[site], static_cast<float*>(buf), n, vec_ok);
     else
         exchange_sum_kernel<double><<<(int)ctas, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site],
-                                                                                 c->site_stride[site], static_cast<double*>(buf), n);
+                                                                                 c->site_stride[site], static_cast<double*>(buf), n, vec_ok);
     B200NN_LAUNCH_CHECK("exchange_sum");
     return B200NN_OK;
 }

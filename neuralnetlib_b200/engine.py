@@ -196,6 +196,7 @@ class Plan:
         updates = []
         cur = err
         i = n - 1
+        self._grad_begin()
         if isinstance(layers[i], Activation):
             if gan:   # models.py:211-212: the real derivative of the last activation, no clip before it
                 first = self.n_slots
@@ -242,6 +243,7 @@ class Plan:
             cur = L._plan_backward(self, self.state[i], _Err(et, cur.chain), mask, need_dx)
             if self._has_weights(L) and not compute_only:
                 updates.append(i)
+                self._grad_bucket_ready(L)
             if mask is not None and cur is not None:
                 cur = _Err(cur.t.reshape(self.outs[j].shape), cur.chain)
                 i = j - 1
@@ -250,14 +252,46 @@ class Plan:
         self._sync_slots(first)
         return updates, cur
 
+    # Gradient buckets (parallel.py): a bucket is summed over the ranks as soon as the backward of the layer that completes
+    # it has been emitted -- large buckets with NCCL on a SIDE stream (forked / joined with events, so the captured graph
+    # overlaps the exchange with the rest of backward), small ones with the one-shot exchange on the main stream.
+    def _grad_begin(self):
+        self._buckets_done = 0
+        self._side_used = False
+
+    def _grad_bucket_ready(self, layer, final=False):
+        dp = self.dp
+        if dp is None or dp.buckets is None:
+            return
+        while self._buckets_done < len(dp.buckets) and (final or dp.bucket_layers[self._buckets_done] is layer):
+            lo, hi, _ = dp.buckets[self._buckets_done]
+            self._buckets_done += 1
+            t = dp.flat[lo:hi]
+            site = dp.comm.site(t.numel() * 4) if t.numel() * 4 <= (64 << 10) else -1
+            if site >= 0 or final:
+                self.emit(lambda t=t, site=site: dp.comm.allreduce(t, site), "grad_allreduce", (t,))
+                continue
+            evt, side, main = torch.cuda.Event(), dp.side, B.stream_obj()
+
+            def fork(t=t, evt=evt):
+                evt.record(main)
+                side.wait_event(evt)
+                dp.comm.allreduce(t, -1, side.cuda_stream)
+            self.emit(fork, "grad_allreduce_async", (t,))
+            self._side_used = True
+
     def _grad_exchange(self, updates):
-        """Sum the gradients of the layers about to be updated over the ranks (NCCL, bucketed; parallel.py)."""
+        """Before the optimizer: flush the buckets not yet issued and join the side stream."""
         if self.dp is None or not updates:
             return
-        dp = self.dp
-        for lo, hi, _ in dp.buckets:
-            t = dp.flat[lo:hi]
-            self.emit(lambda t=t: dp.comm.allreduce(t, -1), "grad_allreduce", (t,))
+        self._grad_bucket_ready(None, final=True)
+        if self._side_used:
+            evt, side, main = torch.cuda.Event(), self.dp.side, B.stream_obj()
+
+            def join():
+                evt.record(side)
+                main.wait_event(evt)
+            self.emit(join, "grad_allreduce_join", ())
 
     def _loss_kind(self):
         lf = self.model.loss_function

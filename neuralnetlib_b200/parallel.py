@@ -142,14 +142,15 @@ class Communicator:
         B.check(B.lib().b200nn_comm_site_create(self.handle, int(nbytes), C.byref(s)))
         return s.value
 
-    def allreduce(self, t: torch.Tensor, site: int = -1):
-        """In-place sum of a contiguous float32 / float64 device tensor over the ranks, asynchronous on the package stream."""
+    def allreduce(self, t: torch.Tensor, site: int = -1, stream: int | None = None):
+        """In-place sum of a contiguous float32 / float64 device tensor over the ranks, asynchronous on `stream` (a raw
+        cudaStream_t; default: the package stream)."""
         if self.world == 1:
             return
         if not t.is_contiguous() or t.dtype not in (torch.float32, torch.float64):
             raise TypeError("allreduce needs a contiguous float32 / float64 device tensor")
         B.check(B.lib().b200nn_comm_allreduce_sum(self.handle, int(site), t.data_ptr(), t.numel(),
-                                                  0 if t.dtype == torch.float32 else 1, B.stream()))
+                                                  0 if t.dtype == torch.float32 else 1, B.stream() if stream is None else stream))
 
     def timeouts(self) -> int:
         return int(B.lib().b200nn_comm_timeouts(self.handle))
@@ -170,7 +171,10 @@ class DataParallel:
         self.flat = None
         self.buckets = None
         self._flat_key = None
-        self.bucket_elems = int(os.environ.get("B200NN_BUCKET_BYTES", str(32 << 20))) // 4
+        # a bucket is closed once it holds this many bytes: it is then reduced on a side stream while backward continues
+        self.bucket_elems = int(os.environ.get("B200NN_BUCKET_BYTES", str(256 << 10))) // 4
+        self.bucket_layers = None   # per bucket: the layer whose backward completes it
+        self.side = torch.cuda.Stream(device=B.device())
 
     def flatten_grads(self, layers):
         """Re-point d_weights / d_bias of every parametrised layer (update order: last layer first) at views of one flat
@@ -192,6 +196,7 @@ class DataParallel:
             view = self.flat[o:o + n]
             setattr(L, name, view.view(old.shape) if old is not None and old.numel() == n else view)
         self.buckets = make_buckets(offs, sizes, total, self.bucket_elems)
+        self.bucket_layers = [params[k][0] for _, _, k in self.buckets]
         self._flat_key = key
 
 
