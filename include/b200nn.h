@@ -205,6 +205,27 @@ int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, u
                            float* dgamma, float* dbeta, int B, int H, int W, int C, int prev_act, float prev_alpha,
                            double* ss_out0, double* ss_out1, double* ss_out2, void* stream);
 
+/* ---- fused FIRST BLOCK: Conv2D(3x3, stride 1, 'same', C <= 3, F % 8 == 0) + Activation -> BatchNormalization(train) ->
+ *      MaxPooling2D(2x2/2), the conv output never touching HBM (recomputed from the input image wherever it is needed;
+ *      csrc/conv_block.cu). Replaces layers.py:442-489, :231-237, :1230-1276, :570-643 and the weight-gradient half of
+ *      :491-530 for this pattern. `mode`: 0 single GPU; 1 / 2 the two halves around the data-parallel sum of
+ *      `stats` (forward, fp64 [2][H*W*F]) resp. dgamma / dbeta (backward); B_total = global batch. */
+int b200nn_convblock_supported(const b200nn_conv_geom* g, int act, float alpha);
+size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g);
+int b200nn_convblock_fwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float* save_mean,
+                         float* save_invstd, double* stats, int mode, long long B_total, float* y_pool, float momentum,
+                         float eps, void* stream);
+/* err: error w.r.t. the pooled output, pending clips (ss, chain). Emits d_gamma / d_beta, the three sums of squares of the
+ * reference's clip points (pool-bwd, BN-bwd, activation-bwd outputs) and dw / db scaled by chain_out (= those three
+ * slots, complete once the main kernel has run). r_out (nullable): the error w.r.t. the conv output, materialised only
+ * when a data gradient is wanted (it still owes chain_out). ws: b200nn_convblock_ws_bytes. */
+int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
+                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                         const float* err, const double* ss, uint64_t chain, float* dgamma, float* dbeta, float* dw, float* db,
+                         float* r_out, int mode, long long B_total, double* ss_out0, double* ss_out1, double* ss_out2,
+                         uint64_t chain_out, float* ws, void* stream);
+
 /* ---- optimizers (optimizers.py:47-50, 167-245) and gradient clip (models.py:240-242) -------- */
 typedef struct {
     float* p;          /* parameter tensor (updated in place, optimizers.py:223) */

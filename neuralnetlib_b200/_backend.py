@@ -80,6 +80,12 @@ _SIGNATURES = {
     "b200nn_bn_pool_fwd_train": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "b200nn_pool_bn_act_bwd": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         c_float, _P, _P, _P, _P]),
+    "b200nn_convblock_supported": (c_int, [C.POINTER(ConvGeom), c_int, c_float]),
+    "b200nn_convblock_ws_bytes": (c_size_t, [C.POINTER(ConvGeom)]),
+    "b200nn_convblock_fwd": (c_int, [C.POINTER(ConvGeom), _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, _P,
+                                      c_float, c_float, _P]),
+    "b200nn_convblock_bwd": (c_int, [C.POINTER(ConvGeom), _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, c_u64, _P, _P, _P, _P,
+                                      _P, c_int, c_ll, _P, _P, _P, c_u64, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
     # data parallelism (csrc/comm.cu) and the split BatchNorm kernels

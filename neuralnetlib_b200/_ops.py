@@ -165,6 +165,33 @@ def convt_bwd(math, g, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, s
                                  stream()))
 
 
+# ---- fused first block (csrc/conv_block.cu) ------------------------------------------------------------
+def convblock_supported(g: ConvGeom, act, alpha):
+    return bool(lib().b200nn_convblock_supported(C.byref(g), int(act), float(alpha)))
+
+
+def convblock_ws_bytes(g: ConvGeom):
+    return int(lib().b200nn_convblock_ws_bytes(C.byref(g)))
+
+
+def convblock_fwd(g, x, w, b, act, alpha, gamma, beta, rmean, rvar, save_mean, save_invstd, stats, mode, b_total, y_pool,
+                  momentum, eps):
+    _f32(x, w, b, gamma, beta, rmean, rvar, save_mean, save_invstd, y_pool)
+    check(lib().b200nn_convblock_fwd(C.byref(g), ptr(x), ptr(w), ptr(b), act, alpha, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar),
+                                     ptr(save_mean), ptr(save_invstd), ptr(stats), int(mode), int(b_total), ptr(y_pool),
+                                     momentum, eps, stream()))
+
+
+def convblock_bwd(g, x, w, b, act, alpha, gamma, beta, save_mean, save_invstd, err, ss, chain, sums_or_dg, dbeta, dw, db, r_out,
+                  mode, b_total, slot0, slot1, slot2, chain_out, ws):
+    """sums_or_dg / dbeta: device pointers (ints) of d_gamma and d_beta."""
+    _f32(x, w, b, gamma, beta, save_mean, save_invstd, err, dw, db, r_out)
+    check(lib().b200nn_convblock_bwd(C.byref(g), ptr(x), ptr(w), ptr(b), act, alpha, ptr(gamma), ptr(beta), ptr(save_mean),
+                                     ptr(save_invstd), ptr(err), ptr(ss), pack_chain(chain), sums_or_dg, dbeta, ptr(dw), ptr(db),
+                                     ptr(r_out), int(mode), int(b_total), _slot_ptr(ss, slot0), _slot_ptr(ss, slot1),
+                                     _slot_ptr(ss, slot2), pack_chain(chain_out), ptr(ws), stream()))
+
+
 # ---- BatchNorm / MaxPool -----------------------------------------------------------------------------
 def bn_fwd_train(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y, momentum, eps):
     _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y)

@@ -10,7 +10,6 @@ namespace b200nn {
 constexpr int BN_COLS = 32;
 constexpr int BN_ROWG = 8;  // 256 threads
 
-__device__ __forceinline__ float clip10(float v) { return fminf(fmaxf(v, -10.0f), 10.0f); }
 
 // reduce `v` across the 8 row-groups of a column; result broadcast to every row-group
 __device__ __forceinline__ float colgroup_sum(float v, float (*sm)[BN_COLS], int cx, int ry) {
@@ -104,17 +103,6 @@ __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float* __re
         stats[col] = S;
         stats[P + col] = (double)m2 + S * S / (double)B;
     }
-}
-
-// mean / batch_var / invstd of one position from the rank-summed moments (layers.py:1237-1238, :1252)
-__device__ __forceinline__ void bn_finalize(double S1, double S2, double n_total, float eps, float& mean, float& batch_var,
-                                            float& invstd) {
-    const double m = S1 / n_total;
-    double var = S2 / n_total - m * m;
-    if (var < 0.0) var = 0.0;
-    mean = (float)m;
-    batch_var = (float)var + eps;
-    invstd = rsqrtf(batch_var + eps);
 }
 
 __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,

@@ -81,6 +81,20 @@ __device__ __forceinline__ float act_grad_from_y(int act, float y, float alpha) 
     }
 }
 
+// ---- BatchNormalization helpers (layers.py:1230-1256) ------------------------------------------------
+__device__ __forceinline__ float clip10(float v) { return fminf(fmaxf(v, -10.0f), 10.0f); }   // layers.py:1234
+
+// mean / batch_var / invstd of one position from the rank-summed moments (layers.py:1237-1238, :1252)
+__device__ __forceinline__ void bn_finalize(double S1, double S2, double n_total, float eps, float& mean, float& batch_var,
+                                            float& invstd) {
+    const double m = S1 / n_total;
+    double var = S2 / n_total - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    batch_var = (float)var + eps;
+    invstd = rsqrtf(batch_var + eps);
+}
+
 // ---- reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

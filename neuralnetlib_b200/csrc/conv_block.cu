@@ -1,0 +1,512 @@
+// conv_block.cu — the first block of a CNN as TWO kernels:  Conv2D(3x3, stride 1, 'same', C in {1..3}) + Activation ->
+// BatchNormalization(train, per-position statistics) -> MaxPooling2D(2x2 / 2)     (BASELINE configs 2 and 3, block 1)
+//
+// With K = 9*C <= 27 taps the convolution is ~5 FLOP per output byte: the block is bound by the HBM traffic of the conv
+// OUTPUT S (B*H*W*F floats: written by the conv, read by BatchNorm, read again by the backward, and the error w.r.t. it
+// written and read once more -> 5 passes over the largest tensor of the model). These kernels never materialise S or its
+// error: the conv is RECOMPUTED from the input image wherever it is needed (36*C FMAs per sample and filter, from a 4x4xC
+// input patch held in shared memory), so the block's HBM traffic drops from ~5*S to x + the pooled tensors:
+//
+//   forward : x -> [conv + act + clip +-10 -> batch mean (pass 1) -> exact two-pass variance (pass 2) -> normalise, 2x2 max
+//             (pass 3)] -> pooled output, running statistics, save_mean / save_invstd
+//   backward: x, pooled error -> [recompute -> pool-bwd (all tied maxima, layers.py:631-637) -> the two BatchNorm batch
+//             reductions (pass 1) -> BN-bwd, act', conv weight / bias gradient (pass 2)] -> per-window dW partials,
+//             d_gamma / d_beta, the three clip slots the reference applies between those layers (models.py:214)
+//
+// Work decomposition: CTA = (pool window, 8 filters); warp = one filter; lane = batch sample (mod 32). Statistics over the batch
+// are warp-shuffle reductions, no shared-memory or cross-CTA reduction exists, all conv outputs of the window stay in registers (batch <= 256 per GPU;
+// larger batches use the unfused kernels), and the 784 CTAs of config 2 balance over 148 SMs. Replaces layers.py:442-489 (+
+// preprocessing.py:34-79), :231-237, :1230-1276, :570-643 and the weight-gradient half of :491-530 for this pattern.
+#include "common.cuh"
+
+namespace b200nn {
+
+constexpr int CB_FPC = 8;        // filters (= warps) per CTA
+constexpr int CB_THREADS = CB_FPC * 32;
+constexpr int CB_MAXB = 256;     // batch rows per CTA: sample s = lane + 32 j, j < CB_NS, all conv outputs stay in registers
+constexpr int CB_NS = CB_MAXB / 32;
+
+template <int C>
+struct CbCfg {
+    static constexpr int K = 9 * C;                 // taps, reference order (c, ky, kx)  (preprocessing.py:77, Q1)
+    static constexpr int EPS = 16 * C;              // patch elements per sample
+    static constexpr int STRIDE = 16 * C + 4;       // floats per staged patch (+4: conflict-free 128-bit rows across lanes)
+};
+
+struct CbArgs {
+    int B, H, W, F;                 // conv input H x W (even), F filters; conv output = H x W x F, pooled = H/2 x W/2 x F
+    const float* x;                 // [B, H, W, C]
+    const float* w;                 // [3, 3, C, F] buffer read as (C, 3, 3, F)
+    const float* bias;              // [F]
+    int act;
+    float alpha;
+    const float* gamma;             // [H, W, F]
+    const float* beta;
+    float* save_mean;
+    float* save_invstd;
+    double n_total;                 // global batch (data parallel) or B
+};
+
+// ACT > 0: compile-time activation kind; ACT < 0: run-time `act`
+template <int ACT>
+__device__ __forceinline__ float cb_act(float v, int act, float alpha) {
+    if (ACT == B200NN_ACT_RELU) return fmaxf(v, 0.0f);
+    return act_apply(act, v, alpha);
+}
+template <int ACT>
+__device__ __forceinline__ float cb_act_grad(float y, int act, float alpha) {
+    if (ACT == B200NN_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+    return act_grad_from_y(act, y, alpha);
+}
+
+// stage the 4x4xC input patches of all B samples around window (oy, ox): patch[s][c*16 + py*4 + px]
+template <int C>
+__device__ __forceinline__ void cb_stage(float* patch, const CbArgs& a, int oy, int ox) {
+    constexpr int EPS = CbCfg<C>::EPS, ROW = 4 * C;
+    const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
+    int e = threadIdx.x % EPS, s = threadIdx.x / EPS;        // element within the sample (memory order: py, px, c), sample
+    const long long img = (long long)a.H * a.W * C;
+    while (s < a.B) {
+        const int py = e / ROW, r = e % ROW, px = r / C, c = r % C;
+        const int iy = iy0 + py, ix = ix0 + px;
+        float v = 0.0f;                                      // zero padding of 'same' (layers.py:450-465)
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = a.x[(long long)s * img + ((long long)iy * a.W + ix) * C + c];
+        patch[s * CbCfg<C>::STRIDE + c * 16 + py * 4 + px] = v;
+        e += CB_THREADS % EPS;
+        s += CB_THREADS / EPS;
+        if (e >= EPS) { e -= EPS; ++s; }
+    }
+}
+
+// conv + activation of one sample at the window's 4 positions (q = 2*qy + qx) for one filter
+template <int C, int ACT>
+__device__ __forceinline__ void cb_conv(const float* __restrict__ p, const float (&wr)[9 * C], float bias, int act, float alpha,
+                                        float (&S)[4]) {
+    S[0] = S[1] = S[2] = S[3] = bias;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float rows[4][4];
+#pragma unroll
+        for (int py = 0; py < 4; ++py) {
+            const float4 r = *reinterpret_cast<const float4*>(p + c * 16 + py * 4);
+            rows[py][0] = r.x; rows[py][1] = r.y; rows[py][2] = r.z; rows[py][3] = r.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float wv = wr[(c * 3 + ky) * 3 + kx];
+                S[0] = fmaf(rows[ky][kx], wv, S[0]);
+                S[1] = fmaf(rows[ky][kx + 1], wv, S[1]);
+                S[2] = fmaf(rows[ky + 1][kx], wv, S[2]);
+                S[3] = fmaf(rows[ky + 1][kx + 1], wv, S[3]);
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) S[q] = cb_act<ACT>(S[q], act, alpha);     // layers.py:231-234 (auto-appended Activation)
+}
+
+template <int C>
+__device__ __forceinline__ void cb_load_filter(const CbArgs& a, int f, float (&wr)[9 * C], float& bias) {
+#pragma unroll
+    for (int k = 0; k < 9 * C; ++k) wr[k] = a.w[(long long)k * a.F + f];
+    bias = a.bias != nullptr ? a.bias[f] : 0.0f;
+}
+
+// MODE 0: single GPU. MODE 1 (data parallel): local moments only -> stats (fp64 [2][P]: sum, sum of squares).
+// MODE 2: normalise + pool from rank-summed `stats`.
+template <int C, int MODE, int ACT>
+__global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, float* __restrict__ rmean, float* __restrict__ rvar,
+                                                                   double* __restrict__ stats, float* __restrict__ y_pool,
+                                                                   float momentum, float eps) {
+    using Cfg = CbCfg<C>;
+    extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | outs[CB_FPC][CB_MAXB]
+    float* patch = cb_smem;
+    float (*outs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(cb_smem + CB_MAXB * Cfg::STRIDE);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ox = blockIdx.x, oy = blockIdx.y, f0 = blockIdx.z * CB_FPC, f = f0 + wid;
+    const int OW = a.W >> 1, OH = a.H >> 1;
+    const long long P = (long long)a.H * a.W * a.F;
+    float wr[9 * C], bias;
+    cb_load_filter<C>(a, f, wr, bias);
+    long long pos[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pos[q] = ((long long)(2 * oy + (q >> 1)) * a.W + 2 * ox + (q & 1)) * a.F + f;
+    cb_stage<C>(patch, a, oy, ox);
+    __syncthreads();
+    float S[CB_NS][4];                                                        // clip(act(conv)) of this lane's samples (layers.py:1234)
+#pragma unroll
+    for (int j = 0; j < CB_NS; ++j) {
+        const int s = lane + 32 * j;
+        if (s < a.B) {
+            cb_conv<C, ACT>(patch + s * Cfg::STRIDE, wr, bias, a.act, a.alpha, S[j]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) S[j][q] = clip10(S[j][q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) S[j][q] = 0.0f;
+        }
+    }
+    float mean[4], invstd[4], bvar[4];
+    if (MODE != 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                         // batch mean (layers.py:1237)
+            float t = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CB_NS; ++j) t += S[j][q];
+            mean[q] = warp_sum(t) / (float)a.B;
+        }
+        float m2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                         // exact two-pass variance
+            float t = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CB_NS; ++j) {
+                const float d = S[j][q] - mean[q];
+                t = (lane + 32 * j < a.B) ? fmaf(d, d, t) : t;
+            }
+            m2[q] = warp_sum(t);
+        }
+        if (MODE == 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double S1 = (double)mean[q] * (double)a.B;
+                    stats[pos[q]] = S1;
+                    stats[P + pos[q]] = (double)m2[q] + S1 * S1 / (double)a.B;
+                }
+            }
+            return;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bvar[q] = m2[q] / (float)a.B + eps;                               // layers.py:1238
+            invstd[q] = rsqrtf(bvar[q] + eps);                                // layers.py:1252
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bn_finalize(stats[pos[q]], stats[P + pos[q]], a.n_total, eps, mean[q], bvar[q], invstd[q]);
+    }
+    float g[4], bt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        g[q] = a.gamma[pos[q]] * invstd[q];
+        bt[q] = a.beta[pos[q]];
+        if (lane == 0) {
+            rmean[pos[q]] = momentum * rmean[pos[q]] + (1.0f - momentum) * mean[q];      // layers.py:1240-1243
+            rvar[pos[q]] = momentum * rvar[pos[q]] + (1.0f - momentum) * bvar[q];
+            a.save_mean[pos[q]] = mean[q];
+            a.save_invstd[pos[q]] = invstd[q];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CB_NS; ++j) {                                         // normalise, 2x2 max (layers.py:1256, :599-600)
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m = fmaxf(m, fmaf(g[q], S[j][q] - mean[q], bt[q]));
+        outs[wid][lane + 32 * j] = m;
+    }
+    __syncthreads();
+    const long long OP = (long long)OH * OW * a.F, obase = ((long long)oy * OW + ox) * a.F + f0;
+    for (int s = threadIdx.x; s < a.B; s += CB_THREADS) {                     // one 32-byte run (8 filters) per sample
+        const float4 v0 = make_float4(outs[0][s], outs[1][s], outs[2][s], outs[3][s]);
+        const float4 v1 = make_float4(outs[4][s], outs[5][s], outs[6][s], outs[7][s]);
+        float4* dst = reinterpret_cast<float4*>(y_pool + (long long)s * OP + obase);
+        dst[0] = v0;
+        dst[1] = v1;
+    }
+}
+
+// Backward. MODE 0: single GPU. MODE 1: pass 1 only (local sum(u), sum(u*xhat) -> dbeta / dgamma, ss0). MODE 2: pass 2 from
+// rank-summed dbeta / dgamma (ss1, ss2, dW partials).  partial: [windows][9C + 1][F] (row 9C = bias gradient).
+template <int C, int MODE, int ACT>
+__global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kernel(CbArgs a, const float* __restrict__ err,
+                                                                      const double* __restrict__ ss, uint64_t chain,
+                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                      float* __restrict__ partial, float* __restrict__ r_out,
+                                                                      double* ss0, double* ss1, double* ss2) {
+    using Cfg = CbCfg<C>;
+    extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | errs[CB_FPC][CB_MAXB]
+    float* patch = cb_smem;
+    float (*errs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(cb_smem + CB_MAXB * Cfg::STRIDE);
+    __shared__ double scratch[32];
+    const float scale = chain_scale(ss, chain);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ox = blockIdx.x, oy = blockIdx.y, f0 = blockIdx.z * CB_FPC, f = f0 + wid;
+    const int OW = a.W >> 1, OH = a.H >> 1;
+    float wr[9 * C], bias;
+    cb_load_filter<C>(a, f, wr, bias);
+    long long pos[4];
+    float mean[4], invstd[4], g[4], bt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        pos[q] = ((long long)(2 * oy + (q >> 1)) * a.W + 2 * ox + (q & 1)) * a.F + f;
+        mean[q] = a.save_mean[pos[q]];
+        invstd[q] = a.save_invstd[pos[q]];
+        g[q] = a.gamma[pos[q]] * invstd[q];
+        bt[q] = a.beta[pos[q]];
+    }
+    const long long OP = (long long)OH * OW * a.F, obase = ((long long)oy * OW + ox) * a.F + f0;
+    cb_stage<C>(patch, a, oy, ox);
+    for (int s = threadIdx.x; s < a.B; s += CB_THREADS) {                     // pooled error: one 32-byte run per sample
+        const float4* src = reinterpret_cast<const float4*>(err + (long long)s * OP + obase);
+        const float4 v0 = src[0], v1 = src[1];
+        errs[0][s] = v0.x; errs[1][s] = v0.y; errs[2][s] = v0.z; errs[3][s] = v0.w;
+        errs[4][s] = v1.x; errs[5][s] = v1.y; errs[6][s] = v1.z; errs[7][s] = v1.w;
+    }
+    __syncthreads();
+    float S[CB_NS][4];                                                        // act(conv), before the +-10 clip
+#pragma unroll
+    for (int j = 0; j < CB_NS; ++j) {
+        const int s = lane + 32 * j;
+        if (s < a.B) {
+            cb_conv<C, ACT>(patch + s * Cfg::STRIDE, wr, bias, a.act, a.alpha, S[j]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) S[j][q] = 0.0f;
+        }
+    }
+    float su[4] = {0.f, 0.f, 0.f, 0.f}, sux[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != 2) {
+        float a0 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CB_NS; ++j) {                    // pass 1: U = pool-bwd(e); d_beta = sum U, d_gamma = sum U*xhat
+            const int s = lane + 32 * j;
+            const float e = s < a.B ? scale * errs[wid][s] : 0.0f;
+            float y[4], xh[4], m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float d = clip10(S[j][q]) - mean[q];
+                y[q] = fmaf(g[q], d, bt[q]);
+                xh[q] = d * invstd[q];
+                m = fmaxf(m, y[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float u = (y[q] == m) ? e : 0.0f;                     // every tied maximum (layers.py:631-637)
+                su[q] += u;
+                sux[q] = fmaf(u, xh[q], sux[q]);
+                a0 = fmaf(u, u, a0);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            su[q] = warp_sum(su[q]);
+            sux[q] = warp_sum(sux[q]);
+            if (lane == 0) {
+                if (dbeta != nullptr) dbeta[pos[q]] = su[q];                 // layers.py:1262
+                if (dgamma != nullptr) dgamma[pos[q]] = sux[q];              // layers.py:1261
+            }
+        }
+        if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+        if (MODE == 1) return;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            su[q] = dbeta[pos[q]];
+            sux[q] = dgamma[pos[q]];
+        }
+    }
+    const float invB = (float)(1.0 / a.n_total);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        su[q] *= invB;
+        sux[q] *= invB;
+    }
+    float gw[9 * C], gb = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9 * C; ++k) gw[k] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CB_NS; ++j) {                        // pass 2: BN-bwd, act', weight gradient
+        const int s = lane + 32 * j;
+        if (s >= a.B) continue;
+        const float e = scale * errs[wid][s];
+        float y[4], xh[4], r[4], m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float d = clip10(S[j][q]) - mean[q];
+            y[q] = fmaf(g[q], d, bt[q]);
+            xh[q] = d * invstd[q];
+            m = fmaxf(m, y[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float u = (y[q] == m) ? e : 0.0f;
+            float d = g[q] * (u - xh[q] * sux[q] - su[q]);                    // layers.py:1264-1274 in closed form
+            a1 = fmaf(d, d, a1);
+            d *= cb_act_grad<ACT>(S[j][q], a.act, a.alpha);                   // layers.py:237
+            a2 = fmaf(d, d, a2);
+            r[q] = d;
+            gb += d;
+        }
+        if (r_out != nullptr) {
+            const long long nb = (long long)s * a.H * a.W * a.F;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r_out[nb + pos[q]] = r[q];
+        }
+        const float* p = patch + s * Cfg::STRIDE;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float rows[4][4];
+#pragma unroll
+            for (int py = 0; py < 4; ++py) {
+                const float4 rr = *reinterpret_cast<const float4*>(p + c * 16 + py * 4);
+                rows[py][0] = rr.x; rows[py][1] = rr.y; rows[py][2] = rr.z; rows[py][3] = rr.w;
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {                              // layers.py:522-524 (col^T . dY), K order (c,ky,kx)
+                    float t = gw[(c * 3 + ky) * 3 + kx];
+                    t = fmaf(rows[ky][kx], r[0], t);
+                    t = fmaf(rows[ky][kx + 1], r[1], t);
+                    t = fmaf(rows[ky + 1][kx], r[2], t);
+                    t = fmaf(rows[ky + 1][kx + 1], r[3], t);
+                    gw[(c * 3 + ky) * 3 + kx] = t;
+                }
+        }
+    }
+    if (partial != nullptr) {
+        float* dst = partial + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * (Cfg::K + 1)) * a.F + f;
+#pragma unroll
+        for (int k = 0; k < 9 * C; ++k) {
+            const float t = warp_sum(gw[k]);
+            if (lane == 0) dst[(long long)k * a.F] = t;
+        }
+        const float tb = warp_sum(gb);
+        if (lane == 0) dst[(long long)Cfg::K * a.F] = tb;                     // layers.py:521
+    }
+    if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+    if (ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+}
+
+// partial[s][m][n] -> out, fixed order, with the lazy clip multiplier; rows >= n_rows go to db (same contract as the split-K
+// reduction of gemm_simt.cu, kept local so that this file is self-contained)
+__global__ void __launch_bounds__(1024) convblock_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                                const double* __restrict__ ss, uint64_t chain,
+                                                                float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float sm[32][32];
+    const float scale = chain_scale(ss, chain);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long total = (long long)M * N;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    float v = 0.0f;
+    if (i < total) {
+#pragma unroll 4
+        for (int s = w; s < splits; s += 32) v += ws[(long long)s * total + i];
+    }
+    sm[w][lane] = v;
+    __syncthreads();
+    if (w == 0 && i < total) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += sm[k][lane];
+        t *= scale;
+        const int m = (int)(i / N), n = (int)(i % N);
+        if (m == M - 1) { if (db != nullptr) db[n] = t; }
+        else dw[(long long)m * N + n] = t;
+    }
+}
+
+static int cb_check(const char* who, const b200nn_conv_geom* g, int act, float alpha) {
+    B200NN_REQUIRE(g != nullptr, "%s: null geometry", who);
+    B200NN_REQUIRE(g->kh == 3 && g->kw == 3 && g->sh == 1 && g->sw == 1 && g->ph == 1 && g->pw == 1 && g->OH == g->H && g->OW == g->W,
+                   "%s: needs a 3x3 stride-1 'same' convolution", who);
+    B200NN_REQUIRE(g->C >= 1 && g->C <= 3 && g->F % CB_FPC == 0 && g->H % 2 == 0 && g->W % 2 == 0 && g->N > 0 && g->N <= CB_MAXB,
+                   "%s: needs C <= 3, F %% 8 == 0, even H and W, batch <= %d (got C=%d F=%d %dx%d batch %d)", who, CB_MAXB, g->C, g->F,
+                   g->H, g->W, g->N);
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU && (act != B200NN_ACT_LEAKYRELU || alpha > 0.0f), "%s: bad activation", who);
+    B200NN_REQUIRE(g->W / 2 <= 65535 && g->H / 2 <= 65535 && g->F / CB_FPC <= 65535, "%s: grid too large", who);
+    return B200NN_OK;
+}
+
+template <class Kern, class... Args>
+static int cb_launch(Kern kern, dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+    static thread_local const void* configured[64] = {nullptr};
+    bool seen = false;
+    for (auto p : configured) seen = seen || p == (const void*)kern;
+    if (!seen) {
+        B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (auto& p : configured) if (p == nullptr) { p = (const void*)kern; break; }
+    }
+    kern<<<grid, CB_THREADS, smem, st>>>(args...);
+    return B200NN_OK;
+}
+}  // namespace b200nn
+
+using namespace b200nn;
+
+extern "C" {
+
+int b200nn_convblock_supported(const b200nn_conv_geom* g, int act, float alpha) {
+    if (g == nullptr) return 0;
+    return g->kh == 3 && g->kw == 3 && g->sh == 1 && g->sw == 1 && g->ph == 1 && g->pw == 1 && g->OH == g->H && g->OW == g->W &&
+           g->C >= 1 && g->C <= 3 && g->F % CB_FPC == 0 && g->H % 2 == 0 && g->W % 2 == 0 && g->N > 0 && g->N <= CB_MAXB && act >= 0 &&
+           act <= B200NN_ACT_LEAKYRELU && (act != B200NN_ACT_LEAKYRELU || alpha > 0.0f);
+}
+
+size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g) {
+    return (size_t)(g->H / 2) * (g->W / 2) * (9 * g->C + 1) * g->F * sizeof(float);
+}
+
+#define CB_SMEM(C) ((size_t)(CB_MAXB * CbCfg<C>::STRIDE + CB_FPC * CB_MAXB) * sizeof(float))
+#define CB_DISPATCH_C(KERN, MODE, ACT, ...)                                                                   \
+    do {                                                                                                      \
+        int rc_;                                                                                              \
+        if (g->C == 1) rc_ = cb_launch(KERN<1, MODE, ACT>, grid, CB_SMEM(1), st, __VA_ARGS__);                \
+        else if (g->C == 2) rc_ = cb_launch(KERN<2, MODE, ACT>, grid, CB_SMEM(2), st, __VA_ARGS__);           \
+        else rc_ = cb_launch(KERN<3, MODE, ACT>, grid, CB_SMEM(3), st, __VA_ARGS__);                          \
+        if (rc_) return rc_;                                                                                  \
+    } while (0)
+#define CB_DISPATCH(KERN, MODE, ...)                                                             \
+    do {                                                                                         \
+        if (act == B200NN_ACT_RELU) CB_DISPATCH_C(KERN, MODE, B200NN_ACT_RELU, __VA_ARGS__);     \
+        else CB_DISPATCH_C(KERN, MODE, -1, __VA_ARGS__);                                         \
+    } while (0)
+
+int b200nn_convblock_fwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float* save_mean,
+                         float* save_invstd, double* stats, int mode, long long B_total, float* y_pool, float momentum,
+                         float eps, void* stream) {
+    if (int rc = cb_check("convblock_fwd", g, act, alpha)) return rc;
+    B200NN_REQUIRE(mode >= 0 && mode <= 2 && (mode == 0 || stats != nullptr), "convblock_fwd: mode %d needs stats", mode);
+    B200NN_REQUIRE(mode == 1 || (reinterpret_cast<uintptr_t>(y_pool) & 15) == 0, "convblock_fwd: y_pool must be 16-byte aligned");
+    CbArgs a{g->N, g->H, g->W, g->F, x, w, b, act, alpha, gamma, beta, save_mean, save_invstd, (double)(mode == 0 ? g->N : B_total)};
+    const dim3 grid(g->W / 2, g->H / 2, g->F / CB_FPC);
+    cudaStream_t st = as_stream(stream);
+    if (mode == 0) CB_DISPATCH(convblock_fwd_kernel, 0, a, running_mean, running_var, stats, y_pool, momentum, eps);
+    else if (mode == 1) CB_DISPATCH(convblock_fwd_kernel, 1, a, running_mean, running_var, stats, y_pool, momentum, eps);
+    else CB_DISPATCH(convblock_fwd_kernel, 2, a, running_mean, running_var, stats, y_pool, momentum, eps);
+    B200NN_LAUNCH_CHECK("convblock_fwd");
+    return B200NN_OK;
+}
+
+int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
+                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                         const float* err, const double* ss, uint64_t chain, float* dgamma, float* dbeta, float* dw, float* db,
+                         float* r_out, int mode, long long B_total, double* ss_out0, double* ss_out1, double* ss_out2,
+                         uint64_t chain_out, float* ws, void* stream) {
+    if (int rc = cb_check("convblock_bwd", g, act, alpha)) return rc;
+    B200NN_REQUIRE(mode >= 0 && mode <= 2, "convblock_bwd: mode %d", mode);
+    B200NN_REQUIRE((mode == 0 || (dgamma != nullptr && dbeta != nullptr)) && (mode == 1 || ws != nullptr),
+                   "convblock_bwd: missing buffer for mode %d", mode);
+    B200NN_REQUIRE((reinterpret_cast<uintptr_t>(err) & 15) == 0, "convblock_bwd: err must be 16-byte aligned");
+    CbArgs a{g->N, g->H, g->W, g->F, x, w, b, act, alpha, gamma, beta, const_cast<float*>(save_mean), const_cast<float*>(save_invstd),
+             (double)(mode == 0 ? g->N : B_total)};
+    const dim3 grid(g->W / 2, g->H / 2, g->F / CB_FPC);
+    cudaStream_t st = as_stream(stream);
+    if (mode == 0) CB_DISPATCH(convblock_bwd_kernel, 0, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
+    else if (mode == 1) CB_DISPATCH(convblock_bwd_kernel, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
+    else CB_DISPATCH(convblock_bwd_kernel, 2, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
+    B200NN_LAUNCH_CHECK("convblock_bwd");
+    if (mode != 1 && dw != nullptr) {
+        // the weight gradient still owes the three clips this kernel produced (pool-bwd / BN-bwd / act-bwd outputs): chain_out
+        const int M = 9 * g->C + 1, splits = (g->H / 2) * (g->W / 2);
+        const long long total = (long long)M * g->F;
+        convblock_reduce_kernel<<<(int)((total + 31) / 32), 1024, 0, st>>>(ws, splits, M, g->F, ss, chain_out, dw, db);
+        B200NN_LAUNCH_CHECK("convblock_reduce");
+    }
+    return B200NN_OK;
+}
+
+}  // extern "C"

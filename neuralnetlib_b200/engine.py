@@ -22,7 +22,7 @@ import torch
 
 from . import _backend as B
 from . import _ops as ops
-from .layers import Activation, BatchNormalization, Input, _Err
+from .layers import Activation, BatchNormalization, Conv2D, Input, _Err
 from .losses import BinaryCrossentropy, CategoricalCrossentropy
 
 MAX_SLOTS = 256
@@ -86,7 +86,9 @@ class Plan:
         self.outs = [None] * len(self.layers)
         self.fwd_fused = [False] * len(self.layers)   # Activation i applied inside layer i-1's kernel
         self.programs = {}
-        self.fuse_blocks = os.environ.get("B200NN_FUSE_BLOCKS", "1") != "0"
+        # B200NN_FUSE_BLOCKS: 0 = layer by layer, 1 = BatchNorm+MaxPool kernels, 2 (default) = also the first-block kernels
+        level = int(os.environ.get("B200NN_FUSE_BLOCKS", "2"))
+        self.fuse_blocks, self.fuse_first_block = level >= 1, level >= 2
         self._build_forward()
 
     # ---- allocation context used by the layers' plan hooks ---------------------------------------------------
@@ -163,6 +165,9 @@ class Plan:
             nxt = layers[i + 1] if i + 1 < n else None
             fuse = L._fuses_act and isinstance(nxt, Activation) and nxt._fusable
             self.state[i].update(in_shape=tuple(x.shape))
+            if self.fuse_first_block and isinstance(L, Conv2D) and self._try_conv_block(i, x, fuse):
+                i, x = self._block_next
+                continue
             if isinstance(L, BatchNormalization) and self.fuse_blocks and L._can_fuse_pool(x, nxt, self.training):
                 y = L._plan_forward(self, self.state[i], x, None, self.training, pool=nxt)   # BN + MaxPool: one kernel
                 self.outs[i] = None                      # the BatchNorm output is never materialised
@@ -184,6 +189,28 @@ class Plan:
         self.pred = x
         self.programs["forward"] = prog
         self._emit_to = None
+
+    def _try_conv_block(self, i, x, has_act):
+        """Conv2D [+ Activation] -> BatchNormalization -> MaxPooling2D(2) as the fused first-block kernels (conv output never
+        materialised). Returns True and sets self._block_next = (next layer index, pooled output) when the pattern applies."""
+        layers, n = self.layers, len(self.layers)
+        j = i + (2 if has_act else 1)
+        if j + 1 >= n:
+            return False
+        L, act, bn, pool = layers[i], (layers[i + 1] if has_act else None), layers[j], layers[j + 1]
+        if not L._can_fuse_block(x, act, bn, pool, self.training):
+            return False
+        y = L._plan_forward_block(self, self.state[i], self.state[j], x, act, bn)
+        shp = tuple(x.shape[:3]) + (L.filters,)
+        for k in range(i, j + 1):
+            self.outs[k] = None
+            self.state[k].update(in_shape=shp if k > i else tuple(x.shape))
+        if has_act:
+            self.fwd_fused[i + 1] = True
+        self.outs[j + 1] = y
+        self.state[j + 1].update(in_shape=shp, conv_block=(i, j, has_act))
+        self._block_next = (j + 2, y)
+        return True
 
     # ---- backward -----------------------------------------------------------------------------------------------
     def _has_weights(self, L):
@@ -221,6 +248,17 @@ class Plan:
             if isinstance(L, Activation):
                 cur = L._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
                 i -= 1
+                continue
+            if self.state[i].get("conv_block") is not None:
+                ci, bi, has_act = self.state[i]["conv_block"]
+                need_dx_c = want_input_error or any(self._has_weights(layers[k]) for k in range(ci))
+                et = cur.t.reshape(self.outs[i].shape)
+                cur = layers[ci]._plan_backward_block(self, self.state[ci], self.state[bi], layers[bi], _Err(et, cur.chain), has_act,
+                                                      need_dx_c)
+                if not compute_only:
+                    updates.append(ci)
+                    self._grad_bucket_ready(layers[ci])
+                i = ci - 1
                 continue
             if self.state[i].get("fused_into_bn"):
                 # MaxPool whose forward ran inside the preceding BatchNorm kernel: pool-bwd + BN-bwd (+ the backward of

@@ -488,6 +488,80 @@ class Conv2D(Layer, _ParamMixin):
             return None
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
 
+    # -- fused first block: Conv2D(3x3 'same', C <= 3) [+ Activation] -> BatchNormalization -> MaxPooling2D(2) (csrc/conv_block.cu)
+    def _can_fuse_block(self, x, act_layer, bn, pool, training):
+        if not (training and type(self) is Conv2D and isinstance(bn, BatchNormalization) and isinstance(pool, MaxPooling2D)):
+            return False
+        if x.dim() != 4 or (act_layer is not None and not act_layer._fusable):
+            return False
+        if not (pool.pool_size == (2, 2) and pool.strides == (2, 2) and pool.padding == "valid"):
+            return False
+        kind, alpha = _act_of(act_layer)
+        return ops.convblock_supported(self._geometry(x.shape), kind, alpha)
+
+    def _plan_forward_block(self, ctx, st, st_bn, x, act_layer, bn):
+        if self._weights is None:
+            self.initialize_weights(tuple(x.shape))
+        if self._d_weights is None:
+            self.d_weights = np.zeros(self._shapes["weights"]); self.d_bias = np.zeros((self.filters,))
+        assert x.shape[3] == self._weights.shape[2], "Number of input channels must match"
+        g = self._geometry(x.shape)
+        bn._ensure_params((g.OH, g.OW, self.filters))
+        P = bn._gamma.numel()
+        kind, alpha = _act_of(act_layer)
+        ctx.need_ws(max(ops.convblock_ws_bytes(g), ops.conv2d_ws_bytes(g)))
+        yp = ctx.buf((x.shape[0], g.OH // 2, g.OW // 2, self.filters))
+        sm, si = ctx.buf((P,)), ctx.buf((P,))
+        st.update(x=x, g=g, math=ops.MATH_FP32, block=True, act=(kind, alpha))
+        st_bn.update(save_mean=sm, save_invstd=si, trained=True, fused_pool=True)
+        w, b, gm, bt, rm, rv = self._weights, self._bias, bn._gamma, bn._beta, bn._running_mean, bn._running_var
+        mom, eps = float(bn.momentum), float(bn.epsilon)
+        if ctx.dp is not None:
+            stats, b_total = ctx.buf64((2 * P,)), x.shape[0] * ctx.world
+            ctx.emit(lambda: ops.convblock_fwd(g, x, w, b, kind, alpha, gm, bt, rm, rv, sm, si, stats, 1, b_total, None, mom, eps),
+                     "convblock_stats", (x,))
+            ctx.allreduce(stats, "bn_stats_exchange")
+            ctx.emit(lambda: ops.convblock_fwd(g, x, w, b, kind, alpha, gm, bt, rm, rv, sm, si, stats, 2, b_total, yp, mom, eps),
+                     "convblock_fwd_apply", (x, yp))
+        else:
+            ctx.emit(lambda: ops.convblock_fwd(g, x, w, b, kind, alpha, gm, bt, rm, rv, sm, si, None, 0, x.shape[0], yp, mom, eps),
+                     "convblock_fwd", (x, w, yp))
+        return yp
+
+    def _plan_backward_block(self, ctx, st, st_bn, bn, err, has_act, need_dx):
+        """err: error w.r.t. the pooled output. Emits pool-bwd + BN-bwd + act-bwd + conv weight gradient as one kernel (two
+        under data parallelism); returns the error w.r.t. the conv INPUT when `need_dx`, else None."""
+        x, g = st["x"], st["g"]
+        kind, alpha = st["act"]
+        s0, s1 = ctx.slot(), ctx.slot()
+        s2 = ctx.slot() if has_act else None
+        chain_out = tuple(s for s in (s0, s1, s2) if s is not None)
+        P = bn._gamma.numel()
+        r_out = ctx.buf((x.shape[0], g.OH, g.OW, self.filters)) if need_dx else None
+        w, b, dw, db, gm, bt = self._weights, self._bias, self._d_weights, self._d_bias, bn._gamma, bn._beta
+        sm, si, ss, chain, et = st_bn["save_mean"], st_bn["save_invstd"], ctx.ss, err.chain, err.t
+        bn._dgrad_pending = (ctx.ss, s0) if ctx.ss is not None else None
+        if ctx.dp is not None:
+            sums, b_total = bn._dp_sums(ctx), x.shape[0] * ctx.world
+            dgp, dbp = sums.data_ptr() + 4 * P, sums.data_ptr()
+            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, None, 1,
+                                               b_total, s0, None, None, (), None), "convblock_bwd_sums", (x, et))
+            ctx.allreduce(sums, "bn_sums_exchange")
+            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, dw, db, r_out, 2,
+                                               b_total, None, s1, s2, chain_out, ctx.ws), "convblock_bwd_apply", (x, et, dw, r_out))
+        else:
+            dgp, dbp = bn._d_gamma.data_ptr(), bn._d_beta.data_ptr()
+            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, dw, db, r_out, 0,
+                                               x.shape[0], s0, s1, s2, chain_out, ctx.ws), "convblock_bwd", (x, et, dw, r_out))
+        if not need_dx:
+            return None
+        dx = ctx.buf(x.shape)
+        s3 = ctx.slot()
+        math = st["math"]
+        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, r_out, ss, chain_out, dx, None, None, ops.ACT_NONE, 0.0, s3, None, ctx.ws),
+                 "conv2d_dx", (r_out, w, dx))
+        return _Err(dx, (s3,))
+
     def forward_pass(self, input_data):
         x, host = _in(input_data)
         self.input = input_data
@@ -763,14 +837,17 @@ class BatchNormalization(Layer, _ParamMixin):
                 and pool.strides == (2, 2) and pool.padding == "valid" and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0
                 and x.shape[3] % 32 == 0 and x.shape[0] <= ops.fused_block_max_batch())
 
-    def _plan_forward(self, ctx, st, x, act_layer, training, pool=None):
-        shp = tuple(int(s) for s in x.shape[1:])
+    def _ensure_params(self, shp):
         if self._gamma is None or self._running_mean is None or self._running_var is None:
             self.initialize_weights(shp)
         if self._d_gamma is None:
             self.d_gamma, self.d_beta = np.zeros(shp), np.zeros(shp)
         if int(np.prod(shp)) != self._gamma.numel():
             raise ValueError(f"BatchNormalization was initialised for {tuple(self._shapes['gamma'])}, got {shp}")
+
+    def _plan_forward(self, ctx, st, x, act_layer, training, pool=None):
+        shp = tuple(int(s) for s in x.shape[1:])
+        self._ensure_params(shp)
         P = self._gamma.numel()
         gm, bt, rm, rv = self._gamma, self._beta, self._running_mean, self._running_var
         mom, eps = float(self.momentum), float(self.epsilon)

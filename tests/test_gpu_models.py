@@ -90,7 +90,7 @@ def test_train_on_batch_golden(golden, name, cfg, width):
         loss = m.train_on_batch(x, y)
         assert isinstance(loss, float)
         ref = float(g[f"s{s}_loss"])
-        assert abs(loss - ref) <= 1e-5 * max(1.0, abs(ref)), (s, loss, ref)
+        assert abs(loss - ref) <= (1e-4 if (cfg == 3 and s > 0) else 1e-5) * max(1.0, abs(ref)), (s, loss, ref)
         # steps >= 1 start from post-Adam weights; Adam turns fp32-vs-fp64 rounding on |g| ~ eps elements into weight
         # differences of up to lr, which the three batch-4 BatchNorms of config 3 amplify further
         ptol = 5e-5 if (s == 0 or cfg != 3) else 5e-4
@@ -355,3 +355,37 @@ def test_tf32_tensor_core_mode_within_2e3(cfg, batch, width):
             assert nrel(layer.d_bias.reshape(-1), rl["db"].reshape(-1)) < 2 * inherent
     finally:
         nn.set_math("fp32")
+
+
+@pytest.mark.parametrize("level", ["0", "1", "2"])
+@pytest.mark.parametrize("cfg,batch", [(2, 64), (3, 32)])
+def test_fusion_levels_agree_with_oracle(monkeypatch, level, cfg, batch):
+    """B200NN_FUSE_BLOCKS = 0 (layer by layer), 1 (BatchNorm+MaxPool kernels), 2 (first-block kernels: conv output never
+    materialised): every level reproduces the oracle's step, and the public backward_pass (which needs the error w.r.t. the
+    model input, i.e. the materialised-error path of the fused block) agrees between the levels."""
+    monkeypatch.setenv("B200NN_FUSE_BLOCKS", level)
+    m = build_cfg(cfg)
+    x, y = O.synthetic_batch(cfg, batch)
+    specs, _ = O.config_specs(cfg)
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+    assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss))
+    tol = 1e-3 if cfg == 3 else TOL
+    for layer, rl in zip([l for l in m.layers if hasattr(l, "weights")], [r for r in ref.layers if "w" in r]):
+        grads_close(layer.d_weights, rl["dw"], tol, (level, "dw"))
+        grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), tol, (level, "db"))
+    for layer, rl in zip(m.layers, ref.layers):
+        if rl["type"] == "bn":
+            assert nrel(layer.running_mean, rl["running_mean"]) < 2e-5 and nrel(layer.running_var, rl["running_var"]) < 2e-5
+    # public forward + backward on a fresh model: input error against the oracle's
+    m2 = build_cfg(cfg)
+    ref2 = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    p = m2.forward_pass(x)
+    rp = ref2.forward(x)
+    assert nrel(p, rp) < 5e-5
+    m2.y_true = y
+    ref2.y_true = y.astype(np.float64)
+    err = O.loss_derivative("cce", y.astype(np.float64), rp)
+    got = m2.backward_pass(err)
+    want = O.clip_l2(ref2.backward(err, compute_only=False))   # models.py:214 clips before Input too; Input.backward is identity
+    grads_close(got, want, 1e-3 if cfg == 3 else 5e-5, (level, "input error"))

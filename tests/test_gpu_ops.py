@@ -445,3 +445,68 @@ def test_dense_tf32_tcgen05(K, M, N, Kd):
     assert nrel(K.host(db), rdb.reshape(-1)) < 1e-5
     h = K.host(ss)
     assert abs(h[1] - np.sum(rdx ** 2)) < 5e-3 * np.sum(rdx ** 2)
+
+
+@pytest.mark.parametrize("Bn,H,W,C,F,act", [(256, 28, 28, 1, 32, "relu"), (64, 32, 32, 3, 64, "relu"), (37, 8, 6, 2, 8, "leakyrelu"),
+                                            (200, 4, 4, 1, 16, "relu"), (150, 4, 6, 3, 8, "tanh"), (16, 6, 4, 1, 8, "linear")])
+def test_convblock_first_block(K, Bn, H, W, C, F, act):
+    """Fused first block (csrc/conv_block.cu): Conv2D(3x3 'same') + activation + BatchNorm(train) + MaxPool 2x2 with the conv
+    output never materialised, forward and backward (weight / bias gradient, d_gamma / d_beta, the three clip slots, the
+    optional error w.r.t. the conv output), against the unfused oracle chain. Also the two data-parallel halves with a
+    world of one (mode 1 -> mode 2 must reproduce mode 0)."""
+    rng = np.random.default_rng(Bn * 7 + H + C)
+    x = rng.random((Bn, H, W, C)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, C, F)) * 0.3).astype(np.float32)
+    b = (rng.normal(size=(1, F)) * 0.1).astype(np.float32)
+    P = H * W * F
+    shp = (H, W, F)
+    gamma = (1 + 0.1 * rng.normal(size=P)).astype(np.float32); beta = (0.1 * rng.normal(size=P)).astype(np.float32)
+    g = K.B.ConvGeom(Bn, H, W, C, F, 3, 3, 1, 1, 1, 1, H, W)
+    kind, alpha = ACTS[act], 0.01
+    assert K.ops.convblock_supported(g, kind, alpha)
+    xd, wd, bd, gd, btd = K.dev(x), K.dev(w), K.dev(b.reshape(-1)), K.dev(gamma), K.dev(beta)
+    x64, w64, b64 = x.astype(np.float64), w.astype(np.float64), b.astype(np.float64)
+    g64, bt64 = gamma.astype(np.float64).reshape(shp), beta.astype(np.float64).reshape(shp)
+    pre = O.conv2d_fwd(x64, w64, b64, (1, 1), "same")
+    a = O.act_fwd(act, pre, alpha)
+    ybn, rrm, rrv, cache = O.bn_fwd(a, g64, bt64, np.zeros(shp), np.ones(shp), 0.9, 1e-5, True)
+    ryp = O.maxpool_fwd(ybn, (2, 2), (2, 2))
+    e = rng.normal(size=ryp.shape).astype(np.float32)
+    U = O.maxpool_bwd(ybn, O.clip_l2(e.astype(np.float64)), (2, 2), (2, 2))
+    D, rdg, rdb = O.bn_bwd(U, g64, cache, 1e-5)
+    R = O.act_bwd(act, pre, D, alpha)
+    # reference: clip(U) -> bn bwd -> clip -> act bwd -> clip -> conv bwd
+    Rc = O.clip_l2(O.act_bwd(act, pre, O.clip_l2(O.bn_bwd(O.clip_l2(U), g64, cache, 1e-5)[0]), alpha))
+    _, rdw, rdbias = O.conv2d_bwd(x64, w64, Rc, (1, 1), "same")
+    ws = K.empty((max(K.ops.convblock_ws_bytes(g) // 4, 1),))
+    for modes in ((0,), (1, 2)):
+        rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
+        sm, si = K.empty((P,)), K.empty((P,))
+        yp = K.empty((Bn, H // 2, W // 2, F))
+        stats = K.B.zeros((2 * P,), dtype=K.torch.float64)
+        for md in modes:
+            K.ops.convblock_fwd(g, xd, wd, bd, kind, alpha, gd, btd, rm, rv, sm, si, stats, md, Bn, yp if md != 1 else None, 0.9, 1e-5)
+        assert nrel(K.host(yp), ryp) < 2e-5, modes
+        assert nrel(K.host(rm).reshape(shp), rrm) < TOL and nrel(K.host(rv).reshape(shp), rrv) < TOL
+        ed = K.dev(e); ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+        dg, dbt, dw, db, r = K.empty((P,)), K.empty((P,)), K.empty((3, 3, C, F)), K.empty((F,)), K.empty((Bn, H, W, F))
+        s2 = 3 if act != "linear" else None
+        cout = (1, 2, 3) if act != "linear" else (1, 2)
+        if modes == (0,):
+            K.ops.convblock_bwd(g, xd, wd, bd, kind, alpha, gd, btd, sm, si, ed, ss, (0,), dg.data_ptr(), dbt.data_ptr(), dw, db, r, 0, Bn,
+                                1, 2, s2, cout, ws)
+        else:
+            K.ops.convblock_bwd(g, xd, wd, bd, kind, alpha, gd, btd, sm, si, ed, ss, (0,), dg.data_ptr(), dbt.data_ptr(), None, None, None,
+                                1, Bn, 1, None, None, (), None)
+            K.ops.convblock_bwd(g, xd, wd, bd, kind, alpha, gd, btd, sm, si, ed, ss, (0,), dg.data_ptr(), dbt.data_ptr(), dw, db, r, 2, Bn,
+                                None, 2, s2, cout, ws)
+        h = K.host(ss)
+        assert abs(h[1] - np.sum(U ** 2)) < 1e-4 * np.sum(U ** 2)
+        assert abs(h[2] - np.sum(D ** 2)) < 1e-4 * np.sum(D ** 2)
+        if s2 is not None:
+            assert abs(h[3] - np.sum(R ** 2)) < 1e-4 * np.sum(R ** 2)
+        assert nrel(K.host(r), R) < 3e-5
+        assert nrel(K.host(dg).reshape(shp), rdg) < 3e-5 and nrel(K.host(dbt).reshape(shp), rdb) < 3e-5
+        assert nrel(K.host(dw), rdw) < 3e-5, modes
+        # with a linear activation the bias gradient is sum over the batch of a BatchNorm backward output == 0 identically
+        assert np.abs(K.host(db) - rdbias.reshape(-1)).max() < 3e-5 * max(np.abs(rdbias).max(), np.abs(rdw).max())
