@@ -111,6 +111,10 @@ int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y
 size_t b200nn_dense_ws_bytes(int M, int N, int K);
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                      int act, float alpha, float* ws, void* stream);
+/* Classifier head as one kernel (N <= 32): p = softmax(x . w + b) (layers.py:173, activations.py:69-71), loss_acc[0] += CCE
+ * numerator (losses.py:106-109), err = p - y_true (models.py:200-205), loss_acc[1] += argmax hits, ss_out += sum(err^2). */
+int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, const float* y_true, float* p, float* err,
+                             double* loss_acc, double* ss_out, int M, int N, int K, void* stream);
 /* g = chain(err)[M,N];  dx[M,K] = g . w^T (layers.py:189);  dw[K,N] = x^T . g (:196);  db[N] = sum_rows g (:197).
  * dx == NULL skips dx (first parametrised layer inside fit). If prev_act != NONE the backward of the
  * PRECEDING Activation layer (whose output is this layer's input x) is fused into the dx epilogue:

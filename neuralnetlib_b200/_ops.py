@@ -123,6 +123,14 @@ def dense_fwd(math, x, w, b, y, act, alpha, ws):
     check(lib().b200nn_dense_fwd(math, ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, alpha, ptr(ws), stream()))
 
 
+def dense_softmax_cce(x, w, b, y_true, p, err, acc, ss, slot_out):
+    _f32(x, w, b, y_true, p, err)
+    K, N = w.shape
+    M = x.numel() // K
+    check(lib().b200nn_dense_softmax_cce(ptr(x), ptr(w), ptr(b), ptr(y_true), ptr(p), ptr(err), ptr(acc), _slot_ptr(ss, slot_out),
+                                         M, N, K, stream()))
+
+
 def dense_bwd(math, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, ws):
     _f32(x, w, err, dx, dw, db)
     K, N = w.shape

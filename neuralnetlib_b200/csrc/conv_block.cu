@@ -59,22 +59,33 @@ __device__ __forceinline__ float cb_act_grad(float y, int act, float alpha) {
     return act_grad_from_y(act, y, alpha);
 }
 
-// stage the 4x4xC input patches of all B samples around window (oy, ox): patch[s][c*16 + py*4 + px]
+// stage the 4x4xC input patches of all B samples around window (oy, ox): patch[s][c*16 + py*4 + px].
+// Loads are issued 8 at a time into registers before any of them is stored, so their latencies overlap.
 template <int C>
 __device__ __forceinline__ void cb_stage(float* patch, const CbArgs& a, int oy, int ox) {
-    constexpr int EPS = CbCfg<C>::EPS, ROW = 4 * C;
+    constexpr int EPS = CbCfg<C>::EPS, ROW = 4 * C, ITER = CB_MAXB * EPS / CB_THREADS, U = 8;
     const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
-    int e = threadIdx.x % EPS, s = threadIdx.x / EPS;        // element within the sample (memory order: py, px, c), sample
     const long long img = (long long)a.H * a.W * C;
-    while (s < a.B) {
-        const int py = e / ROW, r = e % ROW, px = r / C, c = r % C;
-        const int iy = iy0 + py, ix = ix0 + px;
-        float v = 0.0f;                                      // zero padding of 'same' (layers.py:450-465)
-        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = a.x[(long long)s * img + ((long long)iy * a.W + ix) * C + c];
-        patch[s * CbCfg<C>::STRIDE + c * 16 + py * 4 + px] = v;
-        e += CB_THREADS % EPS;
-        s += CB_THREADS / EPS;
-        if (e >= EPS) { e -= EPS; ++s; }
+    const int total = a.B * EPS;
+#pragma unroll
+    for (int k0 = 0; k0 < ITER; k0 += U) {
+        if (k0 * CB_THREADS >= total) break;
+        float v[U];
+        int dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = (int)threadIdx.x + (k0 + u) * CB_THREADS;
+            const int sidx = i / EPS, e = i % EPS;             // memory order within a sample: py, px, c
+            const int py = e / ROW, r = e % ROW, px = r / C, c = r % C;
+            const int iy = iy0 + py, ix = ix0 + px;
+            dst[u] = i < total ? sidx * CbCfg<C>::STRIDE + c * 16 + py * 4 + px : -1;
+            v[u] = 0.0f;                                        // zero padding of 'same' (layers.py:450-465)
+            if (i < total && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                v[u] = a.x[(long long)sidx * img + ((long long)iy * a.W + ix) * C + c];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (dst[u] >= 0) patch[dst[u]] = v[u];
     }
 }
 

@@ -437,8 +437,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float* __
     const long long total = (long long)M * N;
     const long long i = (long long)blockIdx.x * 32 + lane;
     float v = 0.0f;
-    if (i < total)
+    if (i < total) {
+#pragma unroll 4
         for (int s = w; s < splits; s += 8) v += ws[(long long)s * total + i];
+    }
     sm[w][lane] = v;
     __syncthreads();
     if (w == 0 && i < total) {
@@ -746,6 +748,119 @@ __global__ void __launch_bounds__(256) dense_smalln_dw_kernel(const float* __res
     }
 }
 
+// Classifier head in ONE kernel: logits = x . w + b (N <= 32), Softmax over axis 1 (activations.py:69-71), CCE value
+// (losses.py:106-109), err = p - y (models.py:200-205), argmax accuracy (metrics.py:84-89) and sum(err^2) for the first clip.
+// One warp per row: lanes stride over k, then lane n owns class n.
+__global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ b, const float* __restrict__ y,
+                                                                float* __restrict__ p, float* __restrict__ err,
+                                                                double* loss_acc, double* ss_out, int M, int N, int K) {
+    __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    float lsum = 0.0f, esq = 0.0f, correct = 0.0f;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        float acc[SMALLN_MAX];
+#pragma unroll
+        for (int n = 0; n < SMALLN_MAX; ++n) acc[n] = 0.0f;
+        const float* xr = x + (long long)m * K;
+        for (int k = lane; k < K; k += 32) {
+            const float xv = xr[k];
+            const float* wr = w + (long long)k * N;
+#pragma unroll
+            for (int n = 0; n < SMALLN_MAX; ++n)
+                if (n < N) acc[n] = fmaf(xv, wr[n], acc[n]);
+        }
+        float logit = 0.0f;
+#pragma unroll
+        for (int n = 0; n < SMALLN_MAX; ++n) {
+            if (n < N) {
+                const float t = warp_sum(acc[n]);
+                if (lane == n) logit = t;
+            }
+        }
+        const bool on = lane < N;
+        logit = on ? logit + (b != nullptr ? b[lane] : 0.0f) : -INFINITY;
+        const float mx = warp_max(logit);
+        const float ex = on ? expf(logit - mx) : 0.0f;
+        const float pv = ex / warp_sum(ex);
+        const float yv = on ? y[(long long)m * N + lane] : 0.0f;
+        if (on) {
+            p[(long long)m * N + lane] = pv;
+            const float pc = fminf(fmaxf(pv, 1e-15f), 1.0f);
+            lsum -= yv * logf(pc);
+            const float e = pv - yv;
+            err[(long long)m * N + lane] = e;
+            esq = fmaf(e, e, esq);
+        }
+        float bp = on ? pv : -INFINITY, by = on ? yv : -INFINITY;
+        int ip = on ? lane : 0x7fffffff, iy = ip;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {                                   // first-index tie break (np.argmax)
+            const float obp = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int oip = __shfl_xor_sync(0xffffffffu, ip, o);
+            if (obp > bp || (obp == bp && oip < ip)) { bp = obp; ip = oip; }
+            const float oby = __shfl_xor_sync(0xffffffffu, by, o);
+            const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
+            if (oby > by || (oby == by && oiy < iy)) { by = oby; iy = oiy; }
+        }
+        if (lane == 0 && ip == iy) correct += 1.0f;
+    }
+    const double l = block_sum_to_double(lsum, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[0], l);
+    const double c = block_sum_to_double(correct, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[1], c);
+    if (ss_out != nullptr) block_accumulate(esq, ss_out, scratch);
+}
+
+// Backward of a small Dense (N <= 32, M <= 512) in ONE kernel: CTAs [0, dx_blocks) compute dx (+ fused activation backward
+// and the two clip slots), the remaining CTAs compute dw / db directly (thread = one (k, n) output, the whole batch summed
+// in fixed order: no partials, no reduce pass).
+__global__ void __launch_bounds__(256) dense_smalln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ e, Epilogue epi, float* __restrict__ dw,
+                                                               float* __restrict__ db, int M, int N, int K, int dx_blocks) {
+    __shared__ double scratch[32];
+    if ((int)blockIdx.x >= dx_blocks) {
+        const float scale = chain_scale(epi.ss, epi.chain);
+        const int o = ((int)blockIdx.x - dx_blocks) * blockDim.x + threadIdx.x;   // output index over (K + 1) x N
+        if (o >= (K + 1) * N) return;
+        const int k = o / N, n = o % N;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int m = 0;
+        if (k < K) {
+            for (; m + 4 <= M; m += 4) {                                    // 8 independent loads in flight
+                a0 = fmaf(x[(long long)m * K + k], e[(long long)m * N + n], a0);
+                a1 = fmaf(x[(long long)(m + 1) * K + k], e[(long long)(m + 1) * N + n], a1);
+                a2 = fmaf(x[(long long)(m + 2) * K + k], e[(long long)(m + 2) * N + n], a2);
+                a3 = fmaf(x[(long long)(m + 3) * K + k], e[(long long)(m + 3) * N + n], a3);
+            }
+            for (; m < M; ++m) a0 = fmaf(x[(long long)m * K + k], e[(long long)m * N + n], a0);
+            if (dw != nullptr) dw[(long long)k * N + n] = scale * ((a0 + a1) + (a2 + a3));   // layers.py:196
+        } else {
+            for (; m + 4 <= M; m += 4) {
+                a0 += e[(long long)m * N + n]; a1 += e[(long long)(m + 1) * N + n];
+                a2 += e[(long long)(m + 2) * N + n]; a3 += e[(long long)(m + 3) * N + n];
+            }
+            for (; m < M; ++m) a0 += e[(long long)m * N + n];
+            if (db != nullptr) db[n] = scale * ((a0 + a1) + (a2 + a3));                       // layers.py:197
+        }
+        return;
+    }
+    EpiState st;
+    epi_begin(epi, st);
+    const long long total = (long long)M * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)dx_blocks * blockDim.x) {
+        const int m = (int)(i / K), k = (int)(i % K);
+        const float* er = e + (long long)m * N;
+        const float* wr = w + (long long)k * N;
+        float v = 0.0f;
+        for (int n = 0; n < N; ++n) v = fmaf(er[n], wr[n], v);
+        const float mk = epi.mask_y != nullptr ? epi.mask_y[i] : 0.0f;
+        epi_store_premask(epi, st, m, k, v, mk);
+    }
+    epi_finish(epi, st, scratch);
+}
+
 static int smalln_chunks(int M) {
     int c = (M + 7) / 8;                // >= 8 rows per chunk
     return c > 64 ? 64 : (c < 1 ? 1 : c);
@@ -753,6 +868,7 @@ static int smalln_chunks(int M) {
 static size_t smalln_ws_bytes(int M, int N, int K) { return (size_t)smalln_chunks(M) * (K + 1) * N * sizeof(float); }
 
 }  // namespace b200nn
+#include "dense_skinny.cuh"   // needs Epilogue / launch_splitk_reduce; lives in b200nn::skinny
 #include "gemm_tcgen05.cuh"   // needs Epilogue / launch_splitk_reduce; lives in b200nn::tc
 namespace b200nn {
 
@@ -761,7 +877,7 @@ namespace b200nn {
 // ------------------------------------------------------------------------------------------------
 static int choose_splits(long long M, long long N, long long K) {
     const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    if (tiles >= 2LL * kNumSMs || K < 256) return 1;
+    if (tiles >= 2LL * kNumSMs || K < 512) return 1;   // a short reduction is cheaper than the extra reduce pass
     long long want = (2LL * kNumSMs + tiles - 1) / tiles;
     long long maxs = K / 128;
     if (maxs < 1) maxs = 1;
@@ -834,6 +950,7 @@ size_t b200nn_dense_ws_bytes(int M, int N, int K) {
     mx(tc::tc_ws_bytes(K, N, M));
     mx((size_t)kNumSMs * 2 * N * sizeof(float));  // column-sum partials for db on the tcgen05 path
     if (N <= SMALLN_MAX) mx(smalln_ws_bytes(M, N, K));
+    if (M <= skinny::MAXM && N <= skinny::MAXN) mx(skinny::fwd_ws_bytes(M, N, K));
     return r;
 }
 
@@ -856,11 +973,24 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
     }
     Epilogue e = plain_epilogue(y, N, M);
     e.bias = b; e.act = act; e.alpha = alpha;
+    if (math == B200NN_MATH_FP32 && ws != nullptr && skinny::applicable(x, w, y, M, N, K))
+        return skinny::launch_fwd(x, w, e, M, N, K, ws, as_stream(stream));
     if (math == B200NN_MATH_TF32 && dense_tc_ok(x, w, y, M, N, K))
         return tc::tc_gemm(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream));
     RowMajorA af{x, K, M, K};
     RowMajorB bf{w, N, K, N};
     return launch_gemm("dense_fwd", af, bf, e, M, N, K, ws, as_stream(stream));
+}
+
+int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, const float* y_true, float* p, float* err,
+                             double* loss_acc, double* ss_out, int M, int N, int K, void* stream) {
+    B200NN_REQUIRE(M > 0 && K > 0 && N > 0 && N <= SMALLN_MAX, "dense_softmax_cce: needs N <= %d (M=%d N=%d K=%d)", SMALLN_MAX, M, N, K);
+    B200NN_REQUIRE(x != nullptr && w != nullptr && y_true != nullptr && p != nullptr && err != nullptr, "dense_softmax_cce: null buffer");
+    int blocks = (M + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    dense_softmax_cce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+    B200NN_LAUNCH_CHECK("dense_softmax_cce");
+    return B200NN_OK;
 }
 
 int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err, const double* ss, uint64_t chain,
@@ -870,6 +1000,19 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
     B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_bwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (int rc = check_act("dense_bwd", prev_act, prev_alpha)) return rc;
     cudaStream_t st = as_stream(stream);
+    if (N <= SMALLN_MAX && M <= 512) {
+        long long dx_blocks = dx != nullptr ? ((long long)M * K + 255) / 256 : 0;
+        if (dx_blocks > kNumSMs * 8) dx_blocks = kNumSMs * 8;
+        const int dw_blocks = dw != nullptr ? ((K + 1) * N + 255) / 256 : 0;
+        Epilogue e = plain_epilogue(dx, K, M);
+        e.ss = ss; e.chain = chain;
+        if (dx != nullptr) dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+        if (dx_blocks + dw_blocks > 0) {
+            dense_smalln_bwd_kernel<<<(int)dx_blocks + dw_blocks, 256, 0, st>>>(x, w, err, e, dw, db, M, N, K, (int)dx_blocks);
+            B200NN_LAUNCH_CHECK("dense_smalln_bwd");
+        }
+        return B200NN_OK;
+    }
     if (N <= SMALLN_MAX && ws != nullptr) {
         if (dw != nullptr) {
             const int chunks = smalln_chunks(M);
@@ -891,6 +1034,9 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         }
         return B200NN_OK;
     }
+    if (math == B200NN_MATH_FP32 && skinny::applicable(x, w, err, M, N, K) &&
+        ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
+        return skinny::launch_bwd(x, w, err, ss, chain, dx, dw, db, M, N, K, prev_act, prev_alpha, ss_out0, ss_out1, st);
     const bool use_tc = math == B200NN_MATH_TF32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;
     if (dw != nullptr && use_tc) {
         if (db != nullptr) {   // layers.py:197

@@ -22,7 +22,7 @@ import torch
 
 from . import _backend as B
 from . import _ops as ops
-from .layers import Activation, BatchNormalization, Conv2D, Input, _Err
+from .layers import Activation, BatchNormalization, Conv2D, Dense, Input, _Err
 from .losses import BinaryCrossentropy, CategoricalCrossentropy
 
 MAX_SLOTS = 256
@@ -89,6 +89,7 @@ class Plan:
         # B200NN_FUSE_BLOCKS: 0 = layer by layer, 1 = BatchNorm+MaxPool kernels, 2 (default) = also the first-block kernels
         level = int(os.environ.get("B200NN_FUSE_BLOCKS", "2"))
         self.fuse_blocks, self.fuse_first_block = level >= 1, level >= 2
+        self._head = None
         self._build_forward()
 
     # ---- allocation context used by the layers' plan hooks ---------------------------------------------------
@@ -176,7 +177,14 @@ class Plan:
                 i += 2
                 x = y
                 continue
+            # classifier head Dense(N <= 32) + Softmax as the LAST two layers: remember its two launches so that a train
+            # step can replace them (and the loss kernel) by the fused head kernel
+            is_head = (i == n - 2 and isinstance(L, Dense) and isinstance(nxt, Activation) and not fuse and x.dim() == 2
+                       and type(nxt.activation_function).__name__ == "Softmax" and L.units <= 32)
+            op0 = len(prog.ops)
             y = L._plan_forward(self, self.state[i], x, nxt if fuse else None, self.training)
+            if is_head:
+                self._head = dict(layer=L, x=x, op0=op0)
             self.outs[i] = y
             if fuse:
                 self.outs[i + 1] = y
@@ -187,6 +195,8 @@ class Plan:
                 i += 1
             x = y
         self.pred = x
+        if getattr(self, "_head", None) is not None and len(prog.ops) != self._head["op0"] + 2:
+            self._head = None
         self.programs["forward"] = prog
         self._emit_to = None
 
@@ -363,12 +373,19 @@ class Plan:
             begin_at = len(prog.ops)
             prog.ops.append(None)  # placeholder for step_begin (needs the number of updated layers)
             prog.meta.append(("step_begin", 0))
-            prog.ops.extend(self.programs["forward"].ops)
-            prog.meta.extend(self.programs["forward"].meta)
+            head = getattr(self, "_head", None) if (fused and lk == ops.LOSS_CCE) else None
+            n_fwd = head["op0"] if head is not None else len(self.programs["forward"].ops)
+            prog.ops.extend(self.programs["forward"].ops[:n_fwd])
+            prog.meta.extend(self.programs["forward"].meta[:n_fwd])
             err0 = self.buf(self.pred.shape)
             s0 = self.slot()
             pred, y_in, acc, ss = self.pred, self.y_in, self.acc, self.ss
-            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
+            if head is not None:   # Dense + Softmax + CCE + (p - y) in one launch
+                hx, hw, hb = head["x"], head["layer"]._weights, head["layer"]._bias
+                self.emit(lambda: ops.dense_softmax_cce(hx, hw, hb, y_in, pred, err0, acc, ss, s0), "dense_softmax_cce",
+                          (hx, hw, y_in, pred, err0))
+            else:
+                self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
             if self.dp is not None:
                 self.dp.flatten_grads(self.layers)
                 if s0 == 0:

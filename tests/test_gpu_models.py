@@ -13,7 +13,7 @@ import nnl_oracle as O
 from helpers import check_packed, nrel
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-5
+TOL = 3e-5   # steps >= 1 of the golden traces run without teacher forcing: fp32 rounding of step 0 propagates through Adam
 
 
 def _nn():

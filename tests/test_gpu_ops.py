@@ -119,7 +119,9 @@ def test_dense_golden(K, golden):
 
 
 @pytest.mark.parametrize("M,N,Kd,act", [(32, 128, 784, "relu"), (256, 64, 6272, "relu"), (256, 10, 64, "linear"),
-                                        (100, 70, 33, "sigmoid"), (1, 5, 3, "tanh"), (300, 300, 300, "leakyrelu")])
+                                        (100, 70, 33, "sigmoid"), (1, 5, 3, "tanh"), (300, 300, 300, "leakyrelu"),
+                                        (100, 48, 2048, "relu"), (256, 64, 1028, "tanh"), (7, 4, 1060, "linear"),   # skinny slab kernels
+                                        (64, 10, 4096, "linear"), (512, 10, 64, "relu"), (600, 3, 50, "relu")])     # small-N kernels
 def test_dense_oracle(K, M, N, Kd, act):
     rng = np.random.default_rng(M * 7 + N)
     x = rng.normal(size=(M, Kd)).astype(np.float32)
