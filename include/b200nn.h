@@ -230,6 +230,11 @@ int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float*
                          float* r_out, int mode, long long B_total, double* ss_out0, double* ss_out1, double* ss_out2,
                          uint64_t chain_out, float* ws, void* stream);
 
+/* the reduction of the weight-gradient partials as its own launch: under data parallelism it has to follow the exchange
+ * of the clip slots in chain_out (call b200nn_convblock_bwd with mode 2 and dw = NULL first) */
+int b200nn_convblock_wgrad_reduce(const b200nn_conv_geom* g, const float* ws, const double* ss, uint64_t chain_out, float* dw,
+                                  float* db, void* stream);
+
 /* ---- optimizers (optimizers.py:47-50, 167-245) and gradient clip (models.py:240-242) -------- */
 typedef struct {
     float* p;          /* parameter tensor (updated in place, optimizers.py:223) */

@@ -87,6 +87,7 @@ _SIGNATURES = {
                                       c_float, c_float, _P]),
     "b200nn_convblock_bwd": (c_int, [C.POINTER(ConvGeom), _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, c_u64, _P, _P, _P, _P,
                                       _P, c_int, c_ll, _P, _P, _P, c_u64, _P, _P]),
+    "b200nn_convblock_wgrad_reduce": (c_int, [C.POINTER(ConvGeom), _P, _P, c_u64, _P, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
     # data parallelism (csrc/comm.cu) and the split BatchNorm kernels

@@ -200,6 +200,11 @@ def convblock_bwd(g, x, w, b, act, alpha, gamma, beta, save_mean, save_invstd, e
                                      _slot_ptr(ss, slot2), pack_chain(chain_out), ptr(ws), stream()))
 
 
+def convblock_wgrad_reduce(g, ws, ss, chain_out, dw, db):
+    _f32(ws, dw, db)
+    check(lib().b200nn_convblock_wgrad_reduce(C.byref(g), ptr(ws), ptr(ss), pack_chain(chain_out), ptr(dw), ptr(db), stream()))
+
+
 # ---- BatchNorm / MaxPool -----------------------------------------------------------------------------
 def bn_fwd_train(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y, momentum, eps):
     _f32(x, gamma, beta, rmean, rvar, save_mean, save_invstd, y)

@@ -520,4 +520,16 @@ int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float*
     return B200NN_OK;
 }
 
+// The fixed-order reduction of the per-window weight-gradient partials alone (data parallel: it must run AFTER the clip slots
+// in chain_out have been summed over the ranks, i.e. as a separate launch from b200nn_convblock_bwd(mode 2, dw = NULL)).
+int b200nn_convblock_wgrad_reduce(const b200nn_conv_geom* g, const float* ws, const double* ss, uint64_t chain_out, float* dw,
+                                  float* db, void* stream) {
+    B200NN_REQUIRE(g != nullptr && ws != nullptr && dw != nullptr, "convblock_wgrad_reduce: null argument");
+    const int M = 9 * g->C + 1, splits = (g->H / 2) * (g->W / 2);
+    const long long total = (long long)M * g->F;
+    convblock_reduce_kernel<<<(int)((total + 31) / 32), 1024, 0, as_stream(stream)>>>(ws, splits, M, g->F, ss, chain_out, dw, db);
+    B200NN_LAUNCH_CHECK("convblock_reduce");
+    return B200NN_OK;
+}
+
 }  // extern "C"

@@ -120,9 +120,15 @@ class Plan:
 
     def _sync_slots(self, first):
         """Sum the clip slots [first, n_slots) produced by the op(s) just emitted over the ranks: the reference's clips
-        act on whole-batch tensors (models.py:214), so their norms are global."""
+        act on whole-batch tensors (models.py:214), so their norms are global. Slots already exchanged (sync_slots_now
+        called from inside a layer's hook) are skipped."""
+        first = max(first, getattr(self, "_slots_synced", 0))
         if self.dp is not None and self.n_slots > first:
             self.allreduce(self.ss[first:self.n_slots], "slot_exchange")
+        self._slots_synced = self.n_slots
+
+    def sync_slots_now(self):
+        self._sync_slots(0)
 
     @property
     def ws(self):
@@ -393,6 +399,7 @@ class Plan:
                 else:
                     self.allreduce(self.acc, "loss_exchange")
                     self.allreduce(self.ss[s0:s0 + 1], "slot_exchange")
+                self._slots_synced = self.n_slots
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
             self._grad_exchange(updates)
             ups = []

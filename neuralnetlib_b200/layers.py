@@ -71,6 +71,9 @@ class _EagerCtx:
     def emit(self, fn, name=None, io=()):
         fn()
 
+    def sync_slots_now(self):
+        pass
+
 
 def _act_of(layer):
     """(kind, alpha) of a fusable Activation layer, else (ACT_NONE, 0)."""
@@ -547,8 +550,10 @@ class Conv2D(Layer, _ParamMixin):
             ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, None, 1,
                                                b_total, s0, None, None, (), None), "convblock_bwd_sums", (x, et))
             ctx.allreduce(sums, "bn_sums_exchange")
-            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, dw, db, r_out, 2,
-                                               b_total, None, s1, s2, chain_out, ctx.ws), "convblock_bwd_apply", (x, et, dw, r_out))
+            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, r_out, 2,
+                                               b_total, None, s1, s2, (), ctx.ws), "convblock_bwd_apply", (x, et, r_out))
+            ctx.sync_slots_now()   # the weight gradient owes the three clips just produced: their norms are global
+            ctx.emit(lambda: ops.convblock_wgrad_reduce(g, ctx.ws, ss, chain_out, dw, db), "convblock_reduce", (dw,))
         else:
             dgp, dbp = bn._d_gamma.data_ptr(), bn._d_beta.data_ptr()
             ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, dw, db, r_out, 0,
