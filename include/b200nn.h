@@ -214,21 +214,27 @@ int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, u
  *      csrc/conv_block.cu). Replaces layers.py:442-489, :231-237, :1230-1276, :570-643 and the weight-gradient half of
  *      :491-530 for this pattern. `mode`: 0 single GPU; 1 / 2 the two halves around the data-parallel sum of
  *      `stats` (forward, fp64 [2][H*W*F]) resp. dgamma / dbeta (backward); B_total = global batch. */
+struct b200nn_comm;   /* data-parallel communicator, declared below */
 int b200nn_convblock_supported(const b200nn_conv_geom* g, int act, float alpha);
 size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g);
 int b200nn_convblock_fwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
                          const float* gamma, const float* beta, float* running_mean, float* running_var, float* save_mean,
                          float* save_invstd, double* stats, int mode, long long B_total, float* y_pool, float momentum,
-                         float eps, void* stream);
+                         float eps, struct b200nn_comm* comm, int site, size_t region_off, void* stream);
 /* err: error w.r.t. the pooled output, pending clips (ss, chain). Emits d_gamma / d_beta, the three sums of squares of the
  * reference's clip points (pool-bwd, BN-bwd, activation-bwd outputs) and dw / db scaled by chain_out (= those three
  * slots, complete once the main kernel has run). r_out (nullable): the error w.r.t. the conv output, materialised only
- * when a data gradient is wanted (it still owes chain_out). ws: b200nn_convblock_ws_bytes. */
+ * when a data gradient is wanted (it still owes chain_out). ws: b200nn_convblock_ws_bytes.
+ * mode 3 ("peer-fused", both directions): ONE kernel per direction under data parallelism — every CTA merges its BatchNorm
+ * batch reductions with the other GPUs' through CUDA-IPC peer memory over NVLink inside the kernel (persistent launch; other
+ * CTAs of the SM compute while one waits). comm / site / region_off: a region of b200nn_convblock_region_bytes() bytes from
+ * b200nn_comm_region_create; NULL / -1 / 0 for modes 0-2. */
+size_t b200nn_convblock_region_bytes(const b200nn_conv_geom* g, int world);
 int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
                          const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                          const float* err, const double* ss, uint64_t chain, float* dgamma, float* dbeta, float* dw, float* db,
                          float* r_out, int mode, long long B_total, double* ss_out0, double* ss_out1, double* ss_out2,
-                         uint64_t chain_out, float* ws, void* stream);
+                         uint64_t chain_out, float* ws, struct b200nn_comm* comm, int site, size_t region_off, void* stream);
 
 /* the reduction of the weight-gradient partials as its own launch: under data parallelism it has to follow the exchange
  * of the clip slots in chain_out (call b200nn_convblock_bwd with mode 2 and dw = NULL first) */
@@ -286,6 +292,9 @@ int b200nn_comm_timeouts(const b200nn_comm* comm);
 /* reserve an exchange site (double-buffered inbox of world x payload_bytes) in the symmetric buffer; every rank
  * must create the same sites in the same order */
 int b200nn_comm_site_create(b200nn_comm* comm, size_t payload_bytes, int* site_out);
+/* a raw zero-initialised region of the symmetric buffer (same offset on every rank) with its own round counter, for kernels
+ * that exchange over peer memory themselves (b200nn_convblock_* mode 3) */
+int b200nn_comm_region_create(b200nn_comm* comm, size_t bytes, int* site_out, size_t* offset_out);
 /* buf[0..n) <- sum over ranks, in place. dtype 0 = float32, 1 = float64. site >= 0: one-shot peer-memory exchange
  * through that site; site < 0: ncclAllReduce. */
 int b200nn_comm_allreduce_sum(b200nn_comm* comm, int site, void* buf, long long n, int dtype, void* stream);

@@ -84,9 +84,11 @@ _SIGNATURES = {
     "b200nn_convblock_supported": (c_int, [C.POINTER(ConvGeom), c_int, c_float]),
     "b200nn_convblock_ws_bytes": (c_size_t, [C.POINTER(ConvGeom)]),
     "b200nn_convblock_fwd": (c_int, [C.POINTER(ConvGeom), _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, _P,
-                                      c_float, c_float, _P]),
+                                      c_float, c_float, _P, c_int, c_size_t, _P]),
     "b200nn_convblock_bwd": (c_int, [C.POINTER(ConvGeom), _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, c_u64, _P, _P, _P, _P,
-                                      _P, c_int, c_ll, _P, _P, _P, c_u64, _P, _P]),
+                                      _P, c_int, c_ll, _P, _P, _P, c_u64, _P, _P, c_int, c_size_t, _P]),
+    "b200nn_convblock_region_bytes": (c_size_t, [C.POINTER(ConvGeom), c_int]),
+    "b200nn_comm_region_create": (c_int, [_P, c_size_t, C.POINTER(c_int), C.POINTER(c_size_t)]),
     "b200nn_convblock_wgrad_reduce": (c_int, [C.POINTER(ConvGeom), _P, _P, c_u64, _P, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),

@@ -183,21 +183,28 @@ def convblock_ws_bytes(g: ConvGeom):
 
 
 def convblock_fwd(g, x, w, b, act, alpha, gamma, beta, rmean, rvar, save_mean, save_invstd, stats, mode, b_total, y_pool,
-                  momentum, eps):
+                  momentum, eps, peer=None):
+    """peer: (comm handle, site, region offset) for mode 3."""
     _f32(x, w, b, gamma, beta, rmean, rvar, save_mean, save_invstd, y_pool)
+    ch, site, off = peer if peer is not None else (None, -1, 0)
     check(lib().b200nn_convblock_fwd(C.byref(g), ptr(x), ptr(w), ptr(b), act, alpha, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar),
                                      ptr(save_mean), ptr(save_invstd), ptr(stats), int(mode), int(b_total), ptr(y_pool),
-                                     momentum, eps, stream()))
+                                     momentum, eps, ch, int(site), int(off), stream()))
 
 
 def convblock_bwd(g, x, w, b, act, alpha, gamma, beta, save_mean, save_invstd, err, ss, chain, sums_or_dg, dbeta, dw, db, r_out,
-                  mode, b_total, slot0, slot1, slot2, chain_out, ws):
+                  mode, b_total, slot0, slot1, slot2, chain_out, ws, peer=None):
     """sums_or_dg / dbeta: device pointers (ints) of d_gamma and d_beta."""
     _f32(x, w, b, gamma, beta, save_mean, save_invstd, err, dw, db, r_out)
+    ch, site, off = peer if peer is not None else (None, -1, 0)
     check(lib().b200nn_convblock_bwd(C.byref(g), ptr(x), ptr(w), ptr(b), act, alpha, ptr(gamma), ptr(beta), ptr(save_mean),
                                      ptr(save_invstd), ptr(err), ptr(ss), pack_chain(chain), sums_or_dg, dbeta, ptr(dw), ptr(db),
                                      ptr(r_out), int(mode), int(b_total), _slot_ptr(ss, slot0), _slot_ptr(ss, slot1),
-                                     _slot_ptr(ss, slot2), pack_chain(chain_out), ptr(ws), stream()))
+                                     _slot_ptr(ss, slot2), pack_chain(chain_out), ptr(ws), ch, int(site), int(off), stream()))
+
+
+def convblock_region_bytes(g, world):
+    return int(lib().b200nn_convblock_region_bytes(C.byref(g), int(world)))
 
 
 def convblock_wgrad_reduce(g, ws, ss, chain_out, dw, db):

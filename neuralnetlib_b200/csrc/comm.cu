@@ -17,25 +17,12 @@
 //     inboxes are double-buffered on the parity of a device-resident round counter so that a fast rank can never
 //     overwrite data a slow rank is still summing.
 #include <dlfcn.h>
-#include <nccl.h>   // types and prototypes only; every call goes through dlsym'd pointers
 #include <stddef.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "comm.cuh"   // nccl.h types and prototypes only; every call goes through dlsym'd pointers
 
 namespace b200nn {
-
-constexpr int MAX_WORLD = 8;
-constexpr int MAX_SITES = 96;
-constexpr int MAX_XCTAS = 64;
-
-struct SymHeader {                                       // offset 0 of every rank's symmetric buffer
-    unsigned int flags[MAX_SITES][2][MAX_WORLD][MAX_XCTAS];
-    unsigned int seq[MAX_SITES];                          // completed rounds per site (local)
-    unsigned int done[MAX_SITES];                         // CTAs that finished the current round (local)
-    unsigned int timeouts;                                // waits that gave up (a peer never arrived): results are invalid
-};
-constexpr unsigned long long WAIT_TIMEOUT_NS = 10ull * 1000ull * 1000ull * 1000ull;   // a lost peer must not hang the GPU
 
 struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
@@ -85,29 +72,6 @@ static int load_nccl(const char* path) {
         }                                                                                                  \
     } while (0)
 
-struct PeerPtrs {
-    char* p[MAX_WORLD];
-};
-
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float ld_inbox(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_inbox(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ uint4 ld_inbox16(const uint4* p) {
     uint4 v;
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -154,19 +118,7 @@ __global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int r
         SymHeader* peer = reinterpret_cast<SymHeader*>(peers.p[threadIdx.x]);
         st_release_sys(&peer->flags[site][par][rank][blockIdx.x], seq);
         const unsigned* mine = &me->flags[site][par][threadIdx.x][blockIdx.x];
-        unsigned long long t0 = 0;
-        unsigned spins = 0;
-        while (ld_acquire_sys(mine) != seq) {
-            if ((++spins & 0x3ffu) == 0) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > WAIT_TIMEOUT_NS) {
-                    atomicAdd(&me->timeouts, 1u);
-                    break;
-                }
-            }
-        }
+        wait_flag(mine, seq, &me->timeouts);
     }
     __syncthreads();
     const char* inbox = peers.p[rank] + data_off + (size_t)par * world * rank_stride;
@@ -196,18 +148,6 @@ __global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int r
 }  // namespace b200nn
 
 using namespace b200nn;
-
-struct b200nn_comm {
-    int rank, world, device;
-    ncclComm_t nccl;
-    char* sym_local;
-    size_t sym_bytes;
-    char* peer[MAX_WORLD];
-    bool peer_ready;
-    size_t bump;
-    int n_sites;
-    size_t site_off[MAX_SITES], site_stride[MAX_SITES];
-};
 
 extern "C" {
 
@@ -316,6 +256,24 @@ int b200nn_comm_site_create(b200nn_comm* c, size_t payload_bytes, int* site_out)
     c->site_stride[s] = stride;
     c->bump += need;
     *site_out = s;
+    return B200NN_OK;
+}
+
+// A raw, zero-initialised region of the symmetric buffer (same offset on every rank) plus a site id for its round counter:
+// for kernels that exchange over peer memory THEMSELVES (conv_block.cu's peer-fused mode).
+int b200nn_comm_region_create(b200nn_comm* c, size_t bytes, int* site_out, size_t* offset_out) {
+    B200NN_REQUIRE(c != nullptr && site_out != nullptr && offset_out != nullptr, "comm_region_create: null argument");
+    B200NN_REQUIRE(c->peer_ready, "comm_region_create: peer memory is not mapped");
+    B200NN_REQUIRE(c->n_sites < MAX_SITES, "comm_region_create: more than %d exchange sites", MAX_SITES);
+    const size_t need = (bytes + 255) & ~size_t(255);
+    B200NN_REQUIRE(c->bump + need <= c->sym_bytes, "comm_region_create: symmetric buffer exhausted (%zu + %zu > %zu bytes)", c->bump, need,
+                   c->sym_bytes);
+    const int s = c->n_sites++;
+    c->site_off[s] = c->bump;
+    c->site_stride[s] = 0;
+    *site_out = s;
+    *offset_out = c->bump;
+    c->bump += need;
     return B200NN_OK;
 }
 

@@ -17,7 +17,9 @@
 // are warp-shuffle reductions, no shared-memory or cross-CTA reduction exists, all conv outputs of the window stay in registers (batch <= 256 per GPU;
 // larger batches use the unfused kernels), and the 784 CTAs of config 2 balance over 148 SMs. Replaces layers.py:442-489 (+
 // preprocessing.py:34-79), :231-237, :1230-1276, :570-643 and the weight-gradient half of :491-530 for this pattern.
-#include "common.cuh"
+#include <string.h>
+
+#include "comm.cuh"
 
 namespace b200nn {
 
@@ -124,25 +126,93 @@ __device__ __forceinline__ void cb_load_filter(const CbArgs& a, int f, float (&w
     bias = a.bias != nullptr ? a.bias[f] : 0.0f;
 }
 
+// ---- peer-fused mode (MODE 3): the batch reductions of BatchNorm completed ACROSS GPUs inside the kernel ------------------
+// Every warp contributes 8 floats per item (lane l < 8 sends element l). Low-latency protocol: each element travels as ONE
+// 8-byte store {value, round number} straight into every peer's inbox over NVLink (a naturally aligned 8-byte store is a
+// single transaction, so the value is valid whenever its round number is), and the receiving lane polls its own word:
+// no fence, no separate flag, no block-wide barrier -- warps proceed independently and the other CTAs of the SM compute
+// while one waits. Region (b200nn_comm_region_create): word[2 parity][world][items][64] of 8 bytes, double-buffered on the
+// parity of the device-resident round counter. The launch is persistent (grid <= co-resident CTAs, items strided), so the
+// CTA a rank waits for is always resident on the peer.
+__host__ __device__ inline size_t cb_region_bytes(int items, int world) { return (size_t)2 * world * items * 64 * 8; }
+
+__device__ __forceinline__ void cb_peer_gather(const PeerRegion& pr, unsigned seq, int item, int items, float mine,
+                                               float (&in)[MAX_WORLD]) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned par = seq & 1u;
+    SymHeader* me = reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank]);
+    const size_t slot = (size_t)item * 64 + wid * 8 + lane;
+    const size_t per_rank = (size_t)items * 64;
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) in[r] = 0.0f;
+    if (lane < 8) {
+        const unsigned bits = __float_as_uint(mine);
+#pragma unroll
+        for (int p = 0; p < MAX_WORLD; ++p) {
+            if (p < pr.world) {
+                uint2* dst = reinterpret_cast<uint2*>(pr.peers.p[p] + pr.off) + ((size_t)par * pr.world + pr.rank) * per_rank + slot;
+                asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(bits), "r"(seq) : "memory");
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MAX_WORLD; ++r) {
+            if (r < pr.world) {
+                const uint2* src = reinterpret_cast<const uint2*>(pr.peers.p[pr.rank] + pr.off) + ((size_t)par * pr.world + r) * per_rank + slot;
+                unsigned vx, vy, spins = 0;
+                unsigned long long t0 = 0;
+                for (;;) {
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(src) : "memory");
+                    if (vy == seq) break;
+                    if ((++spins & 0x3ffu) == 0) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
+                    }
+                }
+                in[r] = __uint_as_float(vx);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void cb_round_done(const PeerRegion& pr, unsigned seq) {
+    SymHeader* me = reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&me->done[pr.site], 1u) == gridDim.x - 1) {
+            me->done[pr.site] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&me->seq[pr.site]) = seq;
+        }
+    }
+}
+
 // MODE 0: single GPU. MODE 1 (data parallel): local moments only -> stats (fp64 [2][P]: sum, sum of squares).
-// MODE 2: normalise + pool from rank-summed `stats`.
+// MODE 2: normalise + pool from rank-summed `stats`. MODE 3: one kernel, moments merged across GPUs over peer memory.
+// 1-D grid over items = (pool window, group of 8 filters), strided (persistent in MODE 3).
 template <int C, int MODE, int ACT>
 __global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, float* __restrict__ rmean, float* __restrict__ rvar,
                                                                    double* __restrict__ stats, float* __restrict__ y_pool,
-                                                                   float momentum, float eps) {
+                                                                   float momentum, float eps, PeerRegion pr, int items) {
     using Cfg = CbCfg<C>;
     extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | outs[CB_FPC][CB_MAXB]
     float* patch = cb_smem;
     float (*outs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(cb_smem + CB_MAXB * Cfg::STRIDE);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int ox = blockIdx.x, oy = blockIdx.y, f0 = blockIdx.z * CB_FPC, f = f0 + wid;
     const int OW = a.W >> 1, OH = a.H >> 1;
     const long long P = (long long)a.H * a.W * a.F;
+    unsigned seq = 0;
+    if (MODE == 3) seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ox = item % OW, oy = (item / OW) % OH, f0 = (item / (OW * OH)) * CB_FPC, f = f0 + wid;
     float wr[9 * C], bias;
     cb_load_filter<C>(a, f, wr, bias);
     long long pos[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) pos[q] = ((long long)(2 * oy + (q >> 1)) * a.W + 2 * ox + (q & 1)) * a.F + f;
+    __syncthreads();                                                          // the previous item is done with the shared tiles
     cb_stage<C>(patch, a, oy, ox);
     __syncthreads();
     float S[CB_NS][4];                                                        // clip(act(conv)) of this lane's samples (layers.py:1234)
@@ -187,11 +257,39 @@ __global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, flo
                     stats[P + pos[q]] = (double)m2[q] + S1 * S1 / (double)a.B;
                 }
             }
-            return;
+            continue;
+        }
+        float ntot = (float)a.B;
+        if (MODE == 3) {
+            // merge the per-rank (mean, M2) pairs (equal counts) without cancellation: mean_g = avg(mean_r),
+            // M2_g = sum_r [ M2_r + B * (mean_r - mean_g)^2 ]; every rank sums in rank order => identical statistics
+            float mine = mean[0];                                             // lane l < 4: mean[l]; lane 4 + l: m2[l]
+            mine = lane == 1 ? mean[1] : mine; mine = lane == 2 ? mean[2] : mine; mine = lane == 3 ? mean[3] : mine;
+            mine = lane == 4 ? m2[0] : mine; mine = lane == 5 ? m2[1] : mine; mine = lane == 6 ? m2[2] : mine; mine = lane == 7 ? m2[3] : mine;
+            float mr[MAX_WORLD], qr[MAX_WORLD];
+            cb_peer_gather(pr, seq, item, items, mine, mr);
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) qr[r] = __shfl_sync(0xffffffffu, mr[r], (lane + 4) & 31);   // lane q <- M2_r[q]
+            float mg = 0.0f;
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) mg += r < pr.world ? mr[r] : 0.0f;
+            mg /= (float)pr.world;
+            float M2 = 0.0f;
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) {
+                const float d = mr[r] - mg;
+                M2 += r < pr.world ? fmaf((float)a.B * d, d, qr[r]) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mean[q] = __shfl_sync(0xffffffffu, mg, q);
+                m2[q] = __shfl_sync(0xffffffffu, M2, q);
+            }
+            ntot = (float)a.n_total;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            bvar[q] = m2[q] / (float)a.B + eps;                               // layers.py:1238
+            bvar[q] = m2[q] / ntot + eps;                                     // layers.py:1238
             invstd[q] = rsqrtf(bvar[q] + eps);                                // layers.py:1252
         }
     } else {
@@ -226,6 +324,8 @@ __global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, flo
         dst[0] = v0;
         dst[1] = v1;
     }
+  }
+    if (MODE == 3) cb_round_done(pr, seq);
 }
 
 // Backward. MODE 0: single GPU. MODE 1: pass 1 only (local sum(u), sum(u*xhat) -> dbeta / dgamma, ss0). MODE 2: pass 2 from
@@ -235,7 +335,8 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
                                                                       const double* __restrict__ ss, uint64_t chain,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                       float* __restrict__ partial, float* __restrict__ r_out,
-                                                                      double* ss0, double* ss1, double* ss2) {
+                                                                      double* ss0, double* ss1, double* ss2, PeerRegion pr,
+                                                                      int items) {
     using Cfg = CbCfg<C>;
     extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | errs[CB_FPC][CB_MAXB]
     float* patch = cb_smem;
@@ -243,8 +344,12 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
     __shared__ double scratch[32];
     const float scale = chain_scale(ss, chain);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int ox = blockIdx.x, oy = blockIdx.y, f0 = blockIdx.z * CB_FPC, f = f0 + wid;
     const int OW = a.W >> 1, OH = a.H >> 1;
+    unsigned seq = 0;
+    if (MODE == 3) seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;                                   // clip-slot partials, accumulated over this CTA's items
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ox = item % OW, oy = (item / OW) % OH, f0 = (item / (OW * OH)) * CB_FPC, f = f0 + wid;
     float wr[9 * C], bias;
     cb_load_filter<C>(a, f, wr, bias);
     long long pos[4];
@@ -258,6 +363,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         bt[q] = a.beta[pos[q]];
     }
     const long long OP = (long long)OH * OW * a.F, obase = ((long long)oy * OW + ox) * a.F + f0;
+    __syncthreads();                                                          // the previous item is done with the shared tiles
     cb_stage<C>(patch, a, oy, ox);
     for (int s = threadIdx.x; s < a.B; s += CB_THREADS) {                     // pooled error: one 32-byte run per sample
         const float4* src = reinterpret_cast<const float4*>(err + (long long)s * OP + obase);
@@ -279,7 +385,6 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
     }
     float su[4] = {0.f, 0.f, 0.f, 0.f}, sux[4] = {0.f, 0.f, 0.f, 0.f};
     if (MODE != 2) {
-        float a0 = 0.0f;
 #pragma unroll
         for (int j = 0; j < CB_NS; ++j) {                    // pass 1: U = pool-bwd(e); d_beta = sum U, d_gamma = sum U*xhat
             const int s = lane + 32 * j;
@@ -304,13 +409,30 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         for (int q = 0; q < 4; ++q) {
             su[q] = warp_sum(su[q]);
             sux[q] = warp_sum(sux[q]);
-            if (lane == 0) {
+        }
+        if (MODE == 3) {                                     // sum the two reductions over the ranks, in rank order
+            float mine = su[0];                                               // lane l < 4: su[l]; lane 4 + l: sux[l]
+            mine = lane == 1 ? su[1] : mine; mine = lane == 2 ? su[2] : mine; mine = lane == 3 ? su[3] : mine;
+            mine = lane == 4 ? sux[0] : mine; mine = lane == 5 ? sux[1] : mine; mine = lane == 6 ? sux[2] : mine; mine = lane == 7 ? sux[3] : mine;
+            float in[MAX_WORLD];
+            cb_peer_gather(pr, seq, item, items, mine, in);
+            float tot = 0.0f;
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) tot += r < pr.world ? in[r] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                su[q] = __shfl_sync(0xffffffffu, tot, q);
+                sux[q] = __shfl_sync(0xffffffffu, tot, 4 + q);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
                 if (dbeta != nullptr) dbeta[pos[q]] = su[q];                 // layers.py:1262
                 if (dgamma != nullptr) dgamma[pos[q]] = sux[q];              // layers.py:1261
             }
         }
-        if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
-        if (MODE == 1) return;
+        if (MODE == 1) continue;
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -324,7 +446,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         su[q] *= invB;
         sux[q] *= invB;
     }
-    float gw[9 * C], gb = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    float gw[9 * C], gb = 0.0f;
 #pragma unroll
     for (int k = 0; k < 9 * C; ++k) gw[k] = 0.0f;
 #pragma unroll
@@ -378,7 +500,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         }
     }
     if (partial != nullptr) {
-        float* dst = partial + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * (Cfg::K + 1)) * a.F + f;
+        float* dst = partial + ((long long)(oy * OW + ox) * (Cfg::K + 1)) * a.F + f;
 #pragma unroll
         for (int k = 0; k < 9 * C; ++k) {
             const float t = warp_sum(gw[k]);
@@ -387,8 +509,11 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         const float tb = warp_sum(gb);
         if (lane == 0) dst[(long long)Cfg::K * a.F] = tb;                     // layers.py:521
     }
-    if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
-    if (ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+  }
+    if (MODE != 2 && ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+    if (MODE != 1 && ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+    if (MODE != 1 && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+    if (MODE == 3) cb_round_done(pr, seq);
 }
 
 // partial[s][m][n] -> out, fixed order, with the lazy clip multiplier; rows >= n_rows go to db (same contract as the split-K
@@ -431,18 +556,30 @@ static int cb_check(const char* who, const b200nn_conv_geom* g, int act, float a
     return B200NN_OK;
 }
 
+// grid: one CTA per item, or (persistent) as many CTAs as are co-resident on the device, whichever is smaller
 template <class Kern, class... Args>
-static int cb_launch(Kern kern, dim3 grid, size_t smem, cudaStream_t st, Args... args) {
-    static thread_local const void* configured[64] = {nullptr};
-    bool seen = false;
-    for (auto p : configured) seen = seen || p == (const void*)kern;
-    if (!seen) {
-        B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        for (auto& p : configured) if (p == nullptr) { p = (const void*)kern; break; }
+static int cb_launch(Kern kern, int items, bool persistent, size_t smem, cudaStream_t st, Args... args) {
+    struct Entry { const void* k; int resident; };
+    static thread_local Entry table[64] = {};
+    Entry* e = nullptr;
+    for (auto& t : table) {
+        if (t.k == (const void*)kern) { e = &t; break; }
+        if (t.k == nullptr) {
+            B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            B200NN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CB_THREADS, smem));
+            t.k = (const void*)kern;
+            t.resident = (per_sm > 0 ? per_sm : 1) * kNumSMs;
+            e = &t;
+            break;
+        }
     }
+    B200NN_REQUIRE(e != nullptr, "convblock: kernel table full");
+    const int grid = persistent && items > e->resident ? e->resident : items;
     kern<<<grid, CB_THREADS, smem, st>>>(args...);
     return B200NN_OK;
 }
+
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -461,13 +598,13 @@ size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g) {
 }
 
 #define CB_SMEM(C) ((size_t)(CB_MAXB * CbCfg<C>::STRIDE + CB_FPC * CB_MAXB) * sizeof(float))
-#define CB_DISPATCH_C(KERN, MODE, ACT, ...)                                                                   \
-    do {                                                                                                      \
-        int rc_;                                                                                              \
-        if (g->C == 1) rc_ = cb_launch(KERN<1, MODE, ACT>, grid, CB_SMEM(1), st, __VA_ARGS__);                \
-        else if (g->C == 2) rc_ = cb_launch(KERN<2, MODE, ACT>, grid, CB_SMEM(2), st, __VA_ARGS__);           \
-        else rc_ = cb_launch(KERN<3, MODE, ACT>, grid, CB_SMEM(3), st, __VA_ARGS__);                          \
-        if (rc_) return rc_;                                                                                  \
+#define CB_DISPATCH_C(KERN, MODE, ACT, ...)                                                                              \
+    do {                                                                                                                 \
+        int rc_;                                                                                                         \
+        if (g->C == 1) rc_ = cb_launch(KERN<1, MODE, ACT>, items, MODE == 3, CB_SMEM(1), st, __VA_ARGS__);               \
+        else if (g->C == 2) rc_ = cb_launch(KERN<2, MODE, ACT>, items, MODE == 3, CB_SMEM(2), st, __VA_ARGS__);          \
+        else rc_ = cb_launch(KERN<3, MODE, ACT>, items, MODE == 3, CB_SMEM(3), st, __VA_ARGS__);                         \
+        if (rc_) return rc_;                                                                                             \
     } while (0)
 #define CB_DISPATCH(KERN, MODE, ...)                                                             \
     do {                                                                                         \
@@ -475,19 +612,37 @@ size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g) {
         else CB_DISPATCH_C(KERN, MODE, -1, __VA_ARGS__);                                         \
     } while (0)
 
+static int cb_peer_region(const char* who, int mode, b200nn_comm* comm, int site, size_t region_off, int items, PeerRegion* pr) {
+    memset(pr, 0, sizeof(*pr));
+    if (mode != 3) return B200NN_OK;
+    B200NN_REQUIRE(comm != nullptr && comm->peer_ready && site >= 0 && site < comm->n_sites, "%s: mode 3 needs a peer-mapped communicator", who);
+    B200NN_REQUIRE(region_off == comm->site_off[site] && region_off + cb_region_bytes(items, comm->world) <= comm->sym_bytes,
+                   "%s: exchange region too small (needs %zu bytes)", who, cb_region_bytes(items, comm->world));
+    for (int p = 0; p < MAX_WORLD; ++p) pr->peers.p[p] = p < comm->world ? comm->peer[p] : nullptr;
+    pr->rank = comm->rank; pr->world = comm->world; pr->site = site; pr->off = region_off;
+    return B200NN_OK;
+}
+
+size_t b200nn_convblock_region_bytes(const b200nn_conv_geom* g, int world) {
+    return cb_region_bytes((g->H / 2) * (g->W / 2) * (g->F / CB_FPC), world);
+}
+
 int b200nn_convblock_fwd(const b200nn_conv_geom* g, const float* x, const float* w, const float* b, int act, float alpha,
                          const float* gamma, const float* beta, float* running_mean, float* running_var, float* save_mean,
                          float* save_invstd, double* stats, int mode, long long B_total, float* y_pool, float momentum,
-                         float eps, void* stream) {
+                         float eps, b200nn_comm* comm, int site, size_t region_off, void* stream) {
     if (int rc = cb_check("convblock_fwd", g, act, alpha)) return rc;
-    B200NN_REQUIRE(mode >= 0 && mode <= 2 && (mode == 0 || stats != nullptr), "convblock_fwd: mode %d needs stats", mode);
+    B200NN_REQUIRE(mode >= 0 && mode <= 3 && (mode == 0 || mode == 3 || stats != nullptr), "convblock_fwd: mode %d needs stats", mode);
     B200NN_REQUIRE(mode == 1 || (reinterpret_cast<uintptr_t>(y_pool) & 15) == 0, "convblock_fwd: y_pool must be 16-byte aligned");
     CbArgs a{g->N, g->H, g->W, g->F, x, w, b, act, alpha, gamma, beta, save_mean, save_invstd, (double)(mode == 0 ? g->N : B_total)};
-    const dim3 grid(g->W / 2, g->H / 2, g->F / CB_FPC);
+    const int items = (g->W / 2) * (g->H / 2) * (g->F / CB_FPC);
+    PeerRegion pr;
+    if (int rc = cb_peer_region("convblock_fwd", mode, comm, site, region_off, items, &pr)) return rc;
     cudaStream_t st = as_stream(stream);
-    if (mode == 0) CB_DISPATCH(convblock_fwd_kernel, 0, a, running_mean, running_var, stats, y_pool, momentum, eps);
-    else if (mode == 1) CB_DISPATCH(convblock_fwd_kernel, 1, a, running_mean, running_var, stats, y_pool, momentum, eps);
-    else CB_DISPATCH(convblock_fwd_kernel, 2, a, running_mean, running_var, stats, y_pool, momentum, eps);
+    if (mode == 0) CB_DISPATCH(convblock_fwd_kernel, 0, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else if (mode == 1) CB_DISPATCH(convblock_fwd_kernel, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else if (mode == 2) CB_DISPATCH(convblock_fwd_kernel, 2, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else CB_DISPATCH(convblock_fwd_kernel, 3, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
     B200NN_LAUNCH_CHECK("convblock_fwd");
     return B200NN_OK;
 }
@@ -496,19 +651,22 @@ int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float*
                          const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                          const float* err, const double* ss, uint64_t chain, float* dgamma, float* dbeta, float* dw, float* db,
                          float* r_out, int mode, long long B_total, double* ss_out0, double* ss_out1, double* ss_out2,
-                         uint64_t chain_out, float* ws, void* stream) {
+                         uint64_t chain_out, float* ws, b200nn_comm* comm, int site, size_t region_off, void* stream) {
     if (int rc = cb_check("convblock_bwd", g, act, alpha)) return rc;
-    B200NN_REQUIRE(mode >= 0 && mode <= 2, "convblock_bwd: mode %d", mode);
-    B200NN_REQUIRE((mode == 0 || (dgamma != nullptr && dbeta != nullptr)) && (mode == 1 || ws != nullptr),
+    B200NN_REQUIRE(mode >= 0 && mode <= 3, "convblock_bwd: mode %d", mode);
+    B200NN_REQUIRE((mode == 0 || mode == 3 || (dgamma != nullptr && dbeta != nullptr)) && (mode == 1 || ws != nullptr),
                    "convblock_bwd: missing buffer for mode %d", mode);
     B200NN_REQUIRE((reinterpret_cast<uintptr_t>(err) & 15) == 0, "convblock_bwd: err must be 16-byte aligned");
     CbArgs a{g->N, g->H, g->W, g->F, x, w, b, act, alpha, gamma, beta, const_cast<float*>(save_mean), const_cast<float*>(save_invstd),
              (double)(mode == 0 ? g->N : B_total)};
-    const dim3 grid(g->W / 2, g->H / 2, g->F / CB_FPC);
+    const int items = (g->W / 2) * (g->H / 2) * (g->F / CB_FPC);
+    PeerRegion pr;
+    if (int rc = cb_peer_region("convblock_bwd", mode, comm, site, region_off, items, &pr)) return rc;
     cudaStream_t st = as_stream(stream);
-    if (mode == 0) CB_DISPATCH(convblock_bwd_kernel, 0, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
-    else if (mode == 1) CB_DISPATCH(convblock_bwd_kernel, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
-    else CB_DISPATCH(convblock_bwd_kernel, 2, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2);
+    if (mode == 0) CB_DISPATCH(convblock_bwd_kernel, 0, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else if (mode == 1) CB_DISPATCH(convblock_bwd_kernel, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else if (mode == 2) CB_DISPATCH(convblock_bwd_kernel, 2, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else CB_DISPATCH(convblock_bwd_kernel, 3, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
     B200NN_LAUNCH_CHECK("convblock_bwd");
     if (mode != 1 && dw != nullptr) {
         // the weight gradient still owes the three clips this kernel produced (pool-bwd / BN-bwd / act-bwd outputs): chain_out

@@ -118,6 +118,13 @@ class Plan:
         site = comm.site(t.numel() * t.element_size())
         self.emit(lambda: comm.allreduce(t, site), name, ())
 
+    def peer_region(self, nbytes):
+        """(comm handle, site, offset) of a fresh exchange region for a peer-fused kernel, or None (no peer memory / disabled)."""
+        if self.dp is None or os.environ.get("B200NN_PEER_FUSED", "1") == "0":
+            return None
+        r = self.dp.comm.region(nbytes)
+        return None if r is None else (self.dp.comm.handle, r[0], r[1])
+
     def _sync_slots(self, first):
         """Sum the clip slots [first, n_slots) produced by the op(s) just emitted over the ranks: the reference's clips
         act on whole-batch tensors (models.py:214), so their norms are global. Slots already exchanged (sync_slots_now

@@ -74,6 +74,9 @@ class _EagerCtx:
     def sync_slots_now(self):
         pass
 
+    def peer_region(self, nbytes):
+        return None
+
 
 def _act_of(layer):
     """(kind, alpha) of a fusable Activation layer, else (ACT_NONE, 0)."""
@@ -519,7 +522,12 @@ class Conv2D(Layer, _ParamMixin):
         st_bn.update(save_mean=sm, save_invstd=si, trained=True, fused_pool=True)
         w, b, gm, bt, rm, rv = self._weights, self._bias, bn._gamma, bn._beta, bn._running_mean, bn._running_var
         mom, eps = float(bn.momentum), float(bn.epsilon)
-        if ctx.dp is not None:
+        peer = ctx.peer_region(ops.convblock_region_bytes(g, ctx.world)) if ctx.dp is not None else None
+        if peer is not None:   # one kernel: the batch moments are merged across the GPUs over NVLink peer memory inside it
+            b_total = x.shape[0] * ctx.world
+            ctx.emit(lambda: ops.convblock_fwd(g, x, w, b, kind, alpha, gm, bt, rm, rv, sm, si, None, 3, b_total, yp, mom, eps, peer),
+                     "convblock_fwd_peer", (x, w, yp))
+        elif ctx.dp is not None:
             stats, b_total = ctx.buf64((2 * P,)), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.convblock_fwd(g, x, w, b, kind, alpha, gm, bt, rm, rv, sm, si, stats, 1, b_total, None, mom, eps),
                      "convblock_stats", (x,))
@@ -544,7 +552,15 @@ class Conv2D(Layer, _ParamMixin):
         w, b, dw, db, gm, bt = self._weights, self._bias, self._d_weights, self._d_bias, bn._gamma, bn._beta
         sm, si, ss, chain, et = st_bn["save_mean"], st_bn["save_invstd"], ctx.ss, err.chain, err.t
         bn._dgrad_pending = (ctx.ss, s0) if ctx.ss is not None else None
-        if ctx.dp is not None:
+        peer = ctx.peer_region(ops.convblock_region_bytes(g, ctx.world)) if ctx.dp is not None else None
+        if peer is not None:
+            b_total = x.shape[0] * ctx.world
+            dgp, dbp = bn._d_gamma.data_ptr(), bn._d_beta.data_ptr()
+            ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, r_out, 3,
+                                               b_total, s0, s1, s2, (), ctx.ws, peer), "convblock_bwd_peer", (x, et, r_out))
+            ctx.sync_slots_now()   # the weight gradient owes the three clips just produced: their norms are global
+            ctx.emit(lambda: ops.convblock_wgrad_reduce(g, ctx.ws, ss, chain_out, dw, db), "convblock_reduce", (dw,))
+        elif ctx.dp is not None:
             sums, b_total = bn._dp_sums(ctx), x.shape[0] * ctx.world
             dgp, dbp = sums.data_ptr() + 4 * P, sums.data_ptr()
             ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, None, 1,

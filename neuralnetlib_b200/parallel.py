@@ -116,7 +116,7 @@ class Communicator:
         self.peer = False
         self._n_sites = 0
         self.peer_max_bytes = int(os.environ.get("B200NN_PEER_MAX_BYTES", str(2 << 20)))
-        if use_peer and self.world > 1:
+        if use_peer and (self.world > 1 or use_peer == "force"):   # "force": map the symmetric buffer even for a world of one (tests)
             self._open_peer(sym_bytes or int(os.environ.get("B200NN_SYM_BYTES", str(256 << 20))))
         dist.barrier(group)
 
@@ -141,6 +141,17 @@ class Communicator:
         s = C.c_int(-1)
         B.check(B.lib().b200nn_comm_site_create(self.handle, int(nbytes), C.byref(s)))
         return s.value
+
+    def region(self, nbytes: int):
+        """A raw region of the symmetric buffer for kernels that exchange over peer memory themselves: (site, offset) or
+        None when peer memory is unavailable. Every rank must create the same regions in the same order."""
+        if not self.peer or self._n_sites >= 96:
+            return None
+        s, off = C.c_int(-1), C.c_size_t(0)
+        if B.lib().b200nn_comm_region_create(self.handle, int(nbytes), C.byref(s), C.byref(off)) != 0:
+            return None
+        self._n_sites += 1
+        return s.value, off.value
 
     def allreduce(self, t: torch.Tensor, site: int = -1, stream: int | None = None):
         """In-place sum of a contiguous float32 / float64 device tensor over the ranks, asynchronous on `stream` (a raw

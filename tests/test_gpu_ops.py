@@ -512,3 +512,49 @@ def test_convblock_first_block(K, Bn, H, W, C, F, act):
         assert nrel(K.host(dw), rdw) < 3e-5, modes
         # with a linear activation the bias gradient is sum over the batch of a BatchNorm backward output == 0 identically
         assert np.abs(K.host(db) - rdbias.reshape(-1)).max() < 3e-5 * max(np.abs(rdbias).max(), np.abs(rdw).max())
+
+
+def test_convblock_peer_fused_world_of_one(K):
+    """Mode 3 of the first-block kernels (batch reductions merged across GPUs through peer memory INSIDE the kernel, persistent
+    launch) with a world of one: the rank exchanges with itself through the CUDA-IPC symmetric buffer, so flags, parity
+    double-buffering, round counters and the merge arithmetic all run; results must equal mode 0. Two rounds (both parities)."""
+    import os
+    import torch.distributed as dist
+    from neuralnetlib_b200 import parallel as P
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    comm = P.Communicator(use_peer="force")
+    assert comm.peer
+    Bn, H, W, C, F = 96, 8, 8, 1, 16
+    rng = np.random.default_rng(5)
+    x = rng.random((Bn, H, W, C)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, C, F)) * 0.3).astype(np.float32)
+    b = (rng.normal(size=(F,)) * 0.1).astype(np.float32)
+    Pn = H * W * F
+    gamma = (1 + 0.1 * rng.normal(size=Pn)).astype(np.float32); beta = (0.1 * rng.normal(size=Pn)).astype(np.float32)
+    g = K.B.ConvGeom(Bn, H, W, C, F, 3, 3, 1, 1, 1, 1, H, W)
+    xd, wd, bd, gd, btd = K.dev(x), K.dev(w), K.dev(b), K.dev(gamma), K.dev(beta)
+    e = rng.normal(size=(Bn, H // 2, W // 2, F)).astype(np.float32)
+    ed = K.dev(e)
+    ws = K.empty((max(K.ops.convblock_ws_bytes(g) // 4, 1),))
+    nbytes = K.ops.convblock_region_bytes(g, 1)
+    rf, rb = comm.region(nbytes), comm.region(nbytes)
+    pf, pb = (comm.handle,) + rf, (comm.handle,) + rb
+
+    def run(mode, peer_f, peer_b):
+        rm, rv = K.B.zeros((Pn,)), K.B.to_device(np.ones(Pn))
+        sm, si = K.empty((Pn,)), K.empty((Pn,))
+        yp = K.empty((Bn, H // 2, W // 2, F))
+        K.ops.convblock_fwd(g, xd, wd, bd, 1, 0.0, gd, btd, rm, rv, sm, si, None, mode, Bn, yp, 0.9, 1e-5, peer_f)
+        ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+        dg, dbt, dw, db = K.empty((Pn,)), K.empty((Pn,)), K.empty((3, 3, C, F)), K.empty((F,))
+        K.ops.convblock_bwd(g, xd, wd, bd, 1, 0.0, gd, btd, sm, si, ed, ss, (0,), dg.data_ptr(), dbt.data_ptr(), dw, db, None, mode, Bn,
+                            1, 2, 3, (1, 2, 3), ws, peer_b)
+        return [K.host(t) for t in (yp, rm, rv, dg, dbt, dw, db, ss)]
+    ref = run(0, None, None)
+    for rnd in range(3):
+        got = run(3, pf, pb)
+        for a_, b_ in zip(got, ref):
+            assert nrel(a_, b_) < 2e-6, rnd
+    assert comm.timeouts() == 0
