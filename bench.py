@@ -252,6 +252,9 @@ def run_b200(args):
     achieved = top_bytes / (per_op[top] * 1e-3) / 1e9 if per_op[top] > 0 else 0.0
     step_bytes = sum(b for _, b in prog.meta)
     breakdown = sorted(((names[i], round(per_op[i] * 1e3, 2), prog.meta[i][1]) for i in range(len(per_op))), key=lambda t: -t[1])
+    if os.environ.get("B200NN_BENCH_ALLOPS") and rank == 0:
+        print("[bench] per-op us (program order): " + ", ".join(f"{names[i]}={per_op[i] * 1e3:.1f}" for i in range(len(per_op)))
+              + f" | sum={sum(per_op) * 1e3:.1f}", file=sys.stderr)
 
     if world > 1:
         dist.barrier()

@@ -145,6 +145,63 @@ __global__ void __launch_bounds__(256) exchange_sum_kernel(PeerPtrs peers, int r
     }
 }
 
+// Latency path for <= 4 KB (the clip-norm slots, small gradient buckets): low-latency protocol -- every 4-byte word travels
+// as ONE 8-byte store {bits, round number} into each peer's inbox and is polled by the receiving thread (no fence, no flag,
+// no barrier); sums are formed in rank order. Inbox: word[2 parity][world][rank_words] of 8 bytes (the site's stride is
+// twice the payload).
+constexpr int LL_MAX_BYTES = 4096;                       // up to 1024 four-byte words = one CTA
+template <class T>
+__global__ void __launch_bounds__(1024) exchange_sum_ll_kernel(PeerPtrs peers, int rank, int world, int site, size_t data_off,
+                                                               size_t rank_words, T* __restrict__ buf, int n) {
+    constexpr int WPE = sizeof(T) / 4;                   // 4-byte words per element
+    SymHeader* me = reinterpret_cast<SymHeader*>(peers.p[rank]);
+    const unsigned seq = *reinterpret_cast<volatile unsigned*>(&me->seq[site]) + 1u;
+    const unsigned par = seq & 1u;
+    const int lane = threadIdx.x;                        // word index
+    const int nwords = n * WPE;
+    unsigned mine = 0;
+    if (lane < nwords) mine = reinterpret_cast<const unsigned*>(buf)[lane];
+    if (lane < nwords) {
+        for (int p = 0; p < world; ++p) {
+            uint2* dst = reinterpret_cast<uint2*>(peers.p[p] + data_off) + ((size_t)par * world + rank) * rank_words + lane;
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(mine), "r"(seq) : "memory");
+        }
+    }
+    T total = T(0);
+    for (int r = 0; r < world; ++r) {
+        unsigned vx = 0, vy = 0;
+        if (lane < nwords) {
+            const uint2* src = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + ((size_t)par * world + r) * rank_words + lane;
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(src) : "memory");
+                if (vy == seq) break;
+                if ((++spins & 0x3ffu) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
+                }
+            }
+        }
+        __syncwarp();
+        if (WPE == 1) {
+            total += static_cast<T>(__uint_as_float(vx));
+        } else {                                         // lane 2i holds the low word, lane 2i+1 the high word
+            const unsigned hi = __shfl_down_sync(0xffffffffu, vx, 1);
+            total += static_cast<T>(__hiloint2double((int)hi, (int)vx));
+        }
+    }
+    if (WPE == 1) { if (lane < n) buf[lane] = total; }
+    else if ((lane & 1) == 0 && (lane >> 1) < n) buf[lane >> 1] = total;
+    __syncthreads();
+    if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(&me->seq[site]) = seq;
+    }
+}
+
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -247,7 +304,8 @@ int b200nn_comm_site_create(b200nn_comm* c, size_t payload_bytes, int* site_out)
     B200NN_REQUIRE(c != nullptr && site_out != nullptr, "comm_site_create: null argument");
     B200NN_REQUIRE(c->peer_ready, "comm_site_create: peer memory is not mapped");
     B200NN_REQUIRE(c->n_sites < MAX_SITES, "comm_site_create: more than %d exchange sites", MAX_SITES);
-    const size_t stride = (payload_bytes + 255) & ~size_t(255);
+    // payloads of the latency path carry an 8-byte word per 4 bytes of payload
+    const size_t stride = ((payload_bytes <= LL_MAX_BYTES ? 2 * payload_bytes : payload_bytes) + 255) & ~size_t(255);
     const size_t need = 2 * (size_t)c->world * stride;
     B200NN_REQUIRE(c->bump + need <= c->sym_bytes, "comm_site_create: symmetric buffer exhausted (%zu + %zu > %zu bytes)", c->bump, need,
                    c->sym_bytes);
@@ -294,6 +352,18 @@ int b200nn_comm_allreduce_sum(b200nn_comm* c, int site, void* buf, long long n, 
                    site, c->site_stride[site]);
     PeerPtrs pp;
     for (int p = 0; p < MAX_WORLD; ++p) pp.p[p] = p < c->world ? c->peer[p] : nullptr;
+    if ((size_t)n * esz <= LL_MAX_BYTES && c->site_stride[site] >= 2 * (size_t)n * esz) {   // latency path
+        const int threads = (int)(((size_t)n * esz / 4 + 31) / 32 * 32);
+        const size_t rank_words = c->site_stride[site] / 8;
+        if (dtype == 0)
+            exchange_sum_ll_kernel<float><<<1, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site], rank_words,
+                                                                               static_cast<float*>(buf), (int)n);
+        else
+            exchange_sum_ll_kernel<double><<<1, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site], rank_words,
+                                                                                static_cast<double*>(buf), (int)n);
+        B200NN_LAUNCH_CHECK("exchange_sum_ll");
+        return B200NN_OK;
+    }
     const int vec_ok = (reinterpret_cast<uintptr_t>(buf) & 15) == 0 ? 1 : 0;
     B200NN_REQUIRE(vec_ok || n <= 4096, "comm_allreduce_sum: large payloads must be 16-byte aligned");
     const long long nvec = vec_ok ? (long long)((size_t)n * esz / 16) : 0;

@@ -575,7 +575,10 @@ static int cb_launch(Kern kern, int items, bool persistent, size_t smem, cudaStr
         }
     }
     B200NN_REQUIRE(e != nullptr, "convblock: kernel table full");
-    const int grid = persistent && items > e->resident ? e->resident : items;
+    // persistent launches leave a few CTA slots free: an NCCL gradient allreduce may be running on a side stream, and every
+    // CTA of the grid must be able to become resident while its peers on the other GPUs wait for it
+    const int cap = e->resident > 64 ? e->resident - 24 : e->resident;
+    const int grid = persistent && items > cap ? cap : items;
     kern<<<grid, CB_THREADS, smem, st>>>(args...);
     return B200NN_OK;
 }
