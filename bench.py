@@ -249,6 +249,12 @@ def run_b200(args):
     top = max(range(len(per_op)), key=lambda i: per_op[i])
     top_name, top_bytes = prog.meta[top]
     peak, peak_src = load_peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(top_name)
+    except Exception:
+        pass
     achieved = top_bytes / (per_op[top] * 1e-3) / 1e9 if per_op[top] > 0 else 0.0
     step_bytes = sum(b for _, b in prog.meta)
     breakdown = sorted(((names[i], round(per_op[i] * 1e3, 2), prog.meta[i][1]) for i in range(len(per_op))), key=lambda t: -t[1])
@@ -280,7 +286,7 @@ def run_b200(args):
         "gpu_launches": int(launches_eager_step * K),
         "kernels_per_step": int(launches_eager_step),
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": top_bytes, "kernel_us": per_op[top] * 1e3,
                      "step_algorithmic_bytes": step_bytes,
                      "step_frac_of_hbm_roofline": (step_bytes / (resident_ms * 1e-3) / 1e9) / peak},

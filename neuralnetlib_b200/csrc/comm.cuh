@@ -64,6 +64,7 @@ struct PeerRegion {
     PeerPtrs peers;
     int rank, world, site;
     size_t off;          // byte offset of the region in every rank's symmetric buffer
+    unsigned stagger_ns; // start offset between CTAs that share an SM (peer-fused kernels)
 };
 
 }  // namespace b200nn

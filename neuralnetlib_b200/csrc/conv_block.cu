@@ -17,6 +17,7 @@
 // are warp-shuffle reductions, no shared-memory or cross-CTA reduction exists, all conv outputs of the window stay in registers (batch <= 256 per GPU;
 // larger batches use the unfused kernels), and the 784 CTAs of config 2 balance over 148 SMs. Replaces layers.py:442-489 (+
 // preprocessing.py:34-79), :231-237, :1230-1276, :570-643 and the weight-gradient half of :491-530 for this pattern.
+#include <stdlib.h>
 #include <string.h>
 
 #include "comm.cuh"
@@ -204,7 +205,12 @@ __global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, flo
     const int OW = a.W >> 1, OH = a.H >> 1;
     const long long P = (long long)a.H * a.W * a.F;
     unsigned seq = 0;
-    if (MODE == 3) seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+    if (MODE == 3) {
+        seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+        // CTAs that share an SM (block ids one SM count apart: residues 0, 1, 2 mod 3 since 148 = 1 mod 3) start a third of an
+        // item period apart, so that one computes while another waits on NVLink; every rank applies the same offsets
+        if (pr.stagger_ns > 0) __nanosleep((blockIdx.x % 3) * pr.stagger_ns);
+    }
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int ox = item % OW, oy = (item / OW) % OH, f0 = (item / (OW * OH)) * CB_FPC, f = f0 + wid;
     float wr[9 * C], bias;
@@ -346,7 +352,10 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int OW = a.W >> 1, OH = a.H >> 1;
     unsigned seq = 0;
-    if (MODE == 3) seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+    if (MODE == 3) {
+        seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
+        if (pr.stagger_ns > 0) __nanosleep((blockIdx.x % 3) * pr.stagger_ns);
+    }
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;                                   // clip-slot partials, accumulated over this CTA's items
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int ox = item % OW, oy = (item / OW) % OH, f0 = (item / (OW * OH)) * CB_FPC, f = f0 + wid;
@@ -623,6 +632,12 @@ static int cb_peer_region(const char* who, int mode, b200nn_comm* comm, int site
                    "%s: exchange region too small (needs %zu bytes)", who, cb_region_bytes(items, comm->world));
     for (int p = 0; p < MAX_WORLD; ++p) pr->peers.p[p] = p < comm->world ? comm->peer[p] : nullptr;
     pr->rank = comm->rank; pr->world = comm->world; pr->site = site; pr->off = region_off;
+    static int stagger = -1;
+    if (stagger < 0) {
+        const char* e = getenv("B200NN_PEER_STAGGER_NS");
+        stagger = e != nullptr ? atoi(e) : 0;
+    }
+    pr->stagger_ns = comm->world > 1 ? (unsigned)stagger : 0u;
     return B200NN_OK;
 }
 
