@@ -22,6 +22,9 @@
  *        acc = 1; for i < n: n2 = acc*acc*ss[slot_i]; if (n2 > 1) acc *= rsqrt(n2);
  *    n == 0 (or ss == NULL) means "no clip". Slots must be zeroed before the producer runs
  *    (b200nn_step_begin, or b200nn_zero_f64).
+ *    Range form (bit 63 set; lo in bits 0-15, count in bits 16-31): slots [lo, lo+count) in order. Used when the clips are
+ *    DEFERRED (data parallelism): backward kernels then run without any multiplier, record the raw sums of squares, and the
+ *    whole pending chain is applied once to each weight gradient -- so the slots need a single exchange per step.
  */
 #ifndef B200NN_H_
 #define B200NN_H_
@@ -251,6 +254,7 @@ typedef struct {
     int t_index;       /* Adam: 1-based position j of this tensor's LAYER among the L layers updated per step,
                           last layer first; t = *t_counter - L + j (optimizers.py:236) */
     int clip;          /* 1: scale g by 1/||g|| when ||g|| > 1 (models.py:240-242) */
+    uint64_t chain;    /* error clips still pending on g (deferred clips; 0 = none): g is multiplied by chain(ss) first */
 } b200nn_param;
 /* `params` is a DEVICE array of n_params descriptors; `gss` a device array of n_params float64
  * scratch slots (zeroed and filled by this call with ||g||^2); hyper is a DEVICE float64 array
@@ -261,9 +265,9 @@ typedef struct {
  * ceil(n / B200NN_OPT_CHUNK). */
 #define B200NN_OPT_CHUNK 4096
 int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
-                      const long long* t_counter, const int* block_map, int total_blocks, void* stream);
+                      const long long* t_counter, const int* block_map, int total_blocks, const double* ss, void* stream);
 int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
-                     const int* block_map, int total_blocks, void* stream);
+                     const int* block_map, int total_blocks, const double* ss, void* stream);
 
 /* ---- data parallelism: one process per GPU on one NVLink/NVSwitch box -----------------------
  * The reference is single-process; under a batch shard per GPU its batch-global quantities become sums over ranks:

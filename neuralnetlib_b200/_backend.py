@@ -37,7 +37,7 @@ class PoolGeom(C.Structure):
 
 # numpy mirror of b200nn_param (include/b200nn.h)
 PARAM_DTYPE = np.dtype([("p", np.uint64), ("g", np.uint64), ("m", np.uint64), ("v", np.uint64), ("n", np.int64),
-                        ("t_index", np.int32), ("clip", np.int32)], align=True)
+                        ("t_index", np.int32), ("clip", np.int32), ("chain", np.uint64)], align=True)
 OPT_CHUNK = 4096
 
 _P = c_void_p
@@ -90,8 +90,8 @@ _SIGNATURES = {
     "b200nn_convblock_region_bytes": (c_size_t, [C.POINTER(ConvGeom), c_int]),
     "b200nn_comm_region_create": (c_int, [_P, c_size_t, C.POINTER(c_int), C.POINTER(c_size_t)]),
     "b200nn_convblock_wgrad_reduce": (c_int, [C.POINTER(ConvGeom), _P, _P, c_u64, _P, _P, _P]),
-    "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P]),
-    "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
+    "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
+    "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P]),
     # data parallelism (csrc/comm.cu) and the split BatchNorm kernels
     "b200nn_comm_load_nccl": (c_int, [C.c_char_p]),
     "b200nn_comm_nccl_version": (c_int, []),

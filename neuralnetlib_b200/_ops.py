@@ -20,6 +20,11 @@ MATH_FP32, MATH_TF32 = 0, 1
 
 def pack_chain(chain) -> int:
     chain = tuple(chain or ())
+    if chain and chain[0] == "range":   # ("range", lo, count): every slot of [lo, lo + count), in order (deferred clips)
+        _, lo, cnt = chain
+        if not (0 <= lo < 65536 and 0 <= cnt < 65536):
+            raise ValueError("clip slot range out of bounds")
+        return (1 << 63) | int(lo) | (int(cnt) << 16) if cnt else 0
     if len(chain) > 4:
         raise ValueError("clip chain longer than 4 slots")
     v = len(chain)
@@ -329,18 +334,22 @@ def maxpool_bwd(g: PoolGeom, x, y, err, ss, chain, dx, slot_out):
 # ---- optimizers --------------------------------------------------------------------------------------
 class OptPlan:
     """Device-resident descriptor table for the multi-tensor optimizer kernels.
-    entries: list of (p, g, m, v, t_index, clip) tensors (m, v may be None for SGD)."""
+    entries: list of (p, g, m, v, t_index, clip[, chain]) tensors (m, v may be None for SGD); `ss`: the slot tensor the
+    optional per-tensor chains (deferred error clips) refer to."""
 
-    def __init__(self, entries, n_layers):
+    def __init__(self, entries, n_layers, ss=None):
+        self.ss = ss
         self.keep = entries  # keep tensors alive
         self.n_layers = int(n_layers)
         desc = np.zeros(len(entries), dtype=B.PARAM_DTYPE)
         pairs = []
-        for i, (p, g, m, v, t_index, clip) in enumerate(entries):
+        for i, entry in enumerate(entries):
+            p, g, m, v, t_index, clip = entry[:6]
+            chain = entry[6] if len(entry) > 6 else ()
             _f32(p, g, m, v)
             assert p.numel() == g.numel()
             desc[i] = (p.data_ptr(), g.data_ptr(), 0 if m is None else m.data_ptr(), 0 if v is None else v.data_ptr(),
-                       p.numel(), t_index, int(clip))
+                       p.numel(), t_index, int(clip), pack_chain(chain))
             for c in range((p.numel() + B.OPT_CHUNK - 1) // B.OPT_CHUNK):
                 pairs.append((i, c))
         self.n_params = len(entries)
@@ -352,9 +361,9 @@ class OptPlan:
 
 def adam_multi(plan: OptPlan, hyper, t_counter):
     check(lib().b200nn_adam_multi(ptr(plan.desc), plan.n_params, plan.n_layers, ptr(plan.gss), ptr(hyper), ptr(t_counter),
-                                  ptr(plan.block_map), plan.total_blocks, stream()))
+                                  ptr(plan.block_map), plan.total_blocks, ptr(plan.ss), stream()))
 
 
 def sgd_multi(plan: OptPlan, hyper):
     check(lib().b200nn_sgd_multi(ptr(plan.desc), plan.n_params, ptr(plan.gss), ptr(hyper), ptr(plan.block_map),
-                                 plan.total_blocks, stream()))
+                                 plan.total_blocks, ptr(plan.ss), stream()))

@@ -46,8 +46,18 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // ---- lazy clip chain (see b200nn.h) -------------------------------------------------------------
 __device__ __forceinline__ float chain_scale(const double* __restrict__ ss, uint64_t chain) {
+    if (ss == nullptr) return 1.0f;
+    if (chain >> 63) {   // range form: slots [lo, lo + cnt) in order (deferred clips: every slot since the loss is still pending)
+        const int lo = static_cast<int>(chain & 0xffff), cnt = static_cast<int>((chain >> 16) & 0xffff);
+        double acc = 1.0;
+        for (int i = 0; i < cnt; ++i) {
+            const double n2 = acc * acc * ss[lo + i];
+            if (n2 > 1.0) acc *= rsqrt(n2);
+        }
+        return static_cast<float>(acc);
+    }
     const int n = static_cast<int>(chain & 0xff);
-    if (ss == nullptr || n == 0) return 1.0f;
+    if (n == 0) return 1.0f;
     double acc = 1.0;
     for (int i = 0; i < n; ++i) {
         const int slot = static_cast<int>((chain >> (8 + 12 * i)) & 0xfff);

@@ -239,15 +239,16 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
                                                          const double* __restrict__ gss,
                                                          const double* __restrict__ hyper,
                                                          const long long* __restrict__ step,
-                                                         const int* __restrict__ block_map) {
+                                                         const int* __restrict__ block_map, const double* __restrict__ ss) {
     __shared__ OptScalars sh;
     const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
     const b200nn_param P = params[ti];
     if (threadIdx.x == 0) {
         const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
-        const double n2 = gss[ti];
+        const double pre = (double)chain_scale(ss, P.chain);                 // deferred error clips (models.py:214) owed by g
+        const double n2 = gss[ti] * pre * pre;
         const double t = (double)(*step - (long long)n_layers + P.t_index);  // optimizers.py:236 (Q3)
-        sh.clip = (P.clip && n2 > 1.0) ? (float)rsqrt(n2) : 1.0f;                   // models.py:240-242
+        sh.clip = (float)(pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0));          // models.py:240-242
         sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;
         sh.omb1 = (float)(1.0 - b1); sh.omb2 = (float)(1.0 - b2);
         sh.inv_bc1 = (float)(1.0 / (1.0 - pow(b1, t)));
@@ -286,11 +287,12 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
 __global__ void __launch_bounds__(256) sgd_multi_kernel(const b200nn_param* __restrict__ params,
                                                         const double* __restrict__ gss,
                                                         const double* __restrict__ hyper,
-                                                        const int* __restrict__ block_map) {
+                                                        const int* __restrict__ block_map, const double* __restrict__ ss) {
     const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
     const b200nn_param P = params[ti];
-    const double n2 = gss[ti];
-    const float scale = (float)hyper[0] * ((P.clip && n2 > 1.0) ? (float)rsqrt(n2) : 1.0f);
+    const double pre = (double)chain_scale(ss, P.chain);
+    const double n2 = gss[ti] * pre * pre;
+    const float scale = (float)(hyper[0] * pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0));
     const long long base = (long long)chunk * B200NN_OPT_CHUNK;
     const long long end = min(P.n, base + B200NN_OPT_CHUNK);
     for (long long i = base + threadIdx.x; i < end; i += 256) P.p[i] -= scale * P.g[i];  // optimizers.py:48
@@ -438,23 +440,23 @@ int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y
 }
 
 int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
-                      const long long* step, const int* block_map, int total_blocks, void* stream) {
+                      const long long* step, const int* block_map, int total_blocks, const double* ss, void* stream) {
     B200NN_REQUIRE(n_params > 0 && total_blocks > 0 && n_layers > 0, "adam_multi: empty parameter list");
     B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
     sumsq_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, block_map, gss);
     B200NN_LAUNCH_CHECK("sumsq_multi");
-    adam_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, gss, hyper, step, block_map);
+    adam_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, gss, hyper, step, block_map, ss);
     B200NN_LAUNCH_CHECK("adam_multi");
     return B200NN_OK;
 }
 
 int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
-                     const int* block_map, int total_blocks, void* stream) {
+                     const int* block_map, int total_blocks, const double* ss, void* stream) {
     B200NN_REQUIRE(n_params > 0 && total_blocks > 0, "sgd_multi: empty parameter list");
     B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
     sumsq_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, block_map, gss);
     B200NN_LAUNCH_CHECK("sumsq_multi");
-    sgd_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, gss, hyper, block_map);
+    sgd_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, gss, hyper, block_map, ss);
     B200NN_LAUNCH_CHECK("sgd_multi");
     return B200NN_OK;
 }

@@ -75,6 +75,15 @@ class Plan:
         self.n_slots = 0
         self.dp = getattr(model, "_dp", None)
         self.world = self.dp.world if self.dp is not None else 1
+        # Deferred clips (default under data parallelism; B200NN_DEFER_CLIPS=1 / 0 forces it on / off): every backward op is linear
+        # in the error, so the backward kernels run WITHOUT the clip multipliers, record the raw sums of squares, and the
+        # whole pending chain is applied once to each weight gradient inside the optimizer launch. The clip norms then need
+        # ONE exchange per step instead of one after every backward kernel.
+        mode = os.environ.get("B200NN_DEFER_CLIPS", "auto")
+        self.defer_clips = mode == "1" or (mode != "0" and self.dp is not None)
+        self._raw_begin = 0
+        self._acc_pending = False
+        self._upd_chain = {}
         self._ws = None
         self._ws_bytes = 0
         self._emit_to = None
@@ -125,17 +134,35 @@ class Plan:
         r = self.dp.comm.region(nbytes)
         return None if r is None else (self.dp.comm.handle, r[0], r[1])
 
-    def _sync_slots(self, first):
+    def pending_chain(self):
+        """With deferred clips: the range chain over every slot recorded since the backward began; else None."""
+        if not self.defer_clips:
+            return None
+        return ("range", self._raw_begin, self.n_slots - self._raw_begin)
+
+    def _sync_slots(self, first, final=False):
         """Sum the clip slots [first, n_slots) produced by the op(s) just emitted over the ranks: the reference's clips
         act on whole-batch tensors (models.py:214), so their norms are global. Slots already exchanged (sync_slots_now
-        called from inside a layer's hook) are skipped."""
+        called from inside a layer's hook) are skipped. With deferred clips nothing is exchanged between the backward
+        kernels: one exchange (loss accumulators included) happens when `final`."""
+        if self.defer_clips and not final:
+            return
+        if self.defer_clips:
+            first = getattr(self, "_slots_synced", 0)   # nothing was exchanged since the backward began
         first = max(first, getattr(self, "_slots_synced", 0))
-        if self.dp is not None and self.n_slots > first:
-            self.allreduce(self.ss[first:self.n_slots], "slot_exchange")
+        if self.dp is not None:
+            if self._acc_pending and first == 0:
+                self.allreduce(self._ssacc[0:4 + self.n_slots], "slot_exchange")   # accumulators sit right in front of slot 0
+            else:
+                if self._acc_pending:
+                    self.allreduce(self.acc, "loss_exchange")
+                if self.n_slots > first:
+                    self.allreduce(self.ss[first:self.n_slots], "slot_exchange")
+        self._acc_pending = False
         self._slots_synced = self.n_slots
 
     def sync_slots_now(self):
-        self._sync_slots(0)
+        self._sync_slots(0, final=True)
 
     @property
     def ws(self):
@@ -247,10 +274,16 @@ class Plan:
         cur = err
         i = n - 1
         self._grad_begin()
+        raw = self.defer_clips
+        self._upd_chain = {}
+        if raw:
+            self._raw_begin = min(cur.chain) if cur.chain else self.n_slots
+            cur = _Err(cur.t, ())
         if isinstance(layers[i], Activation):
             if gan:   # models.py:211-212: the real derivative of the last activation, no clip before it
                 first = self.n_slots
                 cur = layers[i]._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
+                cur = _Err(cur.t, ()) if raw else cur
                 self._sync_slots(first)
             # not gan: p - y (recognised pairs) or the raw loss derivative with the activation's derivative
             # skipped (models.py:198-210, Q7) -- both already sit in `err`
@@ -268,8 +301,11 @@ class Plan:
             if not need_dx and not self._has_weights(L):
                 cur = None   # nothing upstream is trainable and nobody observes the input error
                 break
+            n_before = self.n_slots   # the error entering this op still owes slots [_raw_begin, n_before) when clips are deferred
+            pend = ("range", self._raw_begin, n_before - self._raw_begin) if raw else None
             if isinstance(L, Activation):
                 cur = L._plan_backward(self, self.state[i], cur, None, True, y=self.outs[i])
+                cur = _Err(cur.t, ()) if raw else cur
                 i -= 1
                 continue
             if self.state[i].get("conv_block") is not None:
@@ -278,6 +314,10 @@ class Plan:
                 et = cur.t.reshape(self.outs[i].shape)
                 cur = layers[ci]._plan_backward_block(self, self.state[ci], self.state[bi], layers[bi], _Err(et, cur.chain), has_act,
                                                       need_dx_c)
+                if raw and cur is not None:
+                    cur = _Err(cur.t, ())
+                # the block's kernels apply their pending chain to dw / db themselves (the reduce launch), also when deferred
+                layers[ci]._grad_pending = None
                 if not compute_only:
                     updates.append(ci)
                     self._grad_bucket_ready(layers[ci])
@@ -292,6 +332,7 @@ class Plan:
                     mask = layers[j]
                 et = cur.t.reshape(self.outs[i].shape)
                 cur = layers[bn_i]._plan_backward_fused_pool(self, self.state[bn_i], _Err(et, cur.chain), mask)
+                cur = _Err(cur.t, ()) if raw else cur
                 i = j - 1 if mask is not None else bn_i - 1
                 continue
             mask, j = None, i - 1
@@ -302,6 +343,11 @@ class Plan:
                     mask = layers[j]
             et = cur.t.reshape(self.outs[i].shape)
             cur = L._plan_backward(self, self.state[i], _Err(et, cur.chain), mask, need_dx)
+            if raw and cur is not None:
+                cur = _Err(cur.t, ())
+            if self._has_weights(L):
+                L._grad_pending = (self.ss, pend[1], pend[2]) if raw else None
+                self._upd_chain[i] = pend if raw else ()
             if self._has_weights(L) and not compute_only:
                 updates.append(i)
                 self._grad_bucket_ready(L)
@@ -310,7 +356,9 @@ class Plan:
                 i = j - 1
             else:
                 i -= 1
-        self._sync_slots(first)
+        self._sync_slots(first, final=True)
+        if raw and cur is not None:
+            cur = _Err(cur.t, self.pending_chain())   # whoever materialises the input error applies the whole chain
         return updates, cur
 
     # Gradient buckets (parallel.py): a bucket is summed over the ranks as soon as the backward of the layer that completes
@@ -401,6 +449,9 @@ class Plan:
                 self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
             if self.dp is not None:
                 self.dp.flatten_grads(self.layers)
+            if self.defer_clips:
+                self._acc_pending, self._slots_synced = True, s0   # loss accumulators + every slot: ONE exchange after backward
+            elif self.dp is not None:
                 if s0 == 0:
                     self.allreduce(self._ssacc[0:5], "loss_exchange")      # loss numerator, correct count, ||err||^2
                 else:
@@ -412,10 +463,10 @@ class Plan:
             ups = []
             for li in updates:
                 L = self.layers[li]
-                ups.append((li, L._weights, L._d_weights, L._bias, L._d_bias))
+                ups.append((li, L._weights, L._d_weights, L._bias, L._d_bias, self._upd_chain.get(li, ())))
             n_upd = len(ups)
             if n_upd:
-                oplan = opt._make_plan(ups)
+                oplan = opt._make_plan(ups, self.ss)
                 self.emit(lambda: opt._run_plan(oplan), "optimizer_multi", opt._plan_io(oplan))
             prog.ops[begin_at] = lambda: ops.step_begin(ss, acc, counter, n_upd)
             self.train_err0 = err0
@@ -463,11 +514,11 @@ class Plan:
             self.in_err_out = self.buf(in_err.t.shape)
             iet, chain, out = in_err.t, in_err.chain, self.in_err_out
             self.emit(lambda: ops.scale_apply(iet, ss, chain, out), "scale_apply", (iet, out))
-            ups = [(li, self.layers[li]._weights, self.layers[li]._d_weights, self.layers[li]._bias, self.layers[li]._d_bias)
-                   for li in updates]
+            ups = [(li, self.layers[li]._weights, self.layers[li]._d_weights, self.layers[li]._bias, self.layers[li]._d_bias,
+                    self._upd_chain.get(li, ())) for li in updates]
             n_upd = len(ups)
             if n_upd:
-                oplan = opt._make_plan(ups)
+                oplan = opt._make_plan(ups, self.ss)
                 self.emit(lambda: opt._run_plan(oplan), "optimizer_multi", opt._plan_io(oplan))
             prog.ops[begin_at] = lambda: ops.step_begin(ss, None, counter, n_upd)
         else:

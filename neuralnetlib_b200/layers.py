@@ -49,11 +49,30 @@ class _Err:
         self.t, self.chain = t, tuple(chain)
 
 
+def _pending_factor(pend):
+    """Multiplier of a clip chain that is still pending on a gradient attribute: pend = (ss tensor, first slot, count);
+    the same recurrence as chain_scale in csrc/common.cuh, evaluated on the host when the attribute is read."""
+    if pend is None or pend[2] <= 0:
+        return 1.0
+    ss, lo, cnt = pend
+    vals = ss[lo:lo + cnt].cpu().numpy()
+    acc = 1.0
+    for v in vals:
+        n2 = acc * acc * float(v)
+        if n2 > 1.0:
+            acc /= np.sqrt(n2)
+    return acc
+
+
 class _EagerCtx:
     """Allocation context of the layer-by-layer (non-plan) API: fresh buffers per call, no clip slots."""
     ss = None
     dp = None
     world = 1
+    defer_clips = False
+
+    def pending_chain(self):
+        return None
 
     def buf(self, shape):
         return B.empty(tuple(int(s) for s in shape))
@@ -124,7 +143,10 @@ class _ParamMixin:
         t = getattr(self, "_" + name, None)
         if t is None:
             return None
-        return B.to_host(t).reshape(self._shapes[name])
+        a = B.to_host(t).reshape(self._shapes[name])
+        if name in ("d_weights", "d_bias") and getattr(self, "_grad_pending", None) is not None:
+            a = a * _pending_factor(self._grad_pending)   # deferred clips: the device holds the gradient of the UNCLIPPED error
+        return a
 
     def _param_set(self, name, value):
         if value is None:
@@ -546,12 +568,12 @@ class Conv2D(Layer, _ParamMixin):
         kind, alpha = st["act"]
         s0, s1 = ctx.slot(), ctx.slot()
         s2 = ctx.slot() if has_act else None
-        chain_out = tuple(s for s in (s0, s1, s2) if s is not None)
+        chain_out = ctx.pending_chain() or tuple(s for s in (s0, s1, s2) if s is not None)
         P = bn._gamma.numel()
         r_out = ctx.buf((x.shape[0], g.OH, g.OW, self.filters)) if need_dx else None
         w, b, dw, db, gm, bt = self._weights, self._bias, self._d_weights, self._d_bias, bn._gamma, bn._beta
         sm, si, ss, chain, et = st_bn["save_mean"], st_bn["save_invstd"], ctx.ss, err.chain, err.t
-        bn._dgrad_pending = (ctx.ss, s0) if ctx.ss is not None else None
+        bn._dgrad_pending = bn._pending_upto(ctx, s0)
         peer = ctx.peer_region(ops.convblock_region_bytes(g, ctx.world)) if ctx.dp is not None else None
         if peer is not None:
             b_total = x.shape[0] * ctx.world
@@ -579,7 +601,8 @@ class Conv2D(Layer, _ParamMixin):
         dx = ctx.buf(x.shape)
         s3 = ctx.slot()
         math = st["math"]
-        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, r_out, ss, chain_out, dx, None, None, ops.ACT_NONE, 0.0, s3, None, ctx.ws),
+        chain_dx = () if ctx.defer_clips else chain_out
+        ctx.emit(lambda: ops.conv2d_bwd(math, g, x, w, r_out, ss, chain_dx, dx, None, None, ops.ACT_NONE, 0.0, s3, None, ctx.ws),
                  "conv2d_dx", (r_out, w, dx))
         return _Err(dx, (s3,))
 
@@ -826,9 +849,7 @@ class BatchNormalization(Layer, _ParamMixin):
         v = self._param_get(name)
         pend = getattr(self, "_dgrad_pending", None)
         if v is not None and pend is not None:
-            n2 = float(pend[0][pend[1]].item())
-            if n2 > 1.0:
-                v = v / np.sqrt(n2)
+            v = v * _pending_factor(pend)
         return v
 
     d_gamma = property(lambda self: self._dgrad_get("d_gamma"), lambda self, v: self._param_set("d_gamma", v))
@@ -912,10 +933,11 @@ class BatchNormalization(Layer, _ParamMixin):
         x = st["x"]
         dx = ctx.buf(x.shape)
         kind, alpha = _act_of(mask_layer)
+        pc = ctx.pending_chain()   # deferred clips: d_gamma / d_beta owe every slot recorded BEFORE this op
+        self._dgrad_pending = (ctx.ss, pc[1], pc[2]) if pc is not None else None
         s0 = ctx.slot()
         s1 = ctx.slot() if mask_layer is not None else None
         gm, sm, si, ss, chain, et = self._gamma, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
-        self._dgrad_pending = None
         if ctx.dp is not None:
             sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.bn_bwd_partial(x, et, ss, chain, sm, si, sums), "bn_bwd_partial", (x, et))
@@ -926,6 +948,15 @@ class BatchNormalization(Layer, _ParamMixin):
         dg, dbt = self._d_gamma, self._d_beta
         ctx.emit(lambda: ops.bn_bwd(x, et, ss, chain, gm, sm, si, dx, dg, dbt, kind, alpha, s0, s1), "bn_bwd", (x, et, dx))
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
+
+    @staticmethod
+    def _pending_upto(ctx, s0):
+        """d_gamma / d_beta of the fused pool+BN kernels are accumulated before the clip recorded in slot s0 (and, with
+        deferred clips, before every earlier one)."""
+        if ctx.ss is None or s0 is None:
+            return None
+        pc = ctx.pending_chain()
+        return (ctx.ss, pc[1], s0 + 1 - pc[1]) if pc is not None else (ctx.ss, s0, 1)
 
     def _dp_sums(self, ctx):
         """[d_beta | d_gamma] as ONE float32 buffer (a single exchange sums both over the ranks); d_beta / d_gamma become
@@ -947,7 +978,7 @@ class BatchNormalization(Layer, _ParamMixin):
         s0, s1 = ctx.slot(), ctx.slot()
         s2 = ctx.slot() if mask_layer is not None else None
         gm, bt, sm, si, ss, chain, et = self._gamma, self._beta, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
-        self._dgrad_pending = (ctx.ss, s0) if ctx.ss is not None else None
+        self._dgrad_pending = self._pending_upto(ctx, s0)
         if ctx.dp is not None:
             sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.pool_bn_bwd_partial(x, et, ss, chain, gm, bt, sm, si, sums, s0), "pool_bn_bwd_partial", (x, et))

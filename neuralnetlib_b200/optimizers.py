@@ -84,8 +84,8 @@ class Optimizer:
     def _plan_io(plan):
         """Tensors one optimizer launch reads/writes once each: p, g (+ m, v); the clip norm re-reads g."""
         io = []
-        for p, g, m, v, _, _ in plan.keep:
-            io.extend([p, g, m, v])
+        for entry in plan.keep:
+            io.extend(entry[:4])
         return tuple(io)
 
     @staticmethod
@@ -123,14 +123,16 @@ class SGD(Optimizer):
             if host is not None:
                 host[...] = B.to_host(p).reshape(host.shape)
 
-    def _make_plan(self, updates):
+    def _make_plan(self, updates, ss=None):
         self._ensure_device()
         entries = []
-        for j, (idx, w, dw, b, db) in enumerate(updates, start=1):
-            entries.append((w, dw, None, None, j, 1))
+        for j, upd in enumerate(updates, start=1):
+            idx, w, dw, b, db = upd[:5]
+            chain = upd[5] if len(upd) > 5 else ()
+            entries.append((w, dw, None, None, j, 1, chain))
             if b is not None:
-                entries.append((b, db, None, None, j, 1))
-        return ops.OptPlan(entries, max(len(updates), 1))
+                entries.append((b, db, None, None, j, 1, chain))
+        return ops.OptPlan(entries, max(len(updates), 1), ss)
 
     def _run_plan(self, plan):
         ops.sgd_multi(plan, self._hyper)
@@ -209,16 +211,18 @@ class Adam(Optimizer):
             if host is not None:
                 host[...] = B.to_host(pd).reshape(host.shape)
 
-    def _make_plan(self, updates):
+    def _make_plan(self, updates, ss=None):
         self._ensure_device()
         entries = []
-        for j, (idx, w, dw, b, db) in enumerate(updates, start=1):
+        for j, upd in enumerate(updates, start=1):
+            idx, w, dw, b, db = upd[:5]
+            chain = upd[5] if len(upd) > 5 else ()
             m, v = self._moments("w", idx, w)
-            entries.append((w, dw, m, v, j, 1))
+            entries.append((w, dw, m, v, j, 1, chain))
             if b is not None:
                 m, v = self._moments("b", idx, b)
-                entries.append((b, db, m, v, j, 1))
-        return ops.OptPlan(entries, max(len(updates), 1))
+                entries.append((b, db, m, v, j, 1, chain))
+        return ops.OptPlan(entries, max(len(updates), 1), ss)
 
     def _run_plan(self, plan):
         ops.adam_multi(plan, self._hyper, self._t_dev)

@@ -389,3 +389,60 @@ def test_fusion_levels_agree_with_oracle(monkeypatch, level, cfg, batch):
     got = m2.backward_pass(err)
     want = O.clip_l2(ref2.backward(err, compute_only=False))   # models.py:214 clips before Input too; Input.backward is identity
     grads_close(got, want, 1e-3 if cfg == 3 else 5e-5, (level, "input error"))
+
+
+@pytest.mark.parametrize("cfg,batch,level", [(1, 32, "2"), (2, 64, "2"), (2, 64, "1"), (3, 32, "2"), (4, 64, "2")])
+def test_deferred_clips_match_oracle(monkeypatch, cfg, batch, level):
+    """B200NN_DEFER_CLIPS=1 (the data-parallel default, forced here on one GPU): backward kernels run WITHOUT the clip
+    multipliers, record raw sums of squares, and the optimizer applies each gradient's whole pending chain. Linear algebra
+    says the step is identical; this checks it: losses, gradient attributes (scaled on read), weights after 2 steps,
+    and the public backward_pass input error."""
+    monkeypatch.setenv("B200NN_DEFER_CLIPS", "1")
+    monkeypatch.setenv("B200NN_FUSE_BLOCKS", level)
+    width = 256 if cfg == 4 else None
+    m = build_cfg(cfg, width)
+    specs, shp = O.config_specs(cfg)
+    if width:
+        for sp in specs:
+            if sp.get("units") == 4096:
+                sp["units"] = width
+        rng = np.random.default_rng(0)
+        x = rng.random((batch, width)).astype(np.float32)
+        y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+    else:
+        x, y = O.synthetic_batch(cfg, batch)
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    tol = 1e-3 if cfg == 3 else TOL
+    last_pool = max([i for i, l in enumerate(m.layers) if type(l).__name__ == "MaxPooling2D"], default=-1)
+    for s in range(2):
+        loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+        assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss)), (s, loss, rloss)
+        mine = [(i, l) for i, l in enumerate(m.layers) if hasattr(l, "weights")]
+        theirs = [r for r in ref.layers if "w" in r]
+        for (li, layer), rl in zip(mine, theirs):
+            grads_close(layer.d_weights, rl["dw"], tol, (s, li, "dw"))
+            grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), tol, (s, li, "db"))
+            d = np.abs(layer.weights - rl["w"])
+            need = (0.8 if cfg == 3 else 0.9) if li < last_pool else 0.999
+            assert np.mean(d <= 1e-5 * np.abs(rl["w"]).max() + 1e-9) >= need and d.max() <= 2e-3, (s, li)
+        for layer, rl in zip(m.layers, ref.layers):
+            if rl["type"] == "bn":
+                for got, want in ((layer.d_gamma, rl["dgamma"]), (layer.d_beta, rl["dbeta"])):
+                    d, scale = np.abs(got - want), np.abs(want).max()
+                    assert np.mean(d <= max(tol, 1e-4) * scale) >= 0.999 and d.max() <= 0.2 * scale, (s, d.max() / scale)
+        mw, vw, mb, vb = m.optimizer.m_w, m.optimizer.v_w, m.optimizer.m_b, m.optimizer.v_b
+        for (li, layer), rl in zip(mine, theirs):   # teacher forcing
+            rl["w"], rl["b"] = layer.weights, layer.bias
+            ref.optimizer.m_w[li], ref.optimizer.v_w[li] = mw[li], vw[li]
+            ref.optimizer.m_b[li], ref.optimizer.v_b[li] = mb[li], vb[li]
+        for layer, rl in zip(m.layers, ref.layers):
+            if rl["type"] == "bn":
+                rl["running_mean"], rl["running_var"] = layer.running_mean, layer.running_var
+    m2 = build_cfg(cfg, width)
+    ref2 = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    rp = ref2.forward(x)
+    assert nrel(m2.forward_pass(x), rp) < 5e-5
+    m2.y_true = y
+    ref2.y_true = y.astype(np.float64)
+    err = O.loss_derivative("cce", y.astype(np.float64), rp)
+    grads_close(m2.backward_pass(err), ref2.backward(err), 1e-3 if cfg == 3 else 5e-5, "input error")
