@@ -255,28 +255,44 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
         sh.inv_bc2 = (float)(1.0 / (1.0 - pow(b2, t)));
         sh.eps = (float)eps;
     }
-    __syncthreads();
-    const OptScalars s = sh;
     const long long base = (long long)chunk * B200NN_OPT_CHUNK;
     const long long end = min(P.n, base + B200NN_OPT_CHUNK);
     const bool aligned = ((reinterpret_cast<uintptr_t>(P.p) | reinterpret_cast<uintptr_t>(P.g) |
                            reinterpret_cast<uintptr_t>(P.m) | reinterpret_cast<uintptr_t>(P.v)) & 15) == 0;
     long long tail = base;
     if (aligned) {
+        // the chunk's 16 loads per thread are issued up front, BEFORE waiting for thread 0's scalars: one memory round trip
+        constexpr int IT = B200NN_OPT_CHUNK / (256 * 4);
         const long long e4 = base + ((end - base) & ~3LL);
-        for (long long i = base + threadIdx.x * 4; i < e4; i += 256 * 4) {
-            float4 p = *reinterpret_cast<float4*>(P.p + i);
-            const float4 g = *reinterpret_cast<const float4*>(P.g + i);
-            float4 m = *reinterpret_cast<float4*>(P.m + i);
-            float4 v = *reinterpret_cast<float4*>(P.v + i);
-            adam_elem(p.x, g.x, m.x, v.x, s); adam_elem(p.y, g.y, m.y, v.y, s);
-            adam_elem(p.z, g.z, m.z, v.z, s); adam_elem(p.w, g.w, m.w, v.w, s);
-            *reinterpret_cast<float4*>(P.p + i) = p;
-            *reinterpret_cast<float4*>(P.m + i) = m;
-            *reinterpret_cast<float4*>(P.v + i) = v;
+        float4 p[IT], g[IT], m[IT], v[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const long long i = base + ((long long)it * 256 + threadIdx.x) * 4;
+            if (i < e4) {
+                p[it] = *reinterpret_cast<const float4*>(P.p + i);
+                g[it] = *reinterpret_cast<const float4*>(P.g + i);
+                m[it] = *reinterpret_cast<const float4*>(P.m + i);
+                v[it] = *reinterpret_cast<const float4*>(P.v + i);
+            }
+        }
+        __syncthreads();
+        const OptScalars s = sh;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const long long i = base + ((long long)it * 256 + threadIdx.x) * 4;
+            if (i < e4) {
+                adam_elem(p[it].x, g[it].x, m[it].x, v[it].x, s); adam_elem(p[it].y, g[it].y, m[it].y, v[it].y, s);
+                adam_elem(p[it].z, g[it].z, m[it].z, v[it].z, s); adam_elem(p[it].w, g[it].w, m[it].w, v[it].w, s);
+                *reinterpret_cast<float4*>(P.p + i) = p[it];
+                *reinterpret_cast<float4*>(P.m + i) = m[it];
+                *reinterpret_cast<float4*>(P.v + i) = v[it];
+            }
         }
         tail = e4;
+    } else {
+        __syncthreads();
     }
+    const OptScalars s = sh;
     for (long long i = tail + threadIdx.x; i < end; i += 256) {
         float p = P.p[i], m = P.m[i], v = P.v[i];
         adam_elem(p, P.g[i], m, v, s);

@@ -391,7 +391,7 @@ def test_fusion_levels_agree_with_oracle(monkeypatch, level, cfg, batch):
     grads_close(got, want, 1e-3 if cfg == 3 else 5e-5, (level, "input error"))
 
 
-@pytest.mark.parametrize("cfg,batch,level", [(1, 32, "2"), (2, 64, "2"), (2, 64, "1"), (3, 32, "2"), (4, 64, "2")])
+@pytest.mark.parametrize("cfg,batch,level", [(1, 32, "2"), (2, 64, "2"), (2, 64, "1"), (2, 64, "0"), (3, 32, "2"), (4, 64, "2")])
 def test_deferred_clips_match_oracle(monkeypatch, cfg, batch, level):
     """B200NN_DEFER_CLIPS=1 (the data-parallel default, forced here on one GPU): backward kernels run WITHOUT the clip
     multipliers, record raw sums of squares, and the optimizer applies each gradient's whole pending chain. Linear algebra
