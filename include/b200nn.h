@@ -256,8 +256,9 @@ typedef struct {
     int clip;          /* 1: scale g by 1/||g|| when ||g|| > 1 (models.py:240-242) */
     uint64_t chain;    /* error clips still pending on g (deferred clips; 0 = none): g is multiplied by chain(ss) first */
 } b200nn_param;
-/* `params` is a DEVICE array of n_params descriptors; `gss` a device array of n_params float64
- * scratch slots (zeroed and filled by this call with ||g||^2); hyper is a DEVICE float64 array
+/* `params` is a DEVICE array of n_params descriptors; `gss` a device array of n_params + 1 float64
+ * scratch slots, ZERO on first use (slot i receives ||g_i||^2; the extra slot holds the two counters of the
+ * single-launch variant used for small parameter sets, which re-zeroes the array itself); hyper is a DEVICE float64 array
  * {lr, beta1, beta2, eps} (device-resident so a LearningRateScheduler can change lr without
  * re-capturing the step graph); *t_counter is Adam's device-resident `t` AFTER this step's updates (the
  * caller advanced it by n_layers, e.g. through b200nn_step_begin). block_map is a DEVICE

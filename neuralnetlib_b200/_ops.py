@@ -356,14 +356,14 @@ class OptPlan:
         self.total_blocks = len(pairs)
         self.desc = torch.from_numpy(desc.view(np.uint8).copy()).to(B.device())
         self.block_map = torch.from_numpy(np.asarray(pairs, dtype=np.int32).reshape(-1).copy()).to(B.device())
-        self.gss = B.zeros((self.n_params,), dtype=torch.float64)
+        self.gss = B.zeros((self.n_params + 1,), dtype=torch.float64)   # + the two counters of the single-launch Adam
 
 
-def adam_multi(plan: OptPlan, hyper, t_counter):
+def adam_multi(plan: OptPlan, hyper, t_counter, on_stream=None):
     check(lib().b200nn_adam_multi(ptr(plan.desc), plan.n_params, plan.n_layers, ptr(plan.gss), ptr(hyper), ptr(t_counter),
-                                  ptr(plan.block_map), plan.total_blocks, ptr(plan.ss), stream()))
+                                  ptr(plan.block_map), plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))
 
 
-def sgd_multi(plan: OptPlan, hyper):
+def sgd_multi(plan: OptPlan, hyper, on_stream=None):
     check(lib().b200nn_sgd_multi(ptr(plan.desc), plan.n_params, ptr(plan.gss), ptr(hyper), ptr(plan.block_map),
-                                 plan.total_blocks, ptr(plan.ss), stream()))
+                                 plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))

@@ -235,18 +235,40 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
     p -= upd;
 }
 
-__global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __restrict__ params, int n_layers,
-                                                         const double* __restrict__ gss,
+// FUSED: gradient norm + update in ONE launch for parameter sets of at most one CTA per SM (every CTA is resident, so a
+// grid-wide barrier on a device counter is safe): each CTA adds its chunk's sum of squares to gss[tensor], arrives, waits
+// for all, then updates. The last CTA to leave re-zeroes gss and the two counters (stored after gss[n_params]) for the next
+// launch -- no memset node, no separate norm kernel on the critical path of small models.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __restrict__ params, int n_layers, int n_params,
+                                                         double* __restrict__ gss,
                                                          const double* __restrict__ hyper,
                                                          const long long* __restrict__ step,
                                                          const int* __restrict__ block_map, const double* __restrict__ ss) {
     __shared__ OptScalars sh;
+    __shared__ double scratch[32];
     const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
     const b200nn_param P = params[ti];
+    unsigned* sync = reinterpret_cast<unsigned*>(gss + n_params);
+    if (FUSED) {
+        const long long b0 = (long long)chunk * B200NN_OPT_CHUNK, e0 = min(P.n, b0 + B200NN_OPT_CHUNK);
+        float part = 0.0f;
+        for (long long i = b0 + threadIdx.x; i < e0; i += 256) part = fmaf(P.g[i], P.g[i], part);
+        const double r = block_sum_to_double(part, scratch);
+        if (threadIdx.x == 0) {
+            atomicAdd(&gss[ti], r);
+            __threadfence();
+            atomicAdd(&sync[0], 1u);
+            while (*reinterpret_cast<volatile unsigned*>(&sync[0]) < gridDim.x) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
         const double pre = (double)chain_scale(ss, P.chain);                 // deferred error clips (models.py:214) owed by g
-        const double n2 = gss[ti] * pre * pre;
+        const double n2 = *reinterpret_cast<volatile double*>(&gss[ti]) * pre * pre;
         const double t = (double)(*step - (long long)n_layers + P.t_index);  // optimizers.py:236 (Q3)
         sh.clip = (float)(pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0));          // models.py:240-242
         sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;
@@ -297,6 +319,14 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
         float p = P.p[i], m = P.m[i], v = P.v[i];
         adam_elem(p, P.g[i], m, v, s);
         P.p[i] = p; P.m[i] = m; P.v[i] = v;
+    }
+    if (FUSED) {
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&sync[1], 1u) == gridDim.x - 1) {   // last CTA out: everyone has read gss
+            for (int i = 0; i < n_params; ++i) gss[i] = 0.0;
+            sync[0] = 0u;
+            sync[1] = 0u;
+        }
     }
 }
 
@@ -458,10 +488,15 @@ int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y
 int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
                       const long long* step, const int* block_map, int total_blocks, const double* ss, void* stream) {
     B200NN_REQUIRE(n_params > 0 && total_blocks > 0 && n_layers > 0, "adam_multi: empty parameter list");
+    if (total_blocks <= 16) {   // tiny sets only (CTAs spinning at the barrier would steal SM slots from concurrent kernels); gss + counters are zero on entry, restored by the kernel
+        adam_multi_kernel<true><<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, n_params, gss, hyper, step, block_map, ss);
+        B200NN_LAUNCH_CHECK("adam_multi_fused");
+        return B200NN_OK;
+    }
     B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
     sumsq_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, block_map, gss);
     B200NN_LAUNCH_CHECK("sumsq_multi");
-    adam_multi_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, gss, hyper, step, block_map, ss);
+    adam_multi_kernel<false><<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, n_params, gss, hyper, step, block_map, ss);
     B200NN_LAUNCH_CHECK("adam_multi");
     return B200NN_OK;
 }

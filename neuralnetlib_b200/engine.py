@@ -321,6 +321,7 @@ class Plan:
                 if not compute_only:
                     updates.append(ci)
                     self._grad_bucket_ready(layers[ci])
+                    self._maybe_early_update(updates)
                 i = ci - 1
                 continue
             if self.state[i].get("fused_into_bn"):
@@ -351,6 +352,7 @@ class Plan:
             if self._has_weights(L) and not compute_only:
                 updates.append(i)
                 self._grad_bucket_ready(L)
+                self._maybe_early_update(updates)
             if mask is not None and cur is not None:
                 cur = _Err(cur.t.reshape(self.outs[j].shape), cur.chain)
                 i = j - 1
@@ -388,6 +390,45 @@ class Plan:
                 dp.comm.allreduce(t, -1, side.cuda_stream)
             self.emit(fork, "grad_allreduce_async", (t,))
             self._side_used = True
+
+    # Early optimizer launch (single GPU, train step): once every parametrised layer but the FIRST has its gradients, their
+    # Adam / SGD update runs on a side stream while the first layer's backward (the largest kernel of a CNN) still computes;
+    # only the first layer's update remains on the critical path. The per-layer `t` and clip make the split exact.
+    def _early_setup(self, enabled):
+        params = [i for i, L in enumerate(self.layers) if self._has_weights(L)]
+        self._early = None
+        if enabled and len(params) >= 2 and self.dp is None and not self.defer_clips and os.environ.get("B200NN_EARLY_OPT", "1") != "0":
+            self._early = dict(fire_after=params[1], n_layers=len(params), done=False, side=torch.cuda.Stream(device=B.device()))
+
+    def _maybe_early_update(self, updates):
+        e = getattr(self, "_early", None)
+        if e is None or e["done"] or updates[-1] != e["fire_after"]:
+            return
+        e["done"] = True
+        opt = self.model.optimizer
+        ups = [(li, self.layers[li]._weights, self.layers[li]._d_weights, self.layers[li]._bias, self.layers[li]._d_bias, ())
+               for li in updates]
+        oplan = opt._make_plan(ups, self.ss, 1, e["n_layers"])
+        e["count"] = len(ups)
+        evt, side, main = torch.cuda.Event(), e["side"], B.stream_obj()
+
+        def fork():
+            evt.record(main)
+            side.wait_event(evt)
+            opt._run_plan(oplan, side.cuda_stream)
+        self.emit(fork, "optimizer_multi_early", opt._plan_io(oplan))
+
+    def _early_join(self):
+        e = getattr(self, "_early", None)
+        if e is None or not e["done"]:
+            return 0
+        evt, side, main = torch.cuda.Event(), e["side"], B.stream_obj()
+
+        def join():
+            evt.record(side)
+            main.wait_event(evt)
+        self.emit(join, "optimizer_early_join", ())
+        return e["count"]
 
     def _grad_exchange(self, updates):
         """Before the optimizer: flush the buckets not yet issued and join the side stream."""
@@ -458,16 +499,19 @@ class Plan:
                     self.allreduce(self.acc, "loss_exchange")
                     self.allreduce(self.ss[s0:s0 + 1], "slot_exchange")
                 self._slots_synced = self.n_slots
+            self._early_setup(True)
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
             self._grad_exchange(updates)
+            n_early = self._early_join()
             ups = []
-            for li in updates:
+            for li in updates[n_early:]:
                 L = self.layers[li]
                 ups.append((li, L._weights, L._d_weights, L._bias, L._d_bias, self._upd_chain.get(li, ())))
-            n_upd = len(ups)
-            if n_upd:
-                oplan = opt._make_plan(ups, self.ss)
+            n_upd = len(updates)
+            if ups:
+                oplan = opt._make_plan(ups, self.ss, n_early + 1, n_upd)
                 self.emit(lambda: opt._run_plan(oplan), "optimizer_multi", opt._plan_io(oplan))
+            self._early = None
             prog.ops[begin_at] = lambda: ops.step_begin(ss, acc, counter, n_upd)
             self.train_err0 = err0
         elif kind == "loss":
@@ -508,6 +552,7 @@ class Plan:
                 self.emit(lambda: ops.sumsq(err_in, ss, s0), "sumsq", (err_in,))
                 start = _Err(self.err_in, (s0,))
             self._sync_slots(first)
+            self._early = None
             updates, in_err = self._build_backward(start, gan, compute_only, True)
             self._grad_exchange(updates)
             # materialise the returned input error: clip folded in (the reference clips before Input too)

@@ -77,7 +77,7 @@ class Optimizer:
         """updates: list of (layer_index, w, dw, b, db) device tensors in update order (last layer first)."""
         raise NotImplementedError
 
-    def _run_plan(self, plan):
+    def _run_plan(self, plan, stream=None):
         raise NotImplementedError
 
     @staticmethod
@@ -123,19 +123,19 @@ class SGD(Optimizer):
             if host is not None:
                 host[...] = B.to_host(p).reshape(host.shape)
 
-    def _make_plan(self, updates, ss=None):
+    def _make_plan(self, updates, ss=None, j0=1, n_layers=None):
         self._ensure_device()
         entries = []
-        for j, upd in enumerate(updates, start=1):
+        for j, upd in enumerate(updates, start=j0):
             idx, w, dw, b, db = upd[:5]
             chain = upd[5] if len(upd) > 5 else ()
             entries.append((w, dw, None, None, j, 1, chain))
             if b is not None:
                 entries.append((b, db, None, None, j, 1, chain))
-        return ops.OptPlan(entries, max(len(updates), 1), ss)
+        return ops.OptPlan(entries, n_layers or max(len(updates), 1), ss)
 
-    def _run_plan(self, plan):
-        ops.sgd_multi(plan, self._hyper)
+    def _run_plan(self, plan, stream=None):
+        ops.sgd_multi(plan, self._hyper, stream)
 
     def get_config(self) -> dict:
         return {"name": self.__class__.__name__, "learning_rate": self.learning_rate}
@@ -211,10 +211,12 @@ class Adam(Optimizer):
             if host is not None:
                 host[...] = B.to_host(pd).reshape(host.shape)
 
-    def _make_plan(self, updates, ss=None):
+    def _make_plan(self, updates, ss=None, j0=1, n_layers=None):
+        """updates: (layer_index, w, dw, b, db[, pending chain]) in update order (last layer first). j0 / n_layers let one
+        step's updates be split over several launches (the per-layer `t` is counter - n_layers + j, optimizers.py:236)."""
         self._ensure_device()
         entries = []
-        for j, upd in enumerate(updates, start=1):
+        for j, upd in enumerate(updates, start=j0):
             idx, w, dw, b, db = upd[:5]
             chain = upd[5] if len(upd) > 5 else ()
             m, v = self._moments("w", idx, w)
@@ -222,10 +224,10 @@ class Adam(Optimizer):
             if b is not None:
                 m, v = self._moments("b", idx, b)
                 entries.append((b, db, m, v, j, 1, chain))
-        return ops.OptPlan(entries, max(len(updates), 1), ss)
+        return ops.OptPlan(entries, n_layers or max(len(updates), 1), ss)
 
-    def _run_plan(self, plan):
-        ops.adam_multi(plan, self._hyper, self._t_dev)
+    def _run_plan(self, plan, stream=None):
+        ops.adam_multi(plan, self._hyper, self._t_dev, stream)
 
     # reference-shaped views of the state (optimizers.py:247-261) --------------------------------------
     def _host_state(self, kind, which):
