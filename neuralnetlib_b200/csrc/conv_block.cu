@@ -148,14 +148,14 @@ __device__ __forceinline__ void cb_peer_gather(const PeerRegion& pr, unsigned se
     for (int r = 0; r < MAX_WORLD; ++r) in[r] = 0.0f;
     if (lane < 8) {
         const unsigned bits = __float_as_uint(mine);
-#pragma unroll
+#pragma unroll 1
         for (int p = 0; p < MAX_WORLD; ++p) {
             if (p < pr.world) {
                 uint2* dst = reinterpret_cast<uint2*>(pr.peers.p[p] + pr.off) + ((size_t)par * pr.world + pr.rank) * per_rank + slot;
                 asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(bits), "r"(seq) : "memory");
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < MAX_WORLD; ++r) {
             if (r < pr.world) {
                 const uint2* src = reinterpret_cast<const uint2*>(pr.peers.p[pr.rank] + pr.off) + ((size_t)par * pr.world + r) * per_rank + slot;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void cb_round_done(const PeerRegion& pr, unsigned seq
 // MODE 2: normalise + pool from rank-summed `stats`. MODE 3: one kernel, moments merged across GPUs over peer memory.
 // 1-D grid over items = (pool window, group of 8 filters), strided (persistent in MODE 3).
 template <int C, int MODE, int ACT>
-__global__ void __launch_bounds__(CB_THREADS) convblock_fwd_kernel(CbArgs a, float* __restrict__ rmean, float* __restrict__ rvar,
+__global__ void __launch_bounds__(CB_THREADS, C == 1 ? 3 : 2) convblock_fwd_kernel(CbArgs a, float* __restrict__ rmean, float* __restrict__ rvar,
                                                                    double* __restrict__ stats, float* __restrict__ y_pool,
                                                                    float momentum, float eps, PeerRegion pr, int items) {
     using Cfg = CbCfg<C>;
@@ -587,7 +587,10 @@ static int cb_launch(Kern kern, int items, bool persistent, size_t smem, cudaStr
     // persistent launches leave a few CTA slots free: an NCCL gradient allreduce may be running on a side stream, and every
     // CTA of the grid must be able to become resident while its peers on the other GPUs wait for it
     const int cap = e->resident > 64 ? e->resident - 24 : e->resident;
-    const int grid = persistent && items > cap ? cap : items;
+    static int force_persistent = -1;
+    if (force_persistent < 0) { const char* ev = getenv("B200NN_CB_PERSISTENT"); force_persistent = ev != nullptr ? atoi(ev) : 0; }
+    int grid = persistent && items > cap ? cap : items;
+    if (!persistent && force_persistent && items > e->resident) grid = e->resident;
     kern<<<grid, CB_THREADS, smem, st>>>(args...);
     return B200NN_OK;
 }
