@@ -15,7 +15,7 @@ namespace b200nn {
 namespace skinny {
 
 constexpr int MAXM = 256, MAXN = 64;
-constexpr int BK_BWD = 32, BK_FWD = 64;
+constexpr int BK_BWD = 24, BK_FWD = 44;   // slab widths (multiples of 4): 6272 features -> 262 / 143 CTAs on 148 SMs
 constexpr int WS_STRIDE = MAXN + 4;   // padded weight-slab rows: conflict-free 128-bit reads of 8 consecutive rows
 
 __device__ __forceinline__ void cp16(void* smem_dst, const void* gmem_src) {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) dense_skinny_bwd_kernel(const float* __re
     __syncthreads();
 
     // ---- dw[k0 + r, n] = scale * sum_m x[m, k0 + r] * e[m, n]   (layers.py:196): thread = 2 rows x 4 columns
-    if (dw != nullptr) {
+    if (dw != nullptr && tid < (BK_BWD / 2) * 16) {
         const int tk = tid >> 4, tn = tid & 15;          // rows 2tk, 2tk+1 ; columns 4tn .. 4tn+3
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 4
@@ -91,29 +91,30 @@ __global__ void __launch_bounds__(256) dense_skinny_bwd_kernel(const float* __re
                         make_float4(scale * acc[i][0], scale * acc[i][1], scale * acc[i][2], scale * acc[i][3]);
             }
         }
-        if (blockIdx.x == 0 && db != nullptr && tid < N) {   // layers.py:197
-            float s = 0.0f;
-            for (int m = 0; m < M; ++m) s += Es[m * MAXN + tid];
-            db[tid] = scale * s;
-        }
+    }
+    if (dw != nullptr && blockIdx.x == 0 && db != nullptr && tid < N) {   // layers.py:197
+        float s = 0.0f;
+        for (int m = 0; m < M; ++m) s += Es[m * MAXN + tid];
+        db[tid] = scale * s;
     }
     // ---- dx[m, k0 + c] = scale * sum_n e[m, n] * w[k0 + c, n]   (layers.py:189): thread = 8 rows x 4 columns
     if (dx != nullptr) {
+        constexpr int NJ = BK_BWD / 8;
         const int tm = tid >> 3, tc = tid & 7;           // rows tm + 32 i ; columns tc + 8 j
-        float acc[8][4];
+        float acc[8][NJ];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
         for (int n = 0; n < N; n += 4) {
-            float4 bw[4];
+            float4 bw[NJ];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bw[j] = *reinterpret_cast<const float4*>(Ws + (tc + 8 * j) * WS_STRIDE + n);
+            for (int j = 0; j < NJ; ++j) bw[j] = *reinterpret_cast<const float4*>(Ws + (tc + 8 * j) * WS_STRIDE + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 a = *reinterpret_cast<const float4*>(Es + (tm + 32 * i) * MAXN + n);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     acc[i][j] = fmaf(a.x, bw[j].x, acc[i][j]); acc[i][j] = fmaf(a.y, bw[j].y, acc[i][j]);
                     acc[i][j] = fmaf(a.z, bw[j].z, acc[i][j]); acc[i][j] = fmaf(a.w, bw[j].w, acc[i][j]);
                 }
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) dense_skinny_bwd_kernel(const float* __re
             const int m = tm + 32 * i;
             if (m >= M) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int c = tc + 8 * j;
                 if (c >= kw) continue;
                 float v = scale * acc[i][j];
