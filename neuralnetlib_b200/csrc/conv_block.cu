@@ -56,6 +56,12 @@ __device__ __forceinline__ float cb_act(float v, int act, float alpha) {
     if (ACT == B200NN_ACT_RELU) return fmaxf(v, 0.0f);
     return act_apply(act, v, alpha);
 }
+// backward keeps act(conv) per sample; for ReLU the +-10 clip is applied once when the value is produced (the clip keeps
+// the sign, so ReLU' can be read from the clipped value), for the other activations at every use
+template <int ACT>
+__device__ __forceinline__ float cb_keep(float a) { return ACT == B200NN_ACT_RELU ? fminf(a, 10.0f) : a; }
+template <int ACT>
+__device__ __forceinline__ float cb_clipped(float kept) { return ACT == B200NN_ACT_RELU ? kept : clip10(kept); }
 template <int ACT>
 __device__ __forceinline__ float cb_act_grad(float y, int act, float alpha) {
     if (ACT == B200NN_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
@@ -369,7 +375,8 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         mean[q] = a.save_mean[pos[q]];
         invstd[q] = a.save_invstd[pos[q]];
         g[q] = a.gamma[pos[q]] * invstd[q];
-        bt[q] = a.beta[pos[q]];
+        bt[q] = a.beta[pos[q]] - g[q] * mean[q];                              // y = g * c + bt  with c = clip(act(conv))
+        mean[q] = -mean[q] * invstd[q];                                       // xhat = c * invstd + mean   (folded constants)
     }
     const long long OP = (long long)OH * OW * a.F, obase = ((long long)oy * OW + ox) * a.F + f0;
     __syncthreads();                                                          // the previous item is done with the shared tiles
@@ -381,18 +388,21 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         errs[4][s] = v1.x; errs[5][s] = v1.y; errs[6][s] = v1.z; errs[7][s] = v1.w;
     }
     __syncthreads();
-    float S[CB_NS][4];                                                        // act(conv), before the +-10 clip
+    float S[CB_NS][4];                                                        // act(conv) (ReLU: already clipped, see cb_keep)
 #pragma unroll
     for (int j = 0; j < CB_NS; ++j) {
         const int s = lane + 32 * j;
         if (s < a.B) {
             cb_conv<C, ACT>(patch + s * Cfg::STRIDE, wr, bias, a.act, a.alpha, S[j]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) S[j][q] = cb_keep<ACT>(S[j][q]);
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) S[j][q] = 0.0f;
         }
     }
     float su[4] = {0.f, 0.f, 0.f, 0.f}, sux[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned tie = 0u;                                                        // 4 tie bits per sample, kept from pass 1 for pass 2
     if (MODE != 2) {
 #pragma unroll
         for (int j = 0; j < CB_NS; ++j) {                    // pass 1: U = pool-bwd(e); d_beta = sum U, d_gamma = sum U*xhat
@@ -401,14 +411,16 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
             float y[4], xh[4], m = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float d = clip10(S[j][q]) - mean[q];
-                y[q] = fmaf(g[q], d, bt[q]);
-                xh[q] = d * invstd[q];
+                const float c = cb_clipped<ACT>(S[j][q]);
+                y[q] = fmaf(g[q], c, bt[q]);
+                xh[q] = fmaf(c, invstd[q], mean[q]);
                 m = fmaxf(m, y[q]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float u = (y[q] == m) ? e : 0.0f;                     // every tied maximum (layers.py:631-637)
+                const bool hit = y[q] == m;                                 // every tied maximum (layers.py:631-637)
+                tie |= hit ? (1u << (4 * j + q)) : 0u;
+                const float u = hit ? e : 0.0f;
                 su[q] += u;
                 sux[q] = fmaf(u, xh[q], sux[q]);
                 a0 = fmaf(u, u, a0);
@@ -452,8 +464,8 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
     const float invB = (float)(1.0 / a.n_total);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        su[q] *= invB;
-        sux[q] *= invB;
+        su[q] *= -invB * g[q];                                                // d = g*u - xhat * g*sum(u xhat)/B - g*sum(u)/B
+        sux[q] *= -invB * g[q];
     }
     float gw[9 * C], gb = 0.0f;
 #pragma unroll
@@ -463,18 +475,26 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         const int s = lane + 32 * j;
         if (s >= a.B) continue;
         const float e = scale * errs[wid][s];
-        float y[4], xh[4], r[4], m = -INFINITY;
+        float r[4];
+        unsigned bits;
+        if (MODE == 2) {                                                      // pass 1 ran in another launch: recompute the ties
+            float y[4], m = -INFINITY;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float d = clip10(S[j][q]) - mean[q];
-            y[q] = fmaf(g[q], d, bt[q]);
-            xh[q] = d * invstd[q];
-            m = fmaxf(m, y[q]);
+            for (int q = 0; q < 4; ++q) {
+                y[q] = fmaf(g[q], cb_clipped<ACT>(S[j][q]), bt[q]);
+                m = fmaxf(m, y[q]);
+            }
+            bits = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bits |= (y[q] == m) ? (1u << q) : 0u;
+        } else {
+            bits = tie >> (4 * j);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float u = (y[q] == m) ? e : 0.0f;
-            float d = g[q] * (u - xh[q] * sux[q] - su[q]);                    // layers.py:1264-1274 in closed form
+            const float u = (bits >> q) & 1u ? e : 0.0f;
+            const float xh = fmaf(cb_clipped<ACT>(S[j][q]), invstd[q], mean[q]);
+            float d = fmaf(g[q], u, fmaf(xh, sux[q], su[q]));                 // layers.py:1264-1274 in closed form
             a1 = fmaf(d, d, a1);
             d *= cb_act_grad<ACT>(S[j][q], a.act, a.alpha);                   // layers.py:237
             a2 = fmaf(d, d, a2);
