@@ -98,6 +98,35 @@ __device__ __forceinline__ void cb_stage(float* patch, const CbArgs& a, int oy, 
     }
 }
 
+// the same staging with cp.async (4-byte copies, zero-filled when the source pixel is padding): returns immediately, so a
+// persistent CTA can fetch its NEXT item while it computes the current one (double-buffered shared memory)
+template <int C>
+__device__ __forceinline__ void cb_stage_async(float* patch, const CbArgs& a, int oy, int ox) {
+    constexpr int EPS = CbCfg<C>::EPS, ROW = 4 * C;
+    const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
+    const long long img = (long long)a.H * a.W * C;
+    const int total = a.B * EPS;
+    for (int i = threadIdx.x; i < total; i += CB_THREADS) {
+        const int sidx = i / EPS, e = i % EPS;
+        const int py = e / ROW, r = e % ROW, px = r / C, c = r % C;
+        const int iy = iy0 + py, ix = ix0 + px;
+        const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+        const float* src = ok ? a.x + (long long)sidx * img + ((long long)iy * a.W + ix) * C + c : a.x;
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(patch + sidx * CbCfg<C>::STRIDE + c * 16 + py * 4 + px));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0));
+    }
+}
+__device__ __forceinline__ void cb_cp16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cb_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+template <int C>
+struct CbBuf {   // per staging buffer: patch[CB_MAXB][STRIDE] | aux[CB_FPC * CB_MAXB]; two buffers when they fit 3 CTAs per SM
+    static constexpr int FLOATS = CB_MAXB * CbCfg<C>::STRIDE + CB_FPC * CB_MAXB;
+    static constexpr int N = C == 1 ? 2 : 1;
+};
+
 // conv + activation of one sample at the window's 4 positions (q = 2*qy + qx) for one filter
 template <int C, int ACT>
 __device__ __forceinline__ void cb_conv(const float* __restrict__ p, const float (&wr)[9 * C], float bias, int act, float alpha,
@@ -204,12 +233,15 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 3 : 2) convblock_fwd_kern
                                                                    double* __restrict__ stats, float* __restrict__ y_pool,
                                                                    float momentum, float eps, PeerRegion pr, int items) {
     using Cfg = CbCfg<C>;
-    extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | outs[CB_FPC][CB_MAXB]
-    float* patch = cb_smem;
-    float (*outs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(cb_smem + CB_MAXB * Cfg::STRIDE);
+    extern __shared__ __align__(16) float cb_smem[];                         // CbBuf<C>::N x { patch | outs[CB_FPC][CB_MAXB] }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int OW = a.W >> 1, OH = a.H >> 1;
     const long long P = (long long)a.H * a.W * a.F;
+    auto stage = [&](int it, int b) {
+        cb_stage_async<C>(cb_smem + b * CbBuf<C>::FLOATS, a, (it / OW) % OH, it % OW);
+    };
+    int buf = 0;
+    if (CbBuf<C>::N == 2 && (int)blockIdx.x < items) stage(blockIdx.x, 0);
     unsigned seq = 0;
     if (MODE == 3) {
         seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
@@ -224,9 +256,17 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 3 : 2) convblock_fwd_kern
     long long pos[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) pos[q] = ((long long)(2 * oy + (q >> 1)) * a.W + 2 * ox + (q & 1)) * a.F + f;
-    __syncthreads();                                                          // the previous item is done with the shared tiles
-    cb_stage<C>(patch, a, oy, ox);
-    __syncthreads();
+    float* patch = cb_smem + buf * CbBuf<C>::FLOATS;
+    float (*outs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(patch + CB_MAXB * Cfg::STRIDE);
+    if (CbBuf<C>::N == 2) {
+        cb_async_wait();
+        __syncthreads();                                                      // this item's patches have landed; the previous item is done
+        if (item + (int)gridDim.x < items) stage(item + gridDim.x, buf ^ 1);   // fetch the next item while computing this one
+    } else {
+        __syncthreads();                                                      // the previous item is done with the shared tiles
+        cb_stage<C>(patch, a, oy, ox);
+        __syncthreads();
+    }
     float S[CB_NS][4];                                                        // clip(act(conv)) of this lane's samples (layers.py:1234)
 #pragma unroll
     for (int j = 0; j < CB_NS; ++j) {
@@ -269,6 +309,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 3 : 2) convblock_fwd_kern
                     stats[P + pos[q]] = (double)m2[q] + S1 * S1 / (double)a.B;
                 }
             }
+            if (CbBuf<C>::N == 2) buf ^= 1;
             continue;
         }
         float ntot = (float)a.B;
@@ -336,6 +377,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 3 : 2) convblock_fwd_kern
         dst[0] = v0;
         dst[1] = v1;
     }
+    if (CbBuf<C>::N == 2) buf ^= 1;
   }
     if (MODE == 3) cb_round_done(pr, seq);
 }
@@ -350,13 +392,22 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
                                                                       double* ss0, double* ss1, double* ss2, PeerRegion pr,
                                                                       int items) {
     using Cfg = CbCfg<C>;
-    extern __shared__ __align__(16) float cb_smem[];                         // patch[CB_MAXB][STRIDE] | errs[CB_FPC][CB_MAXB]
-    float* patch = cb_smem;
-    float (*errs)[CB_MAXB] = reinterpret_cast<float (*)[CB_MAXB]>(cb_smem + CB_MAXB * Cfg::STRIDE);
+    extern __shared__ __align__(16) float cb_smem[];                         // CbBuf<C>::N x { patch | errs[CB_MAXB][CB_FPC] }
     __shared__ double scratch[32];
     const float scale = chain_scale(ss, chain);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int OW = a.W >> 1, OH = a.H >> 1;
+    const long long OP = (long long)OH * OW * a.F;
+    auto stage = [&](int it, int b) {                                         // patches + the pooled error (one 32-byte run per sample)
+        float* base = cb_smem + b * CbBuf<C>::FLOATS;
+        const int sox = it % OW, soy = (it / OW) % OH, sf0 = (it / (OW * OH)) * CB_FPC;
+        cb_stage_async<C>(base, a, soy, sox);
+        float* eb = base + CB_MAXB * Cfg::STRIDE;
+        const float* src = err + ((long long)soy * OW + sox) * a.F + sf0;
+        for (int i = threadIdx.x; i < 2 * a.B; i += CB_THREADS) cb_cp16(eb + i * 4, src + (long long)(i >> 1) * OP + (i & 1) * 4);
+    };
+    int buf = 0;
+    if (CbBuf<C>::N == 2 && (int)blockIdx.x < items) stage(blockIdx.x, 0);
     unsigned seq = 0;
     if (MODE == 3) {
         seq = *reinterpret_cast<volatile unsigned*>(&reinterpret_cast<SymHeader*>(pr.peers.p[pr.rank])->seq[pr.site]) + 1u;
@@ -378,16 +429,18 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         bt[q] = a.beta[pos[q]] - g[q] * mean[q];                              // y = g * c + bt  with c = clip(act(conv))
         mean[q] = -mean[q] * invstd[q];                                       // xhat = c * invstd + mean   (folded constants)
     }
-    const long long OP = (long long)OH * OW * a.F, obase = ((long long)oy * OW + ox) * a.F + f0;
-    __syncthreads();                                                          // the previous item is done with the shared tiles
-    cb_stage<C>(patch, a, oy, ox);
-    for (int s = threadIdx.x; s < a.B; s += CB_THREADS) {                     // pooled error: one 32-byte run per sample
-        const float4* src = reinterpret_cast<const float4*>(err + (long long)s * OP + obase);
-        const float4 v0 = src[0], v1 = src[1];
-        errs[0][s] = v0.x; errs[1][s] = v0.y; errs[2][s] = v0.z; errs[3][s] = v0.w;
-        errs[4][s] = v1.x; errs[5][s] = v1.y; errs[6][s] = v1.z; errs[7][s] = v1.w;
+    float* patch = cb_smem + buf * CbBuf<C>::FLOATS;
+    const float* errs = patch + CB_MAXB * Cfg::STRIDE;                        // [sample][8 filters]
+    if (CbBuf<C>::N == 2) {
+        cb_async_wait();
+        __syncthreads();
+        if (item + (int)gridDim.x < items) stage(item + gridDim.x, buf ^ 1);
+    } else {
+        __syncthreads();                                                      // the previous item is done with the shared tiles
+        stage(item, 0);
+        cb_async_wait();
+        __syncthreads();
     }
-    __syncthreads();
     float S[CB_NS][4];                                                        // act(conv) (ReLU: already clipped, see cb_keep)
 #pragma unroll
     for (int j = 0; j < CB_NS; ++j) {
@@ -407,7 +460,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
 #pragma unroll
         for (int j = 0; j < CB_NS; ++j) {                    // pass 1: U = pool-bwd(e); d_beta = sum U, d_gamma = sum U*xhat
             const int s = lane + 32 * j;
-            const float e = s < a.B ? scale * errs[wid][s] : 0.0f;
+            const float e = s < a.B ? scale * errs[s * CB_FPC + wid] : 0.0f;
             float y[4], xh[4], m = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -453,7 +506,10 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
                 if (dgamma != nullptr) dgamma[pos[q]] = sux[q];              // layers.py:1261
             }
         }
-        if (MODE == 1) continue;
+        if (MODE == 1) {
+            if (CbBuf<C>::N == 2) buf ^= 1;
+            continue;
+        }
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -474,7 +530,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
     for (int j = 0; j < CB_NS; ++j) {                        // pass 2: BN-bwd, act', weight gradient
         const int s = lane + 32 * j;
         if (s >= a.B) continue;
-        const float e = scale * errs[wid][s];
+        const float e = scale * errs[s * CB_FPC + wid];
         float r[4];
         unsigned bits;
         if (MODE == 2) {                                                      // pass 1 ran in another launch: recompute the ties
@@ -538,6 +594,7 @@ __global__ void __launch_bounds__(CB_THREADS, C == 1 ? 2 : 1) convblock_bwd_kern
         const float tb = warp_sum(gb);
         if (lane == 0) dst[(long long)Cfg::K * a.F] = tb;                     // layers.py:521
     }
+    if (CbBuf<C>::N == 2) buf ^= 1;
   }
     if (MODE != 2 && ss0 != nullptr) block_accumulate(a0, ss0, scratch);
     if (MODE != 1 && ss1 != nullptr) block_accumulate(a1, ss1, scratch);
@@ -587,7 +644,8 @@ static int cb_check(const char* who, const b200nn_conv_geom* g, int act, float a
 
 // grid: one CTA per item, or (persistent) as many CTAs as are co-resident on the device, whichever is smaller
 template <class Kern, class... Args>
-static int cb_launch(Kern kern, int items, bool persistent, size_t smem, cudaStream_t st, Args... args) {
+static int cb_launch(Kern kern, int items, int persistent /* 0 no, 1 yes, 2 yes with head-room for NCCL */, size_t smem,
+                     cudaStream_t st, Args... args) {
     struct Entry { const void* k; int resident; };
     static thread_local Entry table[64] = {};
     Entry* e = nullptr;
@@ -606,11 +664,8 @@ static int cb_launch(Kern kern, int items, bool persistent, size_t smem, cudaStr
     B200NN_REQUIRE(e != nullptr, "convblock: kernel table full");
     // persistent launches leave a few CTA slots free: an NCCL gradient allreduce may be running on a side stream, and every
     // CTA of the grid must be able to become resident while its peers on the other GPUs wait for it
-    const int cap = e->resident > 64 ? e->resident - 24 : e->resident;
-    static int force_persistent = -1;
-    if (force_persistent < 0) { const char* ev = getenv("B200NN_CB_PERSISTENT"); force_persistent = ev != nullptr ? atoi(ev) : 0; }
-    int grid = persistent && items > cap ? cap : items;
-    if (!persistent && force_persistent && items > e->resident) grid = e->resident;
+    const int cap = persistent == 2 && e->resident > 64 ? e->resident - 24 : e->resident;
+    const int grid = persistent && items > cap ? cap : items;
     kern<<<grid, CB_THREADS, smem, st>>>(args...);
     return B200NN_OK;
 }
@@ -632,19 +687,21 @@ size_t b200nn_convblock_ws_bytes(const b200nn_conv_geom* g) {
     return (size_t)(g->H / 2) * (g->W / 2) * (9 * g->C + 1) * g->F * sizeof(float);
 }
 
-#define CB_SMEM(C) ((size_t)(CB_MAXB * CbCfg<C>::STRIDE + CB_FPC * CB_MAXB) * sizeof(float))
-#define CB_DISPATCH_C(KERN, MODE, ACT, ...)                                                                              \
-    do {                                                                                                                 \
-        int rc_;                                                                                                         \
-        if (g->C == 1) rc_ = cb_launch(KERN<1, MODE, ACT>, items, MODE == 3, CB_SMEM(1), st, __VA_ARGS__);               \
-        else if (g->C == 2) rc_ = cb_launch(KERN<2, MODE, ACT>, items, MODE == 3, CB_SMEM(2), st, __VA_ARGS__);          \
-        else rc_ = cb_launch(KERN<3, MODE, ACT>, items, MODE == 3, CB_SMEM(3), st, __VA_ARGS__);                         \
-        if (rc_) return rc_;                                                                                             \
+#define CB_SMEM(C) ((size_t)CbBuf<C>::N * CbBuf<C>::FLOATS * sizeof(float))
+// PERS: launch policy of the single-GPU / split modes (1 = persistent grid with next-item prefetch, 0 = one CTA per item);
+// the peer-fused mode 3 is always persistent with head-room
+#define CB_DISPATCH_C(KERN, MODE, ACT, PERS, ...)                                                                            \
+    do {                                                                                                                     \
+        int rc_;                                                                                                             \
+        if (g->C == 1) rc_ = cb_launch(KERN<1, MODE, ACT>, items, MODE == 3 ? 2 : PERS, CB_SMEM(1), st, __VA_ARGS__);        \
+        else if (g->C == 2) rc_ = cb_launch(KERN<2, MODE, ACT>, items, MODE == 3 ? 2 : 0, CB_SMEM(2), st, __VA_ARGS__);      \
+        else rc_ = cb_launch(KERN<3, MODE, ACT>, items, MODE == 3 ? 2 : 0, CB_SMEM(3), st, __VA_ARGS__);                     \
+        if (rc_) return rc_;                                                                                                 \
     } while (0)
-#define CB_DISPATCH(KERN, MODE, ...)                                                             \
-    do {                                                                                         \
-        if (act == B200NN_ACT_RELU) CB_DISPATCH_C(KERN, MODE, B200NN_ACT_RELU, __VA_ARGS__);     \
-        else CB_DISPATCH_C(KERN, MODE, -1, __VA_ARGS__);                                         \
+#define CB_DISPATCH(KERN, MODE, PERS, ...)                                                             \
+    do {                                                                                               \
+        if (act == B200NN_ACT_RELU) CB_DISPATCH_C(KERN, MODE, B200NN_ACT_RELU, PERS, __VA_ARGS__);     \
+        else CB_DISPATCH_C(KERN, MODE, -1, PERS, __VA_ARGS__);                                         \
     } while (0)
 
 static int cb_peer_region(const char* who, int mode, b200nn_comm* comm, int site, size_t region_off, int items, PeerRegion* pr) {
@@ -680,10 +737,10 @@ int b200nn_convblock_fwd(const b200nn_conv_geom* g, const float* x, const float*
     PeerRegion pr;
     if (int rc = cb_peer_region("convblock_fwd", mode, comm, site, region_off, items, &pr)) return rc;
     cudaStream_t st = as_stream(stream);
-    if (mode == 0) CB_DISPATCH(convblock_fwd_kernel, 0, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
-    else if (mode == 1) CB_DISPATCH(convblock_fwd_kernel, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
-    else if (mode == 2) CB_DISPATCH(convblock_fwd_kernel, 2, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
-    else CB_DISPATCH(convblock_fwd_kernel, 3, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    if (mode == 0) CB_DISPATCH(convblock_fwd_kernel, 0, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else if (mode == 1) CB_DISPATCH(convblock_fwd_kernel, 1, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else if (mode == 2) CB_DISPATCH(convblock_fwd_kernel, 2, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
+    else CB_DISPATCH(convblock_fwd_kernel, 3, 1, a, running_mean, running_var, stats, y_pool, momentum, eps, pr, items);
     B200NN_LAUNCH_CHECK("convblock_fwd");
     return B200NN_OK;
 }
@@ -704,10 +761,10 @@ int b200nn_convblock_bwd(const b200nn_conv_geom* g, const float* x, const float*
     PeerRegion pr;
     if (int rc = cb_peer_region("convblock_bwd", mode, comm, site, region_off, items, &pr)) return rc;
     cudaStream_t st = as_stream(stream);
-    if (mode == 0) CB_DISPATCH(convblock_bwd_kernel, 0, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
-    else if (mode == 1) CB_DISPATCH(convblock_bwd_kernel, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
-    else if (mode == 2) CB_DISPATCH(convblock_bwd_kernel, 2, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
-    else CB_DISPATCH(convblock_bwd_kernel, 3, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    if (mode == 0) CB_DISPATCH(convblock_bwd_kernel, 0, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else if (mode == 1) CB_DISPATCH(convblock_bwd_kernel, 1, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else if (mode == 2) CB_DISPATCH(convblock_bwd_kernel, 2, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
+    else CB_DISPATCH(convblock_bwd_kernel, 3, 1, a, err, ss, chain, dgamma, dbeta, ws, r_out, ss_out0, ss_out1, ss_out2, pr, items);
     B200NN_LAUNCH_CHECK("convblock_bwd");
     if (mode != 1 && dw != nullptr) {
         // the weight gradient still owes the three clips this kernel produced (pool-bwd / BN-bwd / act-bwd outputs): chain_out
