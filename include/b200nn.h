@@ -117,7 +117,14 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
 /* Classifier head as one kernel (N <= 32): p = softmax(x . w + b) (layers.py:173, activations.py:69-71), loss_acc[0] += CCE
  * numerator (losses.py:106-109), err = p - y_true (models.py:200-205), loss_acc[1] += argmax hits, ss_out += sum(err^2). */
 int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, const float* y_true, float* p, float* err,
-                             double* loss_acc, double* ss_out, int M, int N, int K, void* stream);
+                             double* loss_acc, double* ss_out, int M, int N, int K, float* dw_partial, void* stream);
+/* dw_partial (nullable): [b200nn_dense_head_partials(M, K)][(K + 1) * N] per-CTA partials of x^T . err (+ "ones" row = db),
+ * formed while err is still in registers; b200nn_dense_bwd_head then replaces b200nn_dense_bwd for that layer: it adds the
+ * partials in fixed order (times the pending chain) instead of re-reading x and err. 0 partials = shape not supported. */
+int b200nn_dense_head_partials(int M, int K);
+int b200nn_dense_bwd_head(const float* x, const float* w, const float* err, const double* ss, uint64_t chain, float* dx, float* dw,
+                          float* db, int M, int N, int K, int prev_act, float prev_alpha, double* ss_out0, double* ss_out1,
+                          const float* dw_partial, void* stream);
 /* g = chain(err)[M,N];  dx[M,K] = g . w^T (layers.py:189);  dw[K,N] = x^T . g (:196);  db[N] = sum_rows g (:197).
  * dx == NULL skips dx (first parametrised layer inside fit). If prev_act != NONE the backward of the
  * PRECEDING Activation layer (whose output is this layer's input x) is fused into the dx epilogue:

@@ -128,12 +128,24 @@ def dense_fwd(math, x, w, b, y, act, alpha, ws):
     check(lib().b200nn_dense_fwd(math, ptr(x), ptr(w), ptr(b), ptr(y), M, N, K, act, alpha, ptr(ws), stream()))
 
 
-def dense_softmax_cce(x, w, b, y_true, p, err, acc, ss, slot_out):
-    _f32(x, w, b, y_true, p, err)
+def dense_softmax_cce(x, w, b, y_true, p, err, acc, ss, slot_out, dw_partial=None):
+    _f32(x, w, b, y_true, p, err, dw_partial)
     K, N = w.shape
     M = x.numel() // K
     check(lib().b200nn_dense_softmax_cce(ptr(x), ptr(w), ptr(b), ptr(y_true), ptr(p), ptr(err), ptr(acc), _slot_ptr(ss, slot_out),
-                                         M, N, K, stream()))
+                                         M, N, K, ptr(dw_partial), stream()))
+
+
+def dense_head_partials(M, K):
+    return int(lib().b200nn_dense_head_partials(int(M), int(K)))
+
+
+def dense_bwd_head(x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, dw_partial):
+    _f32(x, w, err, dx, dw, db, dw_partial)
+    K, N = w.shape
+    M = x.numel() // K
+    check(lib().b200nn_dense_bwd_head(ptr(x), ptr(w), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), ptr(dw), ptr(db), M, N, K,
+                                      prev_act, prev_alpha, _slot_ptr(ss, slot0), _slot_ptr(ss, slot1), ptr(dw_partial), stream()))
 
 
 def dense_bwd(math, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot0, slot1, ws):

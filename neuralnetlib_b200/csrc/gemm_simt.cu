@@ -659,6 +659,7 @@ static int smallk_wgrad_blocks(const b200nn_conv_geom* g) {
 // padding and the layer is pure latency, so these kernels map threads to the long dimensions instead.
 // ------------------------------------------------------------------------------------------------
 constexpr int SMALLN_MAX = 32;
+constexpr int HEAD_MAXK = 256;   // the fused head can also emit per-CTA weight-gradient partials for inputs this wide
 
 // y[m, :] = act(b + x[m, :] . w)   — one warp per row, lanes stride over k, N accumulators per lane, shuffle-reduce
 __global__ void __launch_bounds__(256) dense_smalln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -754,11 +755,18 @@ __global__ void __launch_bounds__(256) dense_smalln_dw_kernel(const float* __res
 __global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ b, const float* __restrict__ y,
                                                                 float* __restrict__ p, float* __restrict__ err,
-                                                                double* loss_acc, double* ss_out, int M, int N, int K) {
+                                                                double* loss_acc, double* ss_out, int M, int N, int K,
+                                                                float* __restrict__ dwp) {
     __shared__ double scratch[32];
+    __shared__ float xs[8][HEAD_MAXK];
+    __shared__ float es[8][SMALLN_MAX];
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     float lsum = 0.0f, esq = 0.0f, correct = 0.0f;
+    if (dwp != nullptr) {                                                    // rows past M contribute nothing to the partial
+        es[threadIdx.x >> 5][lane] = 0.0f;
+        for (int k = lane; k < K; k += 32) xs[threadIdx.x >> 5][k] = 0.0f;
+    }
     for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
         float acc[SMALLN_MAX];
 #pragma unroll
@@ -792,7 +800,10 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __r
             const float e = pv - yv;
             err[(long long)m * N + lane] = e;
             esq = fmaf(e, e, esq);
+            if (dwp != nullptr) es[threadIdx.x >> 5][lane] = e;
         }
+        if (dwp != nullptr)
+            for (int k = lane; k < K; k += 32) xs[threadIdx.x >> 5][k] = xr[k];
         float bp = on ? pv : -INFINITY, by = on ? yv : -INFINITY;
         int ip = on ? lane : 0x7fffffff, iy = ip;
 #pragma unroll
@@ -806,6 +817,19 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __r
         }
         if (lane == 0 && ip == iy) correct += 1.0f;
     }
+    if (dwp != nullptr) {
+        // this CTA's 8 rows of the weight gradient of the head (x^T . err, + the "ones" row for db), fixed order: the backward
+        // kernel of the layer only has to add the per-CTA partials (layers.py:196-197)
+        __syncthreads();
+        float* dst = dwp + (long long)blockIdx.x * (K + 1) * N;
+        for (int o = threadIdx.x; o < (K + 1) * N; o += blockDim.x) {
+            const int k = o / N, n = o % N;
+            float t = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t = fmaf(k < K ? xs[r][k] : 1.0f, es[r][n], t);
+            dst[o] = t;
+        }
+    }
     const double l = block_sum_to_double(lsum, scratch);
     if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[0], l);
     const double c = block_sum_to_double(correct, scratch);
@@ -818,13 +842,23 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __r
 // in fixed order: no partials, no reduce pass).
 __global__ void __launch_bounds__(256) dense_smalln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ e, Epilogue epi, float* __restrict__ dw,
-                                                               float* __restrict__ db, int M, int N, int K, int dx_blocks) {
+                                                               float* __restrict__ db, int M, int N, int K, int dx_blocks,
+                                                               const float* __restrict__ dwp, int n_partial) {
     __shared__ double scratch[32];
     if ((int)blockIdx.x >= dx_blocks) {
         const float scale = chain_scale(epi.ss, epi.chain);
         const int o = ((int)blockIdx.x - dx_blocks) * blockDim.x + threadIdx.x;   // output index over (K + 1) x N
         if (o >= (K + 1) * N) return;
         const int k = o / N, n = o % N;
+        if (dwp != nullptr) {                            // the fused head already formed per-CTA partials: add them in order
+            float t = 0.0f;
+#pragma unroll 8
+            for (int c = 0; c < n_partial; ++c) t += dwp[(long long)c * (K + 1) * N + o];
+            t *= scale;
+            if (k < K) { if (dw != nullptr) dw[o] = t; }
+            else if (db != nullptr) db[n] = t;
+            return;
+        }
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         int m = 0;
         if (k < K) {
@@ -983,13 +1017,34 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
 }
 
 int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, const float* y_true, float* p, float* err,
-                             double* loss_acc, double* ss_out, int M, int N, int K, void* stream) {
+                             double* loss_acc, double* ss_out, int M, int N, int K, float* dw_partial, void* stream) {
     B200NN_REQUIRE(M > 0 && K > 0 && N > 0 && N <= SMALLN_MAX, "dense_softmax_cce: needs N <= %d (M=%d N=%d K=%d)", SMALLN_MAX, M, N, K);
     B200NN_REQUIRE(x != nullptr && w != nullptr && y_true != nullptr && p != nullptr && err != nullptr, "dense_softmax_cce: null buffer");
     int blocks = (M + 7) / 8;
+    B200NN_REQUIRE(dw_partial == nullptr || (K <= HEAD_MAXK && blocks <= kNumSMs * 8), "dense_softmax_cce: partials need K <= %d", HEAD_MAXK);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    dense_softmax_cce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+    dense_softmax_cce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K, dw_partial);
     B200NN_LAUNCH_CHECK("dense_softmax_cce");
+    return B200NN_OK;
+}
+
+int b200nn_dense_head_partials(int M, int K) { return (K <= HEAD_MAXK && M <= 512) ? (M + 7) / 8 : 0; }
+
+int b200nn_dense_bwd_head(const float* x, const float* w, const float* err, const double* ss, uint64_t chain, float* dx, float* dw,
+                          float* db, int M, int N, int K, int prev_act, float prev_alpha, double* ss_out0, double* ss_out1,
+                          const float* dw_partial, void* stream) {
+    B200NN_REQUIRE(M > 0 && K > 0 && N > 0 && N <= SMALLN_MAX && M <= 512 && K <= HEAD_MAXK && dw_partial != nullptr && dw != nullptr,
+                   "dense_bwd_head: unsupported shape M=%d N=%d K=%d", M, N, K);
+    if (int rc = check_act("dense_bwd_head", prev_act, prev_alpha)) return rc;
+    long long dx_blocks = dx != nullptr ? ((long long)M * K + 255) / 256 : 0;
+    if (dx_blocks > kNumSMs * 8) dx_blocks = kNumSMs * 8;
+    const int dw_blocks = ((K + 1) * N + 255) / 256;
+    Epilogue e = plain_epilogue(dx, K, M);
+    e.ss = ss; e.chain = chain;
+    if (dx != nullptr) dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+    dense_smalln_bwd_kernel<<<(int)dx_blocks + dw_blocks, 256, 0, as_stream(stream)>>>(x, w, err, e, dw, db, M, N, K, (int)dx_blocks,
+                                                                                     dw_partial, (M + 7) / 8);
+    B200NN_LAUNCH_CHECK("dense_bwd_head");
     return B200NN_OK;
 }
 
@@ -1008,7 +1063,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         e.ss = ss; e.chain = chain;
         if (dx != nullptr) dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
         if (dx_blocks + dw_blocks > 0) {
-            dense_smalln_bwd_kernel<<<(int)dx_blocks + dw_blocks, 256, 0, st>>>(x, w, err, e, dw, db, M, N, K, (int)dx_blocks);
+            dense_smalln_bwd_kernel<<<(int)dx_blocks + dw_blocks, 256, 0, st>>>(x, w, err, e, dw, db, M, N, K, (int)dx_blocks, nullptr, 0);
             B200NN_LAUNCH_CHECK("dense_smalln_bwd");
         }
         return B200NN_OK;

@@ -482,10 +482,16 @@ class Plan:
             err0 = self.buf(self.pred.shape)
             s0 = self.slot()
             pred, y_in, acc, ss = self.pred, self.y_in, self.acc, self.ss
-            if head is not None:   # Dense + Softmax + CCE + (p - y) in one launch
+            head_state = None
+            if head is not None:   # Dense + Softmax + CCE + (p - y) in one launch (+ the head's weight-gradient partials)
                 hx, hw, hb = head["x"], head["layer"]._weights, head["layer"]._bias
-                self.emit(lambda: ops.dense_softmax_cce(hx, hw, hb, y_in, pred, err0, acc, ss, s0), "dense_softmax_cce",
+                n_part = ops.dense_head_partials(hx.shape[0], hw.shape[0])
+                dwp = self.buf((n_part, (hw.shape[0] + 1) * hw.shape[1])) if n_part > 0 else None
+                self.emit(lambda: ops.dense_softmax_cce(hx, hw, hb, y_in, pred, err0, acc, ss, s0, dwp), "dense_softmax_cce",
                           (hx, hw, y_in, pred, err0))
+                if dwp is not None:
+                    head_state = self.state[self.layers.index(head["layer"])]
+                    head_state["dw_partial"] = dwp
             else:
                 self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
             if self.dp is not None:
@@ -501,6 +507,8 @@ class Plan:
                 self._slots_synced = self.n_slots
             self._early_setup(True)
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
+            if head_state is not None:
+                del head_state["dw_partial"]   # other programs of this plan (public backward_pass) run the plain Dense backward
             self._grad_exchange(updates)
             n_early = self._early_join()
             ups = []

@@ -290,8 +290,13 @@ class Dense(Layer, _ParamMixin):
         s1 = ctx.slot() if (need_dx and mask_layer is not None) else None
         w, dw, db, ss, chain, math = self._weights, self._d_weights, self._d_bias, ctx.ss, err.chain, st["math"]
         et = err.t
-        ctx.emit(lambda: ops.dense_bwd(math, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws), "dense_bwd",
-                 (x, et, dw, db) + ((w, dx) if need_dx else ()))
+        dwp = st.get("dw_partial")   # set by the engine when the fused head kernel of this train step already formed x^T . err partials
+        if dwp is not None:
+            ctx.emit(lambda: ops.dense_bwd_head(x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, dwp), "dense_bwd_head",
+                     (et, dw, db) + ((w, dx) if need_dx else ()))
+        else:
+            ctx.emit(lambda: ops.dense_bwd(math, x, w, et, ss, chain, dx, dw, db, kind, alpha, s0, s1, ctx.ws), "dense_bwd",
+                     (x, et, dw, db) + ((w, dx) if need_dx else ()))
         if not need_dx:
             return None
         return _Err(dx, tuple(s for s in (s0, s1) if s is not None))
