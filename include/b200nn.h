@@ -78,6 +78,10 @@ int b200nn_gather_rows(const float* src, const long long* idx, float* dst, long 
                        void* stream);
 int b200nn_zero_f64(double* p, int n, void* stream);
 
+/* ---- host <-> device plumbing of the public entry points (models.py:251-264: the batch goes in, the loss comes out) ---- */
+int b200nn_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream);          /* async H2D on `stream` */
+int b200nn_read_sync(void* dst_host, const void* src_dev, size_t bytes, void* stream);      /* D2H + stream sync */
+
 /* ---- CUDA graph helpers (capture every launch made on `stream` between begin and end) ------ */
 int b200nn_graph_begin(void* stream);
 int b200nn_graph_end(void* stream, void** graph_exec_out);

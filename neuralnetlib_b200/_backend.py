@@ -49,6 +49,8 @@ _SIGNATURES = {
     "b200nn_step_begin": (c_int, [_P, c_int, _P, c_int, _P, c_ll, _P]),
     "b200nn_zero_f64": (c_int, [_P, c_int, _P]),
     "b200nn_gather_rows": (c_int, [_P, _P, _P, c_ll, c_ll, _P]),
+    "b200nn_upload": (c_int, [_P, _P, c_size_t, _P]),
+    "b200nn_read_sync": (c_int, [_P, _P, c_size_t, _P]),
     "b200nn_graph_begin": (c_int, [_P]),
     "b200nn_graph_end": (c_int, [_P, C.POINTER(c_void_p)]),
     "b200nn_graph_launch": (c_int, [_P, _P]),

@@ -219,6 +219,17 @@ __global__ void __launch_bounds__(256) sumsq_multi_kernel(const b200nn_param* __
     block_accumulate(acc, &gss[ti], scratch);
 }
 
+// b^t for an integer t >= 0 by repeated squaring (t counts optimizer updates): ~2 log2(t) fp64 multiplies instead of pow()
+__device__ __forceinline__ double powi(double b, long long t) {
+    double r = 1.0;
+    while (t > 0) {
+        if (t & 1) r *= b;
+        b *= b;
+        t >>= 1;
+    }
+    return r;
+}
+
 struct OptScalars {
     float clip, lr, b1, b2, omb1, omb2, inv_bc1, inv_bc2, eps;
 };
@@ -269,12 +280,12 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
         const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
         const double pre = (double)chain_scale(ss, P.chain);                 // deferred error clips (models.py:214) owed by g
         const double n2 = *reinterpret_cast<volatile double*>(&gss[ti]) * pre * pre;
-        const double t = (double)(*step - (long long)n_layers + P.t_index);  // optimizers.py:236 (Q3)
+        const long long t = *step - (long long)n_layers + P.t_index;         // optimizers.py:236 (Q3)
         sh.clip = (float)(pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0));          // models.py:240-242
         sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;
         sh.omb1 = (float)(1.0 - b1); sh.omb2 = (float)(1.0 - b2);
-        sh.inv_bc1 = (float)(1.0 / (1.0 - pow(b1, t)));
-        sh.inv_bc2 = (float)(1.0 / (1.0 - pow(b2, t)));
+        sh.inv_bc1 = (float)(1.0 / (1.0 - powi(b1, t)));
+        sh.inv_bc2 = (float)(1.0 / (1.0 - powi(b2, t)));
         sh.eps = (float)eps;
     }
     const long long base = (long long)chunk * B200NN_OPT_CHUNK;
@@ -393,6 +404,23 @@ int b200nn_zero_f64(double* p, int n, void* stream) {
     if (n <= 0) return B200NN_OK;
     zero_f64_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p, n);
     B200NN_LAUNCH_CHECK("zero_f64");
+    return B200NN_OK;
+}
+
+// Host <-> device plumbing of the public entry points (Sequential.train_on_batch: batch upload, loss read-back) as single
+// calls, so that the host side of a step is three ctypes calls: upload x, upload y, launch graph + read loss.
+int b200nn_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    B200NN_REQUIRE(dst_dev != nullptr && src_host != nullptr, "upload: null pointer");
+    if (bytes == 0) return B200NN_OK;
+    B200NN_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return B200NN_OK;
+}
+
+// copies `bytes` from the device to (preferably pinned) host memory and waits for the stream: the value is valid on return
+int b200nn_read_sync(void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+    B200NN_REQUIRE(dst_host != nullptr && src_dev != nullptr, "read_sync: null pointer");
+    B200NN_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    B200NN_CUDA(cudaStreamSynchronize(as_stream(stream)));
     return B200NN_OK;
 }
 

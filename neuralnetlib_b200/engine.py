@@ -594,7 +594,11 @@ class Plan:
                 return
             src_t = src
         else:
-            a = np.asarray(src)
+            a = src if type(src) is np.ndarray else np.asarray(src)
+            if a.dtype == np.float32 and a.flags.c_contiguous and a.size == dst.numel():
+                # straight from the caller's buffer (asynchronous when it is pinned): one cudaMemcpyAsync through the C ABI
+                B.check(B.lib().b200nn_upload(dst.data_ptr(), a.__array_interface__["data"][0], a.nbytes, B.stream()))
+                return
             if a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable:
                 src_t = torch.from_numpy(a)
             else:
@@ -612,6 +616,14 @@ class Plan:
                 setattr(owner, stage_attr + "_evt", evt)
                 return
         dst.copy_(src_t.reshape(dst.shape), non_blocking=True)
+
+    def read_acc(self):
+        """(loss numerator, correct count) of the step just run: one D2H copy into pinned memory + stream sync."""
+        if getattr(self, "_acc_host", None) is None:
+            self._acc_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+            self._acc_host_np = self._acc_host.numpy()
+        B.check(B.lib().b200nn_read_sync(self._acc_host.data_ptr(), self.acc.data_ptr(), 16, B.stream()))
+        return float(self._acc_host_np[0]), float(self._acc_host_np[1])
 
     def set_input(self, x):
         self._upload(self.x_in, "x_stage", self, x)

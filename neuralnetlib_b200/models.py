@@ -191,7 +191,7 @@ class Sequential(BaseModel):
         plan = self._plan(shape, True)
         prog = plan.program("train")
         plan.set_input(x_batch)
-        plan.set_target(y_batch if isinstance(y_batch, torch.Tensor) else np.asarray(y_batch).reshape(tuple(plan.y_in.shape)))
+        plan.set_target(y_batch)   # same element count as the prediction buffer: uploaded flat
         prog.run()
         self._last_plan, self._last_rows, self._pred_host = plan, shape[0], None
         return plan
@@ -203,7 +203,7 @@ class Sequential(BaseModel):
             raise ValueError("The model must be compiled before training")
         self.y_true = y_batch
         plan = self._train_step(x_batch, y_batch)
-        return float(plan.acc[0].item()) / self._loss_denominator(plan, True)
+        return plan.read_acc()[0] / self._loss_denominator(plan, True)
 
     # ------------------------------------------------------------------------------------------------------------
     def fit(self, x_train, y_train, epochs: int, batch_size: int | None = None, verbose: bool = True,
