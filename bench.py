@@ -255,8 +255,18 @@ def run_b200(args):
             traffic = json.load(f).get(top_name)
     except Exception:
         pass
+    # ALGORITHMIC bytes per SURVEY.md 8(d) (fp32, perfect fusion inside a layer, tensors materialised when saved for backward or
+    # separated by a batch-wide reduction; S = conv-output, P = pooled elements per sample): conv block forward 2S + 2P, backward of the
+    # first block 4S + 3P. The fused first-block kernels cover exactly those layer groups; every other kernel's figure is the
+    # tensors it reads / writes once (Plan.emit io lists), which is the survey's definition for Dense / optimizer kernels.
+    S_el, P_el = 28 * 28 * 32, 14 * 14 * 32
+    survey_bytes = {"convblock_fwd": (2 * S_el + 2 * P_el) * 4 * BATCH_PER_GPU, "convblock_fwd_peer": (2 * S_el + 2 * P_el) * 4 * BATCH_PER_GPU,
+                    "convblock_bwd": (4 * S_el + 3 * P_el) * 4 * BATCH_PER_GPU, "convblock_bwd_peer": (4 * S_el + 3 * P_el) * 4 * BATCH_PER_GPU}
+    io_bytes = top_bytes
+    top_bytes = survey_bytes.get(top_name, top_bytes)
     achieved = top_bytes / (per_op[top] * 1e-3) / 1e9 if per_op[top] > 0 else 0.0
-    step_bytes = sum(b for _, b in prog.meta)
+    step_bytes = (6 * S_el + 5 * P_el) * 4 * BATCH_PER_GPU + sum(b for n_, b in prog.meta if n_.startswith("optimizer"))
+    io_step_bytes = sum(b for _, b in prog.meta)
     breakdown = sorted(((names[i], round(per_op[i] * 1e3, 2), prog.meta[i][1]) for i in range(len(per_op))), key=lambda t: -t[1])
     if os.environ.get("B200NN_BENCH_ALLOPS") and rank == 0:
         print("[bench] per-op us (program order): " + ", ".join(f"{names[i]}={per_op[i] * 1e3:.1f}" for i in range(len(per_op)))
@@ -288,7 +298,11 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": top_bytes, "kernel_us": per_op[top] * 1e3,
-                     "step_algorithmic_bytes": step_bytes,
+                     "algorithmic_bytes_definition": "SURVEY.md 8(d) per-sample figure x 256 samples per launch (conv block bwd: (4S+3P)*4 B, "
+                                                     "fwd: (2S+2P)*4 B); the kernel itself touches only io_bytes_per_launch because the conv "
+                                                     "output is recomputed from the input image instead of being stored (traffic = ncu DRAM bytes)",
+                     "io_bytes_per_launch": io_bytes,
+                     "step_algorithmic_bytes": step_bytes, "step_io_bytes": io_step_bytes,
                      "step_frac_of_hbm_roofline": (step_bytes / (resident_ms * 1e-3) / 1e9) / peak},
         "kernel_breakdown_us": breakdown[:8],
         "clocks": clocks,
