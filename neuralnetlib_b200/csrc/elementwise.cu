@@ -341,6 +341,71 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const b200nn_param* __r
     }
 }
 
+// Single-launch Adam for tiny parameter sets (<= 16 chunks: the last layer updated in a step): every load the kernel needs is
+// issued before the grid-wide barrier that completes the gradient norms, so the critical path is one memory round trip, the
+// barrier, and the update. gss and its two trailing counters are zero on entry and re-zeroed by the last CTA to leave.
+__global__ void __launch_bounds__(256) adam_small_fused_kernel(const b200nn_param* __restrict__ params, int n_layers, int n_params,
+                                                               double* __restrict__ gss, const double* __restrict__ hyper,
+                                                               const long long* __restrict__ step,
+                                                               const int* __restrict__ block_map, const double* __restrict__ ss) {
+    __shared__ OptScalars sh;
+    __shared__ double scratch[32];
+    constexpr int IT = B200NN_OPT_CHUNK / 256;
+    const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
+    const b200nn_param P = params[ti];
+    unsigned* sync = reinterpret_cast<unsigned*>(gss + n_params);
+    const long long base = (long long)chunk * B200NN_OPT_CHUNK, end = min(P.n, base + B200NN_OPT_CHUNK);
+    float p[IT], g[IT], m[IT], v[IT];
+    float part = 0.0f;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const long long i = base + it * 256 + threadIdx.x;
+        p[it] = g[it] = m[it] = v[it] = 0.0f;
+        if (i < end) { p[it] = P.p[i]; g[it] = P.g[i]; m[it] = P.m[i]; v[it] = P.v[i]; }
+    }
+    double lr = 0, b1 = 0, b2 = 0, eps = 0, pre = 1;
+    long long t = 1;
+    if (threadIdx.x == 0) {
+        lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3];
+        pre = (double)chain_scale(ss, P.chain);
+        t = *step - (long long)n_layers + P.t_index;                          // optimizers.py:236 (Q3)
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) part = fmaf(g[it], g[it], part);
+    const double r = block_sum_to_double(part, scratch);
+    if (threadIdx.x == 0) {
+        atomicAdd(&gss[ti], r);
+        __threadfence();
+        atomicAdd(&sync[0], 1u);
+        sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;              // everything that does not need the norm
+        sh.omb1 = (float)(1.0 - b1); sh.omb2 = (float)(1.0 - b2);
+        sh.inv_bc1 = (float)(1.0 / (1.0 - powi(b1, t)));
+        sh.inv_bc2 = (float)(1.0 / (1.0 - powi(b2, t)));
+        sh.eps = (float)eps;
+        while (*reinterpret_cast<volatile unsigned*>(&sync[0]) < gridDim.x) {
+        }
+        __threadfence();
+        const double n2 = *reinterpret_cast<volatile double*>(&gss[ti]) * pre * pre;
+        sh.clip = (float)(pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0));          // models.py:214 (deferred) and :240-242
+    }
+    __syncthreads();
+    const OptScalars s = sh;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const long long i = base + it * 256 + threadIdx.x;
+        if (i < end) {
+            adam_elem(p[it], g[it], m[it], v[it], s);
+            P.p[i] = p[it]; P.m[i] = m[it]; P.v[i] = v[it];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&sync[1], 1u) == gridDim.x - 1) {       // last CTA out: everyone has read gss
+        for (int i = 0; i < n_params; ++i) gss[i] = 0.0;
+        sync[0] = 0u;
+        sync[1] = 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256) sgd_multi_kernel(const b200nn_param* __restrict__ params,
                                                         const double* __restrict__ gss,
                                                         const double* __restrict__ hyper,
@@ -517,8 +582,8 @@ int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, do
                       const long long* step, const int* block_map, int total_blocks, const double* ss, void* stream) {
     B200NN_REQUIRE(n_params > 0 && total_blocks > 0 && n_layers > 0, "adam_multi: empty parameter list");
     if (total_blocks <= 16) {   // tiny sets only (CTAs spinning at the barrier would steal SM slots from concurrent kernels); gss + counters are zero on entry, restored by the kernel
-        adam_multi_kernel<true><<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, n_params, gss, hyper, step, block_map, ss);
-        B200NN_LAUNCH_CHECK("adam_multi_fused");
+        adam_small_fused_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, n_params, gss, hyper, step, block_map, ss);
+        B200NN_LAUNCH_CHECK("adam_small_fused");
         return B200NN_OK;
     }
     B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, as_stream(stream)));
