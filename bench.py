@@ -94,19 +94,24 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def oracle_steps_per_second(steps, warmup, batch):
-    """The reference's algorithm for this path (numpy fp64 oracle port) on the host cores."""
+def oracle_steps_per_second(steps, warmup, batch, budget_s=45.0):
+    """The reference's algorithm for this path (numpy fp64 oracle port) on the host cores. At most `steps` train steps are timed,
+    fewer when they would not fit `budget_s` seconds of CPU work (the sample is bounded, the rate is what is reported)."""
     import nnl_oracle as O
     x, y = O.synthetic_batch(CFG, batch)
     specs, _ = O.config_specs(CFG)
     m = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
-    for _ in range(warmup):
+    t_w = time.perf_counter()
+    n_w = max(1, min(warmup, 2))
+    for _ in range(n_w):
         m.train_on_batch(x, y)
+    est = (time.perf_counter() - t_w) / n_w
+    steps = max(3, min(steps, int(budget_s / max(est, 1e-6))))
     t0 = time.perf_counter()
     for _ in range(steps):
         m.train_on_batch(x, y)
     dt = time.perf_counter() - t0
-    return steps / dt, dt
+    return steps / dt, dt, steps
 
 
 def run_reference(args):
@@ -114,7 +119,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count()
-    sps, dt = oracle_steps_per_second(args.steps, args.warmup, BATCH_PER_GPU)
+    sps, dt, n_timed = oracle_steps_per_second(args.steps, args.warmup, BATCH_PER_GPU)
     value = sps * BATCH_PER_GPU
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -122,8 +127,8 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU, "note": "CPU path does not shard; one process on the host"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} train_on_batch steps at batch {BATCH_PER_GPU} after {args.warmup} warm-up "
-                                   f"(numpy {np.__version__}, OPENBLAS threads = all cores)"},
+                         "sample": f"{n_timed} train_on_batch steps at batch {BATCH_PER_GPU} ({dt:.1f} s of CPU work, bounded to ~45 s) "
+                                   f"after warm-up (numpy {np.__version__} fp64 oracle port of the reference path, OPENBLAS threads = all cores)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -308,8 +313,8 @@ def run_b200(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        budget_steps = 12
-        sps, dt = oracle_steps_per_second(budget_steps, 1, BATCH_PER_GPU)
+        budget_steps = 24
+        sps, dt, budget_steps = oracle_steps_per_second(budget_steps, 1, BATCH_PER_GPU, 20.0)
         line["cpu_baseline"] = {"value": sps * BATCH_PER_GPU, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{budget_steps} train_on_batch steps of the same workload at batch {BATCH_PER_GPU} "
                                           f"after 1 warm-up ({dt:.1f} s of CPU work; numpy fp64 oracle port of the reference path)"}
