@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default=os.environ.get("B200NN_MATH", "fp32"), choices=["fp32", "tf32"],
+    ap.add_argument("--math", default=os.environ.get("B200NN_MATH", "fp32"), choices=["fp32", "tf32", "tf32x3"],
                     help="Dense contractions: fp32 = FFMA parity path (rel 1e-5); tf32 = tcgen05 tensor cores (rel 2e-3)")
     args = ap.parse_args()
     if args.impl == "reference":

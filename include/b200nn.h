@@ -55,7 +55,8 @@ extern "C" {
 
 /* GEMM math modes */
 #define B200NN_MATH_FP32 0 /* FFMA, fp32 accumulate: parity path (rel 1e-5)                    */
-#define B200NN_MATH_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM: perf path (rel 2e-3) */
+#define B200NN_MATH_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM: perf path (rel 2e-3 per contraction) */
+#define B200NN_MATH_TF32X3 2 /* tcgen05, error-compensated 3xTF32 (hi/lo operand split in shared memory): fp32 accuracy on tensor cores */
 
 int b200nn_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
@@ -116,6 +117,8 @@ int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y
  * `ws` is a float workspace of at least b200nn_dense_ws_bytes(M,N,K) bytes (split-K partials; the same
  * size serves the forward and the backward of that layer). */
 size_t b200nn_dense_ws_bytes(int M, int N, int K);
+/* the same for a given math mode: B200NN_MATH_TF32X3 cuts its accumulation chains through split-K and needs more */
+size_t b200nn_dense_ws_bytes_math(int math, int M, int N, int K);
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                      int act, float alpha, float* ws, void* stream);
 /* Classifier head as one kernel (N <= 32): p = softmax(x . w + b) (layers.py:173, activations.py:69-71), loss_acc[0] += CCE

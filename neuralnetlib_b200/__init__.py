@@ -16,11 +16,13 @@ _MATH = os.environ.get("B200NN_MATH", "fp32").lower()
 
 def set_math(mode: str) -> None:
     """'fp32': FFMA contractions, parity with the reference within rel 1e-5 (default).
-    'tf32': tcgen05 tensor-core contractions (kind::tf32, fp32 accumulate), within rel 2e-3."""
+    'tf32': tcgen05 tensor-core contractions (kind::tf32, fp32 accumulate), within rel 2e-3 per contraction.
+    'tf32x3': tcgen05 with error compensation (operands split hi/lo in shared memory, three MMAs per k-step): Dense
+    contractions on the tensor cores at fp32 accuracy."""
     global _MATH
     mode = mode.lower()
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("math mode must be 'fp32' or 'tf32'")
+    if mode not in ("fp32", "tf32", "tf32x3"):
+        raise ValueError("math mode must be 'fp32', 'tf32' or 'tf32x3'")
     _MATH = mode
 
 

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "b200nn_softmax_fwd": (c_int, [_P, _P, c_int, c_int, _P]),
     "b200nn_loss_fwd_bwd": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "b200nn_dense_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "b200nn_dense_ws_bytes_math": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200nn_dense_fwd": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P]),
     "b200nn_dense_softmax_cce": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "b200nn_dense_head_partials": (c_int, [c_int, c_int]),

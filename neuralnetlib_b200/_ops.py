@@ -15,7 +15,7 @@ from ._backend import ConvGeom, ConvTGeom, PoolGeom, check, lib, ptr, stream
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKYRELU = 0, 1, 2, 3, 4
 LOSS_MSE, LOSS_BCE, LOSS_CCE = 0, 1, 2
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
 
 
 def pack_chain(chain) -> int:
@@ -117,8 +117,8 @@ def loss_fwd_bwd(loss, fused_pair, p, y, err, acc, ss, slot_out):
 
 
 # ---- Dense -------------------------------------------------------------------------------------------
-def dense_ws_bytes(M, N, K):
-    return int(lib().b200nn_dense_ws_bytes(M, N, K))
+def dense_ws_bytes(M, N, K, math=MATH_FP32):
+    return int(lib().b200nn_dense_ws_bytes_math(math, M, N, K))
 
 
 def dense_fwd(math, x, w, b, y, act, alpha, ws):

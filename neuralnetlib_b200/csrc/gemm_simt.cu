@@ -973,6 +973,17 @@ using namespace b200nn;
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------- Dense
+size_t b200nn_dense_ws_bytes_math(int math, int M, int N, int K) {
+    size_t r = b200nn_dense_ws_bytes(M, N, K);
+    if (math == B200NN_MATH_TF32X3) {             // chain-limited split-K partials of the compensated tensor-core path
+        auto mx = [&](size_t v) { if (v > r) r = v; };
+        mx(tc::tc_ws_bytes(M, N, K, true));
+        mx(tc::tc_ws_bytes(M, K, N, true));
+        mx(tc::tc_ws_bytes(K, N, M, true));
+    }
+    return r;
+}
+
 size_t b200nn_dense_ws_bytes(int M, int N, int K) {
     size_t r = 0;
     auto mx = [&](size_t v) { if (v > r) r = v; };
@@ -995,7 +1006,7 @@ static bool dense_tc_ok(const float* x, const float* w, const float* other, int 
 
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                      int act, float alpha, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32 || math == B200NN_MATH_TF32, "dense_fwd: unknown math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "dense_fwd: unknown math mode %d", math);
     B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_fwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (int rc = check_act("dense_fwd", act, alpha)) return rc;
     if (N <= SMALLN_MAX) {
@@ -1009,8 +1020,8 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
     e.bias = b; e.act = act; e.alpha = alpha;
     if (math == B200NN_MATH_FP32 && ws != nullptr && skinny::applicable(x, w, y, M, N, K))
         return skinny::launch_fwd(x, w, e, M, N, K, ws, as_stream(stream));
-    if (math == B200NN_MATH_TF32 && dense_tc_ok(x, w, y, M, N, K))
-        return tc::tc_gemm(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream));
+    if (math != B200NN_MATH_FP32 && dense_tc_ok(x, w, y, M, N, K))
+        return tc::tc_gemm(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
     RowMajorA af{x, K, M, K};
     RowMajorB bf{w, N, K, N};
     return launch_gemm("dense_fwd", af, bf, e, M, N, K, ws, as_stream(stream));
@@ -1051,7 +1062,7 @@ int b200nn_dense_bwd_head(const float* x, const float* w, const float* err, cons
 int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err, const double* ss, uint64_t chain,
                      float* dx, float* dw, float* db, int M, int N, int K, int prev_act, float prev_alpha,
                      double* ss_out0, double* ss_out1, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32 || math == B200NN_MATH_TF32, "dense_bwd: unknown math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "dense_bwd: unknown math mode %d", math);
     B200NN_REQUIRE(M > 0 && N > 0 && K > 0, "dense_bwd: bad shape M=%d N=%d K=%d", M, N, K);
     if (int rc = check_act("dense_bwd", prev_act, prev_alpha)) return rc;
     cudaStream_t st = as_stream(stream);
@@ -1092,7 +1103,8 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
     if (math == B200NN_MATH_FP32 && skinny::applicable(x, w, err, M, N, K) &&
         ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
         return skinny::launch_bwd(x, w, err, ss, chain, dx, dw, db, M, N, K, prev_act, prev_alpha, ss_out0, ss_out1, st);
-    const bool use_tc = math == B200NN_MATH_TF32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;
+    const bool use_tc = math != B200NN_MATH_FP32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;
+    const bool x3 = math == B200NN_MATH_TF32X3;
     if (dw != nullptr && use_tc) {
         if (db != nullptr) {   // layers.py:197
             int nb = (M + 7) / 8;   // >= 8 rows per CTA; threads run over the columns
@@ -1104,7 +1116,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         }
         Epilogue e = plain_epilogue(dw, N, K);   // dw[K,N] = x^T . err : both operands MN-major, no transposed copies
         e.ss = ss; e.chain = chain;
-        if (int rc = tc::tc_gemm(x, K, true, err, N, true, e, K, N, M, ws, st)) return rc;
+        if (int rc = tc::tc_gemm(x, K, true, err, N, true, e, K, N, M, ws, st, x3)) return rc;
     } else if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
         ColMajorOnesA af{x, K, K, M, db != nullptr ? 1 : 0};
         RowMajorB bf{err, N, M, N};
@@ -1116,7 +1128,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         Epilogue e = plain_epilogue(dx, K, M);
         dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
         if (use_tc) {
-            if (int rc = tc::tc_gemm(err, N, false, w, N, false, e, M, K, N, ws, st)) return rc;
+            if (int rc = tc::tc_gemm(err, N, false, w, N, false, e, M, K, N, ws, st, x3)) return rc;
         } else {
             RowMajorA af{err, N, M, N};
             ColMajorB bf{w, N, N, K};

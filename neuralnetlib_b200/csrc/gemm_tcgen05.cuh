@@ -98,14 +98,30 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// fp32 -> nearest TF32 (low 13 mantissa bits zero), so that the tensor core's own truncation of the operand is exact
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// X3: error-compensated "3xTF32". The epilogue warps, idle during the main loop, split every staged operand tile in shared
+// memory into hi = rn_tf32(x) (written back in place) and lo = rn_tf32(x - hi) (mirror ring), and the MMA warp issues
+// A_hi.B_hi + A_lo.B_hi + A_hi.B_lo into the same TMEM accumulator. Round-to-nearest keeps both the dropped lo.lo term
+// (<= 2^-22 relative) and the rounding of lo zero-mean; splitting by the hardware's truncation instead leaves a
+// same-signed 2^-22 bias per product that grows with K (2e-5 at K = 4096, measured).
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue epi, int M,
                  int N, int K, int kb_per_split, float* __restrict__ ws) {
     constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t LO_OFFSET = STAGES * STAGE_BYTES;   // X3: the lo tiles mirror the raw ring behind it
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 (BLOCK_N in {32,64,128,256})
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double scratch[32];
 
@@ -126,6 +142,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(smem_u32(&full_bar[s]), 1);
                 mbar_init(smem_u32(&empty_bar[s]), 1);
+                mbar_init(smem_u32(&split_bar[s]), 4);     // one arrival per splitter warp
             }
             mbar_init(smem_u32(&tmem_full_bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,7 +188,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t round = i / STAGES;
-                mbar_wait(smem_u32(&full_bar[s]), round & 1);
+                mbar_wait(smem_u32(X3 ? &split_bar[s] : &full_bar[s]), round & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
@@ -179,6 +196,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint64_t ad = A_MN ? desc_mnmajor(sa, j) : desc_kmajor(sa, j);
                     const uint64_t bd = B_MN ? desc_mnmajor(sb, j) : desc_kmajor(sb, j);
                     tc_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                    if (X3) {
+                        const uint64_t adl = A_MN ? desc_mnmajor(sa + LO_OFFSET, j) : desc_kmajor(sa + LO_OFFSET, j);
+                        const uint64_t bdl = B_MN ? desc_mnmajor(sb + LO_OFFSET, j) : desc_kmajor(sb + LO_OFFSET, j);
+                        tc_mma_tf32(tmem_base, adl, bd, idesc, 1u);      // A_lo . B_hi
+                        tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);      // A_hi . B_lo
+                    }
                 }
                 tc_commit(smem_u32(&empty_bar[s]));          // frees the smem stage once these MMAs have read it
             }
@@ -193,6 +216,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __shared__ float xpose[4][32][33];
     EpiState st;
     epi_begin(epi, st);
+    if (X3 && warp >= 2) {
+        // ===== operand splitter (the four epilogue warps, while the main loop runs) =====
+        const int t = threadIdx.x - 64;   // 0..127
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t round = i / STAGES;
+            mbar_wait(smem_u32(&full_bar[s]), round & 1);                 // the TMA tiles of this stage have landed
+            const uint32_t off = (smem_base - smem_u32(smem_raw)) + s * STAGE_BYTES;
+            float4* src = reinterpret_cast<float4*>(smem_raw + off);
+            float4* dst = reinterpret_cast<float4*>(smem_raw + off + LO_OFFSET);
+#pragma unroll 4
+            for (uint32_t v = t; v < STAGE_BYTES / 16; v += 128) {       // elementwise: the swizzled layout carries over unchanged
+                const float4 x = src[v];
+                const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+                src[v] = h;
+                dst[v] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+        }
+    }
     if (warp >= 2) {
         const int q = warp & 3;
         float (*tile)[33] = xpose[warp - 2];
@@ -297,13 +342,42 @@ struct TcPlan {
     int block_n, splits, kb_per_split;
 };
 
-static TcPlan tc_plan(long long M, long long N, long long K) {
+// X3: the tensor core adds into the fp32 accumulator with truncation, a same-signed ~2^-25 relative error per MMA that
+// grows with the chain (2e-5 at 1536 chained MMAs, measured) and would dominate the compensated product error. The chain
+// is therefore cut every X3_CHAIN_KB k-blocks through split-K: each split accumulates 512 k in TMEM, the reduce kernel adds
+// the partials in round-to-nearest fp32 (the idea of Ootomo & Yokota's error-corrected tensor-core GEMM, at tile-chunk
+// granularity). The extra CTAs also let small-M problems keep wide tiles.
+constexpr int X3_CHAIN_KB = 16;
+constexpr long long X3_WS_CAP = 512LL << 20;
+
+static TcPlan tc_plan(long long M, long long N, long long K, bool x3 = false) {
     TcPlan p;
     p.block_n = tc_block_n((int)N);
-    // if the tile grid cannot fill the 148 SMs anyway, narrower tiles spread the (epilogue-heavy) work over more SMs
-    while (p.block_n > 32 && ((M + BLOCK_M - 1) / BLOCK_M) * ((N + p.block_n - 1) / p.block_n) < kNumSMs) p.block_n >>= 1;
-    const long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + p.block_n - 1) / p.block_n);
     const long long kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+    auto tiles_for = [&](int bn) { return ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn); };
+    if (x3) {
+        long long chain = X3_CHAIN_KB;
+        long long splits = (kb_total + chain - 1) / chain;
+        while (splits > 1 && splits * M * N * (long long)sizeof(float) > X3_WS_CAP) {   // bound the partial-sum workspace
+            chain *= 2;
+            splits = (kb_total + chain - 1) / chain;
+        }
+        while (p.block_n > 32 && tiles_for(p.block_n) * splits < kNumSMs) p.block_n >>= 1;
+        const long long tiles = tiles_for(p.block_n);
+        if (tiles * splits < kNumSMs && kb_total >= 8) {          // still short of a wave: split further, as below
+            long long more = (kNumSMs + tiles - 1) / tiles;
+            const long long maxs = kb_total / 4;
+            if (more > maxs) more = maxs;
+            if (more > splits) splits = more;
+        }
+        const long long per = (kb_total + splits - 1) / splits;
+        p.splits = (int)((kb_total + per - 1) / per);
+        p.kb_per_split = (int)per;
+        return p;
+    }
+    // if the tile grid cannot fill the 148 SMs anyway, narrower tiles spread the (epilogue-heavy) work over more SMs
+    while (p.block_n > 32 && tiles_for(p.block_n) < kNumSMs) p.block_n >>= 1;
+    const long long tiles = tiles_for(p.block_n);
     long long splits = 1;
     if (tiles < kNumSMs && kb_total >= 8) {
         splits = (kNumSMs + tiles - 1) / tiles;
@@ -318,16 +392,16 @@ static TcPlan tc_plan(long long M, long long N, long long K) {
     return p;
 }
 
-static size_t tc_ws_bytes(long long M, long long N, long long K) {
-    const TcPlan p = tc_plan(M, N, K);
+static size_t tc_ws_bytes(long long M, long long N, long long K, bool x3 = false) {
+    const TcPlan p = tc_plan(M, N, K, x3);
     return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool X3>
 static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
                             const TcPlan& p, float* ws, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BN * 128) + 1024;
-    auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BN * 128) * (X3 ? 2 : 1) + 1024;
+    auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, X3>;
     static bool configured = false;
     if (!configured) {
         B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -344,15 +418,17 @@ static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const 
 // so that several CTAs (and their epilogue warps) share an SM; long reductions get a deep ring
 template <int BN, bool A_MN, bool B_MN>
 static int tc_launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
-                             const TcPlan& p, float* ws, cudaStream_t st) {
-    if (p.kb_per_split <= 2) return tc_launch_stages<BN, 2, A_MN, B_MN>(ta, tb, epi, M, N, K, p, ws, st);
-    return tc_launch_stages<BN, (BN >= 256 ? 4 : 6), A_MN, B_MN>(ta, tb, epi, M, N, K, p, ws, st);
+                             const TcPlan& p, float* ws, cudaStream_t st, bool x3) {
+    if (x3)   // twice the shared memory per stage (raw + lo tiles): 2 stages at 256 columns, 3 below
+        return tc_launch_stages<BN, (BN >= 256 ? 2 : 3), A_MN, B_MN, true>(ta, tb, epi, M, N, K, p, ws, st);
+    if (p.kb_per_split <= 2) return tc_launch_stages<BN, 2, A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st);
+    return tc_launch_stages<BN, (BN >= 256 ? 4 : 6), A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st);
 }
 
 // D[M,N] = A.B ; a_mn: A stored [K][M] (ld = lda) else [M][K]; b_mn: B stored [K][N] else [N][K]
 static int tc_gemm(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi,
-                   int M, int N, int K, float* ws, cudaStream_t st) {
-    const TcPlan p = tc_plan(M, N, K);
+                   int M, int N, int K, float* ws, cudaStream_t st, bool x3 = false) {
+    const TcPlan p = tc_plan(M, N, K, x3);
     B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "gemm_tf32: split-K needs a workspace");
     CUtensorMap ta, tb;
     if (a_mn) { if (int rc = make_map(&ta, A, M, K, lda, BLOCK_K, true)) return rc; }
@@ -361,9 +437,9 @@ static int tc_gemm(const float* A, long long lda, bool a_mn, const float* B, lon
     else      { if (int rc = make_map(&tb, B, K, N, ldb, p.block_n, false)) return rc; }
     B200NN_REQUIRE(!(a_mn && !b_mn), "gemm_tf32: (A MN-major, B K-major) is not instantiated");
 #define TC_DISPATCH(BN)                                                                              \
-    if (a_mn) return tc_launch_variant<BN, true, true>(ta, tb, epi, M, N, K, p, ws, st);             \
-    if (b_mn) return tc_launch_variant<BN, false, true>(ta, tb, epi, M, N, K, p, ws, st);            \
-    return tc_launch_variant<BN, false, false>(ta, tb, epi, M, N, K, p, ws, st);
+    if (a_mn) return tc_launch_variant<BN, true, true>(ta, tb, epi, M, N, K, p, ws, st, x3);         \
+    if (b_mn) return tc_launch_variant<BN, false, true>(ta, tb, epi, M, N, K, p, ws, st, x3);        \
+    return tc_launch_variant<BN, false, false>(ta, tb, epi, M, N, K, p, ws, st, x3);
     switch (p.block_n) {
         case 32: TC_DISPATCH(32)
         case 64: TC_DISPATCH(64)

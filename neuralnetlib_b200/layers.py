@@ -23,7 +23,7 @@ from .activations import ActivationFunction, Softmax
 
 
 def _math_code():
-    return ops.MATH_TF32 if get_math() == "tf32" else ops.MATH_FP32
+    return {"tf32": ops.MATH_TF32, "tf32x3": ops.MATH_TF32X3}.get(get_math(), ops.MATH_FP32)
 
 
 def _is_dev(x):
@@ -273,7 +273,7 @@ class Dense(Layer, _ParamMixin):
         if self._weights.shape[0] != feat:
             raise ValueError(f"shapes {tuple(x.shape)} and {tuple(self._weights.shape)} not aligned")
         M = x.numel() // feat
-        ctx.need_ws(ops.dense_ws_bytes(M, self.units, feat))
+        ctx.need_ws(ops.dense_ws_bytes(M, self.units, feat, _math_code()))
         y = ctx.buf(tuple(x.shape[:-1]) + (self.units,))
         kind, alpha = _act_of(act_layer)
         math = _math_code()

@@ -357,6 +357,35 @@ def test_tf32_tensor_core_mode_within_2e3(cfg, batch, width):
         nn.set_math("fp32")
 
 
+@pytest.mark.parametrize("cfg,batch,width", [(2, 256, None), (1, 32, None), (4, 256, 1024)])
+def test_tf32x3_tensor_core_mode_matches_fp32_parity(cfg, batch, width):
+    """Math mode 'tf32x3' (tcgen05 with hi/lo operand split): the Dense contractions run on the tensor cores and the
+    step still meets the FFMA path's bar against the fp64 oracle -- loss, predictions and every gradient."""
+    import neuralnetlib_b200 as nn
+    nn.set_math("tf32x3")
+    try:
+        m = build_cfg(cfg, width)
+        specs, shp = O.config_specs(cfg)
+        if width:
+            for sp in specs:
+                if sp.get("units") == 4096:
+                    sp["units"] = width
+            rng = np.random.default_rng(0)
+            x = rng.random((batch, width)).astype(np.float32)
+            y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+        else:
+            x, y = O.synthetic_batch(cfg, batch)
+        ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+        loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+        assert abs(loss - rloss) <= TOL * max(1.0, abs(rloss))
+        assert nrel(m.predictions, ref.predictions) < TOL
+        for layer, rl in zip([l for l in m.layers if hasattr(l, "weights")], [r for r in ref.layers if "w" in r]):
+            grads_close(layer.d_weights, rl["dw"], TOL, "dw")
+            grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), TOL, "db")
+    finally:
+        nn.set_math("fp32")
+
+
 @pytest.mark.parametrize("level", ["0", "1", "2"])
 @pytest.mark.parametrize("cfg,batch", [(2, 64), (3, 32)])
 def test_fusion_levels_agree_with_oracle(monkeypatch, level, cfg, batch):

@@ -449,6 +449,35 @@ def test_dense_tf32_tcgen05(K, M, N, Kd):
     assert abs(h[1] - np.sum(rdx ** 2)) < 5e-3 * np.sum(rdx ** 2)
 
 
+@pytest.mark.parametrize("M,N,Kd", [(256, 64, 6272), (512, 512, 512), (300, 260, 200), (128, 32, 64), (64, 4096, 512),
+                                    (1000, 128, 96), (256, 256, 2048), (256, 4096, 4096)])
+def test_dense_tf32x3_tcgen05(K, M, N, Kd):
+    """Error-compensated tensor-core path (math mode 2): raw + lo operand tiles, three tcgen05 MMAs per k-step. Must
+    reach the FFMA path's accuracy (rel 1e-5 of the fp64 oracle), not single-pass TF32's 2e-3."""
+    rng = np.random.default_rng(M + N + Kd + 1)
+    x = np.maximum(rng.normal(size=(M, Kd)), 0).astype(np.float32)
+    w = (rng.normal(size=(Kd, N)) / np.sqrt(Kd)).astype(np.float32)
+    b = rng.normal(size=(N,)).astype(np.float32)
+    err = rng.normal(size=(M, N)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    ws = K.empty((max(K.ops.dense_ws_bytes(M, N, Kd, 2) // 4, 1),))
+    y = K.empty((M, N))
+    K.ops.dense_fwd(2, xd, wd, bd, y, 1, 0.0, ws)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    assert nrel(K.host(y), np.maximum(x64 @ w64 + b, 0)) < 1e-5
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty((M, Kd)), K.empty((Kd, N)), K.empty((N,))
+    K.ops.dense_bwd(2, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    rdx, rdw, rdb = O.dense_bwd(x64, w64, O.clip_l2(err.astype(np.float64)))
+    assert nrel(K.host(dx), rdx * (x > 0)) < 1e-5
+    assert nrel(K.host(dw), rdw) < 1e-5
+    assert nrel(K.host(db), rdb.reshape(-1)) < 1e-5
+    # and it is far closer to the oracle than single-pass TF32 on the same inputs
+    y1 = K.empty((M, N)); K.ops.dense_fwd(1, xd, wd, bd, y1, 1, 0.0, ws)
+    if N > 32:    # N <= 32 is the FFMA small-N kernel in every math mode
+        assert nrel(K.host(y), np.maximum(x64 @ w64 + b, 0)) * 20 < nrel(K.host(y1), np.maximum(x64 @ w64 + b, 0))
+
+
 @pytest.mark.parametrize("Bn,H,W,C,F,act", [(256, 28, 28, 1, 32, "relu"), (64, 32, 32, 3, 64, "relu"), (37, 8, 6, 2, 8, "leakyrelu"),
                                             (200, 4, 4, 1, 16, "relu"), (150, 4, 6, 3, 8, "tanh"), (16, 6, 4, 1, 8, "linear")])
 def test_convblock_first_block(K, Bn, H, W, C, F, act):
