@@ -153,6 +153,10 @@ typedef struct {
 /* y = act(conv(x, w) + b). w is the reference's (kh,kw,C,F) buffer READ with K order (c,ky,kx)
  * (preprocessing.py:77 vs layers.py:474 — SURVEY Q1). */
 size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g);
+/* the same for a given math mode. With math != FP32, stride-1 'same' convolutions on power-of-two images with C and F
+ * multiples of 32 run as implicit GEMMs on tcgen05 (operands fetched by 4-D TMA boxes, padding = TMA zero fill); every
+ * other geometry keeps the FFMA path in every math mode. */
+size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g);
 int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* b, float* y,
                       int act, float alpha, float* ws, void* stream);
 /* layers.py:513-528: db[F] = sum g, dw (same K-order view), dx = col2im(g . w^T). Same dx epilogue

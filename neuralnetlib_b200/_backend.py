@@ -70,6 +70,7 @@ _SIGNATURES = {
     "b200nn_dense_bwd": (c_int, [c_int, _P, _P, _P, _P, c_u64, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P,
                                   _P, _P]),
     "b200nn_conv2d_ws_bytes": (c_size_t, [C.POINTER(ConvGeom)]),
+    "b200nn_conv2d_ws_bytes_math": (c_size_t, [c_int, C.POINTER(ConvGeom)]),
     "b200nn_conv2d_fwd": (c_int, [c_int, C.POINTER(ConvGeom), _P, _P, _P, _P, c_int, c_float, _P, _P]),
     "b200nn_conv2d_bwd": (c_int, [c_int, C.POINTER(ConvGeom), _P, _P, _P, _P, c_u64, _P, _P, _P, c_int, c_float, _P, _P,
                                    _P, _P]),

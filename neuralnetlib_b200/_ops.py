@@ -158,8 +158,8 @@ def dense_bwd(math, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, slot
 
 
 # ---- Conv2D / Conv2DTranspose ------------------------------------------------------------------------
-def conv2d_ws_bytes(g: ConvGeom):
-    return int(lib().b200nn_conv2d_ws_bytes(C.byref(g)))
+def conv2d_ws_bytes(g: ConvGeom, math=MATH_FP32):
+    return int(lib().b200nn_conv2d_ws_bytes_math(math, C.byref(g)))
 
 
 def conv2d_fwd(math, g, x, w, b, y, act, alpha, ws):

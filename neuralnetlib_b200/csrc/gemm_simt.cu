@@ -1153,6 +1153,18 @@ static int check_conv_geom(const char* who, const b200nn_conv_geom* g) {
     return B200NN_OK;
 }
 
+size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g);
+size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g) {
+    size_t r = b200nn_conv2d_ws_bytes(g);
+    if (math != B200NN_MATH_FP32 && tc::conv_tc_ok(g, nullptr, nullptr, nullptr)) {
+        const size_t t = tc::tc_conv_ws_bytes(g, math == B200NN_MATH_TF32X3);
+        const size_t d = (size_t)kNumSMs * 2 * g->F * sizeof(float);   // column-sum partials for db
+        r = r > t ? r : t;
+        r = r > d ? r : d;
+    }
+    return r;
+}
+
 size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
     const long long Mo = (long long)g->N * g->OH * g->OW, Mi = (long long)g->N * g->H * g->W;
     const long long Kf = (long long)g->kh * g->kw * g->C, Kd = (long long)g->kh * g->kw * g->F;
@@ -1178,10 +1190,15 @@ static PatchGather conv_patches(const b200nn_conv_geom* g, const float* x) {
 
 int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* b, float* y,
                       int act, float alpha, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "conv2d_fwd: unsupported math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "conv2d_fwd: unknown math mode %d", math);
     if (int rc = check_conv_geom("conv2d_fwd", g)) return rc;
     if (int rc = check_act("conv2d_fwd", act, alpha)) return rc;
     const int M = g->N * g->OH * g->OW, K = g->kh * g->kw * g->C;
+    if (math != B200NN_MATH_FP32 && tc::conv_tc_ok(g, x, w, y)) {   // implicit GEMM on tcgen05, operands fetched by TMA
+        Epilogue e = plain_epilogue(y, g->F, M);
+        e.bias = b; e.act = act; e.alpha = alpha;
+        return tc::tc_conv_fwd(g, x, w, e, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
+    }
     if (smallk_fwd_ok(g) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
         long long blocks = ((long long)M + 127) / 128;
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -1202,12 +1219,36 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
 int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const float* w, const float* err,
                       const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
                       float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "conv2d_bwd: unsupported math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "conv2d_bwd: unknown math mode %d", math);
     if (int rc = check_conv_geom("conv2d_bwd", g)) return rc;
     if (int rc = check_act("conv2d_bwd", prev_act, prev_alpha)) return rc;
     cudaStream_t st = as_stream(stream);
     const int Mo = g->N * g->OH * g->OW, Mi = g->N * g->H * g->W;
     const int Kf = g->kh * g->kw * g->C, Kd = g->kh * g->kw * g->F;
+    if (math != B200NN_MATH_FP32 && ws != nullptr && tc::conv_tc_ok(g, x, w, err) &&
+        ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+        const bool x3 = math == B200NN_MATH_TF32X3;
+        if (dw != nullptr) {
+            if (db != nullptr) {   // layers.py:513
+                int nb = (Mo + 7) / 8;
+                if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+                colsum_partial_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
+                B200NN_LAUNCH_CHECK("conv2d_db_partial");
+                colsum_final_kernel<<<(g->F + 127) / 128, 128, 0, st>>>(ws, nb, g->F, ss, chain, db);
+                B200NN_LAUNCH_CHECK("conv2d_db_final");
+            }
+            Epilogue e = plain_epilogue(dw, g->F, Kf);
+            e.ss = ss; e.chain = chain;
+            e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
+            if (int rc = tc::tc_conv_wgrad(g, x, err, e, ws, st, x3)) return rc;
+        }
+        if (dx != nullptr) {
+            Epilogue e = plain_epilogue(dx, g->C, Mi);
+            dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+            if (int rc = tc::tc_conv_dgrad(g, err, w, e, ws, st, x3)) return rc;
+        }
+        return B200NN_OK;
+    }
     if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
         const int nb = smallk_wgrad_blocks(g), TP = smallk_wgrad_tile(g);
         Epilogue e = plain_epilogue(dw, g->F, Kf);

@@ -55,6 +55,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// Implicit-GEMM convolution operands, fetched by TMA straight from the NHWC tensors (stride 1, 'same', odd kernel, power-of-two
+// image, channel counts multiples of 32). The patched tensor is a 4-D map (c, x, y, image); a box of {32 channels, a run of
+// pixels} at (c0, x0 + kx - pad, y0 + ky - pad, image) IS a k-block of im2col rows in the canonical swizzled layout, and the
+// out-of-bounds pixels TMA zero-fills are the padding -- no im2col buffer, no gather functor (replaces preprocessing.py:34-126
+// on the tensor-core path). The weights [(c, ky, kx), F] (the reference's K order, layers.py:470) are a 3-D map (f, tap, c).
+//   mode 1  forward : A rows = output pixels, K = (tap, c)   ; B = W  MN-major, slabs {32 f, tap, 32 c}
+//   mode 2  dgrad   : A rows = input pixels of err (mirrored taps), K = (tap, f) ; B = W K-major, box {32 f, tap, BLOCK_N c}
+//   mode 3  wgrad   : A rows = (tap, c) MN-major, K = pixels ; B = err [pixels, F] MN-major (plain 2-D)
+struct ConvTma {
+    int mode;          // 0: plain 2-D operands (Dense)
+    int C;             // channels per tap: along K (modes 1, 2: C_in resp. F) or along M (mode 3: C_in)
+    int kw, taps;
+    int W, H;          // image size (input = output)
+    int pad_y, pad_x;
+};
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -156,7 +181,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue epi, int M,
-                 int N, int K, int kb_per_split, float* __restrict__ ws) {
+                 int N, int K, int kb_per_split, float* __restrict__ ws, const ConvTma cv) {
     constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t LO_OFFSET = STAGES * STAGE_BYTES;   // X3: the lo tiles mirror the raw ring behind it
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 (BLOCK_N in {32,64,128,256})
@@ -207,17 +232,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t bar = smem_u32(&full_bar[s]);
                 mbar_expect_tx(bar, STAGE_BYTES);
                 const int k0 = (kb_begin + i) * BLOCK_K;
-                if constexpr (A_MN) {
+                if (cv.mode == 1 || cv.mode == 2) {
+                    // A tile = 128 consecutive pixels (whole image rows / whole images), one tap, 32 channels
+                    const int tap = k0 / cv.C, c0 = k0 - tap * cv.C;
+                    const int ky = tap / cv.kw, kx = tap - ky * cv.kw;
+                    const int HW = cv.H * cv.W;
+                    const int img = m0 / HW, y0 = (m0 - img * HW) / cv.W;
+                    const int dy = cv.mode == 1 ? ky - cv.pad_y : cv.pad_y - ky;
+                    const int dx = cv.mode == 1 ? kx - cv.pad_x : cv.pad_x - kx;
+                    tma_load_4d(sa, &tmA, bar, c0, dx, y0 + dy, img);
+                    if constexpr (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * SLAB_BYTES, &tmA, bar, m0 + j * 32, k0);
-                } else {
-                    tma_load_2d(sa, &tmA, bar, k0, m0);
-                }
-                if constexpr (B_MN) {
+                        for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_3d(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, tap, c0);
+                    } else {
+                        tma_load_3d(sb, &tmB, bar, c0, tap, n0);
+                    }
+                } else if (cv.mode == 3) {
+                    // A slab j = 32 (tap, c) rows x 32 consecutive pixels; rows past the last tap are fetched far out of bounds (zeros)
+                    const int HW = cv.H * cv.W;
+                    const int img = k0 / HW, rem = k0 - img * HW;
+                    const int y0 = rem / cv.W, x0 = rem - y0 * cv.W;
+                    if constexpr (A_MN) {
 #pragma unroll
-                    for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
+                        for (int j = 0; j < BLOCK_M / 32; ++j) {
+                            const int r = m0 + j * 32;
+                            const int tap = r / cv.C, c0 = r - tap * cv.C;
+                            const int ky = tap / cv.kw, kx = tap - ky * cv.kw;
+                            const int yy = tap < cv.taps ? y0 + ky - cv.pad_y : -(1 << 20);
+                            tma_load_4d(sa + j * SLAB_BYTES, &tmA, bar, c0, x0 + kx - cv.pad_x, yy, img);
+                        }
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
+                    }
                 } else {
-                    tma_load_2d(sb, &tmB, bar, k0, n0);
+                    if constexpr (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * SLAB_BYTES, &tmA, bar, m0 + j * 32, k0);
+                    } else {
+                        tma_load_2d(sa, &tmA, bar, k0, m0);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
+                    } else {
+                        tma_load_2d(sb, &tmB, bar, k0, n0);
+                    }
                 }
             }
         }
@@ -386,6 +447,19 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
     return B200NN_OK;
 }
 
+// rank-3 / rank-4 fp32 tensor map with explicit byte strides (dims[0] is contiguous) and box
+static int make_map_nd(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box, bool mn_major) {
+    EncodeTiledFn fn = encode_fn();
+    B200NN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200NN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (rank %d) failed with %d", rank, (int)r);
+    return B200NN_OK;
+}
+
 // can this operand be described by a TMA map? (16-byte aligned base and row pitch)
 static bool tma_ok(const float* base, long long ld) {
     return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * sizeof(float)) % 16 == 0 && ld > 0;
@@ -454,7 +528,7 @@ static size_t tc_ws_bytes(long long M, long long N, long long K, bool x3 = false
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool X3>
 static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
-                            const TcPlan& p, float* ws, cudaStream_t st) {
+                            const TcPlan& p, float* ws, cudaStream_t st, const ConvTma& cv) {
     constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BN * 128) * (X3 ? 2 : 1) + 1024;
     auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, X3>;
     static bool configured = false;
@@ -463,7 +537,7 @@ static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const 
         configured = true;
     }
     const dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, p.splits);
-    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr);
+    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr, cv);
     B200NN_LAUNCH_CHECK("gemm_tf32");
     if (p.splits > 1) return launch_splitk_reduce(ws, p.splits, M, N, epi, st);
     return B200NN_OK;
@@ -473,11 +547,27 @@ static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const 
 // so that several CTAs (and their epilogue warps) share an SM; long reductions get a deep ring
 template <int BN, bool A_MN, bool B_MN>
 static int tc_launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Epilogue& epi, int M, int N, int K,
-                             const TcPlan& p, float* ws, cudaStream_t st, bool x3) {
+                             const TcPlan& p, float* ws, cudaStream_t st, bool x3, const ConvTma& cv) {
     if (x3)   // twice the shared memory per stage (raw + lo tiles): 2 stages at 256 columns, 3 below
-        return tc_launch_stages<BN, (BN >= 256 ? 2 : 3), A_MN, B_MN, true>(ta, tb, epi, M, N, K, p, ws, st);
-    if (p.kb_per_split <= 2) return tc_launch_stages<BN, 2, A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st);
-    return tc_launch_stages<BN, (BN >= 256 ? 4 : 6), A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st);
+        return tc_launch_stages<BN, (BN >= 256 ? 2 : 3), A_MN, B_MN, true>(ta, tb, epi, M, N, K, p, ws, st, cv);
+    if (p.kb_per_split <= 2) return tc_launch_stages<BN, 2, A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st, cv);
+    return tc_launch_stages<BN, (BN >= 256 ? 4 : 6), A_MN, B_MN, false>(ta, tb, epi, M, N, K, p, ws, st, cv);
+}
+
+static int tc_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, bool a_mn, bool b_mn, const Epilogue& epi, int M, int N, int K,
+                       const TcPlan& p, float* ws, cudaStream_t st, bool x3, const ConvTma& cv) {
+    B200NN_REQUIRE(!(a_mn && !b_mn), "gemm_tf32: (A MN-major, B K-major) is not instantiated");
+#define TC_DISPATCH(BN)                                                                                  \
+    if (a_mn) return tc_launch_variant<BN, true, true>(ta, tb, epi, M, N, K, p, ws, st, x3, cv);         \
+    if (b_mn) return tc_launch_variant<BN, false, true>(ta, tb, epi, M, N, K, p, ws, st, x3, cv);        \
+    return tc_launch_variant<BN, false, false>(ta, tb, epi, M, N, K, p, ws, st, x3, cv);
+    switch (p.block_n) {
+        case 32: TC_DISPATCH(32)
+        case 64: TC_DISPATCH(64)
+        case 128: TC_DISPATCH(128)
+        default: TC_DISPATCH(256)
+    }
+#undef TC_DISPATCH
 }
 
 // D[M,N] = A.B ; a_mn: A stored [K][M] (ld = lda) else [M][K]; b_mn: B stored [K][N] else [N][K]
@@ -490,18 +580,89 @@ static int tc_gemm(const float* A, long long lda, bool a_mn, const float* B, lon
     else      { if (int rc = make_map(&ta, A, K, M, lda, BLOCK_M, false)) return rc; }
     if (b_mn) { if (int rc = make_map(&tb, B, N, K, ldb, BLOCK_K, true)) return rc; }
     else      { if (int rc = make_map(&tb, B, K, N, ldb, p.block_n, false)) return rc; }
-    B200NN_REQUIRE(!(a_mn && !b_mn), "gemm_tf32: (A MN-major, B K-major) is not instantiated");
-#define TC_DISPATCH(BN)                                                                              \
-    if (a_mn) return tc_launch_variant<BN, true, true>(ta, tb, epi, M, N, K, p, ws, st, x3);         \
-    if (b_mn) return tc_launch_variant<BN, false, true>(ta, tb, epi, M, N, K, p, ws, st, x3);        \
-    return tc_launch_variant<BN, false, false>(ta, tb, epi, M, N, K, p, ws, st, x3);
-    switch (p.block_n) {
-        case 32: TC_DISPATCH(32)
-        case 64: TC_DISPATCH(64)
-        case 128: TC_DISPATCH(128)
-        default: TC_DISPATCH(256)
-    }
-#undef TC_DISPATCH
+    ConvTma cv{};
+    return tc_dispatch(ta, tb, a_mn, b_mn, epi, M, N, K, p, ws, st, x3, cv);
+}
+
+// ---- implicit-GEMM convolution on the same kernel (see ConvTma) ------------------------------------------------
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// stride 1, 'same' with an odd kernel, power-of-two image (W in 4..128), channel counts multiples of 32
+static bool conv_tc_ok(const b200nn_conv_geom* g, const void* p0, const void* p1, const void* p2) {
+    if (((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2)) & 15) != 0) return false;
+    return g->sh == 1 && g->sw == 1 && g->OH == g->H && g->OW == g->W && (g->kh & 1) && (g->kw & 1) &&
+           g->ph == (g->kh - 1) / 2 && g->pw == (g->kw - 1) / 2 && g->C % 32 == 0 && g->F % 32 == 0 && pow2(g->W) &&
+           pow2(g->H) && g->W >= 4 && g->W <= 128 && g->H <= 256 &&
+           (long long)g->N * g->H * g->W * g->F * g->kh * g->kw * g->C >= (1LL << 22);
+}
+
+// 4-D map over an NHWC tensor t[Nimg, H, W, Cn]; the box covers `pixels` consecutive pixels (whole rows / whole images)
+static int make_image_map(CUtensorMap* map, const float* t, int Nimg, int H, int W, int Cn, int pixels, bool mn_major) {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cn * 4, (cuuint64_t)W * Cn * 4, (cuuint64_t)H * W * Cn * 4};
+    const int bx = W < pixels ? W : pixels;
+    const int by = H < pixels / bx ? H : pixels / bx;
+    const int bb = pixels / (bx * by);
+    const cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bb};
+    return make_map_nd(map, t, 4, dims, strides, box, mn_major);
+}
+
+// 3-D map over the weights w[(c, tap), F]: (f, tap, c)
+static int make_weight_map(CUtensorMap* map, const float* w, int taps, int C, int F, int box_c, bool mn_major) {
+    const cuuint64_t dims[3] = {(cuuint64_t)F, (cuuint64_t)taps, (cuuint64_t)C};
+    const cuuint64_t strides[2] = {(cuuint64_t)F * 4, (cuuint64_t)taps * F * 4};
+    const cuuint32_t box[3] = {32, 1, (cuuint32_t)box_c};
+    return make_map_nd(map, w, 3, dims, strides, box, mn_major);
+}
+
+static ConvTma conv_tma(int mode, const b200nn_conv_geom* g, int C) {
+    ConvTma cv;
+    cv.mode = mode; cv.C = C; cv.kw = g->kw; cv.taps = g->kh * g->kw; cv.W = g->W; cv.H = g->H; cv.pad_y = g->ph; cv.pad_x = g->pw;
+    return cv;
+}
+
+// y[pixels, F] = patches(x) . W   (epi: bias + activation)
+static int tc_conv_fwd(const b200nn_conv_geom* g, const float* x, const float* w, const Epilogue& epi, float* ws,
+                       cudaStream_t st, bool x3) {
+    const int M = g->N * g->H * g->W, N = g->F, K = g->kh * g->kw * g->C;
+    const TcPlan p = tc_plan(M, N, K, x3);
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "conv_tf32: split-K needs a workspace");
+    CUtensorMap ta, tb;
+    if (int rc = make_image_map(&ta, x, g->N, g->H, g->W, g->C, BLOCK_M, false)) return rc;
+    if (int rc = make_weight_map(&tb, w, g->kh * g->kw, g->C, g->F, 32, true)) return rc;
+    return tc_dispatch(ta, tb, false, true, epi, M, N, K, p, ws, st, x3, conv_tma(1, g, g->C));
+}
+
+// dx[pixels, C] = patches'(err) . W^T   (mirrored taps; epi: clip multiplier, activation-backward mask, sums of squares)
+static int tc_conv_dgrad(const b200nn_conv_geom* g, const float* err, const float* w, const Epilogue& epi, float* ws,
+                         cudaStream_t st, bool x3) {
+    const int M = g->N * g->H * g->W, N = g->C, K = g->kh * g->kw * g->F;
+    const TcPlan p = tc_plan(M, N, K, x3);
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "conv_tf32: split-K needs a workspace");
+    CUtensorMap ta, tb;
+    if (int rc = make_image_map(&ta, err, g->N, g->H, g->W, g->F, BLOCK_M, false)) return rc;
+    if (int rc = make_weight_map(&tb, w, g->kh * g->kw, g->C, g->F, p.block_n, false)) return rc;
+    return tc_dispatch(ta, tb, false, false, epi, M, N, K, p, ws, st, x3, conv_tma(2, g, g->F));
+}
+
+// dw[(tap, c), F] = patches(x)^T . err   (epi: row_mode 1 writes the reference's (c, ky, kx) row order)
+static int tc_conv_wgrad(const b200nn_conv_geom* g, const float* x, const float* err, const Epilogue& epi, float* ws,
+                         cudaStream_t st, bool x3) {
+    const int M = g->kh * g->kw * g->C, N = g->F, K = g->N * g->H * g->W;
+    const TcPlan p = tc_plan(M, N, K, x3);
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "conv_tf32: split-K needs a workspace");
+    CUtensorMap ta, tb;
+    if (int rc = make_image_map(&ta, x, g->N, g->H, g->W, g->C, BLOCK_K, true)) return rc;
+    if (int rc = make_map(&tb, err, N, K, N, BLOCK_K, true)) return rc;
+    return tc_dispatch(ta, tb, true, true, epi, M, N, K, p, ws, st, x3, conv_tma(3, g, g->C));
+}
+
+static size_t tc_conv_ws_bytes(const b200nn_conv_geom* g, bool x3) {
+    const long long P = (long long)g->N * g->H * g->W, taps = (long long)g->kh * g->kw;
+    size_t r = tc_ws_bytes(P, g->F, taps * g->C, x3);
+    const size_t b = tc_ws_bytes(P, g->C, taps * g->F, x3), c = tc_ws_bytes(taps * g->C, g->F, P, x3);
+    r = r > b ? r : b;
+    return r > c ? r : c;
 }
 
 }  // namespace tc

@@ -499,10 +499,10 @@ class Conv2D(Layer, _ParamMixin):
         g = self._geometry(x.shape)
         if g.OH <= 0 or g.OW <= 0:
             raise ValueError(f"Size mismatch: Conv2D output would be {g.OH}x{g.OW}")
-        ctx.need_ws(ops.conv2d_ws_bytes(g))
+        math = _math_code()   # tensor-core modes apply to the geometries b200nn_conv2d_ws_bytes_math names; FFMA otherwise
+        ctx.need_ws(ops.conv2d_ws_bytes(g, math))
         y = ctx.buf((x.shape[0], g.OH, g.OW, self.filters))
         kind, alpha = _act_of(act_layer)
-        math = ops.MATH_FP32
         st.update(x=x, g=g, math=math)
         w, b = self._weights, self._bias
         ctx.emit(lambda: ops.conv2d_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws), "conv2d_fwd", (x, w, b, y))

@@ -28,7 +28,8 @@ def time_model(m, x, y, steps=20):
 out = {}
 rng = np.random.default_rng(0)
 for name, cfg, batch, math in (("cfg1 MLP 784-128-64-10 b32", 1, 32, "fp32"), ("cfg3 deep CNN 32x32x3 b1024", 3, 1024, "fp32"),
-                               ("cfg3 deep CNN 32x32x3 b256", 3, 256, "fp32"),
+                               ("cfg3 deep CNN 32x32x3 b256", 3, 256, "fp32"), ("cfg3 deep CNN 32x32x3 b1024 tf32x3", 3, 1024, "tf32x3"),
+                               ("cfg3 deep CNN 32x32x3 b256 tf32x3", 3, 256, "tf32x3"), ("cfg3 deep CNN 32x32x3 b1024 tf32", 3, 1024, "tf32"),
                                ("cfg4 wide MLP 4x4096 b8192 fp32", 4, 8192, "fp32"), ("cfg4 wide MLP 4x4096 b8192 tf32", 4, 8192, "tf32"),
                                ("cfg4 wide MLP 4x4096 b8192 tf32x3", 4, 8192, "tf32x3"), ("cfg4 wide MLP 4x4096 b256 fp32", 4, 256, "fp32"),
                                ("cfg4 wide MLP 4x4096 b256 tf32x3", 4, 256, "tf32x3")):

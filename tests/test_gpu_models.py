@@ -357,10 +357,11 @@ def test_tf32_tensor_core_mode_within_2e3(cfg, batch, width):
         nn.set_math("fp32")
 
 
-@pytest.mark.parametrize("cfg,batch,width", [(2, 256, None), (1, 32, None), (4, 256, 1024)])
+@pytest.mark.parametrize("cfg,batch,width", [(2, 256, None), (1, 32, None), (4, 256, 1024), (3, 32, None)])
 def test_tf32x3_tensor_core_mode_matches_fp32_parity(cfg, batch, width):
     """Math mode 'tf32x3' (tcgen05 with hi/lo operand split): the Dense contractions run on the tensor cores and the
-    step still meets the FFMA path's bar against the fp64 oracle -- loss, predictions and every gradient."""
+    step still meets the FFMA path's bar against the fp64 oracle -- loss, predictions and every gradient. Config 3 also
+    puts conv2 / conv3 on the tensor cores (implicit GEMM over TMA boxes)."""
     import neuralnetlib_b200 as nn
     nn.set_math("tf32x3")
     try:
@@ -380,8 +381,10 @@ def test_tf32x3_tensor_core_mode_matches_fp32_parity(cfg, batch, width):
         assert abs(loss - rloss) <= TOL * max(1.0, abs(rloss))
         assert nrel(m.predictions, ref.predictions) < TOL
         for layer, rl in zip([l for l in m.layers if hasattr(l, "weights")], [r for r in ref.layers if "w" in r]):
-            grads_close(layer.d_weights, rl["dw"], TOL, "dw")
-            grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), TOL, "db")
+            # config 3 (three per-position BatchNorm + pool blocks at batch 32) gets the tolerance the FFMA path gets
+            # in test_fusion_levels_agree_with_oracle
+            grads_close(layer.d_weights, rl["dw"], 1e-3 if cfg == 3 else TOL, "dw")
+            grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), 1e-3 if cfg == 3 else TOL, "db")
     finally:
         nn.set_math("fp32")
 

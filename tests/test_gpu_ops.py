@@ -206,6 +206,45 @@ def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
     assert abs(K.host(ss)[1] - np.sum(rdx ** 2)) < 1e-4 * np.sum(rdx ** 2)
 
 
+@pytest.mark.parametrize("math,tol", [(2, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize("N,H,W,C,F,k,act", [(8, 16, 16, 64, 128, 3, 1), (37, 8, 8, 128, 256, 3, 1), (45, 4, 4, 32, 32, 3, 0),
+                                             (3, 32, 32, 32, 96, 5, 1), (2, 4, 128, 32, 64, 3, 0), (7, 64, 8, 64, 32, 1, 1)])
+def test_conv2d_tcgen05_implicit_gemm(K, N, H, W, C, F, k, act, math, tol):
+    """Tensor-core convolution (math modes tf32 / tf32x3): implicit GEMM on the tcgen05 kernel with the im2col rows fetched
+    by 4-D TMA boxes from the NHWC tensor (zero fill = 'same' padding) and the weights by a 3-D map in the reference's
+    (c, ky, kx) K order. Forward, dgrad (mirrored taps, activation-backward mask, clip multiplier, sums of squares) and
+    wgrad (row permutation to (c, ky, kx), db) against the fp64 oracle; tf32x3 must meet the FFMA path's 1e-5."""
+    rng = np.random.default_rng(H * 31 + C + k)
+    x = np.maximum(rng.normal(size=(N, H, W, C)), 0).astype(np.float32)     # x is a ReLU output: used as the dgrad mask
+    w = (rng.normal(size=(k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    geom, oh, ow = _conv_geom(K, N, H, W, C, F, k, k, 1, 1, "same")
+    assert (oh, ow) == (H, W)
+    assert K.ops.conv2d_ws_bytes(geom, math) >= K.ops.conv2d_ws_bytes(geom, 0)
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    ws = K.empty((max(K.ops.conv2d_ws_bytes(geom, math) // 4, 1),))
+    y = K.empty((N, oh, ow, F))
+    K.ops.conv2d_fwd(math, geom, xd, wd, bd, y, act, 0.0, ws)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    ref = O.conv2d_fwd(x64, w64, b.astype(np.float64), (1, 1), "same")
+    ref = np.maximum(ref, 0) if act else ref
+    assert nrel(K.host(y), ref) < tol
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = K.empty(x.shape), K.empty(w.shape), K.empty((F,))
+    K.ops.conv2d_bwd(math, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    rdx, rdw, rdb = O.conv2d_bwd(x64, w64, O.clip_l2(err.astype(np.float64)), (1, 1), "same")
+    assert nrel(K.host(dx), rdx * (x > 0)) < tol
+    assert nrel(K.host(dw), rdw) < tol
+    assert nrel(K.host(db), rdb) < 1e-5
+    h = K.host(ss)
+    assert abs(h[1] - np.sum(rdx ** 2)) < max(1e-4, 4 * tol) * np.sum(rdx ** 2)
+    assert abs(h[2] - np.sum((rdx * (x > 0)) ** 2)) < max(1e-4, 4 * tol) * np.sum((rdx * (x > 0)) ** 2)
+    if math == 2:   # the tensor cores really ran: single-pass TF32 on the same inputs is far from this accuracy
+        y1 = K.empty((N, oh, ow, F)); K.ops.conv2d_fwd(1, geom, xd, wd, bd, y1, act, 0.0, ws)
+        assert nrel(K.host(y1), ref) > 20 * nrel(K.host(y), ref)
+
+
 def _convt_geom(K, N, H, W, C, F, kh, kw, sh, sw, pad):
     oh, ow, pt, pb, pl, pr = O.convT_geometry(H, W, kh, kw, sh, sw, pad)
     return K.B.ConvTGeom(N, H, W, C, F, kh, kw, sh, sw, pt, pl, oh, ow), oh, ow
