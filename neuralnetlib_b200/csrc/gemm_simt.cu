@@ -423,6 +423,57 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     epi_finish(epi, st, scratch);
 }
 
+// The same for plain row-major outputs with N % 4 == 0 (activations and input errors of the tensor-core GEMMs: up to
+// hundreds of MB of partials): float4 traffic, one index division per four outputs, activation kinds at compile time
+// (AM / MM: 0 none, 1 ReLU, 2 run time). The scalar kernel above spends ~47 instructions per element on its generic epilogue
+// and ran at 0.9 TB/s.
+template <int AM, int MM>
+__global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                                Epilogue epi) {
+    __shared__ double scratch[32];
+    EpiState st;
+    epi_begin(epi, st);
+    const int act = AM == 0 ? B200NN_ACT_NONE : (AM == 1 ? B200NN_ACT_RELU : epi.act);
+    const int mact = MM == 1 ? B200NN_ACT_RELU : epi.mask_act;
+    const long long total4 = (long long)M * N / 4;
+    const int N4 = N / 4;
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(ws);
+    float a0 = 0.0f, a1 = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = w4[i];
+        int s = 1;
+        for (; s + 1 < splits; s += 2) {
+            const float4 p = w4[(long long)s * total4 + i], q = w4[(long long)(s + 1) * total4 + i];
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        if (s < splits) {
+            const float4 p = w4[(long long)s * total4 + i];
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        const long long m = i / N4;
+        const int n = (int)(i - m * N4) * 4;
+        const float4 b = epi.bias != nullptr ? *reinterpret_cast<const float4*>(epi.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float o[4] = {fmaf(v.x, st.scale, b.x), fmaf(v.y, st.scale, b.y), fmaf(v.z, st.scale, b.z), fmaf(v.w, st.scale, b.w)};
+        float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MM != 0) mk = *reinterpret_cast<const float4*>(epi.mask_y + m * epi.ldo + n);
+        const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x = act_apply(act, o[j], epi.alpha);
+            a0 = fmaf(x, x, a0);
+            if (MM != 0) {
+                x *= act_grad_from_y(mact, mkv[j], epi.mask_alpha);
+                a1 = fmaf(x, x, a1);
+            }
+            o[j] = x;
+        }
+        *reinterpret_cast<float4*>(epi.out + m * epi.ldo + n) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    st.a0 = a0; st.a1 = a1;
+    epi_finish(epi, st, scratch);
+}
+
 
 // Same reduction for FEW outputs and MANY splits (weight gradients of small-K convolutions: a few hundred
 // outputs, hundreds of per-CTA partials): 32 outputs per CTA, the 8 warps stride over the splits with coalesced
@@ -459,6 +510,22 @@ static int launch_splitk_reduce(const float* ws, int splits, int M, int N, const
         B200NN_LAUNCH_CHECK("splitk_reduce_wide");
         return B200NN_OK;
     }
+    const uintptr_t al = reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(epi.out) |
+                         reinterpret_cast<uintptr_t>(epi.bias) | reinterpret_cast<uintptr_t>(epi.mask_y);
+    if (N % 4 == 0 && epi.ldo % 4 == 0 && (al & 15) == 0 && epi.row_mode == 0 && epi.n_rows >= M && total >= (1 << 16)) {
+        long long blocks = (total / 4 + 255) / 256;
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        const int am = epi.act == B200NN_ACT_NONE ? 0 : (epi.act == B200NN_ACT_RELU ? 1 : 2);
+        const int mm = epi.mask_y == nullptr ? 0 : (epi.mask_act == B200NN_ACT_RELU ? 1 : 2);
+#define RV(A, B) splitk_reduce_vec_kernel<A, B><<<(int)blocks, 256, 0, st>>>(ws, splits, M, N, epi); break;
+        switch (am * 3 + mm) {
+            case 0: RV(0, 0) case 1: RV(0, 1) case 2: RV(0, 2) case 3: RV(1, 0) case 4: RV(1, 1) case 5: RV(1, 2)
+            case 6: RV(2, 0) case 7: RV(2, 1) default: RV(2, 2)
+        }
+#undef RV
+        B200NN_LAUNCH_CHECK("splitk_reduce_vec");
+        return B200NN_OK;
+    }
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(ws, splits, M, N, epi);
@@ -466,25 +533,55 @@ static int launch_splitk_reduce(const float* ws, int splits, int M, int N, const
     return B200NN_OK;
 }
 
-// column sums of a [R, F] matrix with the lazy clip multiplier: out[f] = scale * sum_r x[r, f]
+// column sums of a [R, F] matrix with the lazy clip multiplier: out[f] = scale * sum_r x[r, f].
+// partial: the 256 threads of a CTA form (256 / FT) row lanes x FT columns (FT = min(F rounded up to 32, 256)); each thread
+// keeps four independent accumulators over its rows, the row lanes are folded through shared memory.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, long long R, int F,
                                                              float* __restrict__ partial) {
-    // block handles rows [blockIdx.x * rows_per_block, ...); thread t handles columns t, t+256, ...
+    __shared__ float red[256];
+    const int FT = F >= 256 ? 256 : ((F + 31) & ~31);
+    const int RL = 256 / FT;
+    const int tx = threadIdx.x % FT, ty = threadIdx.x / FT;
     const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(R, r0 + rows_per_block);
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        float s = 0.0f;
-        for (long long r = r0; r < r1; ++r) s += x[r * F + f];
-        partial[(long long)blockIdx.x * F + f] = s;
+    for (int f0 = 0; f0 < F; f0 += FT) {
+        const int f = f0 + tx;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        if (f < F && ty < RL) {
+            long long r = r0 + ty;
+            for (; r + 3LL * RL < r1; r += 4LL * RL) {
+                s0 += x[r * F + f];
+                s1 += x[(r + RL) * F + f];
+                s2 += x[(r + 2LL * RL) * F + f];
+                s3 += x[(r + 3LL * RL) * F + f];
+            }
+            for (; r < r1; r += RL) s0 += x[r * F + f];
+        }
+        red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (ty == 0 && f < F) {
+            float s = red[tx];
+            for (int l = 1; l < RL; ++l) s += red[l * FT + tx];
+            partial[(long long)blockIdx.x * F + f] = s;
+        }
+        __syncthreads();
     }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int F, const double* ss,
-                                    uint64_t chain, float* __restrict__ out) {
+// final: 32 columns x 8 lanes per CTA over the per-block partials
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblocks, int F, const double* ss,
+                                                           uint64_t chain, float* __restrict__ out) {
+    __shared__ float red[8][33];
     const float scale = chain_scale(ss, chain);
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * F + f];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + tx;
+    float s = 0.0f;
+    if (f < F)
+        for (int b = ty; b < nblocks; b += 8) s += partial[(long long)b * F + f];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && f < F) {
+        for (int l = 1; l < 8; ++l) s += red[l][tx];
         out[f] = s * scale;
     }
 }
@@ -1111,7 +1208,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
             if (nb > kNumSMs * 2) nb = kNumSMs * 2;
             colsum_partial_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
             B200NN_LAUNCH_CHECK("dense_db_partial");
-            colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(ws, nb, N, ss, chain, db);
+            colsum_final_kernel<<<(N + 31) / 32, 256, 0, st>>>(ws, nb, N, ss, chain, db);
             B200NN_LAUNCH_CHECK("dense_db_final");
         }
         Epilogue e = plain_epilogue(dw, N, K);   // dw[K,N] = x^T . err : both operands MN-major, no transposed copies
@@ -1234,7 +1331,7 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
                 if (nb > kNumSMs * 2) nb = kNumSMs * 2;
                 colsum_partial_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
                 B200NN_LAUNCH_CHECK("conv2d_db_partial");
-                colsum_final_kernel<<<(g->F + 127) / 128, 128, 0, st>>>(ws, nb, g->F, ss, chain, db);
+                colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(ws, nb, g->F, ss, chain, db);
                 B200NN_LAUNCH_CHECK("conv2d_db_final");
             }
             Epilogue e = plain_epilogue(dw, g->F, Kf);
@@ -1350,7 +1447,7 @@ int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const
         if (nb > kNumSMs * 2) nb = kNumSMs * 2;
         colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
         B200NN_LAUNCH_CHECK("convt_db_partial");
-        colsum_final_kernel<<<(g->F + 127) / 128, 128, 0, st>>>(ws, nb, g->F, ss, chain, db);
+        colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(ws, nb, g->F, ss, chain, db);
         B200NN_LAUNCH_CHECK("convt_db_final");
     }
     if (dw != nullptr) {  // dw[(ky,kx,f), c] = sum_pix window(pix, tap) * x[pix, c]

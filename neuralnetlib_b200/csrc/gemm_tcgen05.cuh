@@ -184,7 +184,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  int N, int K, int kb_per_split, float* __restrict__ ws, const ConvTma cv) {
     constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t LO_OFFSET = STAGES * STAGE_BYTES;   // X3: the lo tiles mirror the raw ring behind it
-    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 (BLOCK_N in {32,64,128,256})
+    // power of two >= 32 (BLOCK_N in {32,64,128,256}); X3 keeps the two lo products in a second accumulator (see below)
+    constexpr int TMEM_COLS = (BLOCK_N < 32 ? 32 : BLOCK_N) * (X3 ? 2 : 1);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -300,8 +301,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (X3) {
                         const uint64_t adl = A_MN ? desc_mnmajor(sa + LO_OFFSET, j) : desc_kmajor(sa + LO_OFFSET, j);
                         const uint64_t bdl = B_MN ? desc_mnmajor(sb + LO_OFFSET, j) : desc_kmajor(sb + LO_OFFSET, j);
-                        tc_mma_tf32(tmem_base, adl, bd, idesc, 1u);      // A_lo . B_hi
-                        tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);      // A_hi . B_lo
+                        // the lo products go to their own accumulator: 2^-11 of the main one, so their truncating adds
+                        // cost nothing, and the main accumulator sees one add per k-step instead of three
+                        tc_mma_tf32(tmem_base + BLOCK_N, adl, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);   // A_lo . B_hi
+                        tc_mma_tf32(tmem_base + BLOCK_N, ad, bdl, idesc, 1u);                           // A_hi . B_lo
                     }
                 }
                 tc_commit(smem_u32(&empty_bar[s]));          // frees the smem stage once these MMAs have read it
@@ -352,6 +355,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[32];
             if (num_kb > 0) {
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                if (X3) {
+                    float lo[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c), lo);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += lo[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
@@ -472,11 +481,12 @@ struct TcPlan {
 };
 
 // X3: the tensor core adds into the fp32 accumulator with truncation, a same-signed ~2^-25 relative error per MMA that
-// grows with the chain (2e-5 at 1536 chained MMAs, measured) and would dominate the compensated product error. The chain
-// is therefore cut every X3_CHAIN_KB k-blocks through split-K: each split accumulates 512 k in TMEM, the reduce kernel adds
+// grows with the chain (2e-5 at 1536 chained MMAs, measured) and would dominate the compensated product error. Two
+// measures: the lo products accumulate in a second TMEM accumulator (a third of the adds on the main one), and the chain
+// is cut every X3_CHAIN_KB k-blocks (2048 k = 256 adds on the main accumulator) through split-K, the reduce kernel adding
 // the partials in round-to-nearest fp32 (the idea of Ootomo & Yokota's error-corrected tensor-core GEMM, at tile-chunk
 // granularity). The extra CTAs also let small-M problems keep wide tiles.
-constexpr int X3_CHAIN_KB = 16;
+constexpr int X3_CHAIN_KB = 64;
 constexpr long long X3_WS_CAP = 512LL << 20;
 
 static TcPlan tc_plan(long long M, long long N, long long K, bool x3 = false) {
@@ -491,10 +501,11 @@ static TcPlan tc_plan(long long M, long long N, long long K, bool x3 = false) {
             chain *= 2;
             splits = (kb_total + chain - 1) / chain;
         }
-        while (p.block_n > 32 && tiles_for(p.block_n) * splits < kNumSMs) p.block_n >>= 1;
+        const long long can = splits > kb_total / 16 ? splits : kb_total / 16;   // splits a long reduction could take
+        while (p.block_n > 32 && tiles_for(p.block_n) < kNumSMs && tiles_for(p.block_n) * can < (3 * kNumSMs) / 4) p.block_n >>= 1;
         const long long tiles = tiles_for(p.block_n);
-        if (tiles * splits < kNumSMs && kb_total >= 8) {          // still short of a wave: split further, as below
-            long long more = (kNumSMs + tiles - 1) / tiles;
+        if (tiles * splits < kNumSMs && kb_total >= 8) {          // short of a wave: split further, tiles kept wide
+            long long more = kNumSMs / tiles;
             const long long maxs = kb_total / 4;
             if (more > maxs) more = maxs;
             if (more > splits) splits = more;
@@ -504,12 +515,15 @@ static TcPlan tc_plan(long long M, long long N, long long K, bool x3 = false) {
         p.kb_per_split = (int)per;
         return p;
     }
-    // if the tile grid cannot fill the 148 SMs anyway, narrower tiles spread the (epilogue-heavy) work over more SMs
-    while (p.block_n > 32 && tiles_for(p.block_n) < kNumSMs) p.block_n >>= 1;
+    // If the tile grid cannot fill the 148 SMs: a long reduction is split over K with the tiles kept wide (the MMA rate grows
+    // with N; the weight-gradient GEMMs of a convolution have a handful of tiles and thousands of k-blocks), a short one gets
+    // narrower tiles that spread the epilogue-heavy work over more SMs.
+    while (p.block_n > 32 && tiles_for(p.block_n) < kNumSMs &&
+           tiles_for(p.block_n) * (kb_total / 16) < (3 * kNumSMs) / 4) p.block_n >>= 1;
     const long long tiles = tiles_for(p.block_n);
     long long splits = 1;
     if (tiles < kNumSMs && kb_total >= 8) {
-        splits = (kNumSMs + tiles - 1) / tiles;
+        splits = kNumSMs / tiles;                  // one wave: a second, nearly empty wave would double the time
         const long long maxs = kb_total / 4;       // at least 4 k-blocks (128 k) per split
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
