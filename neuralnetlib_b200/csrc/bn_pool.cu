@@ -84,14 +84,14 @@ __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float* __re
     const float* xc = x + col;
     float s = 0.0f;
     if (ok) {
-#pragma unroll 4
+#pragma unroll 8
         for (int r = ry; r < B; r += BN_ROWG) s += clip10(xc[(long long)r * P]);
     }
     const float sum = colgroup_sum(s, sm, cx, ry);
     const float mean = sum / (float)B;
     float q = 0.0f;
     if (ok) {
-#pragma unroll 4
+#pragma unroll 8
         for (int r = ry; r < B; r += BN_ROWG) {
             const float d = clip10(xc[(long long)r * P]) - mean;
             q += d * d;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) bn_pool_apply_kernel(const float* __restr
     }
     const long long OP = (long long)OH * OW * C, obase = ((long long)oy * OW + ox) * C + c;
     const int r0 = chunk * FB_APPLY_ROWS, r1 = min(B, r0 + FB_APPLY_ROWS);
-#pragma unroll 2
+#pragma unroll 4
     for (int r = r0; r < r1; ++r) {
         const float* xr = x + (long long)r * P;
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);

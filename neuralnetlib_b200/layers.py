@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import time
 
+import os
+
 import numpy as np
 import torch
 
@@ -898,7 +900,10 @@ class BatchNormalization(Layer, _ParamMixin):
         P = self._gamma.numel()
         gm, bt, rm, rv = self._gamma, self._beta, self._running_mean, self._running_var
         mom, eps = float(self.momentum), float(self.epsilon)
-        if training and ctx.dp is not None:
+        # Large batches on one GPU take the same two streaming kernels: the single-read cluster kernel stages a window's whole
+        # batch in shared memory through 128-byte lines 256 KB apart, which stops paying beyond ~256 rows.
+        big = int(os.environ.get("B200NN_BN_SPLIT_ROWS", "512"))
+        if training and (ctx.dp is not None or x.shape[0] >= big):
             # data parallel (parallel.py): local moments -> sum over ranks -> apply, so that mean / var are those of the
             # GLOBAL batch (layers.py:1237-1238)
             b_total = x.shape[0] * ctx.world

@@ -423,6 +423,28 @@ def test_fusion_levels_agree_with_oracle(monkeypatch, level, cfg, batch):
     grads_close(got, want, 1e-3 if cfg == 3 else 5e-5, (level, "input error"))
 
 
+@pytest.mark.parametrize("cfg,batch", [(2, 64), (3, 32)])
+def test_large_batch_bn_forward_path_matches_oracle(monkeypatch, cfg, batch):
+    """Batches of >= B200NN_BN_SPLIT_ROWS rows (default 512) run BatchNorm's forward as two streaming kernels (per-position
+    moments, then normalise + pool) instead of the single-read cluster kernel; forced here at a size the oracle finishes
+    quickly."""
+    monkeypatch.setenv("B200NN_BN_SPLIT_ROWS", "1")
+    monkeypatch.setenv("B200NN_FUSE_BLOCKS", "1")     # the first-block kernel would bypass BatchNorm's own forward
+    m = build_cfg(cfg)
+    x, y = O.synthetic_batch(cfg, batch)
+    specs, _ = O.config_specs(cfg)
+    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    loss, rloss = m.train_on_batch(x, y), ref.train_on_batch(x, y)
+    assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss))
+    tol = 1e-3 if cfg == 3 else TOL
+    for layer, rl in zip([l for l in m.layers if hasattr(l, "weights")], [r for r in ref.layers if "w" in r]):
+        grads_close(layer.d_weights, rl["dw"], tol, "dw")
+        grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), tol, "db")
+    for layer, rl in zip(m.layers, ref.layers):
+        if rl["type"] == "bn":
+            assert nrel(layer.running_mean, rl["running_mean"]) < 2e-5 and nrel(layer.running_var, rl["running_var"]) < 2e-5
+
+
 @pytest.mark.parametrize("cfg,batch,level", [(1, 32, "2"), (2, 64, "2"), (2, 64, "1"), (2, 64, "0"), (3, 32, "2"), (4, 64, "2")])
 def test_deferred_clips_match_oracle(monkeypatch, cfg, batch, level):
     """B200NN_DEFER_CLIPS=1 (the data-parallel default, forced here on one GPU): backward kernels run WITHOUT the clip
