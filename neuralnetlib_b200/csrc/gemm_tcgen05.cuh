@@ -25,7 +25,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;          // tf32 elements = 128 bytes = one swizzle span
 constexpr int UMMA_K = 8;            // tf32 elements per tcgen05.mma
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;      // TMA warp, MMA warp, four epilogue warps
+constexpr int NUM_THREADS_X3 = 320;   // + four more operand-splitter warps (the split of a stage must not outlast its MMAs)
 constexpr uint32_t SLAB_BYTES = BLOCK_K * 128;   // one 32-wide MN slab of an MN-major operand
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -179,7 +180,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
 // (<= 2^-22 relative) and the rounding of lo zero-mean; splitting by the hardware's truncation instead leaves a
 // same-signed 2^-22 bias per product that grows with K (2e-5 at K = 4096, measured).
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool X3>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue epi, int M,
                  int N, int K, int kb_per_split, float* __restrict__ ws, const ConvTma cv) {
     constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -208,7 +209,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(smem_u32(&full_bar[s]), 1);
                 mbar_init(smem_u32(&empty_bar[s]), 1);
-                mbar_init(smem_u32(&split_bar[s]), 4);     // one arrival per splitter warp
+                mbar_init(smem_u32(&split_bar[s]), 8);     // one arrival per splitter warp
             }
             mbar_init(smem_u32(&tmem_full_bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -321,8 +322,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     EpiState st;
     epi_begin(epi, st);
     if (X3 && warp >= 2) {
-        // ===== operand splitter (the four epilogue warps, while the main loop runs) =====
-        const int t = threadIdx.x - 64;   // 0..127
+        // ===== operand splitter (eight warps: the four epilogue warps, idle during the main loop, and four more) =====
+        constexpr int SPLIT_THREADS = NUM_THREADS_X3 - 64;
+        constexpr int PER = (STAGE_BYTES / 16 + SPLIT_THREADS - 1) / SPLIT_THREADS;   // float4 per thread and stage
+        const int t = threadIdx.x - 64;
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % STAGES;
             const uint32_t round = i / STAGES;
@@ -330,19 +333,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t off = (smem_base - smem_u32(smem_raw)) + s * STAGE_BYTES;
             float4* src = reinterpret_cast<float4*>(smem_raw + off);
             float4* dst = reinterpret_cast<float4*>(smem_raw + off + LO_OFFSET);
-#pragma unroll 4
-            for (uint32_t v = t; v < STAGE_BYTES / 16; v += 128) {       // elementwise: the swizzled layout carries over unchanged
-                const float4 x = src[v];
-                const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
-                src[v] = h;
-                dst[v] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+            float4 x[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {                               // all loads in flight first
+                const uint32_t v = t + u * SPLIT_THREADS;
+                if (v < STAGE_BYTES / 16) x[u] = src[v];
+            }
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {                               // elementwise: the swizzled layout carries over unchanged
+                const uint32_t v = t + u * SPLIT_THREADS;
+                if (v < STAGE_BYTES / 16) {
+                    const float4 h = make_float4(tf32_rn(x[u].x), tf32_rn(x[u].y), tf32_rn(x[u].z), tf32_rn(x[u].w));
+                    src[v] = h;
+                    dst[v] = make_float4(tf32_rn(x[u].x - h.x), tf32_rn(x[u].y - h.y), tf32_rn(x[u].z - h.z), tf32_rn(x[u].w - h.w));
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
         }
     }
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         const int q = warp & 3;
         float (*tile)[33] = xpose[warp - 2];
         if (num_kb > 0) {
@@ -551,7 +562,7 @@ static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const 
         configured = true;
     }
     const dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, p.splits);
-    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr, cv);
+    kern<<<grid, X3 ? NUM_THREADS_X3 : NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr, cv);
     B200NN_LAUNCH_CHECK("gemm_tf32");
     if (p.splits > 1) return launch_splitk_reduce(ws, p.splits, M, N, epi, st);
     return B200NN_OK;
