@@ -41,3 +41,28 @@ def test_chain_packing():
     assert _ops.pack_chain(()) == 0
     assert _ops.pack_chain((5,)) == 1 | (5 << 8)
     assert _ops.pack_chain((1, 2, 3)) == 3 | (1 << 8) | (2 << 20) | (3 << 32)
+
+
+def test_workspace_sizing_per_math_mode():
+    """Host-only entry points (no device work): the tensor-core modes never need less workspace than the FFMA path, the
+    compensated mode (chain-limited split-K) needs room for its partial sums, and geometries the tensor-core convolution
+    does not take keep the FFMA sizing in every mode."""
+    from neuralnetlib_b200 import _backend as B
+    lib = B.lib()
+    for M, N, K in ((256, 4096, 4096), (8192, 4096, 4096), (256, 64, 6272), (32, 128, 784)):
+        base = lib.b200nn_dense_ws_bytes(M, N, K)
+        assert lib.b200nn_dense_ws_bytes_math(0, M, N, K) == base
+        assert lib.b200nn_dense_ws_bytes_math(1, M, N, K) == base
+        assert lib.b200nn_dense_ws_bytes_math(2, M, N, K) >= base
+    # K = 4096 exceeds one 2048-k accumulation chain: at least two partial tiles of [M, N] floats
+    assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) >= 2 * 8192 * 4096 * 4
+    assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) <= (512 << 20) + 8192 * 4096 * 4   # bounded workspace
+    ok = B.ConvGeom(64, 16, 16, 64, 128, 3, 3, 1, 1, 1, 1, 16, 16)          # stride 1, 'same', power-of-two image, C, F % 32 == 0
+    odd = B.ConvGeom(64, 28, 28, 64, 128, 3, 3, 1, 1, 1, 1, 28, 28)         # 28 x 28: FFMA in every mode
+    strided = B.ConvGeom(64, 16, 16, 64, 128, 3, 3, 2, 2, 1, 1, 8, 8)
+    for g in (odd, strided):
+        for math in (0, 1, 2):
+            assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(g)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(g))
+    assert lib.b200nn_conv2d_ws_bytes_math(0, ctypes.byref(ok)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
+    for math in (1, 2):
+        assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(ok)) >= lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
