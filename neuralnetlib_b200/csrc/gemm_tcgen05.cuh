@@ -173,12 +173,15 @@ __device__ __forceinline__ float tf32_rn(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// low part of x with respect to the TF32 the tensor core reads from the raw fp32 word (it truncates the 13 low mantissa
+// bits): hi = trunc(x) is what the MMA sees of the untouched tile, lo = x - hi exactly, rounded to TF32 itself
+__device__ __forceinline__ float tf32_lo(float x) { return tf32_rn(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
 
-// X3: error-compensated "3xTF32". The epilogue warps, idle during the main loop, split every staged operand tile in shared
-// memory into hi = rn_tf32(x) (written back in place) and lo = rn_tf32(x - hi) (mirror ring), and the MMA warp issues
-// A_hi.B_hi + A_lo.B_hi + A_hi.B_lo into the same TMEM accumulator. Round-to-nearest keeps both the dropped lo.lo term
-// (<= 2^-22 relative) and the rounding of lo zero-mean; splitting by the hardware's truncation instead leaves a
-// same-signed 2^-22 bias per product that grows with K (2e-5 at K = 4096, measured).
+// X3: error-compensated "3xTF32". Eight splitter warps (the four epilogue warps, idle during the main loop, plus four)
+// compute lo = x - trunc_tf32(x) of every staged operand tile into a mirror ring; the raw tile is left untouched, the tensor
+// core's own truncation of it IS hi. The MMA warp issues A.B into the main TMEM accumulator and A_lo.B + A.B_lo into a
+// second one. The dropped lo.lo term is a same-signed ~2^-22 fraction of every product, i.e. a 2e-7 relative scaling of the
+// result -- harmless; what does matter is the accumulate (see X3_CHAIN_KB below).
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue epi, int M,
@@ -331,7 +334,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t round = i / STAGES;
             mbar_wait(smem_u32(&full_bar[s]), round & 1);                 // the TMA tiles of this stage have landed
             const uint32_t off = (smem_base - smem_u32(smem_raw)) + s * STAGE_BYTES;
-            float4* src = reinterpret_cast<float4*>(smem_raw + off);
+            const float4* src = reinterpret_cast<const float4*>(smem_raw + off);
             float4* dst = reinterpret_cast<float4*>(smem_raw + off + LO_OFFSET);
             float4 x[PER];
 #pragma unroll
@@ -342,11 +345,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int u = 0; u < PER; ++u) {                               // elementwise: the swizzled layout carries over unchanged
                 const uint32_t v = t + u * SPLIT_THREADS;
-                if (v < STAGE_BYTES / 16) {
-                    const float4 h = make_float4(tf32_rn(x[u].x), tf32_rn(x[u].y), tf32_rn(x[u].z), tf32_rn(x[u].w));
-                    src[v] = h;
-                    dst[v] = make_float4(tf32_rn(x[u].x - h.x), tf32_rn(x[u].y - h.y), tf32_rn(x[u].z - h.z), tf32_rn(x[u].w - h.w));
-                }
+                if (v < STAGE_BYTES / 16)
+                    dst[v] = make_float4(tf32_lo(x[u].x), tf32_lo(x[u].y), tf32_lo(x[u].z), tf32_lo(x[u].w));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
