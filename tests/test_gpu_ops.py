@@ -35,6 +35,28 @@ def _f32(a):
     return np.asarray(a, dtype=np.float32).astype(np.float64)
 
 
+class Guarded:
+    """Output buffers carved out of a larger allocation with sentinel-filled guard bands on both sides (compute-sanitizer is
+    not available on the GPU pool): `check()` asserts that a kernel wrote nothing outside the tensors it was given."""
+    GUARD, SENTINEL = 256, 12345.0
+
+    def __init__(self, K):
+        self.K, self.bufs = K, []
+
+    def __call__(self, shape):
+        n = int(np.prod(shape))
+        flat = self.K.empty((n + 2 * self.GUARD,))
+        flat.fill_(self.SENTINEL)
+        self.bufs.append((flat, n))
+        return flat[self.GUARD:self.GUARD + n].view(*shape)     # 1 KB guard keeps the 16-byte alignment
+
+    def check(self):
+        self.K.B.synchronize()
+        for flat, n in self.bufs:
+            lo, hi = flat[:self.GUARD].cpu().numpy(), flat[self.GUARD + n:].cpu().numpy()
+            assert np.all(lo == self.SENTINEL) and np.all(hi == self.SENTINEL), "write outside an output buffer"
+
+
 ACTS = {"linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "leakyrelu": 4}
 
 
@@ -223,16 +245,18 @@ def test_conv2d_tcgen05_implicit_gemm(K, N, H, W, C, F, k, act, math, tol):
     assert K.ops.conv2d_ws_bytes(geom, math) >= K.ops.conv2d_ws_bytes(geom, 0)
     err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
     xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
-    ws = K.empty((max(K.ops.conv2d_ws_bytes(geom, math) // 4, 1),))
-    y = K.empty((N, oh, ow, F))
+    G = Guarded(K)
+    ws = G((max(K.ops.conv2d_ws_bytes(geom, math) // 4, 1),))     # also: the workspace the sizing call promises is enough
+    y = G((N, oh, ow, F))
     K.ops.conv2d_fwd(math, geom, xd, wd, bd, y, act, 0.0, ws)
     x64, w64 = x.astype(np.float64), w.astype(np.float64)
     ref = O.conv2d_fwd(x64, w64, b.astype(np.float64), (1, 1), "same")
     ref = np.maximum(ref, 0) if act else ref
     assert nrel(K.host(y), ref) < tol
     ss = K.ss(); K.ops.sumsq(ed, ss, 0)
-    dx, dw, db = K.empty(x.shape), K.empty(w.shape), K.empty((F,))
+    dx, dw, db = G(x.shape), G(w.shape), G((F,))
     K.ops.conv2d_bwd(math, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    G.check()
     rdx, rdw, rdb = O.conv2d_bwd(x64, w64, O.clip_l2(err.astype(np.float64)), (1, 1), "same")
     assert nrel(K.host(dx), rdx * (x > 0)) < tol
     assert nrel(K.host(dw), rdw) < tol
@@ -499,14 +523,16 @@ def test_dense_tf32x3_tcgen05(K, M, N, Kd):
     b = rng.normal(size=(N,)).astype(np.float32)
     err = rng.normal(size=(M, N)).astype(np.float32)
     xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
-    ws = K.empty((max(K.ops.dense_ws_bytes(M, N, Kd, 2) // 4, 1),))
-    y = K.empty((M, N))
+    G = Guarded(K)
+    ws = G((max(K.ops.dense_ws_bytes(M, N, Kd, 2) // 4, 1),))
+    y = G((M, N))
     K.ops.dense_fwd(2, xd, wd, bd, y, 1, 0.0, ws)
     x64, w64 = x.astype(np.float64), w.astype(np.float64)
     assert nrel(K.host(y), np.maximum(x64 @ w64 + b, 0)) < 1e-5
     ss = K.ss(); K.ops.sumsq(ed, ss, 0)
-    dx, dw, db = K.empty((M, Kd)), K.empty((Kd, N)), K.empty((N,))
+    dx, dw, db = G((M, Kd)), G((Kd, N)), G((N,))
     K.ops.dense_bwd(2, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    G.check()
     rdx, rdw, rdb = O.dense_bwd(x64, w64, O.clip_l2(err.astype(np.float64)))
     assert nrel(K.host(dx), rdx * (x > 0)) < 1e-5
     assert nrel(K.host(dw), rdw) < 1e-5
