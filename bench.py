@@ -290,8 +290,9 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": total_batch, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB device write outside the timed events)",
-                   "math": ("tf32: Dense GEMMs on tcgen05 kind::tf32 (rel 2e-3), conv/BN/pool/Adam fp32" if args.math == "tf32"
-                            else "fp32 FFMA everywhere (parity path, rel 1e-5)"),
+                   "math": {"tf32": "tf32: Dense GEMMs on tcgen05 kind::tf32 (rel 2e-3), conv/BN/pool/Adam fp32",
+                            "tf32x3": "tf32x3: Dense GEMMs on tcgen05 with hi/lo operand split (rel 1e-5), conv/BN/pool/Adam fp32",
+                            }.get(args.math, "fp32 FFMA everywhere (parity path, rel 1e-5)"),
                    "step": "one captured CUDA graph per step",
                    **({"data_parallel": "exact global-batch semantics: NCCL gradient sum + "
                        + ("one-shot NVLink peer-memory exchanges" if model._dp.comm.peer else "NCCL")
@@ -333,7 +334,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--math", default=os.environ.get("B200NN_MATH", "fp32"), choices=["fp32", "tf32", "tf32x3"],
-                    help="Dense contractions: fp32 = FFMA parity path (rel 1e-5); tf32 = tcgen05 tensor cores (rel 2e-3)")
+                    help="Dense contractions: fp32 = FFMA parity path (rel 1e-5); tf32 = tcgen05 tensor cores (rel 2e-3); "
+                         "tf32x3 = tcgen05 with error compensation (rel 1e-5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
