@@ -52,6 +52,8 @@ extern "C" {
 #define B200NN_LOSS_MSE 0
 #define B200NN_LOSS_BCE 1
 #define B200NN_LOSS_CCE 2
+#define B200NN_LOSS_MAE 3   /* losses.py:146-155 MeanAbsoluteError */
+#define B200NN_LOSS_HUBER 4 /* losses.py:158-180 Huber(delta) */
 
 /* GEMM math modes */
 #define B200NN_MATH_FP32 0 /* FFMA, fp32 accumulate: parity path (rel 1e-5)                    */
@@ -111,6 +113,11 @@ int b200nn_softmax_fwd(const float* x, float* p, int rows, int cols, void* strea
  *   (metrics.py:84-89, first-index tie break);  ss_out (nullable) += sum(err^2). */
 int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
                         double* ss_out, int rows, int cols, void* stream);
+/* The same with (a) `global_rows`: the rows of the WHOLE batch when this call sees one data-parallel shard of it —
+ * MeanSquaredError.derivative divides by y_true.size of the whole batch (losses.py:84); (b) `param`: Huber's delta
+ * (losses.py:158-176; MAE :146-155). SparseCategoricalCrossentropy (losses.py:123-143) is CCE on host-built one-hot rows. */
+int b200nn_loss_fwd_bwd_ex(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
+                           double* ss_out, int rows, int cols, long long global_rows, float param, void* stream);
 
 /* ---- Dense (layers.py:152-198) ------------------------------------------------------------- */
 /* y[M,N] = act(x[M,K] . w[K,N] + b[N])   layers.py:173 (+ the Activation Sequential.add appends).

@@ -11,19 +11,27 @@ import os
 __version__ = "0.1.0"
 __backend__ = "libb200nn (sm_100a CUDA via C ABI)"
 
-_MATH = os.environ.get("B200NN_MATH", "fp32").lower()
+_MATH = os.environ.get("B200NN_MATH", "tf32x3").lower()
+_MATH_VERSION = 0   # bumped by set_math: plans built under another mode are rebuilt (models.Sequential._plan)
 
 
 def set_math(mode: str) -> None:
-    """'fp32': FFMA contractions, parity with the reference within rel 1e-5 (default).
-    'tf32': tcgen05 tensor-core contractions (kind::tf32, fp32 accumulate), within rel 2e-3 per contraction.
-    'tf32x3': tcgen05 with error compensation (operands split hi/lo in shared memory, three MMAs per k-step): Dense
-    contractions on the tensor cores at fp32 accuracy."""
-    global _MATH
+    """'tf32x3' (default): every eligible Dense / Conv2D / Conv2DTranspose contraction runs on the tcgen05 tensor cores with
+    error compensation (hi/lo operand split, three MMAs per k-step) and stays within the FFMA path's rel 1e-5 of the
+    reference; contractions the tensor-core path does not cover (tiny or unaligned shapes) use the FFMA kernels.
+    'tf32': single-pass tcgen05 kind::tf32 (fp32 accumulate), within rel 2e-3 per contraction.
+    'fp32': FFMA contractions everywhere."""
+    global _MATH, _MATH_VERSION
     mode = mode.lower()
     if mode not in ("fp32", "tf32", "tf32x3"):
         raise ValueError("math mode must be 'fp32', 'tf32' or 'tf32x3'")
+    if mode != _MATH:
+        _MATH_VERSION += 1
     _MATH = mode
+
+
+def math_version() -> int:
+    return _MATH_VERSION
 
 
 def get_math() -> str:

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b200nn_sumsq": (c_int, [_P, c_ll, _P, _P]),
     "b200nn_softmax_fwd": (c_int, [_P, _P, c_int, c_int, _P]),
     "b200nn_loss_fwd_bwd": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "b200nn_loss_fwd_bwd_ex": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_ll, c_float, _P]),
     "b200nn_dense_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200nn_dense_ws_bytes_math": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200nn_dense_fwd": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P]),

@@ -14,7 +14,7 @@ from . import _backend as B
 from ._backend import ConvGeom, ConvTGeom, PoolGeom, check, lib, ptr, stream
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKYRELU = 0, 1, 2, 3, 4
-LOSS_MSE, LOSS_BCE, LOSS_CCE = 0, 1, 2
+LOSS_MSE, LOSS_BCE, LOSS_CCE, LOSS_MAE, LOSS_HUBER = 0, 1, 2, 3, 4
 MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
 
 
@@ -109,11 +109,12 @@ def softmax_fwd(x, p):
     check(lib().b200nn_softmax_fwd(ptr(x), ptr(p), x.shape[0], x.numel() // x.shape[0], stream()))
 
 
-def loss_fwd_bwd(loss, fused_pair, p, y, err, acc, ss, slot_out):
+def loss_fwd_bwd(loss, fused_pair, p, y, err, acc, ss, slot_out, world=1, param=1.0):
+    """`world`: data-parallel ranks sharing the batch (MSE's derivative divides by the GLOBAL element count); `param`: Huber delta."""
     _f32(p, y, err)
     rows = p.shape[0]
-    check(lib().b200nn_loss_fwd_bwd(loss, int(fused_pair), ptr(p), ptr(y), ptr(err), ptr(acc), _slot_ptr(ss, slot_out),
-                                    rows, p.numel() // rows, stream()))
+    check(lib().b200nn_loss_fwd_bwd_ex(loss, int(fused_pair), ptr(p), ptr(y), ptr(err), ptr(acc), _slot_ptr(ss, slot_out),
+                                       rows, p.numel() // rows, rows * int(world), float(param), stream()))
 
 
 # ---- Dense -------------------------------------------------------------------------------------------

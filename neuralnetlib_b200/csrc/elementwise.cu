@@ -129,15 +129,26 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
     for (int c = lane; c < cols; c += 32) pr[c] = expf(xr[c] - mx) / sum;
 }
 
-__device__ __forceinline__ float loss_term(int loss, float y, float p) {
+// `param`: Huber's delta (losses.py:158-176)
+__device__ __forceinline__ float loss_term(int loss, float y, float p, float param) {
     if (loss == B200NN_LOSS_MSE) return (y - p) * (y - p);
+    if (loss == B200NN_LOSS_MAE) return fabsf(y - p);                                   // losses.py:148
+    if (loss == B200NN_LOSS_HUBER) {                                                    // losses.py:163-168
+        const float e = fabsf(y - p);
+        return e <= param ? 0.5f * e * e : param * (e - 0.5f * param);
+    }
     const float pc = fminf(fmaxf(p, 1e-15f), 1.0f);  // 1 - 1e-15 rounds to 1 in fp32
     if (loss == B200NN_LOSS_CCE) return -y * logf(pc);
     const float q = fmaxf(1.0f - pc, 1.1102230246251565e-15f);  // fp64 value of 1-(1-1e-15)
     return -(y * logf(pc) + (1.0f - y) * logf(q));
 }
-__device__ __forceinline__ float loss_deriv(int loss, float y, float p, float inv_size) {
+__device__ __forceinline__ float loss_deriv(int loss, float y, float p, float inv_size, float param) {
     if (loss == B200NN_LOSS_MSE) return 2.0f * (p - y) * inv_size;
+    if (loss == B200NN_LOSS_MAE) return p > y ? 1.0f : -1.0f;                           // losses.py:151 (not divided by the size)
+    if (loss == B200NN_LOSS_HUBER) {                                                    // losses.py:170-172: sign as the reference has it
+        const float e = y - p;
+        return fabsf(e) <= param ? e : (e > 0.0f ? param : (e < 0.0f ? -param : 0.0f));
+    }
     const float pc = fminf(fmaxf(p, 1e-15f), 1.0f);
     if (loss == B200NN_LOSS_CCE) return -y / pc;
     const float q = fmaxf(1.0f - pc, 1.1102230246251565e-15f);
@@ -147,15 +158,18 @@ __device__ __forceinline__ float loss_deriv(int loss, float y, float p, float in
 // warp per row (cols > 1) or thread per element (cols == 1)
 __global__ void __launch_bounds__(256) loss_kernel(int loss, int fused_pair, const float* __restrict__ p,
                                                    const float* __restrict__ y, float* __restrict__ err,
-                                                   double* loss_acc, double* ss_out, int rows, int cols) {
+                                                   double* loss_acc, double* ss_out, int rows, int cols, double global_elems,
+                                                   float param) {
     __shared__ double scratch[32];
     float lsum = 0.0f, esq = 0.0f, correct = 0.0f;
-    const float inv_size = 1.0f / ((float)rows * (float)cols);
+    // MeanSquaredError.derivative divides by y_true.size of the WHOLE batch (losses.py:84): under data parallelism that is
+    // the global element count, not this rank's shard
+    const float inv_size = (float)(1.0 / global_elems);
     if (cols == 1) {
         for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
             const float pv = p[r], yv = y[r];
-            lsum += loss_term(loss, yv, pv);
-            const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size);
+            lsum += loss_term(loss, yv, pv, param);
+            const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size, param);
             if (err != nullptr) err[r] = e;
             esq += e * e;
             correct += ((pv >= 0.5f ? 1.0f : 0.0f) == yv) ? 1.0f : 0.0f;
@@ -170,8 +184,8 @@ __global__ void __launch_bounds__(256) loss_kernel(int loss, int fused_pair, con
             int ip = 0x7fffffff, iy = 0x7fffffff;
             for (int c = lane; c < cols; c += 32) {
                 const float pv = pr[c], yv = yr[c];
-                lsum += loss_term(loss, yv, pv);
-                const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size);
+                lsum += loss_term(loss, yv, pv, param);
+                const float e = fused_pair ? (pv - yv) : loss_deriv(loss, yv, pv, inv_size, param);
                 if (err != nullptr) err[(long long)r * cols + c] = e;
                 esq += e * e;
                 if (pv > bp) { bp = pv; ip = c; }  // strict > keeps the first index within a lane
@@ -566,16 +580,23 @@ int b200nn_softmax_fwd(const float* x, float* p, int rows, int cols, void* strea
     return B200NN_OK;
 }
 
-int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
-                        double* ss_out, int rows, int cols, void* stream) {
-    B200NN_REQUIRE(loss >= 0 && loss <= B200NN_LOSS_CCE, "loss: unknown kind %d", loss);
-    B200NN_REQUIRE(rows > 0 && cols > 0, "loss: bad shape %d x %d", rows, cols);
+int b200nn_loss_fwd_bwd_ex(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
+                           double* ss_out, int rows, int cols, long long global_rows, float param, void* stream) {
+    B200NN_REQUIRE(loss >= 0 && loss <= B200NN_LOSS_HUBER, "loss: unknown kind %d", loss);
+    B200NN_REQUIRE(rows > 0 && cols > 0 && global_rows >= rows, "loss: bad shape %d x %d (global rows %lld)", rows, cols, global_rows);
+    B200NN_REQUIRE(loss != B200NN_LOSS_HUBER || param > 0.0f, "loss: Huber needs delta > 0");
     long long threads_needed = cols == 1 ? rows : (long long)rows * 32;
     int blocks = (int)((threads_needed + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(loss, fused_pair, p, y, err, loss_acc, ss_out, rows, cols);
+    loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(loss, fused_pair, p, y, err, loss_acc, ss_out, rows, cols,
+                                                       (double)global_rows * (double)cols, param);
     B200NN_LAUNCH_CHECK("loss");
     return B200NN_OK;
+}
+
+int b200nn_loss_fwd_bwd(int loss, int fused_pair, const float* p, const float* y, float* err, double* loss_acc,
+                        double* ss_out, int rows, int cols, void* stream) {
+    return b200nn_loss_fwd_bwd_ex(loss, fused_pair, p, y, err, loss_acc, ss_out, rows, cols, rows, 1.0f, stream);
 }
 
 int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,

@@ -451,8 +451,9 @@ class Plan:
         fused = False
         if isinstance(last, Activation):
             name = type(last.activation_function).__name__
+            # models.py:200-210: the recognised pairs, and SparseCategoricalCrossentropy behind ANY last activation
             fused = (name == "Softmax" and isinstance(lf, CategoricalCrossentropy)) or \
-                    (name == "Sigmoid" and isinstance(lf, BinaryCrossentropy))
+                    (name == "Sigmoid" and isinstance(lf, BinaryCrossentropy)) or bool(getattr(lf, "_sparse", False))
         return lf._kind, fused
 
     def _ensure_targets(self):
@@ -493,7 +494,9 @@ class Plan:
                     head_state = self.state[self.layers.index(head["layer"])]
                     head_state["dw_partial"] = dwp
             else:
-                self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0), "loss_fwd_bwd", (pred, y_in, err0))
+                world, lparam = self.world, float(getattr(model.loss_function, "_param", 1.0))
+                self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, err0, acc, ss, s0, world, lparam), "loss_fwd_bwd",
+                          (pred, y_in, err0))
             if self.dp is not None:
                 self.dp.flatten_grads(self.layers)
             if self.defer_clips:
@@ -527,7 +530,8 @@ class Plan:
             lk, fused = self._loss_kind()
             pred, y_in, acc = self.pred, self.y_in, self.acc
             self.emit(lambda: ops.step_begin(None, acc, None, 0), "step_begin")
-            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, None, acc, None, None), "loss_fwd_bwd", (pred, y_in))
+            lparam = float(getattr(model.loss_function, "_param", 1.0))
+            self.emit(lambda: ops.loss_fwd_bwd(lk, fused, pred, y_in, None, acc, None, None, 1, lparam), "loss_fwd_bwd", (pred, y_in))
         elif kind in ("backward", "backward_gan", "backward_compute_only"):
             gan, compute_only = kind == "backward_gan", kind == "backward_compute_only"
             opt = model.optimizer

@@ -108,6 +108,10 @@ class Sequential(BaseModel):
         self._last_plan = None
 
     def _plan(self, batch_shape, training: bool) -> Plan:
+        from . import math_version
+        if getattr(self, "_plans_math", None) != math_version():   # set_math() after the first step: the mode is frozen into a plan
+            self._drop_plans()
+            self._plans_math = math_version()
         key = (tuple(int(s) for s in batch_shape), bool(training))
         p = self._plans.get(key)
         if p is None:
@@ -183,7 +187,16 @@ class Sequential(BaseModel):
         cols = plan.pred.numel() // rows
         if after_train:
             rows *= plan.world   # data parallel: a train step leaves the RANK SUM of the numerators in plan.acc
-        return rows if isinstance(self.loss_function, CategoricalCrossentropy) else rows * cols
+        by_rows = isinstance(self.loss_function, CategoricalCrossentropy) or getattr(self.loss_function, "_sparse", False)
+        return rows if by_rows else rows * cols
+
+    def _dense_targets(self, y, n_out):
+        """SparseCategoricalCrossentropy takes integer labels (losses.py:123-143): one-hot rows for the device loss kernel."""
+        if getattr(self.loss_function, "_sparse", False):
+            y = np.asarray(y)
+            if y.ndim == 1 or (y.ndim == 2 and y.shape[1] == 1 and n_out > 1):
+                return self.loss_function.one_hot(y, n_out)
+        return y
 
     def _train_step(self, x_batch, y_batch) -> Plan:
         """One fused step on the device; does not synchronise (the loss numerator stays in plan.acc[0])."""
@@ -191,7 +204,7 @@ class Sequential(BaseModel):
         plan = self._plan(shape, True)
         prog = plan.program("train")
         plan.set_input(x_batch)
-        plan.set_target(y_batch)   # same element count as the prediction buffer: uploaded flat
+        plan.set_target(self._dense_targets(y_batch, plan.pred.shape[-1]))   # same element count as the prediction buffer: uploaded flat
         prog.run()
         self._last_plan, self._last_rows, self._pred_host = plan, shape[0], None
         return plan
@@ -255,6 +268,10 @@ class Sequential(BaseModel):
         dp = self._dp
         if dp is not None:
             from .parallel import shard_rows   # every rank holds the full dataset and trains on its rows of each batch
+        y_metric = y_train.reshape(N, -1) if y_train.ndim > 1 else y_train.reshape(N, 1)   # what the metrics compare against
+        if getattr(self.loss_function, "_sparse", False):   # integer labels -> one-hot rows for the device loss kernel
+            n_out = self._plan((min(bs, N),) + x_train.shape[1:], True).pred.shape[-1]
+            y_train = np.asarray(self._dense_targets(y_train, n_out))
         y2 = y_train.reshape(N, -1) if y_train.ndim > 1 else y_train.reshape(N, 1)
         resident = (x_train.size + y2.size) * 4 <= _RESIDENT_DATASET_BYTES
         if resident:
@@ -270,7 +287,7 @@ class Sequential(BaseModel):
                     cb.on_epoch_begin(epoch, epoch_logs)
                 start = time.time()
                 perm = shuffle_indices(N, seed)                      # models.py:386-389: same seed => same permutation
-                y_shuf = y2[perm] if keep_pred else None
+                y_shuf = y_metric[perm] if keep_pred else None
                 perm_dev = B.to_device(perm, dtype=torch.int64) if resident else None
                 pred_all = None
                 running = 0.0
@@ -367,7 +384,7 @@ class Sequential(BaseModel):
             xb, yb = x_test[i:i + batch_size], y_test[i:i + batch_size]
             out = self._forward_dev(xb, training=False)
             plan = self._last_plan
-            plan.set_target(yb.reshape(tuple(plan.pred.shape)))
+            plan.set_target(np.asarray(self._dense_targets(yb, plan.pred.shape[-1])).reshape(tuple(plan.pred.shape)))
             plan.program("loss").run()
             total += float(plan.acc[0].item()) / self._loss_denominator(plan)
             preds.append(B.to_host(out))

@@ -26,3 +26,16 @@ def golden():
             cache[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
         return cache[name]
     return load
+
+
+@pytest.fixture(autouse=True)
+def _restore_math_mode():
+    """Tests that switch the math mode (set_math) leave the package default behind them."""
+    try:
+        import neuralnetlib_b200 as nn
+    except Exception:   # noqa: BLE001
+        yield
+        return
+    prev = nn.get_math()
+    yield
+    nn.set_math(prev)

@@ -82,5 +82,7 @@ class ShardedOracle(O.OracleSequential):
         total = float(self.allreduce(np.array([local]))[0])
         denom = rows * self.world if self.loss == "cce" else rows * self.world * p.shape[1]
         err = O.loss_derivative(self.loss, y, p.copy())
+        if self.loss == "mse":
+            err = err / self.world   # losses.py:84 divides by y_true.size of the WHOLE batch, not of this rank's shard
         self.backward(err)
         return total / denom

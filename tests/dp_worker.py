@@ -31,6 +31,13 @@ def build(kind):
         m.add(L.Input(784)); m.add(L.Dense(128, activation="relu")); m.add(L.Dense(64, activation="relu"))
         m.add(L.Dense(10, activation="softmax"))
         specs, shp = O.config_specs(1)
+    elif kind == "cfg1mse":   # a non-fused (Tanh, MSE) pair: the loss derivative divides by the GLOBAL element count (losses.py:84)
+        m.add(L.Input(784)); m.add(L.Dense(128, activation="relu")); m.add(L.Dense(64, activation="relu"))
+        m.add(L.Dense(10, activation="tanh"))
+        specs, shp = O.config_specs(1)
+        specs = specs[:-1] + [{"type": "act", "fn": "tanh"}]
+        m.compile(loss_function="mse", optimizer=Opt.Adam())
+        return m, specs, shp
     elif kind == "cfg2":
         m.add(L.Input((28, 28, 1))); m.add(L.Conv2D(32, 3, padding="same", activation="relu")); m.add(L.BatchNormalization())
         m.add(L.MaxPooling2D(2)); m.add(L.Flatten()); m.add(L.Dense(64, activation="relu")); m.add(L.Dense(10, activation="softmax"))
@@ -52,7 +59,7 @@ def run_case(kind, batch, steps, rank, world, comm):
     x = rng.random((batch,) + tuple(shp)).astype(np.float32)
     y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
     lo, hi = P.shard_rows(batch, world, rank)
-    ref = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    ref = O.OracleSequential(specs, "mse" if kind.endswith("mse") else "cce", O.OracleAdam(), seed=42)
     mine = [(i, l) for i, l in enumerate(m.layers) if hasattr(l, "weights")]
     worst = 0.0
     for s in range(steps):
@@ -127,7 +134,7 @@ def main():
     if want_peer:
         assert comm.peer, "CUDA IPC peer mapping failed"
     out = {}
-    for kind, batch, steps in (("cfg1", 32 * world, 3), ("cfg2", 32 * world, 3), ("bn2d", 16 * world, 3)):
+    for kind, batch, steps in (("cfg1", 32 * world, 3), ("cfg1mse", 32 * world, 2), ("cfg2", 32 * world, 3), ("bn2d", 16 * world, 3)):
         out[kind] = run_case(kind, batch, steps, rank, world, comm)
         print(f"[rank {rank}] {kind} ok, timeouts so far {comm.timeouts()}", flush=True)
     run_fit(rank, world, comm)

@@ -88,12 +88,14 @@ def _allreduce_np(a):
     return t.numpy().reshape(np.shape(a))
 
 
-def _sharded_step(rank, world, cfg, batch, steps):
+def _sharded_step(rank, world, cfg, batch, steps, loss="cce"):
     x, y = O.synthetic_batch(cfg, batch)
     specs, _ = O.config_specs(cfg)
-    full = O.OracleSequential(specs, "cce", O.OracleAdam(), seed=42)
+    if loss == "mse":   # a non-fused (activation, loss) pair: the error entering backward is LossFunction.derivative itself
+        specs = specs[:-1] + [{"type": "act", "fn": "tanh"}]
+    full = O.OracleSequential(specs, loss, O.OracleAdam(), seed=42)
     lo, hi = P.shard_rows(batch, world, rank)
-    mine = ShardedOracle(specs, "cce", O.OracleAdam(), 42, _allreduce_np, world)
+    mine = ShardedOracle(specs, loss, O.OracleAdam(), 42, _allreduce_np, world)
     for s in range(steps):
         lf = full.train_on_batch(x, y)
         lm = mine.train_on_batch(x[lo:hi], y[lo:hi])
@@ -113,3 +115,9 @@ def test_sharded_schedule_reproduces_global_batch(cfg, batch, steps):
     """SUM of gradients (Q4), global clip norms (Q2), global BatchNorm moments (Q5) and backward reductions across two
     ranks == the single-process oracle on the whole batch, step after step (Adam state included)."""
     _spawn(_sharded_step, 2, cfg, batch, steps)
+
+
+def test_sharded_schedule_mse_uses_global_size():
+    """MeanSquaredError.derivative divides by the element count of the WHOLE batch (losses.py:84): a rank that divides by its
+    shard's size doubles every gradient on two ranks."""
+    _spawn(_sharded_step, 2, 1, 32, 2, "mse")

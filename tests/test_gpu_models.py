@@ -16,6 +16,15 @@ pytestmark = pytest.mark.gpu
 TOL = 3e-5   # steps >= 1 of the golden traces run without teacher forcing: fp32 rounding of step 0 propagates through Adam
 
 
+@pytest.fixture(autouse=True, params=["tf32x3", "fp32"])
+def math_mode(request):
+    """Every model-level parity test runs under the package default (tf32x3: eligible contractions on tcgen05 with error
+    compensation) AND under fp32 (FFMA everywhere): both must meet the same rel-1e-5 bar."""
+    import neuralnetlib_b200 as nn
+    nn.set_math(request.param)
+    return request.param
+
+
 def _nn():
     from neuralnetlib_b200 import layers, models, optimizers
     return layers, models, optimizers
