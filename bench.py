@@ -412,7 +412,7 @@ def run_leg(cfg, math, T, K, W, world, rank, peaks, tf32_peak, clock_sampler):
                 "e2e": {"value": gb / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 8, "last_loss": loss},
                 "kernel_breakdown": {"columns": ["op", "us (eager upper bound)", "io bytes", "GB/s"], "rows": breakdown[:10]}})
-    roof = {"step_gflop": fl / 1e9, "achieved_tflops": tfl * world / world, "tf32_peak_tflops": tf32_peak,
+    roof = {"step_gflop": fl / 1e9, "achieved_tflops": tfl / world, "tf32_peak_tflops": tf32_peak,
             "frac_of_tf32_peak": tfl / world / tf32_peak}
     if cfg in BYTES_PER_SAMPLE:
         by = BYTES_PER_SAMPLE[cfg] * gb + PARAMS[cfg] * 28 * world
@@ -452,8 +452,9 @@ def gemm_microbench(T, tf32_peak, maths=("tf32", "tf32x3")):
     def rnd(*shape):
         return (torch.rand(*shape, generator=g) - 0.5).to(dev)
 
-    def timeit(fn, reps=5):
-        fn(); fn()
+    def timeit(fn, reps=int(os.environ.get("B200NN_PROBE_REPS", "5"))):
+        if reps > 1:
+            fn(); fn()
         ms, _ = T.time_steps(fn, reps)
         return ms
 
@@ -598,7 +599,7 @@ def run_b200(args):
                    **({"data_parallel": dp_note} if world > 1 else {})},
         "e2e": {"value": total_batch / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(x.nbytes + y.nbytes), "d2h_bytes_per_step": 8, "last_loss": loss},
-        "gpu_launches": int(launches_eager_step * 2 * K),
+        "gpu_launches": int(launches_eager_step * K),
         "kernels_per_step": int(launches_eager_step),
         "roofline": {"bound": "fp32 issue (compared against the HBM roofline of a per-layer implementation)" if issue_bound else "hbm",
                      "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -56,16 +56,30 @@ def headers():
     return sorted(hs)
 
 
+def _deps(src):
+    """The source plus the local headers it includes, transitively (`#include "x"` relative to csrc/)."""
+    import re
+    seen, todo = set(), [src]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        with open(f) as fh:
+            for inc in re.findall(r'^\s*#include\s+"([^"]+)"', fh.read(), flags=re.M):
+                todo.append(os.path.normpath(os.path.join(os.path.dirname(f), inc)))
+    return sorted(seen)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
-    hdrs = headers()
     jobs, objs = [], []
     for src in sources():
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         stamp = obj + ".sha"
-        digest = _hash([src] + hdrs)
+        digest = _hash(_deps(src))
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
             continue

@@ -8,88 +8,12 @@
 //
 // Tile: 64x64x16, 256 threads, 4x4 micro-tile, register prefetch of the next k-slab.
 #include "common.cuh"
+#include "epilogue.cuh"
+#include "gemm_tc_api.cuh"
 
 namespace b200nn {
 
 constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
-
-// ------------------------------------------------------------------------------------------------
-// epilogue
-// ------------------------------------------------------------------------------------------------
-struct Epilogue {
-    float* out;                // out[row * ldo + n]
-    long long ldo;
-    const float* bias;         // per n, nullable
-    int act;                   // forward activation applied after bias
-    float alpha;
-    const double* ss;          // lazy clip multiplier applied to the accumulator (linear ops)
-    uint64_t chain;
-    const float* mask_y;       // preceding activation's OUTPUT (same indexing as out), nullable
-    int mask_act;
-    float mask_alpha;
-    double* ss0;               // += sum(v^2) before the mask
-    double* ss1;               // += sum(v^2) after the mask
-    // weight-gradient row handling: GEMM rows are taps in (ky,kx,c) order (+ an optional trailing
-    // "ones" row that carries db); row_mode 1 maps tap rows to the reference's (c,ky,kx) flat order.
-    int row_mode;              // 0 plain, 1 conv-weight permute
-    int kh, kw, C;
-    int n_rows;                // number of real rows (rows >= n_rows go to db)
-    float* db;                 // nullable
-};
-
-struct EpiState {
-    float scale;
-    float a0, a1;
-};
-
-__device__ __forceinline__ void epi_begin(const Epilogue& e, EpiState& st) {
-    st.scale = chain_scale(e.ss, e.chain);
-    st.a0 = 0.0f;
-    st.a1 = 0.0f;
-}
-
-__device__ __forceinline__ void epi_store(const Epilogue& e, EpiState& st, int m, int n, float v) {
-    v *= st.scale;
-    if (m >= e.n_rows) {  // ones row -> db
-        if (e.db != nullptr) e.db[n] = v;
-        return;
-    }
-    long long row = m;
-    if (e.row_mode == 1) {
-        const int c = m % e.C;
-        const int t = m / e.C;
-        const int kx = t % e.kw, ky = t / e.kw;
-        row = ((long long)c * e.kh + ky) * e.kw + kx;
-    }
-    if (e.bias != nullptr) v += e.bias[n];
-    v = act_apply(e.act, v, e.alpha);
-    const long long idx = row * e.ldo + n;
-    st.a0 += v * v;
-    if (e.mask_y != nullptr) {
-        v *= act_grad_from_y(e.mask_act, e.mask_y[idx], e.mask_alpha);
-        st.a1 += v * v;
-    }
-    e.out[idx] = v;
-}
-
-// same as epi_store for the plain row mode, with the activation-backward mask value already loaded by the caller
-// (lets the caller batch the mask loads of several rows ahead of their use)
-__device__ __forceinline__ void epi_store_premask(const Epilogue& e, EpiState& st, int m, int n, float v, float mask_val) {
-    v *= st.scale;
-    if (e.bias != nullptr) v += e.bias[n];
-    v = act_apply(e.act, v, e.alpha);
-    st.a0 += v * v;
-    if (e.mask_y != nullptr) {
-        v *= act_grad_from_y(e.mask_act, mask_val, e.mask_alpha);
-        st.a1 += v * v;
-    }
-    e.out[(long long)m * e.ldo + n] = v;
-}
-
-__device__ __forceinline__ void epi_finish(const Epilogue& e, EpiState& st, double* scratch) {
-    if (e.ss0 != nullptr) block_accumulate(st.a0, e.ss0, scratch);
-    if (e.ss1 != nullptr) block_accumulate(st.a1, e.ss1, scratch);
-}
 
 // ------------------------------------------------------------------------------------------------
 // operand functors. A(m,k): row(m), col(k), fetch(row, col). B(k,n): row(k), col(n), fetch(row, col).
@@ -503,7 +427,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float* __
     epi_finish(epi, st, scratch);
 }
 
-static int launch_splitk_reduce(const float* ws, int splits, int M, int N, const Epilogue& epi, cudaStream_t st) {
+int launch_splitk_reduce(const float* ws, int splits, int M, int N, const Epilogue& epi, cudaStream_t st) {
     const long long total = (long long)M * N;
     if (total <= 32768 && splits >= 16) {
         splitk_reduce_wide_kernel<<<(int)((total + 31) / 32), 256, 0, st>>>(ws, splits, M, N, epi);
@@ -1000,7 +924,6 @@ static size_t smalln_ws_bytes(int M, int N, int K) { return (size_t)smalln_chunk
 
 }  // namespace b200nn
 #include "dense_skinny.cuh"   // needs Epilogue / launch_splitk_reduce; lives in b200nn::skinny
-#include "gemm_tcgen05.cuh"   // needs Epilogue / launch_splitk_reduce; lives in b200nn::tc
 namespace b200nn {
 
 // ------------------------------------------------------------------------------------------------
@@ -1020,14 +943,6 @@ static int choose_splits(long long M, long long N, long long K) {
 static size_t ws_bytes_for(long long M, long long N, long long K) {
     const int s = choose_splits(M, N, K);
     return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
-}
-
-static Epilogue plain_epilogue(float* out, long long ldo, int n_rows) {
-    Epilogue e;
-    e.out = out; e.ldo = ldo; e.bias = nullptr; e.act = B200NN_ACT_NONE; e.alpha = 0.f;
-    e.ss = nullptr; e.chain = 0; e.mask_y = nullptr; e.mask_act = B200NN_ACT_NONE; e.mask_alpha = 0.f;
-    e.ss0 = nullptr; e.ss1 = nullptr; e.row_mode = 0; e.kh = e.kw = e.C = 1; e.n_rows = n_rows; e.db = nullptr;
-    return e;
 }
 
 template <class AF, class BF>
@@ -1055,6 +970,21 @@ static int check_act(const char* who, int act, float alpha) {
     return B200NN_OK;
 }
 
+// the tensor-core contraction: the persistent CTA-pair kernel (gemm_tc2.cuh) unless B200NN_TC2=0 selects the first-generation one
+static int tc_gemm_any(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi,
+                       int M, int N, int K, float* ws, cudaStream_t st, bool x3) {
+    if (tcapi::tc2_enabled())
+        return x3 ? tcapi::gemm2_x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st)
+                  : tcapi::gemm2_plain(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st);
+    return tcapi::gemm1(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st, x3);
+}
+// which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
+static int tc_conv_any(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws,
+                       cudaStream_t st, bool x3) {
+    if (tcapi::tc2_enabled()) return x3 ? tcapi::conv2_x3(which, g, a, b, epi, ws, st) : tcapi::conv2_plain(which, g, a, b, epi, ws, st);
+    return tcapi::conv1(which, g, a, b, epi, ws, st, x3);
+}
+
 static void dx_epilogue(Epilogue& e, const double* ss, uint64_t chain, const float* mask_y, int prev_act,
                         float prev_alpha, double* ss0, double* ss1) {
     e.ss = ss; e.chain = chain; e.ss0 = ss0;
@@ -1074,9 +1004,12 @@ size_t b200nn_dense_ws_bytes_math(int math, int M, int N, int K) {
     size_t r = b200nn_dense_ws_bytes(M, N, K);
     if (math == B200NN_MATH_TF32X3) {             // chain-limited split-K partials of the compensated tensor-core path
         auto mx = [&](size_t v) { if (v > r) r = v; };
-        mx(tc::tc_ws_bytes(M, N, K, true));
-        mx(tc::tc_ws_bytes(M, K, N, true));
-        mx(tc::tc_ws_bytes(K, N, M, true));
+        mx(tcapi::ws1(M, N, K, true));
+        mx(tcapi::ws1(M, K, N, true));
+        mx(tcapi::ws1(K, N, M, true));
+        mx(tcapi::ws2(M, N, K, true));
+        mx(tcapi::ws2(M, K, N, true));
+        mx(tcapi::ws2(K, N, M, true));
     }
     return r;
 }
@@ -1087,9 +1020,12 @@ size_t b200nn_dense_ws_bytes(int M, int N, int K) {
     mx(ws_bytes_for(M, N, K));                    // fwd  [M,N] over K
     mx(ws_bytes_for(M, K, N));                    // dx   [M,K] over N
     mx(ws_bytes_for((long long)K + 1, N, M));     // dw+db [K+1,N] over M
-    mx(tc::tc_ws_bytes(M, N, K));                 // the same three on the tcgen05 path
-    mx(tc::tc_ws_bytes(M, K, N));
-    mx(tc::tc_ws_bytes(K, N, M));
+    mx(tcapi::ws1(M, N, K));                 // the same three on the tcgen05 path
+    mx(tcapi::ws1(M, K, N));
+    mx(tcapi::ws1(K, N, M));
+    mx(tcapi::ws2(M, N, K, false));
+    mx(tcapi::ws2(M, K, N, false));
+    mx(tcapi::ws2(K, N, M, false));
     mx((size_t)kNumSMs * 2 * N * sizeof(float));  // column-sum partials for db on the tcgen05 path
     if (N <= SMALLN_MAX) mx(smalln_ws_bytes(M, N, K));
     if (M <= skinny::MAXM && N <= skinny::MAXN) mx(skinny::fwd_ws_bytes(M, N, K));
@@ -1098,7 +1034,7 @@ size_t b200nn_dense_ws_bytes(int M, int N, int K) {
 
 static bool dense_tc_ok(const float* x, const float* w, const float* other, int M, int N, int K) {
     // TMA needs 16-byte aligned bases and row pitches; tiny problems stay on the FFMA kernel
-    return tc::tma_ok(x, K) && tc::tma_ok(w, N) && tc::tma_ok(other, N) && (long long)M * N * K >= (1LL << 18);
+    return tcapi::tma_ok(x, K) && tcapi::tma_ok(w, N) && tcapi::tma_ok(other, N) && (long long)M * N * K >= (1LL << 18);
 }
 
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
@@ -1118,7 +1054,7 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
     if (math == B200NN_MATH_FP32 && ws != nullptr && skinny::applicable(x, w, y, M, N, K))
         return skinny::launch_fwd(x, w, e, M, N, K, ws, as_stream(stream));
     if (math != B200NN_MATH_FP32 && dense_tc_ok(x, w, y, M, N, K))
-        return tc::tc_gemm(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
+        return tc_gemm_any(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
     RowMajorA af{x, K, M, K};
     RowMajorB bf{w, N, K, N};
     return launch_gemm("dense_fwd", af, bf, e, M, N, K, ws, as_stream(stream));
@@ -1213,7 +1149,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         }
         Epilogue e = plain_epilogue(dw, N, K);   // dw[K,N] = x^T . err : both operands MN-major, no transposed copies
         e.ss = ss; e.chain = chain;
-        if (int rc = tc::tc_gemm(x, K, true, err, N, true, e, K, N, M, ws, st, x3)) return rc;
+        if (int rc = tc_gemm_any(x, K, true, err, N, true, e, K, N, M, ws, st, x3)) return rc;
     } else if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
         ColMajorOnesA af{x, K, K, M, db != nullptr ? 1 : 0};
         RowMajorB bf{err, N, M, N};
@@ -1225,7 +1161,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         Epilogue e = plain_epilogue(dx, K, M);
         dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
         if (use_tc) {
-            if (int rc = tc::tc_gemm(err, N, false, w, N, false, e, M, K, N, ws, st, x3)) return rc;
+            if (int rc = tc_gemm_any(err, N, false, w, N, false, e, M, K, N, ws, st, x3)) return rc;
         } else {
             RowMajorA af{err, N, M, N};
             ColMajorB bf{w, N, N, K};
@@ -1253,8 +1189,10 @@ static int check_conv_geom(const char* who, const b200nn_conv_geom* g) {
 size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g);
 size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g) {
     size_t r = b200nn_conv2d_ws_bytes(g);
-    if (math != B200NN_MATH_FP32 && tc::conv_tc_ok(g, nullptr, nullptr, nullptr)) {
-        const size_t t = tc::tc_conv_ws_bytes(g, math == B200NN_MATH_TF32X3);
+    if (math != B200NN_MATH_FP32 && tcapi::conv_ok(g, nullptr, nullptr, nullptr)) {
+        size_t t = tcapi::conv_ws1(g, math == B200NN_MATH_TF32X3);
+        const size_t t2 = tcapi::conv_ws2(g, math == B200NN_MATH_TF32X3);
+        t = t > t2 ? t : t2;
         const size_t d = (size_t)kNumSMs * 2 * g->F * sizeof(float);   // column-sum partials for db
         r = r > t ? r : t;
         r = r > d ? r : d;
@@ -1291,10 +1229,10 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
     if (int rc = check_conv_geom("conv2d_fwd", g)) return rc;
     if (int rc = check_act("conv2d_fwd", act, alpha)) return rc;
     const int M = g->N * g->OH * g->OW, K = g->kh * g->kw * g->C;
-    if (math != B200NN_MATH_FP32 && tc::conv_tc_ok(g, x, w, y)) {   // implicit GEMM on tcgen05, operands fetched by TMA
+    if (math != B200NN_MATH_FP32 && tcapi::conv_ok(g, x, w, y)) {   // implicit GEMM on tcgen05, operands fetched by TMA
         Epilogue e = plain_epilogue(y, g->F, M);
         e.bias = b; e.act = act; e.alpha = alpha;
-        return tc::tc_conv_fwd(g, x, w, e, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
+        return tc_conv_any(1, g, x, w, e, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
     }
     if (smallk_fwd_ok(g) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
         long long blocks = ((long long)M + 127) / 128;
@@ -1322,7 +1260,7 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
     cudaStream_t st = as_stream(stream);
     const int Mo = g->N * g->OH * g->OW, Mi = g->N * g->H * g->W;
     const int Kf = g->kh * g->kw * g->C, Kd = g->kh * g->kw * g->F;
-    if (math != B200NN_MATH_FP32 && ws != nullptr && tc::conv_tc_ok(g, x, w, err) &&
+    if (math != B200NN_MATH_FP32 && ws != nullptr && tcapi::conv_ok(g, x, w, err) &&
         ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
         const bool x3 = math == B200NN_MATH_TF32X3;
         if (dw != nullptr) {
@@ -1337,12 +1275,12 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
             Epilogue e = plain_epilogue(dw, g->F, Kf);
             e.ss = ss; e.chain = chain;
             e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
-            if (int rc = tc::tc_conv_wgrad(g, x, err, e, ws, st, x3)) return rc;
+            if (int rc = tc_conv_any(3, g, x, err, e, ws, st, x3)) return rc;
         }
         if (dx != nullptr) {
             Epilogue e = plain_epilogue(dx, g->C, Mi);
             dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
-            if (int rc = tc::tc_conv_dgrad(g, err, w, e, ws, st, x3)) return rc;
+            if (int rc = tc_conv_any(2, g, err, w, e, ws, st, x3)) return rc;
         }
         return B200NN_OK;
     }

@@ -1,0 +1,33 @@
+// gemm_tc_api.cuh — host entry points of the tcgen05 contraction kernels, each generation / math mode in its own translation
+// unit (gemm_tc1.cu: first-generation one-tile-per-CTA kernel; gemm_tc2.cu / gemm_tc2_x3.cu: persistent CTA-pair kernel).
+#pragma once
+#include "epilogue.cuh"
+
+namespace b200nn {
+namespace tcapi {
+
+bool tc2_enabled();   // B200NN_TC2=0 selects the first generation everywhere
+// can this operand be described by a TMA map? (16-byte aligned base and row pitch)
+bool tma_ok(const float* base, long long ld);
+// implicit-GEMM convolution eligibility (stride 1, 'same', odd kernel, power-of-two image, channel counts multiples of 32)
+bool conv_ok(const b200nn_conv_geom* g, const void* p0, const void* p1, const void* p2);
+
+// D[M,N] = A.B ; a_mn: A stored [K][M] (ld = lda) else [M][K]; b_mn: B stored [K][N] else [N][K]
+int gemm1(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
+          int K, float* ws, cudaStream_t st, bool x3);
+int gemm2_plain(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M,
+                int N, int K, float* ws, cudaStream_t st);
+int gemm2_x3(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
+             int K, float* ws, cudaStream_t st);
+// which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
+int conv1(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws, cudaStream_t st, bool x3);
+int conv2_plain(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws, cudaStream_t st);
+int conv2_x3(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws, cudaStream_t st);
+// split-K workspace bytes
+size_t ws1(long long M, long long N, long long K, bool x3 = false);
+size_t ws2(long long M, long long N, long long K, bool x3 = false);
+size_t conv_ws1(const b200nn_conv_geom* g, bool x3);
+size_t conv_ws2(const b200nn_conv_geom* g, bool x3);
+
+}  // namespace tcapi
+}  // namespace b200nn

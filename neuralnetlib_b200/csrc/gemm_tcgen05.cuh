@@ -43,14 +43,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Bounded wait: a pipeline that has not advanced for 4 s of wall time is a protocol bug or a lost peer; trapping turns a
+// device hang into a CUDA error the host sees at its next synchronisation.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -556,10 +565,12 @@ static int tc_launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const 
                             const TcPlan& p, float* ws, cudaStream_t st, const ConvTma& cv) {
     constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + BN * 128) * (X3 ? 2 : 1) + 1024;
     auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN, X3>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // per device (one template instance per kernel variant)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         B200NN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev & 63] = true;
     }
     const dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, p.splits);
     kern<<<grid, X3 ? NUM_THREADS_X3 : NUM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, p.kb_per_split, p.splits > 1 ? ws : nullptr, cv);
