@@ -294,6 +294,17 @@ int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, do
                       const long long* t_counter, const int* block_map, int total_blocks, const double* ss, void* stream);
 int b200nn_sgd_multi(const b200nn_param* params, int n_params, double* gss, const double* hyper,
                      const int* block_map, int total_blocks, const double* ss, void* stream);
+/* The other update rules of optimizers.py on the same descriptors: Adam with its own clip_norm / clip_value (:190-202),
+ * Momentum (:63-111; velocity in `m`), RMSprop (:114-164; squared-gradient average in `v`), AdaBelief (:286-402; `v` = s),
+ * RAdam (:405-523). hyper is a DEVICE float64[6] {lr, beta1 | momentum | rho, beta2, eps, clip_norm, clip_value} (clip_* <= 0:
+ * off); t_counter as for b200nn_adam_multi (NULL for Momentum / RMSprop, which keep no step count). */
+#define B200NN_OPT_ADAM 0
+#define B200NN_OPT_MOMENTUM 1
+#define B200NN_OPT_RMSPROP 2
+#define B200NN_OPT_ADABELIEF 3
+#define B200NN_OPT_RADAM 4
+int b200nn_opt_multi(int kind, const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
+                     const long long* t_counter, const int* block_map, int total_blocks, const double* ss, void* stream);
 
 /* ---- data parallelism: one process per GPU on one NVLink/NVSwitch box -----------------------
  * The reference is single-process; under a batch shard per GPU its batch-global quantities become sums over ranks:

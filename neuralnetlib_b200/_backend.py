@@ -99,6 +99,7 @@ _SIGNATURES = {
     "b200nn_convblock_wgrad_reduce": (c_int, [C.POINTER(ConvGeom), _P, _P, c_u64, _P, _P, _P]),
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P]),
+    "b200nn_opt_multi": (c_int, [c_int, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     # data parallelism (csrc/comm.cu) and the split BatchNorm kernels
     "b200nn_comm_load_nccl": (c_int, [C.c_char_p]),
     "b200nn_comm_nccl_version": (c_int, []),

@@ -377,6 +377,15 @@ def adam_multi(plan: OptPlan, hyper, t_counter, on_stream=None):
                                   ptr(plan.block_map), plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))
 
 
+OPT_ADAM, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADABELIEF, OPT_RADAM = 0, 1, 2, 3, 4
+
+
+def opt_multi(kind, plan: OptPlan, hyper, t_counter, on_stream=None):
+    """hyper: device float64[6] {lr, beta1 | momentum | rho, beta2, eps, clip_norm, clip_value}."""
+    check(lib().b200nn_opt_multi(int(kind), ptr(plan.desc), plan.n_params, plan.n_layers, ptr(plan.gss), ptr(hyper), ptr(t_counter),
+                                 ptr(plan.block_map), plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))
+
+
 def sgd_multi(plan: OptPlan, hyper, on_stream=None):
     check(lib().b200nn_sgd_multi(ptr(plan.desc), plan.n_params, ptr(plan.gss), ptr(hyper), ptr(plan.block_map),
                                  plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))

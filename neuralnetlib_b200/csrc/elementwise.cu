@@ -434,6 +434,99 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const b200nn_param* __re
     for (long long i = base + threadIdx.x; i < end; i += 256) P.p[i] -= scale * P.g[i];  // optimizers.py:48
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The remaining update rules of optimizers.py on the same multi-tensor skeleton (one CTA per 4096-element chunk of one tensor;
+// gss[tensor] = ||g||^2 from sumsq_multi): Momentum (:63-111), RMSprop (:114-164), Adam with its own clip_norm / clip_value
+// (:190-202), AdaBelief (:286-402), RAdam (:405-523). hyper = {lr, beta1 | momentum | rho, beta2, eps, clip_norm, clip_value}
+// (clip_norm / clip_value <= 0: off).
+struct OptScalarsX {
+    float clip, clip_value, lr, b1, b2, omb1, omb2, inv_bc1, inv_bc2, eps, rt;
+    int rect;
+};
+
+template <int KIND>
+__device__ __forceinline__ void opt_elem(float& p, float g, float& m, float& v, const OptScalarsX& s) {
+    g *= s.clip;
+    if (s.clip_value > 0.0f) g = fminf(fmaxf(g, -s.clip_value), s.clip_value);     // np.clip(grad, -clip_value, clip_value)
+    if (KIND == B200NN_OPT_MOMENTUM) {            // optimizers.py:79-82: v = momentum * v - lr * g ; w += v
+        m = s.b1 * m - s.lr * g;
+        p += m;
+        return;
+    }
+    if (KIND == B200NN_OPT_RMSPROP) {             // optimizers.py:130-136
+        v = s.b1 * v + s.omb1 * g * g;
+        p -= s.lr * g / (sqrtf(v) + s.eps);
+        return;
+    }
+    float upd;
+    m = s.b1 * m + s.omb1 * g;
+    if (KIND == B200NN_OPT_ADABELIEF) {           // optimizers.py:322-341: second moment of the residual g - m
+        const float r = g - m;
+        v = s.b2 * v + s.omb2 * r * r;
+        const float denom = sqrtf(v * s.inv_bc2 + s.eps);
+        upd = s.lr * (m * s.inv_bc1) / fmaxf(denom, 1e-16f);
+    } else {
+        v = s.b2 * v + s.omb2 * g * g;
+        if (KIND == B200NN_OPT_RADAM) {           // optimizers.py:446-466
+            if (s.rect) upd = s.rt * s.lr * (m * s.inv_bc1) / fmaxf(sqrtf(v * s.inv_bc2) + s.eps, 1e-16f);
+            else upd = s.lr * (m * s.inv_bc1);
+        } else {                                  // Adam, optimizers.py:204-225
+            upd = s.lr * (m * s.inv_bc1) / fmaxf(sqrtf(v * s.inv_bc2) + s.eps, 1e-16f);
+        }
+    }
+    if (!isfinite(upd)) upd = 0.0f;               // np.nan_to_num(update, nan=0, posinf=0, neginf=0)
+    p -= upd;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) opt_multi_kernel(const b200nn_param* __restrict__ params, int n_layers,
+                                                        const double* __restrict__ gss, const double* __restrict__ hyper,
+                                                        const long long* __restrict__ step, const int* __restrict__ block_map,
+                                                        const double* __restrict__ ss) {
+    __shared__ OptScalarsX sh;
+    const int ti = block_map[2 * blockIdx.x], chunk = block_map[2 * blockIdx.x + 1];
+    const b200nn_param P = params[ti];
+    if (threadIdx.x == 0) {
+        const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], cn = hyper[4], cv = hyper[5];
+        const double pre = (double)chain_scale(ss, P.chain);                 // deferred error clips (models.py:214) owed by g
+        const double n2 = gss[ti] * pre * pre;
+        double clip = pre * ((P.clip && n2 > 1.0) ? rsqrt(n2) : 1.0);        // models.py:240-242
+        if (cn > 0.0) {                                                       // the optimizer's own clip_norm on the clipped gradient
+            const double norm = sqrt(gss[ti]) * clip;
+            if (norm > cn) clip *= cn / (norm + 1e-16);
+        }
+        sh.clip = (float)clip;
+        sh.clip_value = (float)cv;
+        sh.lr = (float)lr; sh.b1 = (float)b1; sh.b2 = (float)b2;
+        sh.omb1 = (float)(1.0 - b1); sh.omb2 = (float)(1.0 - b2); sh.eps = (float)eps;
+        sh.inv_bc1 = sh.inv_bc2 = 1.0f; sh.rt = 1.0f; sh.rect = 0;
+        if (KIND == B200NN_OPT_ADAM || KIND == B200NN_OPT_ADABELIEF || KIND == B200NN_OPT_RADAM) {
+            const long long t = *step - (long long)n_layers + P.t_index;     // t counts update() calls = layers (Q3)
+            const double b1t = powi(b1, t), b2t = powi(b2, t);
+            sh.inv_bc1 = (float)(1.0 / (1.0 - b1t));
+            sh.inv_bc2 = (float)(1.0 / (1.0 - b2t));
+            if (KIND == B200NN_OPT_RADAM) {
+                const double rho_inf = 2.0 / (1.0 - b2) - 1.0;
+                const double rho_t = rho_inf - 2.0 * (double)t * b2t / (1.0 - b2t);
+                sh.rect = rho_t > 4.0 ? 1 : 0;
+                if (sh.rect) sh.rt = (float)sqrt(((rho_t - 4.0) * (rho_t - 2.0) * rho_inf) / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t));
+            }
+        }
+    }
+    __syncthreads();
+    const OptScalarsX s = sh;
+    const long long base = (long long)chunk * B200NN_OPT_CHUNK;
+    const long long end = min(P.n, base + B200NN_OPT_CHUNK);
+    for (long long i = base + threadIdx.x; i < end; i += 256) {
+        float p = P.p[i], m = P.m != nullptr ? P.m[i] : 0.0f, v = P.v != nullptr ? P.v[i] : 0.0f;
+        opt_elem<KIND>(p, P.g[i], m, v, s);
+        P.p[i] = p;
+        if (P.m != nullptr) P.m[i] = m;
+        if (P.v != nullptr) P.v[i] = v;
+    }
+}
+
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -612,6 +705,26 @@ int b200nn_adam_multi(const b200nn_param* params, int n_params, int n_layers, do
     B200NN_LAUNCH_CHECK("sumsq_multi");
     adam_multi_kernel<false><<<total_blocks, 256, 0, as_stream(stream)>>>(params, n_layers, n_params, gss, hyper, step, block_map, ss);
     B200NN_LAUNCH_CHECK("adam_multi");
+    return B200NN_OK;
+}
+
+int b200nn_opt_multi(int kind, const b200nn_param* params, int n_params, int n_layers, double* gss, const double* hyper,
+                     const long long* step, const int* block_map, int total_blocks, const double* ss, void* stream) {
+    B200NN_REQUIRE(kind >= B200NN_OPT_ADAM && kind <= B200NN_OPT_RADAM, "opt_multi: unknown update rule %d", kind);
+    B200NN_REQUIRE(n_params > 0 && total_blocks > 0 && n_layers > 0, "opt_multi: empty parameter list");
+    B200NN_REQUIRE(step != nullptr || kind == B200NN_OPT_MOMENTUM || kind == B200NN_OPT_RMSPROP, "opt_multi: this rule needs the t counter");
+    cudaStream_t st = as_stream(stream);
+    B200NN_CUDA(cudaMemsetAsync(gss, 0, sizeof(double) * n_params, st));
+    sumsq_multi_kernel<<<total_blocks, 256, 0, st>>>(params, block_map, gss);
+    B200NN_LAUNCH_CHECK("sumsq_multi");
+    switch (kind) {
+        case B200NN_OPT_ADAM: opt_multi_kernel<B200NN_OPT_ADAM><<<total_blocks, 256, 0, st>>>(params, n_layers, gss, hyper, step, block_map, ss); break;
+        case B200NN_OPT_MOMENTUM: opt_multi_kernel<B200NN_OPT_MOMENTUM><<<total_blocks, 256, 0, st>>>(params, n_layers, gss, hyper, step, block_map, ss); break;
+        case B200NN_OPT_RMSPROP: opt_multi_kernel<B200NN_OPT_RMSPROP><<<total_blocks, 256, 0, st>>>(params, n_layers, gss, hyper, step, block_map, ss); break;
+        case B200NN_OPT_ADABELIEF: opt_multi_kernel<B200NN_OPT_ADABELIEF><<<total_blocks, 256, 0, st>>>(params, n_layers, gss, hyper, step, block_map, ss); break;
+        default: opt_multi_kernel<B200NN_OPT_RADAM><<<total_blocks, 256, 0, st>>>(params, n_layers, gss, hyper, step, block_map, ss); break;
+    }
+    B200NN_LAUNCH_CHECK("opt_multi");
     return B200NN_OK;
 }
 

@@ -236,6 +236,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int m0 = (wk.m_blk * CG + (int)rank) * BLOCK_M;
                 const int n0 = wk.n_blk * BN + (int)rank * BNH;
                 const int kb_begin = wk.split * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+                // convolution producers: every division is hoisted out of the k loop (the loop below is the serial path that
+                // feeds the whole SM); tap / channel / pixel positions advance incrementally
+                int tap = 0, c0 = 0, ky = 0, kx = 0, img = 0, y0 = 0, x0 = 0;
+                if (cv.mode == 1 || cv.mode == 2) {
+                    const int k0 = kb_begin * BLOCK_K, HW = cv.H * cv.W;
+                    tap = k0 / cv.C; c0 = k0 - tap * cv.C; ky = tap / cv.kw; kx = tap - ky * cv.kw;
+                    img = m0 / HW; y0 = (m0 - img * HW) / cv.W;
+                } else if (cv.mode == 3) {
+                    const int k0 = kb_begin * BLOCK_K, HW = cv.H * cv.W;
+                    img = k0 / HW;
+                    const int rem = k0 - img * HW;
+                    y0 = rem / cv.W; x0 = rem - y0 * cv.W;
+                }
+                int a_tap[BLOCK_M / 32], a_c0[BLOCK_M / 32], a_ky[BLOCK_M / 32], a_kx[BLOCK_M / 32];
+                if (cv.mode == 3) {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_M / 32; ++j) {
+                        const int r = m0 + j * 32;
+                        a_tap[j] = r / cv.C; a_c0[j] = r - a_tap[j] * cv.C;
+                        a_ky[j] = a_tap[j] / cv.kw; a_kx[j] = a_tap[j] - a_ky[j] * cv.kw;
+                    }
+                }
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t round = it / STAGES;
@@ -248,10 +270,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int k0 = kb * BLOCK_K;
                     if (cv.mode == 1 || cv.mode == 2) {
                         // A tile = 128 consecutive pixels (whole image rows / whole images), one tap, 32 channels
-                        const int tap = k0 / cv.C, c0 = k0 - tap * cv.C;
-                        const int ky = tap / cv.kw, kx = tap - ky * cv.kw;
-                        const int HW = cv.H * cv.W;
-                        const int img = m0 / HW, y0 = (m0 - img * HW) / cv.W;
                         const int dy = cv.mode == 1 ? ky - cv.pad_y : cv.pad_y - ky;
                         const int dx = cv.mode == 1 ? kx - cv.pad_x : cv.pad_x - kx;
                         tma2_load_4d<LG>(sa, &tmA, bar, c0, dx, y0 + dy, img);
@@ -261,25 +279,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else {
                             tma2_load_3d<LG>(sb, &tmB, bar, c0, tap, n0);
                         }
+                        c0 += BLOCK_K;
+                        if (c0 >= cv.C) {
+                            c0 = 0; ++tap;
+                            if (++kx == cv.kw) { kx = 0; ++ky; }
+                        }
                     } else if (cv.mode == 3) {
                         // A slab j = 32 (tap, c) rows x 32 consecutive pixels; rows past the last tap are fetched far out of bounds (zeros)
-                        const int HW = cv.H * cv.W;
-                        const int img = k0 / HW, rem = k0 - img * HW;
-                        const int y0 = rem / cv.W, x0 = rem - y0 * cv.W;
                         if constexpr (A_MN) {
 #pragma unroll
                             for (int j = 0; j < BLOCK_M / 32; ++j) {
-                                const int r = m0 + j * 32;
-                                const int tap = r / cv.C, c0 = r - tap * cv.C;
-                                const int ky = tap / cv.kw, kx = tap - ky * cv.kw;
-                                const int yy = tap < cv.taps ? y0 + ky - cv.pad_y : -(1 << 20);
-                                tma2_load_4d<LG>(sa + j * SLAB_BYTES, &tmA, bar, c0, x0 + kx - cv.pad_x, yy, img);
+                                const int yy = a_tap[j] < cv.taps ? y0 + a_ky[j] - cv.pad_y : -(1 << 20);
+                                tma2_load_4d<LG>(sa + j * SLAB_BYTES, &tmA, bar, a_c0[j], x0 + a_kx[j] - cv.pad_x, yy, img);
                             }
                         }
                         if constexpr (B_MN) {
 #pragma unroll
                             for (int j = 0; j < BNH / 32; ++j) tma2_load_2d<LG>(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
                         }
+                        x0 += BLOCK_K;                       // 32 pixels further (W divides 32 or 32 divides W: conv_tc_ok)
+                        while (x0 >= cv.W) { x0 -= cv.W; ++y0; }
+                        while (y0 >= cv.H) { y0 -= cv.H; ++img; }
                     } else {
                         if constexpr (A_MN) {
 #pragma unroll
