@@ -411,7 +411,8 @@ def run_leg(cfg, math, T, K, W, world, rank, peaks, tf32_peak, clock_sampler):
     res.update({"ms_per_step": resident_ms, "value": gb / (resident_ms * 1e-3), "unit": "samples/s", "kernels_per_step": int(launches),
                 "e2e": {"value": gb / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4), "d2h_bytes_per_step": 8, "last_loss": loss},
-                "kernel_breakdown": {"columns": ["op", "us (eager upper bound)", "io bytes", "GB/s"], "rows": breakdown[:10]}})
+                "kernel_breakdown": {"columns": ["op", "us (eager upper bound)", "io bytes", "GB/s"],
+                                     "rows": breakdown if os.environ.get("B200NN_BENCH_ALLOPS") else breakdown[:10]}})
     roof = {"step_gflop": fl / 1e9, "achieved_tflops": tfl / world, "tf32_peak_tflops": tf32_peak,
             "frac_of_tf32_peak": tfl / world / tf32_peak}
     if cfg in BYTES_PER_SAMPLE:

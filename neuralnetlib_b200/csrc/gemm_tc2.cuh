@@ -45,7 +45,9 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default .release.cta semantics (what CUTLASS' umma_arrive_2x1SM_sm0 issues): the .cluster-scope form costs a MEMBAR.ALL +
+    // ERRBAR per arrival; the data the arrival orders (TMEM reads, smem writes behind fence.proxy.async) is fenced explicitly
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in the executing CTA, the bytes are counted on the LEADER's mbarrier
 template <int CG>
