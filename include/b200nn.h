@@ -367,6 +367,23 @@ int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double*
                                  const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
                                  int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream);
 
+/* STREAMING forms of the batch-coupled kernels for large batches (any batch size; thread = (pool window, channel quad) or 4
+ * adjacent positions, blockIdx.y = a chunk of batch rows, every access a whole 128-byte line). `ws`: float workspace of
+ * *_ws_bytes. The statistics are merged over the chunks in a fixed order (deterministic, no float atomics).
+ *   b200nn_bn_stats_stream            = b200nn_bn_stats_partial in ONE sweep over x (shifted sums, Chan merge in fp64)
+ *   b200nn_pool_bn_bwd_stream_partial = b200nn_pool_bn_bwd_partial   (dgamma / dbeta receive the LOCAL sums)
+ *   b200nn_pool_bn_act_bwd_stream_apply = b200nn_pool_bn_act_bwd_apply */
+size_t b200nn_bn_stats_stream_ws_bytes(int B, long long P);
+int b200nn_bn_stats_stream(const float* x, double* stats, float* ws, int B, long long P, void* stream);
+size_t b200nn_pool_bn_bwd_stream_ws_bytes(int B, int H, int W, int C);
+int b200nn_pool_bn_bwd_stream_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                      const float* beta, const float* save_mean, const float* save_invstd, float* dgamma,
+                                      float* dbeta, float* ws, int B, int H, int W, int C, double* ss_out0, void* stream);
+int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                        const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                                        const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
+                                        int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

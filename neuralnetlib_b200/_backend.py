@@ -119,6 +119,12 @@ _SIGNATURES = {
     "b200nn_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, c_int, c_ll, _P]),
     "b200nn_bn_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_int, c_float, _P, _P, _P]),
     "b200nn_pool_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "b200nn_bn_stats_stream_ws_bytes": (c_size_t, [c_int, c_ll]),
+    "b200nn_bn_stats_stream": (c_int, [_P, _P, _P, c_int, c_ll, _P]),
+    "b200nn_pool_bn_bwd_stream_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200nn_pool_bn_bwd_stream_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "b200nn_pool_bn_act_bwd_stream_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_ll,
+                                                     c_int, c_float, _P, _P, _P]),
     "b200nn_pool_bn_act_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_ll,
                                               c_int, c_float, _P, _P, _P]),
 }

@@ -333,6 +333,45 @@ def pool_bn_act_bwd_apply(x, err, ss, chain, gamma, beta, save_mean, save_invstd
                                              _slot_ptr(ss, slot2), stream()))
 
 
+# streaming forms for large batches (csrc/bn_pool.cu); `ws` is the plan's float workspace
+def bn_stats_stream_ws_bytes(Bn, P):
+    return int(lib().b200nn_bn_stats_stream_ws_bytes(int(Bn), int(P)))
+
+
+def bn_stats_stream(x, stats, ws):
+    _f32(x, ws)
+    Bn = x.shape[0]
+    P = x.numel() // Bn
+    assert stats.dtype == torch.float64 and stats.numel() == 2 * P and ws.numel() * 4 >= bn_stats_stream_ws_bytes(Bn, P)
+    check(lib().b200nn_bn_stats_stream(ptr(x), ptr(stats), ptr(ws), Bn, P, stream()))
+
+
+def pool_bn_bwd_stream_ws_bytes(Bn, H, W, Cc):
+    return int(lib().b200nn_pool_bn_bwd_stream_ws_bytes(int(Bn), int(H), int(W), int(Cc)))
+
+
+def pool_bn_bwd_stream_partial(x, err, ss, chain, gamma, beta, save_mean, save_invstd, sums, ws, slot0):
+    """sums: float32 [2P] = dbeta | dgamma (receives the LOCAL sums)."""
+    _f32(x, err, gamma, beta, save_mean, save_invstd, sums, ws)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    P = H * W * Cc
+    assert ws.numel() * 4 >= pool_bn_bwd_stream_ws_bytes(Bn, H, W, Cc)
+    check(lib().b200nn_pool_bn_bwd_stream_partial(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(beta), ptr(save_mean),
+                                                  ptr(save_invstd), sums.data_ptr() + 4 * P, sums.data_ptr(), ptr(ws), Bn, H, W, Cc,
+                                                  _slot_ptr(ss, slot0), stream()))
+
+
+def pool_bn_act_bwd_stream_apply(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0, sums, b_total, prev_act, prev_alpha,
+                                 slot1, slot2):
+    _f32(x, err, gamma, beta, save_mean, save_invstd, r0, sums)
+    Bn, H, W, Cc = (int(v) for v in x.shape)
+    P = H * W * Cc
+    check(lib().b200nn_pool_bn_act_bwd_stream_apply(ptr(x), ptr(err), ptr(ss), pack_chain(chain), ptr(gamma), ptr(beta),
+                                                    ptr(save_mean), ptr(save_invstd), ptr(r0), sums.data_ptr() + 4 * P, sums.data_ptr(),
+                                                    Bn, H, W, Cc, int(b_total), prev_act, prev_alpha, _slot_ptr(ss, slot1),
+                                                    _slot_ptr(ss, slot2), stream()))
+
+
 def maxpool_fwd(g: PoolGeom, x, y):
     _f32(x, y)
     check(lib().b200nn_maxpool_fwd(C.byref(g), ptr(x), ptr(y), stream()))

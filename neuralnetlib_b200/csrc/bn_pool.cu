@@ -608,6 +608,214 @@ __global__ void __launch_bounds__(FB_THREADS, 2) pool_bn_act_bwd_kernel(
     if (MODE == 0 && csize > 1) cluster_sync_all();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// STREAMING form of the fused block kernels for large batches (config 3 at batch 1024: the cluster kernels above stage a
+// window's whole batch through 128-byte lines 256 KB apart and run at ~0.8 TB/s there). Mapping: thread = (pool window,
+// channel quad) as in bn_pool_apply_kernel — a CTA of 256 threads covers a run of adjacent windows, i.e. two contiguous
+// multi-KB segments of every batch row — and blockIdx.y = a chunk of SB_ROWS batch rows, so every load instruction of a warp
+// covers whole 128-byte lines and each thread keeps several rows in flight. Backward = three launches:
+//   partial : per (chunk, position) sums of U and U * (x - mean)  (U = pool-bwd of the incoming error)   -> ws[chunk][2][P]
+//   reduce  : fixed-order sum over the chunks -> d_beta, d_gamma (deterministic; no float atomics)
+//   apply   : BN-bwd + activation-bwd from the (rank-summed) reductions -> r0, clip slots
+// x and err are read twice (2 * (S + P) + S bytes against the single-pass 2S + P), at several TB/s instead of 0.8.
+constexpr int SB_ROWS = 32;
+
+struct SbPos {
+    long long pos[4];
+    long long obase;
+};
+__device__ __forceinline__ SbPos sb_positions(long long idx, int H, int W, int C) {
+    const int CQ = C >> 2, OW = W >> 1;
+    const int cq = (int)(idx % CQ); long long t = idx / CQ;
+    const int ox = (int)(t % OW); const int oy = (int)(t / OW);
+    const int c = cq * 4;
+    SbPos r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.pos[q] = ((long long)(2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * C + c;
+    r.obase = ((long long)oy * OW + ox) * C + c;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) pool_bn_bwd_stream_partial_kernel(
+    const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, float* __restrict__ part, double* ss0, int B, int H, int W, int C, long long items) {
+    __shared__ double scratch[32];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < items;
+    const float scale = chain_scale(ss, chain);
+    const long long P = (long long)H * W * C, OP = P >> 2;
+    float a0 = 0.0f;
+    if (ok) {
+        const SbPos sp = sb_positions(idx, H, W, C);
+        float4 mean[4], gq[4], bq[4], is[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mean[q] = *reinterpret_cast<const float4*>(save_mean + sp.pos[q]);
+            is[q] = *reinterpret_cast<const float4*>(save_invstd + sp.pos[q]);
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + sp.pos[q]);
+            gq[q] = make_float4(gm.x * is[q].x, gm.y * is[q].y, gm.z * is[q].z, gm.w * is[q].w);
+            bq[q] = *reinterpret_cast<const float4*>(beta + sp.pos[q]);
+        }
+        float4 sb[4], sg[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sb[q] = sg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r0 = blockIdx.y * SB_ROWS, r1 = min(B, r0 + SB_ROWS);
+#pragma unroll 2
+        for (int r = r0; r < r1; ++r) {
+            const float* xr = x + (long long)r * P;
+            float4 e = *reinterpret_cast<const float4*>(err + (long long)r * OP + sp.obase);
+            float4 xv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xv[q] = *reinterpret_cast<const float4*>(xr + sp.pos[q]);
+            e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
+            FB_FOR4(
+                float yq[4], dq[4];
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    dq[q] = clip10(f4_at(xv[q], k_)) - f4_at(mean[q], k_);
+                    yq[q] = fmaf(f4_at(gq[q], k_), dq[q], f4_at(bq[q], k_));
+                }
+                const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;      /* every tied maximum, layers.py:631-637 */
+                    f4_at(sb[q], k_) += u;
+                    f4_at(sg[q], k_) = fmaf(u, dq[q], f4_at(sg[q], k_));
+                    a0 = fmaf(u, u, a0);
+                })
+        }
+        float* pb = part + (long long)blockIdx.y * 2 * P;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<float4*>(pb + sp.pos[q]) = sb[q];                                                   // sum U
+            *reinterpret_cast<float4*>(pb + P + sp.pos[q]) = make_float4(sg[q].x * is[q].x, sg[q].y * is[q].y,  // sum U * xhat
+                                                                         sg[q].z * is[q].z, sg[q].w * is[q].w);
+        }
+    }
+    if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+}
+
+// out0[i] = sum_c part[c][i], out1[i] = sum_c part[c][P + i]  (fixed chunk order)
+__global__ void __launch_bounds__(256) stream_reduce2_kernel(const float* __restrict__ part, int chunks, long long P,
+                                                             float* __restrict__ out0, float* __restrict__ out1) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= 2 * P) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int c = 0; c < chunks; ++c) acc = f4_add(acc, *reinterpret_cast<const float4*>(part + (long long)c * 2 * P + i4));
+    float* o = i4 < P ? out0 + i4 : out1 + (i4 - P);
+    *reinterpret_cast<float4*>(o) = acc;
+}
+
+__global__ void __launch_bounds__(256) pool_bn_act_bwd_stream_apply_kernel(
+    const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, float* __restrict__ r0out, const float* __restrict__ dgamma,
+    const float* __restrict__ dbeta, int B, int H, int W, int C, float inv_total, int prev_act, float prev_alpha, double* ss1,
+    double* ss2, long long items) {
+    __shared__ double scratch[32];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < items;
+    const float scale = chain_scale(ss, chain);
+    const long long P = (long long)H * W * C, OP = P >> 2;
+    float a1 = 0.0f, a2 = 0.0f;
+    if (ok) {
+        const SbPos sp = sb_positions(idx, H, W, C);
+        float4 mean[4], gq[4], bq[4], ka[4], kb[4], isv[4];   // dx = g * (U - xhat * kb - ka), ka = dbeta / N, kb = dgamma / N
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mean[q] = *reinterpret_cast<const float4*>(save_mean + sp.pos[q]);
+            const float4 is = *reinterpret_cast<const float4*>(save_invstd + sp.pos[q]);
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + sp.pos[q]);
+            gq[q] = make_float4(gm.x * is.x, gm.y * is.y, gm.z * is.z, gm.w * is.w);
+            bq[q] = *reinterpret_cast<const float4*>(beta + sp.pos[q]);
+            const float4 db = *reinterpret_cast<const float4*>(dbeta + sp.pos[q]), dg = *reinterpret_cast<const float4*>(dgamma + sp.pos[q]);
+            ka[q] = make_float4(db.x * inv_total, db.y * inv_total, db.z * inv_total, db.w * inv_total);
+            kb[q] = make_float4(dg.x * inv_total, dg.y * inv_total, dg.z * inv_total, dg.w * inv_total);
+            isv[q] = is;
+        }
+        const int r0 = blockIdx.y * SB_ROWS, r1 = min(B, r0 + SB_ROWS);
+#pragma unroll 2
+        for (int r = r0; r < r1; ++r) {
+            const float* xr = x + (long long)r * P;
+            float4 e = *reinterpret_cast<const float4*>(err + (long long)r * OP + sp.obase);
+            float4 xraw[4], out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xraw[q] = *reinterpret_cast<const float4*>(xr + sp.pos[q]);
+            e = make_float4(scale * e.x, scale * e.y, scale * e.z, scale * e.w);
+            FB_FOR4(
+                float yq[4], xh[4];
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    const float d = clip10(f4_at(xraw[q], k_)) - f4_at(mean[q], k_);
+                    yq[q] = fmaf(f4_at(gq[q], k_), d, f4_at(bq[q], k_));
+                    xh[q] = d * f4_at(isv[q], k_);
+                }
+                const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {
+                    const float u = (yq[q] == m) ? f4_at(e, k_) : 0.0f;
+                    float d = f4_at(gq[q], k_) * (u - xh[q] * f4_at(kb[q], k_) - f4_at(ka[q], k_));   /* layers.py:1264-1274 */
+                    a1 = fmaf(d, d, a1);
+                    if (prev_act != B200NN_ACT_NONE) {
+                        d *= act_grad_from_y(prev_act, f4_at(xraw[q], k_), prev_alpha);               /* layers.py:237 */
+                        a2 = fmaf(d, d, a2);
+                    }
+                    f4_at(out[q], k_) = d;
+                })
+            float* rb = r0out + (long long)r * P;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(rb + sp.pos[q]) = out[q];
+        }
+    }
+    if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+    if (prev_act != B200NN_ACT_NONE && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+}
+
+// Forward statistics, streaming form: ONE sweep over x. Thread = 4 adjacent positions (float4), blockIdx.y = a chunk of
+// SS_ROWS batch rows; per chunk the sums are taken about a per-position shift K = clip(x[first row of the chunk]) so that
+// sum((x - K)^2) - sum(x - K)^2 / n loses nothing to cancellation (a one-pass variance about zero would); the chunks are then
+// merged pairwise-exactly (Chan) in fp64 by stream_stats_combine_kernel into the [sum | sum of squares] format of
+// bn_stats_partial. part = [chunk][3][P]: K, sum(x - K), sum((x - K)^2).
+constexpr int SS_ROWS = 64;
+__global__ void __launch_bounds__(256) bn_stats_stream_kernel(const float* __restrict__ x, float* __restrict__ part, int B, long long P) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= P) return;
+    const int r0 = blockIdx.y * SS_ROWS, r1 = min(B, r0 + SS_ROWS);
+    const float* xc = x + i4;
+    const float4 K = f4_clip10(*reinterpret_cast<const float4*>(xc + (long long)r0 * P));
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        const float4 v = f4_clip10(*reinterpret_cast<const float4*>(xc + (long long)r * P));      // layers.py:1234
+        const float4 d = make_float4(v.x - K.x, v.y - K.y, v.z - K.z, v.w - K.w);
+        s1 = f4_add(s1, d);
+        s2 = make_float4(fmaf(d.x, d.x, s2.x), fmaf(d.y, d.y, s2.y), fmaf(d.z, d.z, s2.z), fmaf(d.w, d.w, s2.w));
+    }
+    float* pb = part + (long long)blockIdx.y * 3 * P + i4;
+    *reinterpret_cast<float4*>(pb) = K;
+    *reinterpret_cast<float4*>(pb + P) = s1;
+    *reinterpret_cast<float4*>(pb + 2 * P) = s2;
+}
+
+__global__ void __launch_bounds__(256) stream_stats_combine_kernel(const float* __restrict__ part, int chunks, int B, long long P,
+                                                                   double* __restrict__ stats) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double n = 0.0, mean = 0.0, M2 = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        const float* pb = part + (long long)c * 3 * P + i;
+        const double nc = (double)min(SS_ROWS, B - c * SS_ROWS);
+        const double K = (double)pb[0], S1 = (double)pb[P], S2 = (double)pb[2 * P];
+        const double mc = K + S1 / nc, m2c = fmax(S2 - S1 * S1 / nc, 0.0);
+        const double tot = n + nc, delta = mc - mean;
+        mean += delta * nc / tot;
+        M2 += m2c + delta * delta * n * nc / tot;
+        n = tot;
+    }
+    const double S = mean * n;
+    stats[i] = S;                       // sum clip(x)
+    stats[P + i] = M2 + S * S / n;      // sum clip(x)^2, formed from the exact M2 (see bn_stats_partial_kernel)
+}
+
 static int check_fused_block(const char* who, int B, int H, int W, int C) {
     B200NN_REQUIRE(B > 0 && B <= FB_ROWS * FB_MAX_CLUSTER, "%s: batch %d outside the single-pass range (1..%d)", who, B,
                    FB_ROWS * FB_MAX_CLUSTER);
@@ -836,6 +1044,70 @@ int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double*
                               C, as_stream(stream), x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0,
                               const_cast<float*>(dgamma), const_cast<float*>(dbeta), g, (int)B_total, prev_act, prev_alpha,
                               (double*)nullptr, ss_out1, ss_out2);
+}
+
+// ---- streaming forms (large batches; any batch size, C % 4 == 0) -----------------------------------------------------------
+static int check_stream_block(const char* who, int B, int H, int W, int C, const void* a, const void* b, const void* c) {
+    B200NN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0,
+                   "%s: needs even H, W and C %% 4 == 0 (got %dx%dx%d)", who, H, W, C);
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0,
+                   "%s: tensors must be 16-byte aligned", who);
+    return B200NN_OK;
+}
+
+size_t b200nn_pool_bn_bwd_stream_ws_bytes(int B, int H, int W, int C) {
+    return (size_t)((B + SB_ROWS - 1) / SB_ROWS) * 2 * H * W * C * sizeof(float);
+}
+
+int b200nn_pool_bn_bwd_stream_partial(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                      const float* beta, const float* save_mean, const float* save_invstd, float* dgamma,
+                                      float* dbeta, float* ws, int B, int H, int W, int C, double* ss_out0, void* stream) {
+    if (int rc = check_stream_block("pool_bn_bwd_stream_partial", B, H, W, C, x, err, ws)) return rc;
+    B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && ws != nullptr, "pool_bn_bwd_stream_partial: dgamma / dbeta / ws are required");
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0,
+                   "pool_bn_bwd_stream_partial: dgamma / dbeta must be 16-byte aligned");
+    const long long items = (long long)(H / 2) * (W / 2) * (C / 4), P = (long long)H * W * C;
+    const int chunks = (B + SB_ROWS - 1) / SB_ROWS;
+    const dim3 grid((unsigned)((items + 255) / 256), (unsigned)chunks);
+    cudaStream_t st = as_stream(stream);
+    pool_bn_bwd_stream_partial_kernel<<<grid, 256, 0, st>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, ws, ss_out0, B, H,
+                                                          W, C, items);
+    B200NN_LAUNCH_CHECK("pool_bn_bwd_stream_partial");
+    stream_reduce2_kernel<<<(unsigned)((2 * P / 4 + 255) / 256), 256, 0, st>>>(ws, chunks, P, dbeta, dgamma);
+    B200NN_LAUNCH_CHECK("stream_reduce2");
+    return B200NN_OK;
+}
+
+int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const double* ss, uint64_t chain, const float* gamma,
+                                        const float* beta, const float* save_mean, const float* save_invstd, float* r0,
+                                        const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
+                                        int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream) {
+    if (int rc = check_stream_block("pool_bn_act_bwd_stream_apply", B, H, W, C, x, err, r0)) return rc;
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd_stream_apply: unknown activation %d", prev_act);
+    B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && B_total >= B, "pool_bn_act_bwd_stream_apply: bad argument");
+    const long long items = (long long)(H / 2) * (W / 2) * (C / 4);
+    const dim3 grid((unsigned)((items + 255) / 256), (unsigned)((B + SB_ROWS - 1) / SB_ROWS));
+    pool_bn_act_bwd_stream_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0,
+                                                                           dgamma, dbeta, B, H, W, C, 1.0f / (float)B_total, prev_act,
+                                                                           prev_alpha, ss_out1, ss_out2, items);
+    B200NN_LAUNCH_CHECK("pool_bn_act_bwd_stream_apply");
+    return B200NN_OK;
+}
+
+size_t b200nn_bn_stats_stream_ws_bytes(int B, long long P) { return (size_t)((B + SS_ROWS - 1) / SS_ROWS) * 3 * P * sizeof(float); }
+
+/* one-sweep form of b200nn_bn_stats_partial for large batches (same `stats` format); P % 4 == 0 */
+int b200nn_bn_stats_stream(const float* x, double* stats, float* ws, int B, long long P, void* stream) {
+    B200NN_REQUIRE(B > 0 && P > 0 && P % 4 == 0 && x != nullptr && stats != nullptr && ws != nullptr, "bn_stats_stream: bad argument");
+    B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0, "bn_stats_stream: x / ws must be 16-byte aligned");
+    const int chunks = (B + SS_ROWS - 1) / SS_ROWS;
+    const dim3 grid((unsigned)((P / 4 + 255) / 256), (unsigned)chunks);
+    cudaStream_t st = as_stream(stream);
+    bn_stats_stream_kernel<<<grid, 256, 0, st>>>(x, ws, B, P);
+    B200NN_LAUNCH_CHECK("bn_stats_stream");
+    stream_stats_combine_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ws, chunks, B, P, stats);
+    B200NN_LAUNCH_CHECK("stream_stats_combine");
+    return B200NN_OK;
 }
 
 }  // extern "C"

@@ -882,9 +882,16 @@ class BatchNormalization(Layer, _ParamMixin):
 
     def _can_fuse_pool(self, x, pool, training):
         """BatchNorm(train) -> MaxPool 2x2/s2 'valid' on an even, 32-channel-aligned NHWC tensor runs as one kernel."""
+        # batches beyond the single-pass cluster kernels (fused_block_max_batch) take the streaming kernels, which have no batch limit
         return (training and isinstance(pool, MaxPooling2D) and x.dim() == 4 and pool.pool_size == (2, 2)
                 and pool.strides == (2, 2) and pool.padding == "valid" and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0
-                and x.shape[3] % 32 == 0 and x.shape[0] <= ops.fused_block_max_batch())
+                and x.shape[3] % 32 == 0 and (x.shape[0] <= ops.fused_block_max_batch() or x.shape[0] >= self._stream_rows()))
+
+    @staticmethod
+    def _stream_rows():
+        """Batch rows from which the batch-coupled kernels run in their streaming form (csrc/bn_pool.cu): the single-read cluster
+        kernels stage a window's whole batch through 128-byte lines 256 KB apart, which stops paying beyond ~256 rows."""
+        return int(os.environ.get("B200NN_BN_SPLIT_ROWS", "512"))
 
     def _ensure_params(self, shp):
         if self._gamma is None or self._running_mean is None or self._running_var is None:
@@ -902,7 +909,7 @@ class BatchNormalization(Layer, _ParamMixin):
         mom, eps = float(self.momentum), float(self.epsilon)
         # Large batches on one GPU take the same two streaming kernels: the single-read cluster kernel stages a window's whole
         # batch in shared memory through 128-byte lines 256 KB apart, which stops paying beyond ~256 rows.
-        big = int(os.environ.get("B200NN_BN_SPLIT_ROWS", "512"))
+        big = self._stream_rows()
         if training and (ctx.dp is not None or x.shape[0] >= big):
             # data parallel (parallel.py): local moments -> sum over ranks -> apply, so that mean / var are those of the
             # GLOBAL batch (layers.py:1237-1238)
@@ -910,7 +917,11 @@ class BatchNormalization(Layer, _ParamMixin):
             stats = ctx.buf64((2 * P,))
             sm, si = ctx.buf((P,)), ctx.buf((P,))
             st.update(x=x, save_mean=sm, save_invstd=si, trained=True, fused_pool=pool is not None)
-            ctx.emit(lambda: ops.bn_stats_partial(x, stats), "bn_stats_partial", (x,))
+            if x.shape[0] >= 128 and P % 4 == 0:   # one sweep over x (shifted sums per batch chunk, merged in fp64)
+                ctx.need_ws(ops.bn_stats_stream_ws_bytes(x.shape[0], P))
+                ctx.emit(lambda: ops.bn_stats_stream(x, stats, ctx.ws), "bn_stats_stream", (x,))
+            else:
+                ctx.emit(lambda: ops.bn_stats_partial(x, stats), "bn_stats_partial", (x,))
             ctx.allreduce(stats, "bn_stats_exchange")
             if pool is not None:
                 yp = ctx.buf((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
@@ -989,6 +1000,16 @@ class BatchNormalization(Layer, _ParamMixin):
         s2 = ctx.slot() if mask_layer is not None else None
         gm, bt, sm, si, ss, chain, et = self._gamma, self._beta, st["save_mean"], st["save_invstd"], ctx.ss, err.chain, err.t
         self._dgrad_pending = self._pending_upto(ctx, s0)
+        if x.shape[0] >= self._stream_rows():
+            # streaming form (any batch size): partial sums per batch chunk -> fixed-order reduce [-> sum over ranks] -> apply
+            sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
+            ctx.need_ws(ops.pool_bn_bwd_stream_ws_bytes(*x.shape))
+            ctx.emit(lambda: ops.pool_bn_bwd_stream_partial(x, et, ss, chain, gm, bt, sm, si, sums, ctx.ws, s0),
+                     "pool_bn_bwd_stream_partial", (x, et))
+            ctx.allreduce(sums, "bn_sums_exchange")
+            ctx.emit(lambda: ops.pool_bn_act_bwd_stream_apply(x, et, ss, chain, gm, bt, sm, si, r0, sums, b_total, kind, alpha, s1, s2),
+                     "pool_bn_act_bwd_stream_apply", (x, et, r0))
+            return _Err(r0, tuple(s for s in (s0, s1, s2) if s is not None))
         if ctx.dp is not None:
             sums, b_total = self._dp_sums(ctx), x.shape[0] * ctx.world
             ctx.emit(lambda: ops.pool_bn_bwd_partial(x, et, ss, chain, gm, bt, sm, si, sums, s0), "pool_bn_bwd_partial", (x, et))
