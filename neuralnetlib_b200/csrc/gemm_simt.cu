@@ -858,6 +858,125 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_kernel(const float* __r
     if (ss_out != nullptr) block_accumulate(esq, ss_out, scratch);
 }
 
+
+// Large-batch form of the classifier head (config 4: 8192 rows x 4096 features x 10 classes). The one-warp-per-row kernel above
+// re-reads the whole weight matrix from L2 for every row (8192 x 164 KB = 1.3 GB, 207 us); here a CTA owns 8 warps x R rows,
+// stages the weights one 40 KB chunk of features at a time in shared memory (padded to an odd pitch: conflict-free for lanes striding
+// over k) and every warp applies a chunk to its R rows: per 32 features R coalesced x loads + N LDS for R * N FMAs.
+template <int R, int NMAX>
+__global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ b, const float* __restrict__ y,
+                                                                     float* __restrict__ p, float* __restrict__ err,
+                                                                     double* loss_acc, double* ss_out, int M, int N, int K) {
+    __shared__ double scratch[32];
+    constexpr int PITCH = NMAX | 1;
+    constexpr int HR_KC = ((10240 / PITCH) / 32) * 32;       // 40 KB of staged weights per chunk
+    __shared__ float ws[HR_KC * PITCH];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int m0 = (blockIdx.x * 8 + wid) * R;
+    float acc[R][NMAX];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) acc[r][n] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += HR_KC) {
+        const int kc = min(HR_KC, K - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kc * N; i += blockDim.x) ws[(i / N) * PITCH + (i % N)] = w[(long long)k0 * N + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = lane; kk < kc; kk += 32) {     // unrolled: 4 x R independent 128-byte row loads in flight per warp
+            float xv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) xv[r] = (m0 + r < M) ? __ldg(x + (long long)(m0 + r) * K + k0 + kk) : 0.0f;
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) {
+                if (n < N) {
+                    const float wv = ws[kk * PITCH + n];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r][n] = fmaf(xv[r], wv, acc[r][n]);
+                }
+            }
+        }
+    }
+    float lsum = 0.0f, esq = 0.0f, correct = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int m = m0 + r;
+        if (m >= M) break;                                                   // warp-uniform
+        float logit = 0.0f;
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+            if (n < N) {
+                const float t = warp_sum(acc[r][n]);
+                if (lane == n) logit = t;
+            }
+        }
+        const bool on = lane < N;
+        logit = on ? logit + (b != nullptr ? b[lane] : 0.0f) : -INFINITY;
+        const float mx = warp_max(logit);
+        const float ex = on ? expf(logit - mx) : 0.0f;
+        const float pv = ex / warp_sum(ex);
+        const float yv = on ? y[(long long)m * N + lane] : 0.0f;
+        if (on) {
+            p[(long long)m * N + lane] = pv;
+            const float pc = fminf(fmaxf(pv, 1e-15f), 1.0f);
+            lsum -= yv * logf(pc);
+            const float e = pv - yv;
+            err[(long long)m * N + lane] = e;
+            esq = fmaf(e, e, esq);
+        }
+        float bp = on ? pv : -INFINITY, by = on ? yv : -INFINITY;
+        int ip = on ? lane : 0x7fffffff, iy = ip;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {                                   // first-index tie break (np.argmax)
+            const float obp = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int oip = __shfl_xor_sync(0xffffffffu, ip, o);
+            if (obp > bp || (obp == bp && oip < ip)) { bp = obp; ip = oip; }
+            const float oby = __shfl_xor_sync(0xffffffffu, by, o);
+            const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
+            if (oby > by || (oby == by && oiy < iy)) { by = oby; iy = oiy; }
+        }
+        if (lane == 0 && ip == iy) correct += 1.0f;
+    }
+    const double l = block_sum_to_double(lsum, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[0], l);
+    const double c = block_sum_to_double(correct, scratch);
+    if (threadIdx.x == 0 && loss_acc != nullptr) atomicAdd(&loss_acc[1], c);
+    if (ss_out != nullptr) block_accumulate(esq, ss_out, scratch);
+}
+
+// Large-batch dx of a small Dense: thread = one input feature k with w[k, :] in registers, CTA = 256 features x DXR rows whose
+// error rows sit in shared memory (broadcast reads); the mask load and the dx store are coalesced 1 KB runs per row.
+constexpr int DXR = 32;
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_smalln_dx_rows_kernel(const float* __restrict__ e, const float* __restrict__ w,
+                                                                   Epilogue epi, int M, int N, int K) {
+    __shared__ double scratch[32];
+    __shared__ float es[DXR][NMAX];
+    EpiState st;
+    epi_begin(epi, st);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = blockIdx.y * DXR, nr = min(DXR, M - m0);
+    for (int i = threadIdx.x; i < nr * N; i += blockDim.x) es[i / N][i % N] = e[(long long)m0 * N + i];
+    float wr[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) wr[n] = (k < K && n < N) ? w[(long long)k * N + n] : 0.0f;
+    __syncthreads();
+    if (k < K) {
+#pragma unroll 4
+        for (int r = 0; r < nr; ++r) {
+            float v = 0.0f;
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) v = fmaf(es[r][n < N ? n : 0], wr[n], v);
+            const long long i = (long long)(m0 + r) * K + k;
+            const float mk = epi.mask_y != nullptr ? epi.mask_y[i] : 0.0f;
+            epi_store_premask(epi, st, m0 + r, k, v, mk);
+        }
+    }
+    epi_finish(epi, st, scratch);
+}
+
 // Backward of a small Dense (N <= 32, M <= 512) in ONE kernel: CTAs [0, dx_blocks) compute dx (+ fused activation backward
 // and the two clip slots), the remaining CTAs compute dw / db directly (thread = one (k, n) output, the whole batch summed
 // in fixed order: no partials, no reduce pass).
@@ -1064,6 +1183,14 @@ int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, con
                              double* loss_acc, double* ss_out, int M, int N, int K, float* dw_partial, void* stream) {
     B200NN_REQUIRE(M > 0 && K > 0 && N > 0 && N <= SMALLN_MAX, "dense_softmax_cce: needs N <= %d (M=%d N=%d K=%d)", SMALLN_MAX, M, N, K);
     B200NN_REQUIRE(x != nullptr && w != nullptr && y_true != nullptr && p != nullptr && err != nullptr, "dense_softmax_cce: null buffer");
+    if (dw_partial == nullptr && M >= 1024 && K >= 256) {   // large batch: weights staged per CTA, several rows per warp
+        cudaStream_t st = as_stream(stream);
+        if (N <= 12) dense_softmax_cce_rows_kernel<8, 12><<<(M + 63) / 64, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+        else if (N <= 16) dense_softmax_cce_rows_kernel<4, 16><<<(M + 31) / 32, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+        else dense_softmax_cce_rows_kernel<2, 32><<<(M + 15) / 16, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+        B200NN_LAUNCH_CHECK("dense_softmax_cce_rows");
+        return B200NN_OK;
+    }
     int blocks = (M + 7) / 8;
     B200NN_REQUIRE(dw_partial == nullptr || (K <= HEAD_MAXK && blocks <= kNumSMs * 8), "dense_softmax_cce: partials need K <= %d", HEAD_MAXK);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
@@ -1126,10 +1253,18 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         if (dx != nullptr) {
             Epilogue e = plain_epilogue(dx, K, M);
             dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
-            long long blocks = ((long long)M * K + 255) / 256;
-            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-            dense_smalln_dx_kernel<<<(int)blocks, 256, 0, st>>>(err, w, e, M, N, K);
-            B200NN_LAUNCH_CHECK("dense_smalln_dx");
+            if (M >= 256 && K >= 256) {
+                const dim3 grid((K + 255) / 256, (M + DXR - 1) / DXR);
+                if (N <= 12) dense_smalln_dx_rows_kernel<12><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
+                else if (N <= 16) dense_smalln_dx_rows_kernel<16><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
+                else dense_smalln_dx_rows_kernel<32><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
+                B200NN_LAUNCH_CHECK("dense_smalln_dx_rows");
+            } else {
+                long long blocks = ((long long)M * K + 255) / 256;
+                if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+                dense_smalln_dx_kernel<<<(int)blocks, 256, 0, st>>>(err, w, e, M, N, K);
+                B200NN_LAUNCH_CHECK("dense_smalln_dx");
+            }
         }
         return B200NN_OK;
     }
