@@ -367,15 +367,15 @@ def run_leg(cfg, math, T, K, W, world, rank, peaks, tf32_peak, clock_sampler):
                 return {"skipped": "GAN under data parallelism is not wired"}
             parallel.make_gan_data_parallel(gan)
         real = np.random.default_rng(0).random((gb, 28, 28, 1)).astype(np.float32)
-        real_l = np.ascontiguousarray(real[rank * lb:(rank + 1) * lb])
+        real_l = real   # every rank passes the GLOBAL batch; GAN.train_on_batch keeps this rank's rows of the seeded index choice
         for _ in range(W):
-            out = gan.train_on_batch(real_l, None, lb, 1)
+            out = gan.train_on_batch(real, None, gb, 1)
         l0 = lib.b200nn_launch_count()
-        e2e_ms, out = T.time_steps(lambda: gan.train_on_batch(real_l, None, lb, 1), K)
+        e2e_ms, out = T.time_steps(lambda: gan.train_on_batch(real, None, gb, 1), K)
         launches = (lib.b200nn_launch_count() - l0) // K
         res.update({"ms_per_step": e2e_ms, "value": gb / (e2e_ms * 1e-3), "unit": "samples/s", "kernels_per_step": int(launches),
                     "e2e": {"value": gb / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
-                            "h2d_bytes_per_step": int(real_l.nbytes + lb * 32 * 4 * 2 + 3 * lb * 4), "d2h_bytes_per_step": 16,
+                            "h2d_bytes_per_step": int(lb * 784 * 4 + lb * 32 * 4 * 2 + 3 * lb * 4), "d2h_bytes_per_step": 16,
                             "last_losses": [float(out[0]), float(out[1])]},
                     "note": "GAN.train_on_batch through the public API (host noise + real batch uploaded, two losses read back every "
                             "step): value == e2e, there is no separate resident replay for the alternating G/D step"})

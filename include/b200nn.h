@@ -181,6 +181,8 @@ typedef struct {
 } b200nn_convt_geom;
 /* w is (kh,kw,F,C). y = act(scatter(x,w)[crop] + b). */
 size_t b200nn_convt_ws_bytes(const b200nn_convt_geom* g);
+/* math != FP32: the tensor-core path (column buffer + tcgen05 contractions, see gemm_simt.cu) needs the larger workspace */
+size_t b200nn_convt_ws_bytes_math(int math, const b200nn_convt_geom* g);
 int b200nn_convt_fwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* b,
                      float* y, int act, float alpha, float* ws, void* stream);
 /* Reference backward: windows read from the cropped error with NO pad offset; an input pixel whose

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "b200nn_conv2d_bwd": (c_int, [c_int, C.POINTER(ConvGeom), _P, _P, _P, _P, c_u64, _P, _P, _P, c_int, c_float, _P, _P,
                                    _P, _P]),
     "b200nn_convt_ws_bytes": (c_size_t, [C.POINTER(ConvTGeom)]),
+    "b200nn_convt_ws_bytes_math": (c_size_t, [c_int, C.POINTER(ConvTGeom)]),
     "b200nn_convt_fwd": (c_int, [c_int, C.POINTER(ConvTGeom), _P, _P, _P, _P, c_int, c_float, _P, _P]),
     "b200nn_convt_bwd": (c_int, [c_int, C.POINTER(ConvTGeom), _P, _P, _P, _P, c_u64, _P, _P, _P, c_int, c_float, _P, _P,
                                   _P, _P]),

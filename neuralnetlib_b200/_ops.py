@@ -175,8 +175,8 @@ def conv2d_bwd(math, g, x, w, err, ss, chain, dx, dw, db, prev_act, prev_alpha, 
                                   stream()))
 
 
-def convt_ws_bytes(g: ConvTGeom):
-    return int(lib().b200nn_convt_ws_bytes(C.byref(g)))
+def convt_ws_bytes(g: ConvTGeom, math=MATH_FP32):
+    return int(lib().b200nn_convt_ws_bytes_math(int(math), C.byref(g)))
 
 
 def convt_fwd(math, g, x, w, b, y, act, alpha, ws):

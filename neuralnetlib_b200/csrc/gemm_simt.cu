@@ -1307,6 +1307,339 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
 }
 
 // ---------------------------------------------------------------------------------------------- Conv2D
+
+// ------------------------------------------------------------------------------------------------
+// Convolutions the TMA implicit-GEMM path does not cover (strides, 'valid', any image size, any filter count incl. F = 1) in the
+// tensor-core math modes: im2col into a column buffer, then the Dense kernels — col[(n,oy,ox), (ky,kx,c)] . Wp[(ky,kx,c), f] —
+// i.e. tcgen05 (TF32 / 3xTF32), the skinny kernels, or the small-N kernels, whichever the shape selects (replaces
+// preprocessing.py:34-126 for those geometries). The column order (ky,kx,c) keeps both the gather and the column stores full
+// 16-byte accesses; the weights are permuted once per call from the reference's (c,ky,kx) order (Q1) and the weight gradient back.
+__global__ void __launch_bounds__(256) conv_im2col_kernel(b200nn_conv_geom g, const float* __restrict__ x, float* __restrict__ col,
+                                                          long long total4) {
+    const int C4 = g.C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4; long long t = i / C4;
+        const int kx = (int)(t % g.kw); t /= g.kw;
+        const int ky = (int)(t % g.kh); t /= g.kh;
+        const int ox = (int)(t % g.OW); t /= g.OW;
+        const int oy = (int)(t % g.OH); const int n = (int)(t / g.OH);
+        const int iy = oy * g.sh - g.ph + ky, ix = ox * g.sw - g.pw + kx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = *reinterpret_cast<const float4*>(x + (((long long)n * g.H + iy) * g.W + ix) * g.C + c);
+        *reinterpret_cast<float4*>(col + i * 4) = v;
+    }
+}
+
+// to_ref == 0: wp[(ky,kx,c), f] = w_flat[(c,ky,kx), f];  to_ref == 1: the inverse (weight gradient back to the reference order)
+__global__ void __launch_bounds__(256) conv_weight_permute_kernel(const float* __restrict__ src, float* __restrict__ dst, int kh, int kw,
+                                                                  int C, int F, int to_ref) {
+    const int total = kh * kw * C * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int f = i % F; int t = i / F;
+        const int c = t % C; t /= C;
+        const int kx = t % kw, ky = t / kw;                       // i indexes the (ky,kx,c) order
+        const int r = ((c * kh + ky) * kw + kx) * F + f;          // the same element in the reference order
+        if (to_ref) dst[r] = src[i]; else dst[i] = src[r];
+    }
+}
+
+// dx[n,iy,ix,c] = sum over the taps that reach (iy,ix) of dcol[(n,oy,ox), (ky,kx,c)]  (col2im, preprocessing.py:82-126), then the
+// preceding activation's backward and the two sum-of-squares slots
+__global__ void __launch_bounds__(256) conv_col2im_kernel(b200nn_conv_geom g, const float* __restrict__ dcol, const float* __restrict__ mask_y,
+                                                          int mask_act, float mask_alpha, float* __restrict__ dx, double* ss0, double* ss1,
+                                                          long long total4) {
+    __shared__ double scratch[32];
+    const int C4 = g.C >> 2, K = g.kh * g.kw * g.C;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4; long long t = i / C4;
+        const int ix = (int)(t % g.W); t /= g.W;
+        const int iy = (int)(t % g.H); const int n = (int)(t / g.H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int ty = iy + g.ph - ky;
+            if (ty < 0 || ty % g.sh != 0) continue;
+            const int oy = ty / g.sh;
+            if (oy >= g.OH) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int tx = ix + g.pw - kx;
+                if (tx < 0 || tx % g.sw != 0) continue;
+                const int ox = tx / g.sw;
+                if (ox >= g.OW) continue;
+                const float4 v = *reinterpret_cast<const float4*>(dcol + (((long long)n * g.OH + oy) * g.OW + ox) * K +
+                                                                  (long long)(ky * g.kw + kx) * g.C + c);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        a0 += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+        if (mask_y != nullptr) {
+            const float4 m = *reinterpret_cast<const float4*>(mask_y + i * 4);
+            acc.x *= act_grad_from_y(mask_act, m.x, mask_alpha); acc.y *= act_grad_from_y(mask_act, m.y, mask_alpha);
+            acc.z *= act_grad_from_y(mask_act, m.z, mask_alpha); acc.w *= act_grad_from_y(mask_act, m.w, mask_alpha);
+            a1 += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+        }
+        *reinterpret_cast<float4*>(dx + i * 4) = acc;
+    }
+    if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+    if (mask_y != nullptr && ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+}
+
+constexpr long long CONV_COL_MAX_BYTES = 1536LL << 20;   // per column buffer
+static bool conv_col_ok(const b200nn_conv_geom* g) {
+    const long long M = (long long)g->N * g->OH * g->OW, K = (long long)g->kh * g->kw * g->C;
+    return g->C % 4 == 0 && K >= 32 && M * K * 4 <= CONV_COL_MAX_BYTES && M * K * g->F >= (1LL << 20) && M < (1LL << 31) / 2;
+}
+struct ConvColWs {
+    float *col, *dcol, *wp, *dwp, *rest;
+};
+static size_t align64(size_t n) { return (n + 63) / 64 * 64; }
+static ConvColWs conv_col_ws(const b200nn_conv_geom* g, float* ws) {
+    const size_t MK = align64((size_t)g->N * g->OH * g->OW * g->kh * g->kw * g->C), KF = align64((size_t)g->kh * g->kw * g->C * g->F);
+    ConvColWs r;
+    r.col = ws; r.dcol = ws + MK; r.wp = r.dcol + MK; r.dwp = r.wp + KF; r.rest = r.dwp + KF;
+    return r;
+}
+
+
+}  // extern "C" (templates below)
+
+// ------------------------------------------------------------------------------------------------
+// Convolutions with a handful of filters (F <= 4: the generator's output layer, 28x28x32 -> 1) or a handful of input channels on
+// the data-gradient side (C <= 4: the discriminator's first layer). As GEMMs they have N <= 4, i.e. a tile that is almost all
+// padding; they are bandwidth problems (read the wide tensor once) and get direct kernels. Weights in the reference's effective
+// order W[c,ky,kx,f] = flat[((c*kh+ky)*kw+kx)*F + f] (Q1), staged in shared memory.
+constexpr int FEWF_MAX = 4;
+constexpr int FEW_SMEM_FLOATS = 8192;
+
+// y[n,oy,ox,f] = act(b[f] + sum_{ky,kx,c} x[n,iy,ix,c] * W[c,ky,kx,f]); thread = output pixel, float4 over c
+__global__ void __launch_bounds__(256) conv_fewf_fwd_kernel(b200nn_conv_geom g, const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int act, float alpha,
+                                                            long long n_pix) {
+    __shared__ float ws[FEW_SMEM_FLOATS];            // [(ky,kx)][c][f]
+    const int K = g.kh * g.kw * g.C, F = g.F;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) {
+        const int f = i % F; int t = i / F;
+        const int c = t % g.C, tap = t / g.C;
+        ws[i] = w[((long long)(c * g.kh + tap / g.kw) * g.kw + tap % g.kw) * F + f];
+    }
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(p % g.OW); long long t = p / g.OW;
+        const int oy = (int)(t % g.OH); const int n = (int)(t / g.OH);
+        float acc[FEWF_MAX];
+#pragma unroll
+        for (int f = 0; f < FEWF_MAX; ++f) acc[f] = (bias != nullptr && f < F) ? bias[f] : 0.0f;
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int iy = oy * g.sh - g.ph + ky;
+            if (iy < 0 || iy >= g.H) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int ix = ox * g.sw - g.pw + kx;
+                if (ix < 0 || ix >= g.W) continue;
+                const float4* xp = reinterpret_cast<const float4*>(x + (((long long)n * g.H + iy) * g.W + ix) * g.C);
+                const float* wt = ws + (ky * g.kw + kx) * g.C * F;
+                for (int c4 = 0; c4 < g.C / 4; ++c4) {
+                    const float4 v = xp[c4];
+#pragma unroll
+                    for (int f = 0; f < FEWF_MAX; ++f)
+                        if (f < F) {
+                            acc[f] = fmaf(v.x, wt[(c4 * 4 + 0) * F + f], acc[f]); acc[f] = fmaf(v.y, wt[(c4 * 4 + 1) * F + f], acc[f]);
+                            acc[f] = fmaf(v.z, wt[(c4 * 4 + 2) * F + f], acc[f]); acc[f] = fmaf(v.w, wt[(c4 * 4 + 3) * F + f], acc[f]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < FEWF_MAX; ++f)
+            if (f < F) y[p * F + f] = act_apply(act, acc[f], alpha);
+    }
+}
+
+// dx[n,iy,ix,c] = scale * sum_{ky,kx,f} err[n,oy,ox,f] * W[c,ky,kx,f] (+ activation backward, sum-of-squares slots).
+// thread = (input pixel, channel quad); works for few filters (scalar err loads) and any C % 4 == 0
+__global__ void __launch_bounds__(256) conv_fewf_dx_kernel(b200nn_conv_geom g, const float* __restrict__ err, const float* __restrict__ w,
+                                                           Epilogue epi, long long total4) {
+    __shared__ float ws[FEW_SMEM_FLOATS];            // [(ky,kx)][f][c]
+    __shared__ double scratch[32];
+    const int K = g.kh * g.kw * g.C, F = g.F, C4 = g.C >> 2;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) {
+        const int c = i % g.C; int t = i / g.C;
+        const int f = t % F, tap = t / F;
+        ws[i] = w[((long long)(c * g.kh + tap / g.kw) * g.kw + tap % g.kw) * F + f];
+    }
+    EpiState st;
+    epi_begin(epi, st);
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4; long long t = i / C4;
+        const int ix = (int)(t % g.W); t /= g.W;
+        const int iy = (int)(t % g.H); const int n = (int)(t / g.H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int ty = iy + g.ph - ky;
+            if (ty < 0 || ty % g.sh != 0) continue;
+            const int oy = ty / g.sh;
+            if (oy >= g.OH) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int tx = ix + g.pw - kx;
+                if (tx < 0 || tx % g.sw != 0) continue;
+                const int ox = tx / g.sw;
+                if (ox >= g.OW) continue;
+                const float* ep = err + (((long long)n * g.OH + oy) * g.OW + ox) * F;
+                const float* wt = ws + (ky * g.kw + kx) * F * g.C + c;
+                for (int f = 0; f < F; ++f) {
+                    const float e = ep[f];
+                    const float4 wv = *reinterpret_cast<const float4*>(wt + f * g.C);
+                    acc.x = fmaf(e, wv.x, acc.x); acc.y = fmaf(e, wv.y, acc.y); acc.z = fmaf(e, wv.z, acc.z); acc.w = fmaf(e, wv.w, acc.w);
+                }
+            }
+        }
+        float v[4] = {acc.x * st.scale, acc.y * st.scale, acc.z * st.scale, acc.w * st.scale};
+        float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (epi.mask_y != nullptr) mk = *reinterpret_cast<const float4*>(epi.mask_y + i * 4);
+        const float m[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            st.a0 = fmaf(v[j], v[j], st.a0);
+            if (epi.mask_y != nullptr) {
+                v[j] *= act_grad_from_y(epi.mask_act, m[j], epi.mask_alpha);
+                st.a1 = fmaf(v[j], v[j], st.a1);
+            }
+        }
+        *reinterpret_cast<float4*>(epi.out + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    epi_finish(epi, st, scratch);
+}
+
+// dx for a few INPUT channels (C <= 4, F % 4 == 0): thread = (input pixel, c), float4 over the filters of the error
+__global__ void __launch_bounds__(256) conv_fewc_dx_kernel(b200nn_conv_geom g, const float* __restrict__ err, const float* __restrict__ w,
+                                                           Epilogue epi, long long total) {
+    __shared__ float ws[FEW_SMEM_FLOATS];            // [c][(ky,kx)][f] == the flat weight buffer
+    __shared__ double scratch[32];
+    const int K = g.kh * g.kw * g.C, F = g.F;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) ws[i] = w[i];
+    EpiState st;
+    epi_begin(epi, st);
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % g.C); long long t = i / g.C;
+        const int ix = (int)(t % g.W); t /= g.W;
+        const int iy = (int)(t % g.H); const int n = (int)(t / g.H);
+        float acc = 0.0f;
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int ty = iy + g.ph - ky;
+            if (ty < 0 || ty % g.sh != 0) continue;
+            const int oy = ty / g.sh;
+            if (oy >= g.OH) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int tx = ix + g.pw - kx;
+                if (tx < 0 || tx % g.sw != 0) continue;
+                const int ox = tx / g.sw;
+                if (ox >= g.OW) continue;
+                const float4* ep = reinterpret_cast<const float4*>(err + (((long long)n * g.OH + oy) * g.OW + ox) * F);
+                const float4* wt = reinterpret_cast<const float4*>(ws + ((c * g.kh + ky) * g.kw + kx) * F);
+                for (int f4 = 0; f4 < F / 4; ++f4) {
+                    const float4 e = ep[f4], wv = wt[f4];
+                    acc = fmaf(e.x, wv.x, acc); acc = fmaf(e.y, wv.y, acc); acc = fmaf(e.z, wv.z, acc); acc = fmaf(e.w, wv.w, acc);
+                }
+            }
+        }
+        const float mk = epi.mask_y != nullptr ? epi.mask_y[i] : 0.0f;
+        float v = acc * st.scale;
+        st.a0 = fmaf(v, v, st.a0);
+        if (epi.mask_y != nullptr) {
+            v *= act_grad_from_y(epi.mask_act, mk, epi.mask_alpha);
+            st.a1 = fmaf(v, v, st.a1);
+        }
+        epi.out[i] = v;
+    }
+    epi_finish(epi, st, scratch);
+}
+
+// Weight / bias gradient for a few filters: dW[c,ky,kx,f] = sum_pix x[n,iy,ix,c] * err[n,oy,ox,f]. A warp owns one channel quad and
+// a strided set of INPUT pixels (lane = pixel); each lane accumulates its pixel's contribution to the (tap, 4 channels, f) outputs of
+// the quad in registers, the warp folds them with shuffles and writes one partial row block: partial[group][(c,ky,kx) | bias][f].
+template <int TAPS, int FM>
+__global__ void __launch_bounds__(256) conv_fewf_wgrad_kernel(b200nn_conv_geom g, const float* __restrict__ x, const float* __restrict__ err,
+                                                              float* __restrict__ partial, long long n_in_pix, long long n_out_pix) {
+    const int lane = threadIdx.x & 31;
+    const int C4 = g.C >> 2, F = g.F, K = g.kh * g.kw * g.C;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
+    const int cq = wg % C4, group = wg / C4, n_groups = total_warps / C4;
+    if (group >= n_groups) return;
+    float acc[TAPS][4][FM];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f) acc[t][j][f] = 0.0f;
+    for (long long p = (long long)group * 32 + lane; p < n_in_pix; p += (long long)n_groups * 32) {
+        const int ix = (int)(p % g.W); long long t = p / g.W;
+        const int iy = (int)(t % g.H); const int n = (int)(t / g.H);
+        const float4 xv = *reinterpret_cast<const float4*>(x + p * g.C + cq * 4);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) {
+            const int ky = tap / g.kw, kx = tap % g.kw;
+            const int ty = iy + g.ph - ky, tx = ix + g.pw - kx;
+            if (ty < 0 || tx < 0 || ty % g.sh != 0 || tx % g.sw != 0) continue;
+            const int oy = ty / g.sh, ox = tx / g.sw;
+            if (oy >= g.OH || ox >= g.OW) continue;
+            const float* ep = err + (((long long)n * g.OH + oy) * g.OW + ox) * F;
+#pragma unroll
+            for (int f = 0; f < FM; ++f) {
+                if (f < F) {
+                    const float e = ep[f];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[tap][j][f] = fmaf(xs[j], e, acc[tap][j][f]);
+                }
+            }
+        }
+    }
+    float* pb = partial + (long long)group * (K + 1) * F;
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f) {
+                const float r = warp_sum(acc[tap][j][f]);
+                if (lane == 0 && f < F) {
+                    const int c = cq * 4 + j;
+                    pb[((long long)(c * g.kh + tap / g.kw) * g.kw + tap % g.kw) * F + f] = r;   // reference row order (c,ky,kx)
+                }
+            }
+    if (cq == 0) {   // bias row: sum of the error over this group's share of the OUTPUT pixels
+        float bs[FM];
+#pragma unroll
+        for (int f = 0; f < FM; ++f) bs[f] = 0.0f;
+        for (long long p = (long long)group * 32 + lane; p < n_out_pix; p += (long long)n_groups * 32)
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                if (f < F) bs[f] += err[p * F + f];
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+            const float r = warp_sum(bs[f]);
+            if (lane == 0 && f < F) pb[(long long)K * F + f] = r;
+        }
+    }
+}
+
+static bool conv_fewf_ok(const b200nn_conv_geom* g) {
+    return g->F <= FEWF_MAX && g->C % 4 == 0 && g->kh * g->kw * g->C * g->F <= FEW_SMEM_FLOATS && g->kh * g->kw == 9;
+}
+static bool conv_fewc_dx_ok(const b200nn_conv_geom* g) {
+    return g->C <= 4 && g->F % 4 == 0 && g->kh * g->kw * g->C * g->F <= FEW_SMEM_FLOATS;
+}
+static int conv_fewf_groups(const b200nn_conv_geom* g) {
+    const int C4 = g->C / 4;
+    int warps = kNumSMs * 2 * 8;
+    int groups = warps / C4;
+    return groups < 1 ? 1 : groups;
+}
+
+extern "C" {
+
 static int check_conv_geom(const char* who, const b200nn_conv_geom* g) {
     B200NN_REQUIRE(g != nullptr, "%s: null geometry", who);
     B200NN_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->F > 0 && g->kh > 0 && g->kw > 0 && g->sh > 0 &&
@@ -1324,6 +1657,12 @@ static int check_conv_geom(const char* who, const b200nn_conv_geom* g) {
 size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g);
 size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g) {
     size_t r = b200nn_conv2d_ws_bytes(g);
+    if (math != B200NN_MATH_FP32 && !tcapi::conv_ok(g, nullptr, nullptr, nullptr) && conv_col_ok(g)) {
+        const long long M = (long long)g->N * g->OH * g->OW, K = (long long)g->kh * g->kw * g->C;
+        const size_t cw = (size_t)(conv_col_ws(g, nullptr).rest - (float*)nullptr) * sizeof(float) +
+                          b200nn_dense_ws_bytes_math(math, (int)M, g->F, (int)K) + 256;
+        r = r > cw ? r : cw;
+    }
     if (math != B200NN_MATH_FP32 && tcapi::conv_ok(g, nullptr, nullptr, nullptr)) {
         size_t t = tcapi::conv_ws1(g, math == B200NN_MATH_TF32X3);
         const size_t t2 = tcapi::conv_ws2(g, math == B200NN_MATH_TF32X3);
@@ -1347,6 +1686,10 @@ size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
         const size_t d = (size_t)smallk_wgrad_blocks(g) * (Kf + 1) * g->F * sizeof(float);
         r = r > d ? r : d;
     }
+    if (conv_fewf_ok(g)) {
+        const size_t d = (size_t)conv_fewf_groups(g) * (Kf + 1) * g->F * sizeof(float);
+        r = r > d ? r : d;
+    }
     return r;
 }
 
@@ -1368,6 +1711,27 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
         Epilogue e = plain_epilogue(y, g->F, M);
         e.bias = b; e.act = act; e.alpha = alpha;
         return tc_conv_any(1, g, x, w, e, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
+    }
+    if (conv_fewf_ok(g) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {       // a handful of filters: direct kernel, every math mode
+        long long blocks = ((long long)M + 255) / 256;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        conv_fewf_fwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(*g, x, w, b, y, act, alpha, M);
+        B200NN_LAUNCH_CHECK("conv_fewf_fwd");
+        return B200NN_OK;
+    }
+    if (math != B200NN_MATH_FP32 && ws != nullptr && conv_col_ok(g) &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0) {
+        // im2col + the Dense kernels (tcgen05 / skinny / small-N, by shape)
+        cudaStream_t st = as_stream(stream);
+        const ConvColWs cw = conv_col_ws(g, ws);
+        const long long total4 = (long long)M * K / 4;
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+        conv_im2col_kernel<<<(int)blocks, 256, 0, st>>>(*g, x, cw.col, total4);
+        B200NN_LAUNCH_CHECK("conv_im2col");
+        conv_weight_permute_kernel<<<(K * g->F + 255) / 256, 256, 0, st>>>(w, cw.wp, g->kh, g->kw, g->C, g->F, 0);
+        B200NN_LAUNCH_CHECK("conv_weight_permute");
+        return b200nn_dense_fwd(math, cw.col, cw.wp, b, y, M, g->F, K, act, alpha, cw.rest, stream);
     }
     if (smallk_fwd_ok(g) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
         long long blocks = ((long long)M + 127) / 128;
@@ -1419,6 +1783,60 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
         }
         return B200NN_OK;
     }
+    if (conv_fewf_ok(g) && ws != nullptr && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+        // a handful of filters: direct bandwidth kernels in every math mode
+        if (dw != nullptr) {
+            const int groups = conv_fewf_groups(g);
+            const int warps = groups * (g->C / 4);
+            Epilogue e = plain_epilogue(dw, g->F, Kf);
+            e.ss = ss; e.chain = chain; e.db = db;
+            if (g->F == 1) conv_fewf_wgrad_kernel<9, 1><<<(warps + 7) / 8, 256, 0, st>>>(*g, x, err, ws, Mi, Mo);
+            else if (g->F == 2) conv_fewf_wgrad_kernel<9, 2><<<(warps + 7) / 8, 256, 0, st>>>(*g, x, err, ws, Mi, Mo);
+            else conv_fewf_wgrad_kernel<9, 4><<<(warps + 7) / 8, 256, 0, st>>>(*g, x, err, ws, Mi, Mo);
+            B200NN_LAUNCH_CHECK("conv_fewf_wgrad");
+            if (int rc = launch_splitk_reduce(ws, groups, Kf + 1, g->F, e, st)) return rc;
+        }
+        if (dx != nullptr) {
+            Epilogue e = plain_epilogue(dx, g->C, Mi);
+            dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+            const long long t4 = (long long)Mi * g->C / 4;
+            long long b2 = (t4 + 255) / 256;
+            if (b2 > kNumSMs * 16) b2 = kNumSMs * 16;
+            conv_fewf_dx_kernel<<<(int)b2, 256, 0, st>>>(*g, err, w, e, t4);
+            B200NN_LAUNCH_CHECK("conv_fewf_dx");
+        }
+        return B200NN_OK;
+    }
+    if (math != B200NN_MATH_FP32 && ws != nullptr && conv_col_ok(g) &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(ws) |
+          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0) {
+        // im2col + the Dense backward on the column matrix; the data gradient comes back through col2im (+ activation backward)
+        const ConvColWs cw = conv_col_ws(g, ws);
+        const long long total4 = (long long)Mo * Kf / 4;
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+        if (dw != nullptr) {
+            conv_im2col_kernel<<<(int)blocks, 256, 0, st>>>(*g, x, cw.col, total4);
+            B200NN_LAUNCH_CHECK("conv_im2col");
+        }
+        conv_weight_permute_kernel<<<(Kf * g->F + 255) / 256, 256, 0, st>>>(w, cw.wp, g->kh, g->kw, g->C, g->F, 0);
+        B200NN_LAUNCH_CHECK("conv_weight_permute");
+        if (int rc = b200nn_dense_bwd(math, cw.col, cw.wp, err, ss, chain, dx != nullptr ? cw.dcol : nullptr, dw != nullptr ? cw.dwp : nullptr, db,
+                                      Mo, g->F, Kf, B200NN_ACT_NONE, 0.0f, nullptr, nullptr, cw.rest, stream)) return rc;
+        if (dw != nullptr) {
+            conv_weight_permute_kernel<<<(Kf * g->F + 255) / 256, 256, 0, st>>>(cw.dwp, dw, g->kh, g->kw, g->C, g->F, 1);
+            B200NN_LAUNCH_CHECK("conv_weight_permute_back");
+        }
+        if (dx != nullptr) {
+            const long long t4 = (long long)Mi * g->C / 4;
+            long long b2 = (t4 + 255) / 256;
+            if (b2 > kNumSMs * 16) b2 = kNumSMs * 16;
+            conv_col2im_kernel<<<(int)b2, 256, 0, st>>>(*g, cw.dcol, prev_act != B200NN_ACT_NONE ? x : nullptr, prev_act, prev_alpha, dx,
+                                                       ss_out0, ss_out1, t4);
+            B200NN_LAUNCH_CHECK("conv_col2im");
+        }
+        return B200NN_OK;
+    }
     if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
         const int nb = smallk_wgrad_blocks(g), TP = smallk_wgrad_tile(g);
         Epilogue e = plain_epilogue(dw, g->F, Kf);
@@ -1449,7 +1867,15 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
         e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
         if (int rc = launch_gemm("conv2d_dw", af, bf, e, Kf + (db != nullptr ? 1 : 0), g->F, Mo, ws, st)) return rc;
     }
-    if (dx != nullptr) {  // gather form of col2im(err . W^T), preprocessing.py:82-126
+    if (dx != nullptr && conv_fewc_dx_ok(g) && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {   // a handful of input channels
+        Epilogue e = plain_epilogue(dx, g->C, Mi);
+        dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
+        const long long total = (long long)Mi * g->C;
+        long long b2 = (total + 255) / 256;
+        if (b2 > kNumSMs * 16) b2 = kNumSMs * 16;
+        conv_fewc_dx_kernel<<<(int)b2, 256, 0, st>>>(*g, err, w, e, total);
+        B200NN_LAUNCH_CHECK("conv_fewc_dx");
+    } else if (dx != nullptr) {  // gather form of col2im(err . W^T), preprocessing.py:82-126
         StridedGatherA af;
         af.src = err; af.SH = g->OH; af.SW = g->OW; af.SC = g->F; af.DH = g->H; af.DW = g->W;
         af.kh = g->kh; af.kw = g->kw; af.sh = g->sh; af.sw = g->sw; af.py = g->ph; af.px = g->pw;
@@ -1463,6 +1889,71 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
 }
 
 // ---------------------------------------------------------------------------------------------- Conv2DTranspose
+
+// ------------------------------------------------------------------------------------------------
+// Conv2DTranspose on the tensor cores (layers.py:2588-2659). The scatter form of the reference IS a plain contraction per INPUT
+// pixel: Ycol[(n,h,w), (i,j,f)] = sum_c x[n,h,w,c] * W[i,j,f,c] — A = x [pixels, C] and B = the weight buffer [(i,j,f), C], both
+// K-major as they lie in memory — followed by the overlap-add (each output pixel gathers its <= ceil(k/s)^2 contributions, bias
+// and activation fused). The backward is two more plain contractions on Ecol[(n,h,w), (i,j,f)] = the stride-s window of the
+// cropped error (no pad offset; a window truncated at the border is SKIPPED entirely, layers.py:2651, Q12), pending clips folded
+// in: dX = Ecol . W[(i,j,f), c] and dW = Ecol^T . x. The column buffers (k*k/s*s times the output) live in the workspace.
+__global__ void __launch_bounds__(256) convt_overlap_add_kernel(b200nn_convt_geom g, const float* __restrict__ ycol,
+                                                                const float* __restrict__ bias, float* __restrict__ y, int act,
+                                                                float alpha, long long total4) {
+    const int F4 = g.F >> 2, NC = g.kh * g.kw * g.F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F4) * 4; long long t = i / F4;
+        const int ox = (int)(t % g.OW); t /= g.OW;
+        const int oy = (int)(t % g.OH); const int n = (int)(t / g.OH);
+        float4 acc = bias != nullptr ? *reinterpret_cast<const float4*>(bias + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int ty = oy + g.pt - ky;
+            if (ty < 0 || ty % g.sh != 0) continue;
+            const int h = ty / g.sh;
+            if (h >= g.H) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int tx = ox + g.pl - kx;
+                if (tx < 0 || tx % g.sw != 0) continue;
+                const int w_ = tx / g.sw;
+                if (w_ >= g.W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(ycol + (((long long)n * g.H + h) * g.W + w_) * NC +
+                                                                  (long long)(ky * g.kw + kx) * g.F + f);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        acc = make_float4(act_apply(act, acc.x, alpha), act_apply(act, acc.y, alpha), act_apply(act, acc.z, alpha), act_apply(act, acc.w, alpha));
+        *reinterpret_cast<float4*>(y + i * 4) = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) convt_window_gather_kernel(b200nn_convt_geom g, const float* __restrict__ err,
+                                                                  const double* __restrict__ ss, uint64_t chain,
+                                                                  float* __restrict__ ecol, long long total4) {
+    const float scale = chain_scale(ss, chain);
+    const int F4 = g.F >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F4) * 4; long long t = i / F4;
+        const int kx = (int)(t % g.kw); t /= g.kw;
+        const int ky = (int)(t % g.kh); t /= g.kh;
+        const int w_ = (int)(t % g.W); t /= g.W;
+        const int h = (int)(t % g.H); const int n = (int)(t / g.H);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool whole = h * g.sh + g.kh <= g.OH && w_ * g.sw + g.kw <= g.OW;          // layers.py:2651: truncated windows are skipped
+        if (whole) {
+            v = *reinterpret_cast<const float4*>(err + (((long long)n * g.OH + h * g.sh + ky) * g.OW + w_ * g.sw + kx) * g.F + f);
+            v = make_float4(scale * v.x, scale * v.y, scale * v.z, scale * v.w);
+        }
+        *reinterpret_cast<float4*>(ecol + i * 4) = v;
+    }
+}
+
+static bool convt_tc_ok(const b200nn_convt_geom* g, const void* a, const void* b, const void* c) {
+    if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) != 0) return false;
+    return g->C % 4 == 0 && g->F % 4 == 0 && g->C >= 32 && (long long)g->kh * g->kw * g->F >= 64 &&
+           (long long)g->N * g->H * g->W * g->C * g->kh * g->kw * g->F >= (1LL << 22);
+}
+static size_t convt_col_floats(const b200nn_convt_geom* g) { return (size_t)g->N * g->H * g->W * g->kh * g->kw * g->F; }
+
 static int check_convt_geom(const char* who, const b200nn_convt_geom* g) {
     B200NN_REQUIRE(g != nullptr, "%s: null geometry", who);
     B200NN_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->F > 0 && g->kh > 0 && g->kw > 0 && g->sh > 0 &&
@@ -1484,11 +1975,41 @@ size_t b200nn_convt_ws_bytes(const b200nn_convt_geom* g) {
     return r > d ? r : d;
 }
 
+size_t b200nn_convt_ws_bytes_math(int math, const b200nn_convt_geom* g) {
+    size_t r = b200nn_convt_ws_bytes(g);
+    if (math != B200NN_MATH_FP32 && g != nullptr && convt_tc_ok(g, nullptr, nullptr, nullptr)) {
+        const bool x3 = math == B200NN_MATH_TF32X3;
+        const long long M = (long long)g->N * g->H * g->W, NC = (long long)g->kh * g->kw * g->F;
+        size_t t = tcapi::ws2(M, NC, g->C, x3);                       // forward  Ycol = x . W^T
+        const size_t d = tcapi::ws2(M, g->C, NC, x3), e = tcapi::ws2(NC, g->C, M, x3);
+        t = t > d ? t : d; t = t > e ? t : e;
+        const size_t db = (size_t)kNumSMs * 2 * g->F * sizeof(float);
+        t = t > db ? t : db;
+        const size_t tc = convt_col_floats(g) * sizeof(float) + 256 + t;   // column buffer | GEMM split-K / db partials
+        r = r > tc ? r : tc;
+    }
+    return r;
+}
+
 int b200nn_convt_fwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* b,
                      float* y, int act, float alpha, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "convt_fwd: unsupported math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "convt_fwd: unknown math mode %d", math);
     if (int rc = check_convt_geom("convt_fwd", g)) return rc;
     if (int rc = check_act("convt_fwd", act, alpha)) return rc;
+    if (math != B200NN_MATH_FP32 && ws != nullptr && tcapi::tc2_enabled() && convt_tc_ok(g, x, w, y)) {
+        cudaStream_t st = as_stream(stream);
+        const int M = g->N * g->H * g->W, NC = g->kh * g->kw * g->F;
+        float* ycol = ws;
+        float* gws = ws + ((convt_col_floats(g) + 63) / 64) * 64;
+        Epilogue e = plain_epilogue(ycol, NC, M);
+        if (int rc = tc_gemm_any(x, g->C, false, w, g->C, false, e, M, NC, g->C, gws, st, math == B200NN_MATH_TF32X3)) return rc;
+        const long long total4 = (long long)g->N * g->OH * g->OW * (g->F / 4);
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        convt_overlap_add_kernel<<<(int)blocks, 256, 0, st>>>(*g, ycol, b, y, act, alpha, total4);
+        B200NN_LAUNCH_CHECK("convt_overlap_add");
+        return B200NN_OK;
+    }
     StridedGatherA af;
     af.src = x; af.SH = g->H; af.SW = g->W; af.SC = g->C; af.DH = g->OH; af.DW = g->OW;
     af.kh = g->kh; af.kw = g->kw; af.sh = g->sh; af.sw = g->sw; af.py = g->pt; af.px = g->pl;
@@ -1502,12 +2023,42 @@ int b200nn_convt_fwd(int math, const b200nn_convt_geom* g, const float* x, const
 int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const float* w, const float* err,
                      const double* ss, uint64_t chain, float* dx, float* dw, float* db, int prev_act,
                      float prev_alpha, double* ss_out0, double* ss_out1, float* ws, void* stream) {
-    B200NN_REQUIRE(math == B200NN_MATH_FP32, "convt_bwd: unsupported math mode %d", math);
+    B200NN_REQUIRE(math >= B200NN_MATH_FP32 && math <= B200NN_MATH_TF32X3, "convt_bwd: unknown math mode %d", math);
     if (int rc = check_convt_geom("convt_bwd", g)) return rc;
     if (int rc = check_act("convt_bwd", prev_act, prev_alpha)) return rc;
     cudaStream_t st = as_stream(stream);
     const int Mi = g->N * g->H * g->W;
     const int Kb = g->kh * g->kw * g->F;
+    if (math != B200NN_MATH_FP32 && ws != nullptr && tcapi::tc2_enabled() && convt_tc_ok(g, x, w, err) &&
+        ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0) {
+        const bool x3 = math == B200NN_MATH_TF32X3;
+        float* ecol = ws;
+        float* gws = ws + ((convt_col_floats(g) + 63) / 64) * 64;
+        if (db != nullptr) {  // layers.py:2641: sum over ALL error pixels
+            const long long R = (long long)g->N * g->OH * g->OW;
+            int nb = (int)((R + 63) / 64);
+            if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+            colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, gws);
+            B200NN_LAUNCH_CHECK("convt_db_partial");
+            colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(gws, nb, g->F, ss, chain, db);
+            B200NN_LAUNCH_CHECK("convt_db_final");
+        }
+        const long long total4 = (long long)Mi * g->kh * g->kw * (g->F / 4);
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        convt_window_gather_kernel<<<(int)blocks, 256, 0, st>>>(*g, err, ss, chain, ecol, total4);   // pending clips folded in here
+        B200NN_LAUNCH_CHECK("convt_window_gather");
+        if (dw != nullptr) {  // dw[(ky,kx,f), c] = Ecol^T . x : both operands MN-major
+            Epilogue e = plain_epilogue(dw, g->C, Kb);
+            if (int rc = tc_gemm_any(ecol, Kb, true, x, g->C, true, e, Kb, g->C, Mi, gws, st, x3)) return rc;
+        }
+        if (dx != nullptr) {  // dx[pix, c] = Ecol . w[(ky,kx,f), c]
+            Epilogue e = plain_epilogue(dx, g->C, Mi);
+            dx_epilogue(e, nullptr, 0, x, prev_act, prev_alpha, ss_out0, ss_out1);
+            if (int rc = tc_gemm_any(ecol, Kb, false, w, g->C, true, e, Mi, g->C, Kb, gws, st, x3)) return rc;
+        }
+        return B200NN_OK;
+    }
     // windows over the (cropped) error, stride s, no pad offset, truncated windows skipped (layers.py:2645-2651)
     PatchGather p;
     p.src = err; p.SH = g->OH; p.SW = g->OW; p.SC = g->F; p.OH = g->H; p.OW = g->W;

@@ -696,10 +696,10 @@ class Conv2DTranspose(Conv2D):
             self.d_weights = np.zeros(self._shapes["weights"]); self.d_bias = np.zeros((1, 1, 1, self.filters))
         assert x.shape[3] == self._weights.shape[3], "Number of input channels must match"
         g = self._geometry(x.shape)
-        ctx.need_ws(ops.convt_ws_bytes(g))
+        math = _math_code()   # tensor-core modes: column buffer + tcgen05 contractions where eligible, FFMA otherwise
+        ctx.need_ws(ops.convt_ws_bytes(g, math))
         y = ctx.buf((x.shape[0], g.OH, g.OW, self.filters))
         kind, alpha = _act_of(act_layer)
-        math = ops.MATH_FP32
         st.update(x=x, g=g, math=math)
         w, b = self._weights, self._bias
         ctx.emit(lambda: ops.convt_fwd(math, g, x, w, b, y, kind, alpha, ctx.ws), "convt_fwd", (x, w, b, y))

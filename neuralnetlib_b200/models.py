@@ -463,6 +463,7 @@ class GAN(BaseModel):
         self._image_height, self._image_width = image_height, image_width
         self.label_smoothing = label_smoothing
         self._train_step = 0
+        self._dp = None   # parallel.make_gan_data_parallel
 
     def compile(self, generator: Sequential, discriminator: Sequential, generator_optimizer, discriminator_optimizer,
                 loss_function="bce", verbose: bool = False, metrics: list | None = None):
@@ -501,12 +502,20 @@ class GAN(BaseModel):
         real_samples = np.asarray(real_samples)
         rng = np.random.default_rng(self.random_state)
         d_loss_total = 0.0
+        # data parallel (parallel.make_gan_data_parallel): every rank is given the same GLOBAL arguments; the globally seeded
+        # index choice and latent noise are generated in full and this rank keeps its rows [lo, hi) of each
+        gdp = getattr(self, "_dp", None)
+        lo, hi = (0, batch_size)
+        if gdp is not None:
+            from .parallel import shard_rows
+            lo, hi = shard_rows(batch_size, gdp.world, gdp.rank)
+        global_batch, batch_size = batch_size, hi - lo
         comb_labels = np.zeros((2 * batch_size, 1), dtype=np.float32)
         comb_labels[:batch_size] = self.label_smoothing
         comb_labels[batch_size:] = 1 - self.label_smoothing
         for _ in range(n_critic):
-            idx = rng.choice(len(real_samples), batch_size, replace=False)
-            z, _ = self._generate_latent_points(batch_size)
+            idx = rng.choice(len(real_samples), global_batch, replace=False)[lo:hi]
+            z = self._generate_latent_points(global_batch)[0][lo:hi]
             fake = G._forward_dev(z, training=False)
             d_in_shape = (2 * batch_size,) + tuple(real_samples.shape[1:])
             d_plan = D._plan(d_in_shape, True)
@@ -520,7 +529,7 @@ class GAN(BaseModel):
             d_loss_total += self._loss_value(D, d_plan, True)
         d_loss_avg = d_loss_total / n_critic
 
-        z, _ = self._generate_latent_points(batch_size)
+        z = self._generate_latent_points(global_batch)[0][lo:hi]
         fake = G._forward_dev(z, training=True)
         D._forward_dev(fake.reshape((batch_size,) + tuple(real_samples.shape[1:])), training=False)
         ones = np.ones((batch_size, 1), dtype=np.float32)
@@ -528,7 +537,9 @@ class GAN(BaseModel):
         dp = D._last_plan
         dp.set_target(ones)
         dp.program("loss").run()
-        g_loss = self._loss_value(D, dp)
+        if self._dp is not None:   # the generator loss is the mean over the GLOBAL batch: sum the numerators over the ranks
+            self._dp.comm.allreduce(dp.acc[0:1])
+        g_loss = self._loss_value(D, dp) / (self._dp.world if self._dp is not None else 1)
         # models.py:2661-2664: g_grad = loss.derivative(ones, predictions); with a Sigmoid+BCE discriminator the
         # shortcut in Sequential.backward_pass replaces it by predictions - ones
         g_grad = B.empty(tuple(dp.pred.shape))

@@ -220,3 +220,19 @@ def make_data_parallel(model, comm: Communicator | None = None, group=None):
     model._dp = DataParallel(comm) if comm.world > 1 else None
     model._drop_plans()
     return model
+
+
+def make_gan_data_parallel(gan, comm: Communicator | None = None, group=None):
+    """Data-parallel `GAN.train_on_batch` / `fit` (models.py:2609-2667 on a sharded batch): generator and discriminator become
+    data-parallel replicas sharing ONE communicator, and `train_on_batch(real_samples, None, batch_size=G)` — called with the same
+    GLOBAL arguments on every rank — trains on this rank's rows of the globally seeded real-index choice and latent noise. The
+    discriminator sees 2 * G / world rows per rank; gradient sums, clip norms and both losses are those of the global batch."""
+    if gan.generator is None or gan.discriminator is None:
+        raise ValueError("compile the GAN before make_gan_data_parallel")
+    if comm is None:
+        comm = Communicator(group)
+    for net in (gan.generator, gan.discriminator):
+        net._dp = DataParallel(comm) if comm.world > 1 else None
+        net._drop_plans()
+    gan._dp = gan.discriminator._dp
+    return gan

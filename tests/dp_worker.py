@@ -124,6 +124,29 @@ def run_fit(rank, world, comm):
     assert abs(h["loss"][0] - float(np.mean(losses))) <= 2e-4 * abs(np.mean(losses)), (h["loss"][0], np.mean(losses))
 
 
+def run_gan(rank, world, comm):
+    """GAN.train_on_batch under data parallelism (every rank passes the GLOBAL batch) against the single-process oracle on the
+    global batch: both losses, and bit-identical generator replicas."""
+    from neuralnetlib_b200 import parallel as P
+    sys.path.insert(0, ROOT)
+    from bench import build_gan
+    gan = build_gan()
+    P.make_gan_data_parallel(gan, comm)
+    bs = 8 * world
+    real = np.random.default_rng(5).random((bs, 28, 28, 1)).astype(np.float32)
+    gs, ds = O.gan_specs()
+    Gr, Dr = O.OracleSequential(gs, "bce", O.OracleAdam(), seed=7), O.OracleSequential(ds, "bce", O.OracleAdam(), seed=7)
+    for s in range(2):
+        dl, gl = gan.train_on_batch(real, None, bs, 1)
+        rdl, rgl = O.gan_train_on_batch(Gr, Dr, real.astype(np.float64), bs, 32, 7)
+        tol = 2e-5 if s == 0 else 2e-3   # step 1 starts from post-Adam weights (no teacher forcing here)
+        assert abs(dl - rdl) <= tol * max(1.0, abs(rdl)) and abs(gl - rgl) <= tol * max(1.0, abs(rgl)), (s, dl, rdl, gl, rgl)
+    w = torch.from_numpy(np.concatenate([l.weights.ravel() for l in gan.generator.layers if hasattr(l, "weights")])).to(torch.float64)
+    ws = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert all(torch.equal(ws[0], t) for t in ws), "GAN: generator replicas diverged"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -139,6 +162,8 @@ def main():
         print(f"[rank {rank}] {kind} ok, timeouts so far {comm.timeouts()}", flush=True)
     run_fit(rank, world, comm)
     print(f"[rank {rank}] fit ok", flush=True)
+    run_gan(rank, world, comm)
+    print(f"[rank {rank}] gan ok", flush=True)
     assert comm.timeouts() == 0, "a peer exchange timed out"
     dist.barrier()
     if rank == 0:

@@ -149,9 +149,16 @@ def test_full_size_step_golden(golden, name, cfg, batch, math):
     assert m.optimizer.t == int(g["adam_t"])
 
 
-def test_gan_batch64_golden(golden):
-    """Two GAN.train_on_batch steps of the notebook GAN at batch 64 (the round-1 trace was batch 4)."""
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+def test_gan_batch64_golden(golden, math):
+    """Two GAN.train_on_batch steps of the notebook GAN at batch 64 (the round-1 trace was batch 4). fp32: every gradient within
+    5e-5. tf32x3 (Conv2DTranspose and the strided convolutions on the tensor cores): losses 2e-5, every gradient with no ReLU
+    between it and the loss (the generator's output convolution, the whole discriminator) within 1e-4; the generator's layers BELOW
+    its ReLUs are bounded at 5e-2 — a ~1e-6 forward difference flips a few of the 1.6 M ReLU masks and each flip moves one element
+    of an error tensor whose norm is tiny at this point of training (the same effect as in test_full_size_step_golden)."""
+    import neuralnetlib_b200 as nn
     from bench import build_gan
+    nn.set_math(math)
     g = golden("gan_b64")
     gan = build_gan()
     real = g["real"].astype(np.float32)
@@ -161,9 +168,12 @@ def test_gan_batch64_golden(golden):
         assert abs(gl - float(g[f"s{s}_g_loss"])) <= 2e-5 * max(1.0, abs(float(g[f"s{s}_g_loss"]))), (s, gl)
         if s == 0:
             for nm, M in (("G", gan.generator), ("D", gan.discriminator)):
+                last = max(li for li, L in enumerate(M.layers) if hasattr(L, "weights"))
                 for li, L in enumerate(M.layers):
                     if hasattr(L, "weights"):
-                        check_packed(g, f"s0_{nm}{li}_dw", L.d_weights, 5e-5, what=f"{nm}{li} ")
+                        below_relu = nm == "G" and li < last
+                        tol = 5e-5 if math == "fp32" else (5e-2 if below_relu else 1e-4)
+                        check_packed(g, f"s0_{nm}{li}_dw", L.d_weights, tol, what=f"{nm}{li} ")
 
 
 # ---- streaming BatchNorm / pool kernels (large batches) -------------------------------------------------------------------
@@ -223,3 +233,86 @@ def test_streaming_bn_pool_kernels(Bn, H, W, C):
     assert nrel(host(r0), R) < 2e-5
     hs = host(sums)
     assert nrel(hs[:P].reshape(shp), rdb) < 2e-5 and nrel(hs[P:].reshape(shp), rdg) < 2e-5
+
+
+# ---- Conv2DTranspose on the tensor cores -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("math,tol", [(2, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize("N,H,W,C,F,k,s,pad", [(64, 7, 7, 128, 64, 3, 2, "same"), (64, 14, 14, 64, 32, 3, 2, "same"),
+                                                 (37, 5, 6, 32, 16, 3, 2, "valid"), (16, 6, 6, 64, 32, 4, 2, "same"),
+                                                 (16, 8, 8, 32, 32, 3, 1, "same")])
+def test_convt_tensor_cores(N, H, W, C, F, k, s, pad, math, tol):
+    """Conv2DTranspose as tcgen05 contractions on column buffers (csrc/gemm_simt.cu: Ycol = x . W^T + overlap-add forward; window
+    gather + Ecol . W and Ecol^T . x backward) against the oracle: strides 1 / 2, 'same' / 'valid', 3x3 / 4x4 kernels, the Q12 edge
+    skip, bias + ReLU epilogue, pending clip + ReLU' mask + both sum-of-squares slots, guard bands around every output."""
+    import torch
+    import types
+    from neuralnetlib_b200 import _backend as B, _ops as ops
+    from test_gpu_ops import Guarded
+    G = Guarded(types.SimpleNamespace(empty=B.empty, B=B))
+    rng = np.random.default_rng(H + C + k)
+    x = np.maximum(rng.normal(size=(N, H, W, C)), 0).astype(np.float32)
+    w = (rng.normal(size=(k, k, F, C)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    oh, ow, pt, _pb, pl, _pr = O.convT_geometry(H, W, k, k, s, s, pad)
+    geom = B.ConvTGeom(N, H, W, C, F, k, k, s, s, pt, pl, oh, ow)
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    dev = lambda a: B.to_device(np.asarray(a, dtype=np.float32))   # noqa: E731
+    host = lambda t: (B.synchronize(), t.detach().cpu().numpy().astype(np.float64))[1]   # noqa: E731
+    xd, wd, bd, ed = dev(x), dev(w), dev(b), dev(err)
+    ws = G((max(ops.convt_ws_bytes(geom, math) // 4, 1),))
+    y = G((N, oh, ow, F))
+    ops.convt_fwd(math, geom, xd, wd, bd, y, 1, 0.0, ws)
+    ref = np.maximum(O.convT_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), pad), 0)
+    assert nrel(host(y), ref) < tol
+    ss = B.zeros((16,), dtype=torch.float64); ops.sumsq(ed, ss, 0)
+    dx, dw, db = G(x.shape), G(w.shape), G((F,))
+    ops.convt_bwd(math, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    G.check()
+    rdx, rdw, rdb = O.convT_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (s, s))
+    assert nrel(host(dx), rdx * (x > 0)) < tol
+    assert nrel(host(dw), rdw) < tol
+    assert nrel(host(db), rdb.reshape(-1)) < 1e-5
+    h = host(ss)
+    assert abs(h[1] - np.sum(rdx ** 2)) < max(10 * tol, 1e-4) * np.sum(rdx ** 2)
+
+
+# ---- strided / 'valid' / small-F convolutions in the tensor-core math modes: im2col + the Dense kernels -------------------------
+@pytest.mark.parametrize("math,tol", [(2, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize("N,H,W,C,F,k,s,pad", [(64, 28, 28, 32, 1, 3, 1, "same"), (64, 13, 13, 32, 64, 3, 2, "same"),
+                                                 (16, 12, 10, 8, 16, 5, 1, "valid"), (37, 9, 9, 64, 48, 3, 2, "valid"),
+                                                 (8, 28, 28, 32, 64, 3, 2, "same")])
+def test_conv2d_column_path(N, H, W, C, F, k, s, pad, math, tol):
+    """Geometries outside the TMA implicit-GEMM path (non-power-of-two images, stride 2 incl. the Q11 'same' padding, 'valid',
+    F = 1) run as im2col + Dense contractions in the tensor-core math modes; forward (bias + ReLU), data gradient (pending clip,
+    ReLU' mask of the layer below, both sum-of-squares slots), weight / bias gradients in the reference's (c,ky,kx) order (Q1)."""
+    import torch
+    import types
+    from neuralnetlib_b200 import _backend as B, _ops as ops
+    from test_gpu_ops import Guarded
+    G = Guarded(types.SimpleNamespace(empty=B.empty, B=B))
+    rng = np.random.default_rng(H * 31 + C + F)
+    x = np.maximum(rng.normal(size=(N, H, W, C)), 0).astype(np.float32)
+    w = (rng.normal(size=(k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    oh, ow, ph, pw = O.conv2d_geometry(H, W, k, k, s, s, pad)
+    geom = B.ConvGeom(N, H, W, C, F, k, k, s, s, ph, pw, oh, ow)
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    dev = lambda a: B.to_device(np.asarray(a, dtype=np.float32))   # noqa: E731
+    host = lambda t: (B.synchronize(), t.detach().cpu().numpy().astype(np.float64))[1]   # noqa: E731
+    xd, wd, bd, ed = dev(x), dev(w), dev(b), dev(err)
+    ws = G((max(ops.conv2d_ws_bytes(geom, math) // 4, 1),))
+    y = G((N, oh, ow, F))
+    ops.conv2d_fwd(math, geom, xd, wd, bd, y, 1, 0.0, ws)
+    ref = np.maximum(O.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), pad), 0)
+    assert nrel(host(y), ref) < tol
+    ss = B.zeros((16,), dtype=torch.float64); ops.sumsq(ed, ss, 0)
+    dx, dw, db = G(x.shape), G(w.shape), G((F,))
+    ops.conv2d_bwd(math, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+    G.check()
+    rdx, rdw, rdb = O.conv2d_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (s, s), pad)
+    assert nrel(host(dx), rdx * (x > 0)) < tol
+    assert nrel(host(dw), rdw) < tol
+    assert nrel(host(db), rdb) < 1e-5
+    h = host(ss)
+    assert abs(h[1] - np.sum(rdx ** 2)) < max(10 * tol, 1e-4) * np.sum(rdx ** 2)
+    assert abs(h[2] - np.sum((rdx * (x > 0)) ** 2)) < max(10 * tol, 1e-4) * np.sum((rdx * (x > 0)) ** 2)
