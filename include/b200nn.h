@@ -47,6 +47,11 @@ extern "C" {
 #define B200NN_ACT_SIGMOID 2   /* 1/(1+exp(-clip(x,+-50)))   activations.py:33-43  */
 #define B200NN_ACT_TANH 3      /*                            activations.py:57-65  */
 #define B200NN_ACT_LEAKYRELU 4 /* max(x, a*x); f' = x>0?1:a  activations.py:92-109 */
+#define B200NN_ACT_ELU 5       /* x>0 ? x : exp(x)-1         activations.py:112-123 */
+#define B200NN_ACT_SELU 6      /* s*(x>0 ? x : a(exp(x)-1)), a = alpha, s = 1.0507009873554805   activations.py:126-147 */
+#define B200NN_ACT_MAX_FUSED 6 /* kinds 0..6 are strictly monotone or piecewise so that f' is a function of the OUTPUT: they fuse into
+                                  GEMM / BatchNorm epilogues; GELU (7) needs the pre-activation and runs through b200nn_act_fwd / _bwd only */
+#define B200NN_ACT_GELU 7      /* tanh approximation         activations.py:150-166; b200nn_act_bwd takes the INPUT x in place of y */
 
 /* loss kinds (losses.py:79-120) */
 #define B200NN_LOSS_MSE 0
@@ -368,6 +373,25 @@ int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double*
                                  const float* beta, const float* save_mean, const float* save_invstd, float* r0,
                                  const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
                                  int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream);
+
+/* ---- sibling layers of the same kernel families (csrc/layers_extra.cu) ---------------------------------
+ * Every backward follows the lazy-clip protocol: dx = chain(ss) * (...), ss_out (nullable) += sum(dx^2).
+ * b200nn_mul: out = chain * a * b — Dropout (layers.py:264-342) with the host-generated mask / (1 - rate) as `b`.
+ * AveragePooling2D (layers.py:908-1011): mean over each window of the zero-padded input. GlobalAveragePooling2D
+ * (:1419-1442) over HW positions. UpSampling2D nearest (:2695-2815): np.repeat forward, block sums backward.
+ * b200nn_im2col / b200nn_col2im: columns ordered (ky, kx, c) for any channel count; with kh == 1 this is im2col_1d / col2im_1d
+ * (preprocessing.py:128-186), which puts Conv1D (layers.py:667-816) on the Dense kernels. */
+int b200nn_mul(const float* a, const float* b, const double* ss, uint64_t chain, float* out, double* ss_out, long long n, void* stream);
+int b200nn_avgpool2d_fwd(const b200nn_pool_geom* g, const float* x, float* y, void* stream);
+int b200nn_avgpool2d_bwd(const b200nn_pool_geom* g, const float* err, const double* ss, uint64_t chain, float* dx, double* ss_out,
+                         void* stream);
+int b200nn_gap2d_fwd(const float* x, float* y, int N, int HW, int C, void* stream);
+int b200nn_gap2d_bwd(const float* err, const double* ss, uint64_t chain, float* dx, double* ss_out, int N, int HW, int C, void* stream);
+int b200nn_upsample2d_fwd(const float* x, float* y, int N, int H, int W, int C, int fh, int fw, void* stream);
+int b200nn_upsample2d_bwd(const float* err, const double* ss, uint64_t chain, float* dx, double* ss_out, int N, int H, int W, int C,
+                          int fh, int fw, void* stream);
+int b200nn_im2col(const b200nn_conv_geom* g, const float* x, float* col, void* stream);
+int b200nn_col2im(const b200nn_conv_geom* g, const float* dcol, const double* ss, uint64_t chain, float* dx, double* ss_out, void* stream);
 
 /* STREAMING forms of the batch-coupled kernels for large batches (any batch size; thread = (pool window, channel quad) or 4
  * adjacent positions, blockIdx.y = a chunk of batch rows, every access a whole 128-byte line). `ws`: float workspace of

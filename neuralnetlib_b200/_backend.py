@@ -120,6 +120,15 @@ _SIGNATURES = {
     "b200nn_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, c_int, c_ll, _P]),
     "b200nn_bn_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_int, c_float, _P, _P, _P]),
     "b200nn_pool_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "b200nn_mul": (c_int, [_P, _P, _P, c_u64, _P, _P, c_ll, _P]),
+    "b200nn_avgpool2d_fwd": (c_int, [C.POINTER(PoolGeom), _P, _P, _P]),
+    "b200nn_avgpool2d_bwd": (c_int, [C.POINTER(PoolGeom), _P, _P, c_u64, _P, _P, _P]),
+    "b200nn_gap2d_fwd": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "b200nn_gap2d_bwd": (c_int, [_P, _P, c_u64, _P, _P, c_int, c_int, c_int, _P]),
+    "b200nn_upsample2d_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "b200nn_upsample2d_bwd": (c_int, [_P, _P, c_u64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "b200nn_im2col": (c_int, [C.POINTER(ConvGeom), _P, _P, _P]),
+    "b200nn_col2im": (c_int, [C.POINTER(ConvGeom), _P, _P, c_u64, _P, _P, _P]),
     "b200nn_bn_stats_stream_ws_bytes": (c_size_t, [c_int, c_ll]),
     "b200nn_bn_stats_stream": (c_int, [_P, _P, _P, c_int, c_ll, _P]),
     "b200nn_pool_bn_bwd_stream_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

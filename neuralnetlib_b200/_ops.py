@@ -13,7 +13,7 @@ import torch
 from . import _backend as B
 from ._backend import ConvGeom, ConvTGeom, PoolGeom, check, lib, ptr, stream
 
-ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKYRELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKYRELU, ACT_ELU, ACT_SELU, ACT_GELU = 0, 1, 2, 3, 4, 5, 6, 7
 LOSS_MSE, LOSS_BCE, LOSS_CCE, LOSS_MAE, LOSS_HUBER = 0, 1, 2, 3, 4
 MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
 
@@ -331,6 +331,57 @@ def pool_bn_act_bwd_apply(x, err, ss, chain, gamma, beta, save_mean, save_invstd
                                              ptr(save_mean), ptr(save_invstd), ptr(r0), sums.data_ptr() + 4 * P, sums.data_ptr(),
                                              Bn, H, W, Cc, int(b_total), prev_act, prev_alpha, _slot_ptr(ss, slot1),
                                              _slot_ptr(ss, slot2), stream()))
+
+
+# ---- sibling layers (csrc/layers_extra.cu) -------------------------------------------------------------------------------
+def mul(a, b, ss, chain, out, slot_out):
+    _f32(a, b, out)
+    check(lib().b200nn_mul(ptr(a), ptr(b), ptr(ss), pack_chain(chain), ptr(out), _slot_ptr(ss, slot_out), a.numel(), stream()))
+
+
+def avgpool2d_fwd(g: PoolGeom, x, y):
+    _f32(x, y)
+    check(lib().b200nn_avgpool2d_fwd(C.byref(g), ptr(x), ptr(y), stream()))
+
+
+def avgpool2d_bwd(g: PoolGeom, err, ss, chain, dx, slot_out):
+    _f32(err, dx)
+    check(lib().b200nn_avgpool2d_bwd(C.byref(g), ptr(err), ptr(ss), pack_chain(chain), ptr(dx), _slot_ptr(ss, slot_out), stream()))
+
+
+def gap2d_fwd(x, y):
+    _f32(x, y)
+    N, H, W, Cc = (int(v) for v in x.shape)
+    check(lib().b200nn_gap2d_fwd(ptr(x), ptr(y), N, H * W, Cc, stream()))
+
+
+def gap2d_bwd(err, ss, chain, dx, slot_out):
+    _f32(err, dx)
+    N, H, W, Cc = (int(v) for v in dx.shape)
+    check(lib().b200nn_gap2d_bwd(ptr(err), ptr(ss), pack_chain(chain), ptr(dx), _slot_ptr(ss, slot_out), N, H * W, Cc, stream()))
+
+
+def upsample2d_fwd(x, y, fh, fw):
+    _f32(x, y)
+    N, H, W, Cc = (int(v) for v in x.shape)
+    check(lib().b200nn_upsample2d_fwd(ptr(x), ptr(y), N, H, W, Cc, int(fh), int(fw), stream()))
+
+
+def upsample2d_bwd(err, ss, chain, dx, slot_out, fh, fw):
+    _f32(err, dx)
+    N, H, W, Cc = (int(v) for v in dx.shape)
+    check(lib().b200nn_upsample2d_bwd(ptr(err), ptr(ss), pack_chain(chain), ptr(dx), _slot_ptr(ss, slot_out), N, H, W, Cc, int(fh), int(fw),
+                                      stream()))
+
+
+def im2col(g: ConvGeom, x, col):
+    _f32(x, col)
+    check(lib().b200nn_im2col(C.byref(g), ptr(x), ptr(col), stream()))
+
+
+def col2im(g: ConvGeom, dcol, ss, chain, dx, slot_out):
+    _f32(dcol, dx)
+    check(lib().b200nn_col2im(C.byref(g), ptr(dcol), ptr(ss), pack_chain(chain), ptr(dx), _slot_ptr(ss, slot_out), stream()))
 
 
 # streaming forms for large batches (csrc/bn_pool.cu); `ws` is the plan's float workspace

@@ -1,4 +1,4 @@
-"""Mirror of neuralnetlib/activations.py:1-109 (Sigmoid, ReLU, Tanh, Softmax, Linear, LeakyReLU) on the device.
+"""Mirror of neuralnetlib/activations.py:1-166 (Sigmoid, ReLU, Tanh, Softmax, Linear, LeakyReLU, ELU, SELU, GELU) on the device.
 
 `fn(x)` / `fn.derivative(x)` keep the reference's NumPy-in / NumPy-out contract (float64 results, Q10);
 inside a compiled Sequential plan the same kernels are fused into the producing GEMM's epilogue instead.
@@ -56,11 +56,16 @@ class ActivationFunction:
         ops.act_fwd(self._kind, self._alpha, xd, yd)
         return B.to_host(yd).reshape(x.shape)
 
+    _from_input = False   # GELU: the derivative is a function of the INPUT (the C ABI takes x in place of y)
+
     def _derivative_host(self, x) -> np.ndarray:
         x = np.asarray(x)
         xd = B.to_device(x)
         yd = B.empty(xd.shape)
-        ops.act_fwd(self._kind, self._alpha, xd, yd)
+        if self._from_input:
+            yd = xd
+        else:
+            ops.act_fwd(self._kind, self._alpha, xd, yd)
         ones = B.to_device(np.ones(x.shape, dtype=np.float32))
         dd = B.empty(xd.shape)
         ops.act_bwd(self._kind, self._alpha, yd, ones, None, (), dd, None)
@@ -131,3 +136,34 @@ class LeakyReLU(_Elementwise):    # activations.py:92-109
 
     def __str__(self):
         return f"{self.__class__.__name__}(alpha={self.alpha})"
+
+
+class ELU(_Elementwise):          # activations.py:112-123
+    _kind = ops.ACT_ELU
+
+
+class SELU(_Elementwise):         # activations.py:126-147
+    _kind = ops.ACT_SELU
+    DEFAULT_ALPHA = 1.6732632423543772848170429916717
+    DEFAULT_SCALE = 1.0507009873554804934193349852946
+
+    def __init__(self, alpha: float = None, scale: float = None):
+        self.alpha = alpha if alpha is not None else SELU.DEFAULT_ALPHA
+        self.scale = scale if scale is not None else SELU.DEFAULT_SCALE
+        if abs(self.scale - SELU.DEFAULT_SCALE) > 1e-12:
+            raise NotImplementedError("SELU with a non-default scale is not on the B200 path (the kernels carry one parameter)")
+
+    @property
+    def _alpha(self):
+        return float(self.alpha)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "alpha": self.alpha, "scale": self.scale}
+
+    def __str__(self):
+        return f"{self.__class__.__name__}(alpha={self.alpha}, scale={self.scale})"
+
+
+class GELU(_Elementwise):         # activations.py:150-166 (tanh approximation); its derivative needs the pre-activation
+    _kind = ops.ACT_GELU
+    _from_input = True

@@ -886,7 +886,7 @@ int b200nn_bn_bwd(const float* x, const float* err, const double* ss, uint64_t c
                   const float* save_mean, const float* save_invstd, float* dx, float* dgamma, float* dbeta, int B,
                   long long P, int prev_act, float prev_alpha, double* ss_out0, double* ss_out1, void* stream) {
     B200NN_REQUIRE(B > 0 && P > 0, "bn_bwd: bad shape B=%d P=%lld", B, P);
-    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "bn_bwd: unknown activation %d", prev_act);
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_MAX_FUSED, "bn_bwd: unknown activation %d", prev_act);
     const long long blocks = (P + BN_COLS - 1) / BN_COLS;
     bn_bwd_kernel<0><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, save_mean, save_invstd, dx, dgamma,
                                                                dbeta, B, P, B, prev_act, prev_alpha, ss_out0, ss_out1);
@@ -930,7 +930,7 @@ int b200nn_bn_bwd_apply(const float* x, const float* err, const double* ss, uint
                         int B, long long P, long long B_total, int prev_act, float prev_alpha, double* ss_out0,
                         double* ss_out1, void* stream) {
     B200NN_REQUIRE(B > 0 && P > 0 && B_total >= B && dgamma != nullptr && dbeta != nullptr, "bn_bwd_apply: bad argument");
-    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "bn_bwd_apply: unknown activation %d", prev_act);
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_MAX_FUSED, "bn_bwd_apply: unknown activation %d", prev_act);
     const long long blocks = (P + BN_COLS - 1) / BN_COLS;
     bn_bwd_kernel<2><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, save_mean, save_invstd, dx,
                                                                const_cast<float*>(dgamma), const_cast<float*>(dbeta), B, P,
@@ -990,7 +990,7 @@ int b200nn_pool_bn_act_bwd(const float* x, const float* err, const double* ss, u
                            float* dgamma, float* dbeta, int B, int H, int W, int C, int prev_act, float prev_alpha,
                            double* ss_out0, double* ss_out1, double* ss_out2, void* stream) {
     if (int rc = check_fused_block("pool_bn_act_bwd", B, H, W, C)) return rc;
-    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd: unknown activation %d", prev_act);
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_MAX_FUSED, "pool_bn_act_bwd: unknown activation %d", prev_act);
     B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
                    "pool_bn_act_bwd: x and err must be 16-byte aligned");
     const FbGeom g{B, H, W, C};
@@ -1035,7 +1035,7 @@ int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double*
                                  const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
                                  int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream) {
     if (int rc = check_fused_block("pool_bn_act_bwd_apply", B, H, W, C)) return rc;
-    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd_apply: unknown activation %d", prev_act);
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_MAX_FUSED, "pool_bn_act_bwd_apply: unknown activation %d", prev_act);
     B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && B_total >= B, "pool_bn_act_bwd_apply: bad argument");
     B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(err)) & 15) == 0,
                    "pool_bn_act_bwd_apply: x and err must be 16-byte aligned");
@@ -1083,7 +1083,7 @@ int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const 
                                         const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
                                         int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream) {
     if (int rc = check_stream_block("pool_bn_act_bwd_stream_apply", B, H, W, C, x, err, r0)) return rc;
-    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_LEAKYRELU, "pool_bn_act_bwd_stream_apply: unknown activation %d", prev_act);
+    B200NN_REQUIRE(prev_act >= 0 && prev_act <= B200NN_ACT_MAX_FUSED, "pool_bn_act_bwd_stream_apply: unknown activation %d", prev_act);
     B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && B_total >= B, "pool_bn_act_bwd_stream_apply: bad argument");
     const long long items = (long long)(H / 2) * (W / 2) * (C / 4);
     const dim3 grid((unsigned)((items + 255) / 256), (unsigned)((B + SB_ROWS - 1) / SB_ROWS));

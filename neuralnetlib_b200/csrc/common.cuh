@@ -77,6 +77,12 @@ __device__ __forceinline__ float act_apply(int act, float x, float alpha) {
         }
         case B200NN_ACT_TANH: return tanhf(x);
         case B200NN_ACT_LEAKYRELU: return fmaxf(x, x * alpha);
+        case B200NN_ACT_ELU: return x > 0.0f ? x : expm1f(x);
+        case B200NN_ACT_SELU: return 1.0507009873554805f * (x > 0.0f ? x : alpha * expm1f(x));
+        case B200NN_ACT_GELU: {
+            const float z = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+            return 0.5f * x * (1.0f + tanhf(z));
+        }
         default: return x;
     }
 }
@@ -87,6 +93,14 @@ __device__ __forceinline__ float act_grad_from_y(int act, float y, float alpha) 
         case B200NN_ACT_SIGMOID: return y * (1.0f - y);
         case B200NN_ACT_TANH: return 1.0f - y * y;
         case B200NN_ACT_LEAKYRELU: return y > 0.0f ? 1.0f : alpha;
+        case B200NN_ACT_ELU: return y > 0.0f ? 1.0f : y + 1.0f;                                   // exp(x) = y + 1 for x <= 0
+        case B200NN_ACT_SELU: return y > 0.0f ? 1.0507009873554805f : y + 1.0507009873554805f * alpha;   // s*a*exp(x) = y + s*a
+        case B200NN_ACT_GELU: {   // the argument is the INPUT x here (activations.py:157-161)
+            const float x = y;
+            const float z = 0.7978845608028654f * (x + 0.044715f * x * x * x), t = tanhf(z);
+            const float g = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+            return 0.5f * (1.0f + t + x * (1.0f - t * t) * g);
+        }
         default: return 1.0f;
     }
 }

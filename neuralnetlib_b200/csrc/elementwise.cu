@@ -626,7 +626,7 @@ int b200nn_graph_destroy(void* graph_exec) {
 }
 
 int b200nn_act_fwd(int act, float alpha, const float* x, float* y, long long n, void* stream) {
-    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "act_fwd: unknown activation %d", act);
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_GELU, "act_fwd: unknown activation %d", act);
     B200NN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                    "act_fwd: buffers must be 16-byte aligned");
     if (n <= 0) return B200NN_OK;
@@ -637,7 +637,7 @@ int b200nn_act_fwd(int act, float alpha, const float* x, float* y, long long n, 
 
 int b200nn_act_bwd(int act, float alpha, const float* y, const float* err, const double* ss, uint64_t chain,
                    float* dx, double* ss_out, long long n, void* stream) {
-    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "act_bwd: unknown activation %d", act);
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_GELU, "act_bwd: unknown activation %d", act);
     B200NN_REQUIRE(act != B200NN_ACT_LEAKYRELU || alpha > 0.0f, "act_bwd: LeakyReLU needs alpha > 0 (got %g)", alpha);
     B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
                    "act_bwd: buffers must be 16-byte aligned");

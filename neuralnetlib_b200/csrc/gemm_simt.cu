@@ -1084,7 +1084,7 @@ static int launch_gemm(const char* name, const AF& af, const BF& bf, const Epilo
 }
 
 static int check_act(const char* who, int act, float alpha) {
-    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_LEAKYRELU, "%s: unknown activation %d", who, act);
+    B200NN_REQUIRE(act >= 0 && act <= B200NN_ACT_MAX_FUSED, "%s: unknown activation %d", who, act);
     B200NN_REQUIRE(act != B200NN_ACT_LEAKYRELU || alpha > 0.0f, "%s: LeakyReLU needs alpha > 0", who);
     return B200NN_OK;
 }
@@ -1153,7 +1153,9 @@ size_t b200nn_dense_ws_bytes(int M, int N, int K) {
 
 static bool dense_tc_ok(const float* x, const float* w, const float* other, int M, int N, int K) {
     // TMA needs 16-byte aligned bases and row pitches; tiny problems stay on the FFMA kernel
-    return tcapi::tma_ok(x, K) && tcapi::tma_ok(w, N) && tcapi::tma_ok(other, N) && (long long)M * N * K >= (1LL << 18);
+    // below ~8 M multiply-adds the persistent kernel's fixed cost (cluster launch, TMEM allocation, tensor-map fetch) exceeds the
+    // FFMA kernel's whole run time (config 1's 32 x 784 x 128 layer: 3.2 M)
+    return tcapi::tma_ok(x, K) && tcapi::tma_ok(w, N) && tcapi::tma_ok(other, N) && (long long)M * N * K >= (1LL << 23);
 }
 
 int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, float* y, int M, int N, int K,
@@ -1170,7 +1172,9 @@ int b200nn_dense_fwd(int math, const float* x, const float* w, const float* b, f
     }
     Epilogue e = plain_epilogue(y, N, M);
     e.bias = b; e.act = act; e.alpha = alpha;
-    if (math == B200NN_MATH_FP32 && ws != nullptr && skinny::applicable(x, w, y, M, N, K))
+    // K >> M, N (config 2's Dense(64) on 6272 features): the slab kernels beat a tensor-core tile that is mostly padding, and they
+    // are exact fp32 — so they serve every math mode except single-pass tf32 (where the caller asked for the tensor cores)
+    if (math != B200NN_MATH_TF32 && ws != nullptr && skinny::applicable(x, w, y, M, N, K))
         return skinny::launch_fwd(x, w, e, M, N, K, ws, as_stream(stream));
     if (math != B200NN_MATH_FP32 && dense_tc_ok(x, w, y, M, N, K))
         return tc_gemm_any(x, K, false, w, N, true, e, M, N, K, ws, as_stream(stream), math == B200NN_MATH_TF32X3);
@@ -1268,7 +1272,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         }
         return B200NN_OK;
     }
-    if (math == B200NN_MATH_FP32 && skinny::applicable(x, w, err, M, N, K) &&
+    if (math != B200NN_MATH_TF32 && skinny::applicable(x, w, err, M, N, K) &&
         ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
         return skinny::launch_bwd(x, w, err, ss, chain, dx, dw, db, M, N, K, prev_act, prev_alpha, ss_out0, ss_out1, st);
     const bool use_tc = math != B200NN_MATH_FP32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;

@@ -347,7 +347,8 @@ class Activation(Layer):
     @property
     def _fusable(self):
         f = self.activation_function
-        return f._kind is not None and not (f._kind == ops.ACT_LEAKYRELU and f._alpha <= 0)
+        return (f._kind is not None and not (f._kind == ops.ACT_LEAKYRELU and f._alpha <= 0)
+                and not getattr(f, "_from_input", False))   # GELU's derivative needs the pre-activation: never fused
 
     def _plan_forward(self, ctx, st, x, act_layer, training):
         y = ctx.buf(x.shape)
@@ -359,7 +360,7 @@ class Activation(Layer):
         else:
             kind, alpha = f._kind, float(f._alpha)
             ctx.emit(lambda: ops.act_fwd(kind, alpha, x, y), "act_fwd", (x, y))
-        st.update(y=y)
+        st.update(y=y, x=x)
         return y
 
     def _plan_backward(self, ctx, st, err, mask_layer, need_dx, y=None):
@@ -367,6 +368,8 @@ class Activation(Layer):
         if f._kind is None:
             raise NotImplementedError("Derivative of Softmax is not implemented. It is not needed for backpropagation.")
         y = st["y"] if y is None else y
+        if getattr(f, "_from_input", False):
+            y = st["x"]          # b200nn_act_bwd takes the INPUT for GELU (activations.py:157-161)
         dx = ctx.buf(y.shape)
         s = ctx.slot()
         kind, alpha, ss, chain, et = f._kind, float(f._alpha), ctx.ss, err.chain, err.t
@@ -1049,9 +1052,388 @@ class BatchNormalization(Layer, _ParamMixin):
         return layer
 
 
+
+# =======================================================================================================
+# Sibling layers of the same kernel families (csrc/layers_extra.cu)
+class Dropout(Layer):
+    """layers.py:264-342. The mask is drawn on the HOST with the reference's own generator call (default_rng(random_state)
+    .binomial(1, 1 - rate, shape) / (1 - rate), re-seeded on every call: with a fixed seed the SAME mask every step) and
+    applied on the device; inference is the identity."""
+
+    def __init__(self, rate: float = 0.5, adaptive: bool = False, min_rate: float = 0.1, max_rate: float = 0.9,
+                 temperature: float = 1.0, random_state: int = None, **kwargs):
+        super().__init__()
+        if adaptive:
+            raise NotImplementedError("adaptive Dropout (layers.py:280-289) is outside the B200 hot path")
+        self.rate, self.adaptive, self.random_state = rate, adaptive, random_state
+        self.mask = None
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def __str__(self) -> str:
+        return f"Dropout(rate={self.rate})"
+
+    def _host_mask(self, shape):
+        rng = np.random.default_rng(self.random_state if self.random_state is not None else int(time.time_ns()))
+        self.mask = rng.binomial(1, 1 - self.rate, size=tuple(shape)) / (1 - self.rate)
+        return self.mask
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        if not training:
+            st.update(mask=None)
+            return x
+        mask = B.to_device(self._host_mask(x.shape))
+        y = ctx.buf(x.shape)
+        st.update(mask=mask)
+        layer, fixed = self, self.random_state is not None
+
+        def run():
+            if not fixed:   # time-seeded: a fresh mask per step, uploaded outside any captured graph replay is impossible -> eager only
+                mask.copy_(B.to_device(layer._host_mask(x.shape)))
+            ops.mul(x, mask, None, (), y, None)
+        ctx.emit(run, "dropout_fwd", (x, mask, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        mask = st.get("mask")
+        if mask is None:
+            return err
+        dx = ctx.buf(err.t.shape)
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.mul(et, mask, ss, chain, dx, s), "dropout_bwd", (et, mask, dx))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data, training: bool = True):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, training), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "rate": self.rate, "adaptive": self.adaptive, "min_rate": 0.1, "max_rate": 0.9,
+                "temperature": 1.0, "random_state": self.random_state}
+
+    @staticmethod
+    def from_config(config: dict):
+        return Dropout(rate=config["rate"], adaptive=config["adaptive"], random_state=config["random_state"])
+
+
+class AveragePooling2D(MaxPooling2D):
+    """layers.py:908-1011: the mean over every window of the zero-padded input (padding counts in the divisor)."""
+
+    def __str__(self) -> str:
+        return f"AveragePooling2D(pool_size={self.pool_size}, strides={self.strides}, padding={self.padding})"
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, f"AveragePooling2D input must be 4D (batch_size, height, width, channels), got {tuple(x.shape)}"
+        g = self._geometry(x.shape)
+        y = ctx.buf((x.shape[0], g.OH, g.OW, x.shape[3]))
+        st.update(x=x, g=g)
+        ctx.emit(lambda: ops.avgpool2d_fwd(g, x, y), "avgpool2d_fwd", (x, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, g = st["x"], st["g"]
+        dx = ctx.buf(x.shape)
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.avgpool2d_bwd(g, et, ss, chain, dx, s), "avgpool2d_bwd", (et, dx))
+        return _Err(dx, () if s is None else (s,))
+
+    @staticmethod
+    def from_config(config: dict):
+        return AveragePooling2D(config["pool_size"], config["strides"], config["padding"])
+
+
+class GlobalAveragePooling2D(Layer):
+    """layers.py:1419-1442."""
+
+    def __init__(self):
+        self.input_shape = None
+
+    def __str__(self) -> str:
+        return "GlobalAveragePooling2D"
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0], in_shape[3])
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, f"GlobalAveragePooling2D input must be 4D (batch_size, height, width, channels), got {tuple(x.shape)}"
+        self.input_shape = tuple(x.shape)
+        y = ctx.buf((x.shape[0], x.shape[3]))
+        st.update(in_shape=tuple(x.shape))
+        ctx.emit(lambda: ops.gap2d_fwd(x, y), "gap2d_fwd", (x, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        dx = ctx.buf(st["in_shape"])
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.gap2d_bwd(et, ss, chain, dx, s), "gap2d_bwd", (et, dx))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__}
+
+    @staticmethod
+    def from_config(config: dict):
+        return GlobalAveragePooling2D()
+
+
+class UpSampling2D(Layer):
+    """layers.py:2695-2815, nearest-neighbour interpolation (np.repeat along H then W; block sums backward)."""
+
+    def __init__(self, size=(2, 2), interpolation="nearest", **kwargs):
+        super().__init__()
+        self.size = tuple(size) if isinstance(size, (list, tuple)) else (size, size)
+        self.interpolation = interpolation
+        if len(self.size) != 2:
+            raise ValueError("Size must have exactly 2 elements.")
+        if not all(isinstance(v, (int, np.integer)) and v > 0 for v in self.size):
+            raise ValueError("Size elements must be positive integers.")
+        if interpolation not in ["nearest", "bilinear", "bicubic"]:
+            raise ValueError('interpolation must be one of "nearest", "bilinear", or "bicubic"')
+        if interpolation != "nearest":
+            raise NotImplementedError("UpSampling2D: only nearest-neighbour interpolation is on the B200 path")
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def __str__(self) -> str:
+        return f"UpSampling2D(size={self.size}, interpolation={self.interpolation})"
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0], in_shape[1] * self.size[0], in_shape[2] * self.size[1], in_shape[3])
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 4, "UpSampling2D input must be 4D (batch_size, height, width, channels)"
+        fh, fw = (int(v) for v in self.size)
+        y = ctx.buf(self._out_shape(tuple(x.shape)))
+        st.update(in_shape=tuple(x.shape))
+        ctx.emit(lambda: ops.upsample2d_fwd(x, y, fh, fw), "upsample2d_fwd", (x, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        fh, fw = (int(v) for v in self.size)
+        dx = ctx.buf(st["in_shape"])
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.upsample2d_bwd(et, ss, chain, dx, s, fh, fw), "upsample2d_bwd", (et, dx))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "size": self.size, "interpolation": self.interpolation}
+
+    @staticmethod
+    def from_config(config: dict):
+        return UpSampling2D(size=config["size"], interpolation=config["interpolation"])
+
+
+class MaxPooling1D(Layer):
+    """layers.py:819-905 on the 2-D pooling kernels (an image of height 1)."""
+
+    def __init__(self, pool_size: int, strides: int = None, padding: str = "valid"):
+        self.pool_size = pool_size
+        self.strides = strides if strides is not None else pool_size
+        self.padding = padding
+
+    def __str__(self) -> str:
+        return f"MaxPooling1D(pool_size={self.pool_size}, strides={self.strides}, padding={self.padding})"
+
+    def _geometry(self, shape):
+        N, L, Cc = (int(v) for v in shape)
+        pad = ((L - 1) * self.strides + self.pool_size - L) // 2 if self.padding == "same" else 0
+        if self.padding == "same" and pad <= 0:
+            raise ValueError("MaxPooling1D(padding='same') needs a positive pad; the reference backward breaks otherwise")
+        out_l = (L + 2 * pad - self.pool_size) // self.strides + 1
+        return B.PoolGeom(N, 1, L, Cc, 1, int(self.pool_size), 1, int(self.strides), 0, pad, 1, out_l)
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0], self._geometry(in_shape).OW, in_shape[2])
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 3, f"MaxPooling1D input must be 3D (batch_size, length, channels), got {tuple(x.shape)}"
+        g = self._geometry(x.shape)
+        y = ctx.buf((x.shape[0], g.OW, x.shape[2]))
+        st.update(x=x, y=y, g=g)
+        ctx.emit(lambda: ops.maxpool_fwd(g, x, y), "maxpool1d_fwd", (x, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, y, g = st["x"], st["y"], st["g"]
+        dx = ctx.buf(x.shape)
+        s = ctx.slot()
+        ss, chain, et = ctx.ss, err.chain, err.t
+        ctx.emit(lambda: ops.maxpool_bwd(g, x, y, et, ss, chain, dx, s), "maxpool1d_bwd", (x, y, et, dx))
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        return {"name": self.__class__.__name__, "pool_size": self.pool_size, "strides": self.strides, "padding": self.padding}
+
+    @staticmethod
+    def from_config(config: dict):
+        return MaxPooling1D(config["pool_size"], config["strides"], config["padding"])
+
+
+class Conv1D(Layer, _ParamMixin):
+    """layers.py:667-816 as im2col_1d (preprocessing.py:128-156: columns ordered (tap, c), which is also the order of
+    weights.reshape(-1, F) -- no K-order quirk in 1-D) + the Dense kernels (tcgen05 / FFMA by math mode and shape)."""
+    _fuses_act = True
+    weights = _param_property("weights")
+    bias = _param_property("bias")
+    d_weights = _param_property("d_weights")
+    d_bias = _param_property("d_bias")
+
+    def __init__(self, filters: int, kernel_size: int, strides: int = 1, padding: str = "valid", weights_init: str = "default",
+                 bias_init: str = "default", random_state: int = None, **kwargs):
+        self.filters, self.kernel_size, self.strides, self.padding = filters, kernel_size, strides, padding
+        self._weights = self._bias = self._d_weights = self._d_bias = None
+        self._shapes = {}
+        self.weights_init, self.bias_init, self.random_state = weights_init, bias_init, random_state
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+
+    def __str__(self) -> str:
+        return (f"Conv1D(num_filters={self.filters}, kernel_size={self.kernel_size}, strides={self.strides}, "
+                f"padding={self.padding})")
+
+    def initialize_weights(self, input_shape: tuple):
+        _, _, in_channels = input_shape
+        self.rng = np.random.default_rng(self.random_state if self.random_state is not None else int(time.time_ns()))
+        shape = (self.kernel_size, in_channels, self.filters)
+        if self.weights_init == "xavier":
+            w = self.rng.normal(0, np.sqrt(2 / (self.kernel_size * in_channels)), shape)
+        elif self.weights_init == "he":
+            w = self.rng.normal(0, np.sqrt(2 / (in_channels * self.kernel_size)), shape)
+        elif self.weights_init == "default":
+            w = self.rng.normal(0, 0.01, shape)
+        else:
+            raise ValueError("Invalid weights_init value. Possible values are 'xavier', 'he', and 'default'.")
+        if self.bias_init == "default":
+            b = np.zeros((1, self.filters))
+        elif self.bias_init == "normal":
+            b = self.rng.normal(0, 0.01, (1, self.filters))
+        elif self.bias_init == "uniform":
+            b = self.rng.uniform(-0.1, 0.1, (1, self.filters))
+        elif self.bias_init == "small":
+            b = np.full((1, self.filters), 0.01)
+        else:
+            raise ValueError("Invalid bias_init value. Possible values are 'normal', 'uniform', 'small' and 'default'.")
+        self.weights, self.bias = w, b
+        self.d_weights, self.d_bias = np.zeros_like(w), np.zeros((self.filters,))   # d_bias is (F,) after backward (layers.py:801)
+
+    def _geometry(self, shape):
+        N, L, Cin = (int(v) for v in shape)
+        k, s = int(self.kernel_size), int(self.strides)
+        pad = ((L - 1) * s + k - L) // 2 if self.padding == "same" else 0
+        out_l = (L + 2 * pad - k) // s + 1
+        return B.ConvGeom(N, 1, L, Cin, self.filters, 1, k, 1, s, 0, pad, 1, out_l)
+
+    def _out_shape(self, in_shape):
+        return (in_shape[0], self._geometry(in_shape).OW, self.filters)
+
+    def _plan_forward(self, ctx, st, x, act_layer, training):
+        assert x.dim() == 3, f"Conv1D input must be 3D (batch_size, length, channels), got {tuple(x.shape)}"
+        if self._weights is None:
+            self.initialize_weights(tuple(x.shape))
+        if self._d_weights is None:
+            self.d_weights = np.zeros(self._shapes["weights"]); self.d_bias = np.zeros((self.filters,))
+        assert x.shape[2] == self._weights.shape[1], "Number of input channels must match"
+        g = self._geometry(x.shape)
+        M, K = x.shape[0] * g.OW, int(self.kernel_size) * x.shape[2]
+        math = _math_code()
+        ctx.need_ws(ops.dense_ws_bytes(M, self.filters, K, math))
+        col = ctx.buf((M, K))
+        y = ctx.buf((x.shape[0], g.OW, self.filters))
+        kind, alpha = _act_of(act_layer)
+        st.update(x=x, g=g, col=col, math=math)
+        w2, b = self._weights.view(K, self.filters), self._bias
+        ctx.emit(lambda: ops.im2col(g, x, col), "im2col_1d", (x, col))
+        ctx.emit(lambda: ops.dense_fwd(math, col, w2, b, y, kind, alpha, ctx.ws), "conv1d_fwd", (col, w2, b, y))
+        return y
+
+    def _plan_backward(self, ctx, st, err, mask_layer, need_dx):
+        x, g, col, math = st["x"], st["g"], st["col"], st["math"]
+        K = col.shape[1]
+        dcol = ctx.buf(col.shape) if need_dx else None
+        w2, dw2, db = self._weights.view(K, self.filters), self._d_weights.view(K, self.filters), self._d_bias
+        ss, chain, et = ctx.ss, err.chain, err.t.reshape(col.shape[0], self.filters)
+        ctx.emit(lambda: ops.dense_bwd(math, col, w2, et, ss, chain, dcol, dw2, db, ops.ACT_NONE, 0.0, None, None, ctx.ws), "conv1d_bwd",
+                 (col, et, dw2, db) + ((w2, dcol) if need_dx else ()))
+        if not need_dx:
+            return None
+        dx = ctx.buf(x.shape)
+        s = ctx.slot()
+        ctx.emit(lambda: ops.col2im(g, dcol, None, (), dx, s), "col2im_1d", (dcol, dx))   # the pending clips were applied to dcol
+        return _Err(dx, () if s is None else (s,))
+
+    def forward_pass(self, input_data):
+        x, host = _in(input_data)
+        self.input = input_data
+        self._st = {}
+        return _out(self._plan_forward(_EagerCtx(), self._st, x, None, True), host)
+
+    def backward_pass(self, output_error):
+        e, host = _in(output_error)
+        return _out(self._plan_backward(_EagerCtx(), self._st, _Err(e), None, True).t, host)
+
+    def get_config(self) -> dict:
+        w, b = self.weights, self.bias
+        return {"name": self.__class__.__name__, "weights": w.tolist() if w is not None else None,
+                "bias": b.tolist() if b is not None else None, "filters": self.filters, "kernel_size": self.kernel_size,
+                "strides": self.strides, "padding": self.padding, "weights_init": self.weights_init, "bias_init": self.bias_init,
+                "random_state": self.random_state}
+
+    @staticmethod
+    def from_config(config: dict):
+        layer = Conv1D(config["filters"], config["kernel_size"], config["strides"], config["padding"], config["weights_init"],
+                       config["bias_init"], config["random_state"])
+        if config["weights"] is not None:
+            layer.weights = np.array(config["weights"])
+            layer.bias = np.array(config["bias"])
+        return layer
+
+
 # =======================================================================================================
 # layer-ordering validation used by Sequential.add (layers.py:3916-3980, restricted to the layers that exist here)
 incompatibility_dict = {
-    Input: [], Dense: [Conv2D, Conv2DTranspose], Activation: [], Conv2D: [], Conv2DTranspose: [], MaxPooling2D: [],
-    Flatten: [], BatchNormalization: [], Reshape: [],
+    Input: [], Dense: [Conv1D, Conv2D, UpSampling2D], Activation: [], Conv2D: [Conv1D], UpSampling2D: [Conv1D],
+    Conv2DTranspose: [Conv1D], MaxPooling2D: [Conv1D, MaxPooling1D], AveragePooling2D: [Conv1D, MaxPooling1D],
+    GlobalAveragePooling2D: [Conv1D, MaxPooling1D],
+    Conv1D: [Conv2D, UpSampling2D, Conv2DTranspose, MaxPooling2D, AveragePooling2D, GlobalAveragePooling2D],
+    MaxPooling1D: [Conv2D, UpSampling2D, Conv2DTranspose, MaxPooling2D, AveragePooling2D, GlobalAveragePooling2D],
+    Flatten: [], Dropout: [], BatchNormalization: [], Reshape: [],
 }

@@ -46,7 +46,7 @@ def test_chain_packing():
 def test_workspace_sizing_per_math_mode():
     """Host-only entry points (no device work): the tensor-core modes never need less workspace than the FFMA path, the
     compensated mode (chain-limited split-K) needs room for its partial sums, and geometries the tensor-core convolution
-    does not take keep the FFMA sizing in every mode."""
+    does not take keep the FFMA sizing in fp32 and get room for their column buffers in the tensor-core modes."""
     from neuralnetlib_b200 import _backend as B
     lib = B.lib()
     for M, N, K in ((256, 4096, 4096), (8192, 4096, 4096), (256, 64, 6272), (32, 128, 784)):
@@ -58,11 +58,13 @@ def test_workspace_sizing_per_math_mode():
     assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) >= 2 * 8192 * 4096 * 4
     assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) <= (512 << 20) + 8192 * 4096 * 4   # bounded workspace
     ok = B.ConvGeom(64, 16, 16, 64, 128, 3, 3, 1, 1, 1, 1, 16, 16)          # stride 1, 'same', power-of-two image, C, F % 32 == 0
-    odd = B.ConvGeom(64, 28, 28, 64, 128, 3, 3, 1, 1, 1, 1, 28, 28)         # 28 x 28: FFMA in every mode
+    odd = B.ConvGeom(64, 28, 28, 64, 128, 3, 3, 1, 1, 1, 1, 28, 28)         # 28 x 28: im2col + Dense kernels in the tensor-core modes
     strided = B.ConvGeom(64, 16, 16, 64, 128, 3, 3, 2, 2, 1, 1, 8, 8)
     for g in (odd, strided):
-        for math in (0, 1, 2):
-            assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(g)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(g))
+        assert lib.b200nn_conv2d_ws_bytes_math(0, ctypes.byref(g)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(g))
+        col = g.N * g.OH * g.OW * g.kh * g.kw * g.C * 4
+        for math in (1, 2):   # column buffer (forward) + its gradient (backward) + the permuted weights and their gradient
+            assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(g)) >= 2 * col
     assert lib.b200nn_conv2d_ws_bytes_math(0, ctypes.byref(ok)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
     for math in (1, 2):
         assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(ok)) >= lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
