@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "gemm_tc_api.cuh"
+#include "conv_smallk3.cuh"
 
 namespace b200nn {
 
@@ -654,6 +655,7 @@ __global__ void __launch_bounds__(256) conv2d_smallk_wgrad_kernel(b200nn_conv_ge
     }
 }
 
+
 static bool smallk_fwd_ok(const b200nn_conv_geom* g) {
     const int K = g->kh * g->kw * g->C;
     return K <= SMALLK_MAX && (g->F == 32 || g->F == 64 || g->F == 16);
@@ -871,6 +873,7 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float
     __shared__ double scratch[32];
     constexpr int PITCH = NMAX | 1;
     constexpr int HR_KC = ((10240 / PITCH) / 32) * 32;       // 40 KB of staged weights per chunk
+    constexpr int NL = NMAX <= 16 ? 16 : 32;                 // staging lanes per feature row
     __shared__ float ws[HR_KC * PITCH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int m0 = (blockIdx.x * 8 + wid) * R;
@@ -879,23 +882,28 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int n = 0; n < NMAX; ++n) acc[r][n] = 0.0f;
+    const float* xr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) xr[r] = x + (long long)(m0 + r < M ? m0 + r : M - 1) * K;   // clamped: rows >= M are never stored
     for (int k0 = 0; k0 < K; k0 += HR_KC) {
         const int kc = min(HR_KC, K - k0);
         __syncthreads();
-        for (int i = threadIdx.x; i < kc * N; i += blockDim.x) ws[(i / N) * PITCH + (i % N)] = w[(long long)k0 * N + i];
+        {   // columns >= N are staged as zeros, so the FMA loop below carries no bound checks (no branches between its loads)
+            const int n = threadIdx.x % NL;
+            for (int k = threadIdx.x / NL; k < kc; k += 256 / NL)
+                if (n < NMAX) ws[k * PITCH + n] = n < N ? w[(long long)(k0 + k) * N + n] : 0.0f;
+        }
         __syncthreads();
 #pragma unroll 4
         for (int kk = lane; kk < kc; kk += 32) {     // unrolled: 4 x R independent 128-byte row loads in flight per warp
             float xv[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) xv[r] = (m0 + r < M) ? __ldg(x + (long long)(m0 + r) * K + k0 + kk) : 0.0f;
+            for (int r = 0; r < R; ++r) xv[r] = __ldg(xr[r] + k0 + kk);
 #pragma unroll
             for (int n = 0; n < NMAX; ++n) {
-                if (n < N) {
-                    const float wv = ws[kk * PITCH + n];
+                const float wv = ws[kk * PITCH + n];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r][n] = fmaf(xv[r], wv, acc[r][n]);
-                }
+                for (int r = 0; r < R; ++r) acc[r][n] = fmaf(xv[r], wv, acc[r][n]);
             }
         }
     }
@@ -1189,9 +1197,13 @@ int b200nn_dense_softmax_cce(const float* x, const float* w, const float* b, con
     B200NN_REQUIRE(x != nullptr && w != nullptr && y_true != nullptr && p != nullptr && err != nullptr, "dense_softmax_cce: null buffer");
     if (dw_partial == nullptr && M >= 1024 && K >= 256) {   // large batch: weights staged per CTA, several rows per warp
         cudaStream_t st = as_stream(stream);
-        if (N <= 12) dense_softmax_cce_rows_kernel<8, 12><<<(M + 63) / 64, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
-        else if (N <= 16) dense_softmax_cce_rows_kernel<4, 16><<<(M + 31) / 32, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
-        else dense_softmax_cce_rows_kernel<2, 32><<<(M + 15) / 16, 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K);
+        // rows per warp: as many as keep >= one CTA (8 warps) per SM
+        const int R = M >= 8 * 8 * kNumSMs ? 8 : M >= 8 * 4 * kNumSMs ? 4 : M >= 8 * 2 * kNumSMs ? 2 : 1;
+#define B200NN_HEAD_ROWS(RR, NN) dense_softmax_cce_rows_kernel<RR, NN><<<(M + 8 * RR - 1) / (8 * RR), 256, 0, st>>>(x, w, b, y_true, p, err, loss_acc, ss_out, M, N, K)
+        if (N <= 12) { if (R == 8) B200NN_HEAD_ROWS(8, 12); else if (R == 4) B200NN_HEAD_ROWS(4, 12); else if (R == 2) B200NN_HEAD_ROWS(2, 12); else B200NN_HEAD_ROWS(1, 12); }
+        else if (N <= 16) { if (R >= 4) B200NN_HEAD_ROWS(4, 16); else if (R == 2) B200NN_HEAD_ROWS(2, 16); else B200NN_HEAD_ROWS(1, 16); }
+        else { if (R >= 2) B200NN_HEAD_ROWS(2, 32); else B200NN_HEAD_ROWS(1, 32); }
+#undef B200NN_HEAD_ROWS
         B200NN_LAUNCH_CHECK("dense_softmax_cce_rows");
         return B200NN_OK;
     }
@@ -1694,6 +1706,10 @@ size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
         const size_t d = (size_t)conv_fewf_groups(g) * (Kf + 1) * g->F * sizeof(float);
         r = r > d ? r : d;
     }
+    if (smallk3::ok(g)) {
+        const size_t d = (size_t)smallk3::blocks(g) * (Kf + 1) * g->F * sizeof(float);
+        r = r > d ? r : d;
+    }
     return r;
 }
 
@@ -1736,6 +1752,11 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
         conv_weight_permute_kernel<<<(K * g->F + 255) / 256, 256, 0, st>>>(w, cw.wp, g->kh, g->kw, g->C, g->F, 0);
         B200NN_LAUNCH_CHECK("conv_weight_permute");
         return b200nn_dense_fwd(math, cw.col, cw.wp, b, y, M, g->F, K, act, alpha, cw.rest, stream);
+    }
+    if (smallk3::ok(g) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+        smallk3::launch_fwd(g, x, w, b, y, act, alpha, M, as_stream(stream));
+        B200NN_LAUNCH_CHECK("conv2d_smallk_fwd3");
+        return B200NN_OK;
     }
     if (smallk_fwd_ok(g) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
         long long blocks = ((long long)M + 127) / 128;
@@ -1841,7 +1862,15 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
         }
         return B200NN_OK;
     }
-    if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
+    if (dw != nullptr && smallk3::ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
+        const int nb = smallk3::blocks(g);
+        Epilogue e = plain_epilogue(dw, g->F, Kf);
+        e.ss = ss; e.chain = chain; e.db = db;
+        e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
+        B200NN_REQUIRE(smallk3::launch_wgrad(g, x, err, ws, Mo, st) == 0, "conv2d_smallk_wgrad3: cannot configure shared memory");
+        B200NN_LAUNCH_CHECK("conv2d_smallk_wgrad3");
+        if (int rc = launch_splitk_reduce(ws, nb, Kf + 1, g->F, e, st)) return rc;
+    } else if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {
         const int nb = smallk_wgrad_blocks(g), TP = smallk_wgrad_tile(g);
         Epilogue e = plain_epilogue(dw, g->F, Kf);
         e.ss = ss; e.chain = chain; e.db = db;

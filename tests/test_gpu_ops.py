@@ -204,7 +204,10 @@ def test_conv2d_golden(K, golden, gi):
 
 @pytest.mark.parametrize("N,H,W,C,F,k,s,pad", [(16, 28, 28, 1, 32, 3, 1, "same"), (8, 32, 32, 3, 64, 3, 1, "same"),
                                                (4, 16, 16, 64, 128, 3, 1, "same"), (8, 28, 28, 1, 32, 3, 2, "same"),
-                                               (8, 13, 13, 32, 64, 3, 2, "same"), (4, 28, 28, 32, 1, 3, 1, "same")])
+                                               (8, 13, 13, 32, 64, 3, 2, "same"), (4, 28, 28, 32, 1, 3, 1, "same"),
+                                               # large-batch small-K kernels (conv_smallk3.cuh): ragged last tile, generic K, strides
+                                               (7, 30, 30, 2, 64, 3, 1, "valid"), (6, 31, 29, 1, 32, 5, 1, "same"),
+                                               (33, 28, 28, 1, 64, 3, 2, "same"), (12, 32, 32, 3, 32, 3, 1, "same")])
 def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
     rng = np.random.default_rng(H * 31 + C)
     x = rng.normal(size=(N, H, W, C)).astype(np.float32)
