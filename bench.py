@@ -80,6 +80,26 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml = self.handle = None
+        try:   # NVML in-process: one sample costs a few microseconds of host time, so it can be taken between timed steps
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        """One in-process NVML sample (called from the timing loops while the device is executing the timed steps)."""
+        if self.nvml is None:
+            return
+        try:
+            n, h = self.nvml, self.handle
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            flag = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731
+            self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
+                              str(n.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+        except Exception:
+            pass
 
     def start(self):
         try:
@@ -264,6 +284,7 @@ class Timer:
 
     def __init__(self, torch, dist, world, B):
         self.torch, self.dist, self.world, self.B = torch, dist, world, B
+        self.sampler = None                   # ClockSampler on rank 0: sampled between the timed steps
         self.stream = B.stream_obj()
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=B.device())
 
@@ -285,11 +306,14 @@ class Timer:
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         self.barrier()
         out = None
-        for s, e in ev:
+        every = max(1, K // 40)
+        for i, (s, e) in enumerate(ev):
             self.flush.zero_()                # evict L2 (126 MB) between steps; outside the timed events
             s.record(self.stream)
             out = fn()
             e.record(self.stream)
+            if self.sampler is not None and i % every == 0:
+                self.sampler.sample()         # host-side NVML read while the device runs the queued steps; outside the events
         self.barrier()
         return self.reduce_max(sum(s.elapsed_time(e) for s, e in ev)) / K, out
 
@@ -535,6 +559,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        T.sampler = sampler
 
     # ---- (1) resident: K replays of the captured step graph, inputs already in HBM -------------------------------
     launches0 = lib.b200nn_launch_count()

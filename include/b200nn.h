@@ -410,6 +410,36 @@ int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const 
                                         const float* dgamma, const float* dbeta, int B, int H, int W, int C, long long B_total,
                                         int prev_act, float prev_alpha, double* ss_out1, double* ss_out2, void* stream);
 
+/* ---- single-launch train step of a small MLP (models.py:159-264 for Dense [+ Activation] ... Dense + Softmax, CCE, Adam) -------
+ * One persistent cooperative kernel runs step_begin, every Dense forward (layers.py:173), the classifier head with
+ * softmax / CCE / p - y (models.py:200-205), every Dense backward (layers.py:189-197) with the clips of models.py:214 carried as
+ * the usual sum-of-squares slots, the per-tensor gradient clip (models.py:240-242) and Adam (optimizers.py:204-245, per-layer t),
+ * separated by grid-wide barriers instead of kernel boundaries (config 1: 16 graph nodes -> 1). Results are those of the
+ * layer-by-layer kernels (same slots, same stored gradients). Limits: batch <= 64, 2..8 Dense layers, last layer N <= 32.
+ * `layer[l]`: w[K,N], b[N] (nullable), dw, db, out[B,N] (activation output; the last layer's is the prediction), err[B,N] (error
+ * entering the layer's backward: written by the layer above; the last layer's is p - y), act / alpha of the Activation fused
+ * behind the layer (ignored for the last layer: softmax), chain = the clip slots pending on err, s_out0 / s_out1 = slots that
+ * receive ||dx||^2 before / after the activation backward of the layer below (-1: none), gi_w / gi_b = index of dw / db in the
+ * optimizer descriptor table `params` (b200nn_param, as for b200nn_adam_multi; block_map / gss likewise). `sync`: two zeroed
+ * device words (barrier state, re-zeroed by the kernel). */
+#define B200NN_MLP_MAX_LAYERS 8
+#define B200NN_MLP_MAX_BATCH 64
+typedef struct {
+    const float* w; const float* b; float* dw; float* db; float* out; float* err;
+    int K, N, act; float alpha;
+    uint64_t chain;
+    int s_out0, s_out1, gi_w, gi_b;
+} b200nn_mlp_layer;
+typedef struct {
+    int L, B, n_slots, n_params, n_layers_opt, total_blocks;
+    const float* x; const float* y;
+    double* ss; double* acc; double* gss; const double* hyper; long long* t_counter;
+    const b200nn_param* params; const int* block_map; unsigned* sync;
+    int s0;                                   /* slot of ||p - y||^2 */
+    b200nn_mlp_layer layer[B200NN_MLP_MAX_LAYERS];
+} b200nn_mlp_step;
+int b200nn_mlp_train_step(const b200nn_mlp_step* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,23 @@ class PoolGeom(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "H", "W", "C", "ph", "pw", "sh", "sw", "pad_h", "pad_w", "OH", "OW")]
 
 
+class MlpLayer(C.Structure):
+    """b200nn_mlp_layer (include/b200nn.h)."""
+    _fields_ = [(n, c_void_p) for n in ("w", "b", "dw", "db", "out", "err")] + \
+               [("K", c_int), ("N", c_int), ("act", c_int), ("alpha", c_float), ("chain", c_u64),
+                ("s_out0", c_int), ("s_out1", c_int), ("gi_w", c_int), ("gi_b", c_int)]
+
+
+MLP_MAX_LAYERS, MLP_MAX_BATCH = 8, 64
+
+
+class MlpStep(C.Structure):
+    """b200nn_mlp_step (include/b200nn.h)."""
+    _fields_ = [(n, c_int) for n in ("L", "B", "n_slots", "n_params", "n_layers_opt", "total_blocks")] + \
+               [(n, c_void_p) for n in ("x", "y", "ss", "acc", "gss", "hyper", "t_counter", "params", "block_map", "sync")] + \
+               [("s0", c_int), ("layer", MlpLayer * MLP_MAX_LAYERS)]
+
+
 # numpy mirror of b200nn_param (include/b200nn.h)
 PARAM_DTYPE = np.dtype([("p", np.uint64), ("g", np.uint64), ("m", np.uint64), ("v", np.uint64), ("n", np.int64),
                         ("t_index", np.int32), ("clip", np.int32), ("chain", np.uint64)], align=True)
@@ -101,6 +118,7 @@ _SIGNATURES = {
     "b200nn_adam_multi": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     "b200nn_sgd_multi": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P]),
     "b200nn_opt_multi": (c_int, [c_int, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
+    "b200nn_mlp_train_step": (c_int, [C.POINTER(MlpStep), _P]),
     # data parallelism (csrc/comm.cu) and the split BatchNorm kernels
     "b200nn_comm_load_nccl": (c_int, [C.c_char_p]),
     "b200nn_comm_nccl_version": (c_int, []),

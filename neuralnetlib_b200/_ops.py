@@ -479,3 +479,8 @@ def opt_multi(kind, plan: OptPlan, hyper, t_counter, on_stream=None):
 def sgd_multi(plan: OptPlan, hyper, on_stream=None):
     check(lib().b200nn_sgd_multi(ptr(plan.desc), plan.n_params, ptr(plan.gss), ptr(hyper), ptr(plan.block_map),
                                  plan.total_blocks, ptr(plan.ss), stream() if on_stream is None else on_stream))
+
+
+def mlp_train_step(desc):
+    """desc: a filled _backend.MlpStep (kept alive by the caller). One launch = one whole train step of a small MLP."""
+    check(lib().b200nn_mlp_train_step(C.byref(desc), stream()))

@@ -443,6 +443,100 @@ class Plan:
                 main.wait_event(evt)
             self.emit(join, "grad_allreduce_join", ())
 
+    def _try_mlp_step(self, prog):
+        """The whole train step of a small MLP as ONE cooperative kernel (csrc/mlp_step.cu; include/b200nn.h b200nn_mlp_train_step):
+        [Input] (Dense [+ fusable Activation])+ Dense + Softmax, categorical cross-entropy, plain Adam, batch <= 64, one GPU.
+        Same buffers, slots, stored gradients and optimizer state as the layer-by-layer program. B200NN_MLP_STEP=0 disables it."""
+        from .optimizers import Adam
+        if os.environ.get("B200NN_MLP_STEP", "1") == "0" or self.dp is not None or self.defer_clips or not self.training:
+            return False
+        opt, lf = self.model.optimizer, self.model.loss_function
+        if type(opt) is not Adam or opt.clip_norm is not None or opt.clip_value is not None:
+            return False
+        if not isinstance(lf, CategoricalCrossentropy) or getattr(lf, "_sparse", False) or lf._kind != ops.LOSS_CCE:
+            return False
+        if self.B > B.MLP_MAX_BATCH or len(self.batch_shape) != 2:
+            return False
+        layers, n = self.layers, len(self.layers)
+        dense = []          # (layer index, Dense, activation layer or None)
+        i = 0
+        while i < n:
+            L = layers[i]
+            if isinstance(L, Input):
+                if i != 0:
+                    return False
+                i += 1
+                continue
+            if type(L) is not Dense:
+                return False
+            nxt = layers[i + 1] if i + 1 < n else None
+            if isinstance(nxt, Activation):
+                dense.append((i, L, nxt))
+                i += 2
+            else:
+                dense.append((i, L, None))
+                i += 1
+        if not 2 <= len(dense) <= B.MLP_MAX_LAYERS:
+            return False
+        hi, head, hact = dense[-1]
+        if hact is None or type(hact.activation_function).__name__ != "Softmax" or head.units > 32 or hi != n - 2:
+            return False
+        for li, L, act in dense[:-1]:
+            if act is not None and (not act._fusable or not self.fwd_fused[li + 1]):
+                return False
+            if L.units > 4096:
+                return False
+        if any(L._weights is None or L._bias is None or L._d_weights is None for _, L, _ in dense):
+            return False
+        self._ensure_targets()
+        nl = len(dense)
+        desc = B.MlpStep()
+        keep = []
+        s0 = self.slot()
+        chain = (s0,)
+        # optimizer table in update order (last layer first), as the layer-by-layer program builds it
+        ups = [(li, L._weights, L._d_weights, L._bias, L._d_bias, ()) for li, L, _ in reversed(dense)]
+        oplan = opt._make_plan(ups, self.ss, 1, nl)
+        sync = torch.zeros(2, dtype=torch.int32, device=B.device())
+        errs = [None] * nl
+        errs[nl - 1] = self.buf(self.pred.shape)
+        for l in range(nl - 1, -1, -1):
+            li, L, act = dense[l]
+            d = desc.layer[l]
+            out = self.pred if l == nl - 1 else self.outs[li + 1 if act is not None else li]
+            K, N = int(L._weights.shape[0]), int(L._weights.shape[1])
+            kind, alpha = (ops.ACT_NONE, 0.0) if (l == nl - 1 or act is None) else (act.activation_function._kind,
+                                                                                 float(act.activation_function._alpha))
+            d.w, d.b, d.dw, d.db = L._weights.data_ptr(), L._bias.data_ptr(), L._d_weights.data_ptr(), L._d_bias.data_ptr()
+            d.out, d.err = out.data_ptr(), errs[l].data_ptr()
+            d.K, d.N, d.act, d.alpha = K, N, int(kind), alpha
+            d.chain = ops.pack_chain(chain)
+            j = nl - 1 - l                      # position in the optimizer table: (w, b) pairs, last layer first
+            d.gi_w, d.gi_b = 2 * j, 2 * j + 1
+            d.s_out0 = d.s_out1 = -1
+            if l > 0:
+                pli, pL, pact = dense[l - 1]
+                errs[l - 1] = self.buf((self.B, K))
+                d.s_out0 = self.slot()
+                chain = (d.s_out0,)
+                if pact is not None:
+                    d.s_out1 = self.slot()
+                    chain = (d.s_out0, d.s_out1)
+            L._grad_pending = None
+            keep.append(out)
+        desc.L, desc.B, desc.n_slots = nl, self.B, self.n_slots
+        desc.n_params, desc.n_layers_opt, desc.total_blocks = oplan.n_params, nl, oplan.total_blocks
+        desc.x, desc.y = self.x_in.data_ptr(), self.y_in.data_ptr()
+        desc.ss, desc.acc, desc.gss = self.ss.data_ptr(), self.acc.data_ptr(), oplan.gss.data_ptr()
+        desc.hyper, desc.t_counter = opt._hyper.data_ptr(), opt._t_counter().data_ptr()
+        desc.params, desc.block_map, desc.sync = oplan.desc.data_ptr(), oplan.block_map.data_ptr(), sync.data_ptr()
+        desc.s0 = s0
+        self._mlp_keep = (desc, oplan, sync, errs, keep)
+        io = (self.x_in, self.y_in) + tuple(t for _, L, _ in dense for t in (L._weights, L._d_weights)) + opt._plan_io(oplan)
+        self.emit(lambda: ops.mlp_train_step(desc), "mlp_train_step", io)
+        self.train_err0 = errs[nl - 1]
+        return True
+
     def _loss_kind(self):
         lf = self.model.loss_function
         if lf is None or lf._kind is None:
@@ -468,6 +562,10 @@ class Plan:
         prog = _Program(kind)
         self._emit_to = prog
         model = self.model
+        if kind == "train" and self._try_mlp_step(prog):
+            self._emit_to = None
+            self.programs[kind] = prog
+            return prog
         if kind == "train":
             self._ensure_targets()
             opt = model.optimizer
