@@ -420,8 +420,9 @@ int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const 
  * entering the layer's backward: written by the layer above; the last layer's is p - y), act / alpha of the Activation fused
  * behind the layer (ignored for the last layer: softmax), chain = the clip slots pending on err, s_out0 / s_out1 = slots that
  * receive ||dx||^2 before / after the activation backward of the layer below (-1: none), gi_w / gi_b = index of dw / db in the
- * optimizer descriptor table `params` (b200nn_param, as for b200nn_adam_multi; block_map / gss likewise). `sync`: two zeroed
- * device words (barrier state, re-zeroed by the kernel). */
+ * optimizer descriptor table `params` (b200nn_param, as for b200nn_adam_multi; block_map / gss likewise). `sync`: 64 zeroed
+ * device words (barrier counters in [0], [1], re-zeroed by the kernel; [2..31] = 15 x 8 bytes of per-phase %globaltimer stamps
+ * written by CTA 0). */
 #define B200NN_MLP_MAX_LAYERS 8
 #define B200NN_MLP_MAX_BATCH 64
 typedef struct {

@@ -80,8 +80,19 @@ __device__ __forceinline__ float chain_scale_cg(const double* ss, uint64_t chain
     return static_cast<float>(acc);
 }
 
+// phase time stamps for scripts/mlp_step_phases.py: CTA 0 records %globaltimer when it enters and leaves every barrier
+// (stamps 2e + 1, 2e + 2, 8 bytes each, behind the two barrier words)
+__device__ __forceinline__ void stamp(unsigned* sync, int idx) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && idx < 15) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        reinterpret_cast<unsigned long long*>(sync + 2)[idx] = now;
+    }
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch) {
     __syncthreads();
+    stamp(sync, 2 * (int)epoch + 1);
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(&sync[0], 1u);
@@ -100,6 +111,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch) {
     }
     ++epoch;
     __syncthreads();
+    stamp(sync, 2 * (int)epoch);
 }
 
 // out[r0.., n0..] = act(in . w + b) for one 8 x 32 tile
@@ -204,12 +216,15 @@ __device__ void head_rows(const b200nn_mlp_step& a, Shared& sh) {
                 for (int j = 0; j < 8; ++j) if (k0 + 32 * j < K) xs[k0 + 32 * j] = v[j];
             }
             __syncwarp();
-            for (int n = 0; n < N; ++n) {
-                float t = 0.0f;
-                for (int k = lane; k < K; k += 32) t = fmaf(xs[k], Wh[k * N + n], t);
-                t = warp_sum(t);
-                if (lane == n) logit = t;
-            }
+            // lane <-> (class n, k part): every lane runs one serial dot product over its share of k, the parts are folded with
+            // log2(parts) shuffles (instead of N warp-wide reductions of 5 dependent shuffles each)
+            const int NP = N <= 8 ? 8 : (N <= 16 ? 16 : 32), parts = 32 / NP;
+            const int n = lane % NP, part = lane / NP;
+            float t = 0.0f;
+            if (n < N)
+                for (int k = part; k < K; k += parts) t = fmaf(xs[k], Wh[k * N + n], t);
+            for (int o = NP; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            logit = t;                                   // lanes < N hold the logit of class `lane` (n == lane there)
         } else {
             for (int n = 0; n < N; ++n) {
                 float t = 0.0f;
@@ -244,12 +259,27 @@ __device__ void head_rows(const b200nn_mlp_step& a, Shared& sh) {
             const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
             if (oby > by || (oby == by && oiy < iy)) { by = oby; iy = oiy; }
         }
-        const double l = warp_sum((double)lsum), q = warp_sum((double)esq);
+        const float l = warp_sum(lsum), q = warp_sum(esq);      // <= 32 terms each
         if (lane == 0) {
-            atomicAdd(&a.acc[0], l);
+            atomicAdd(&a.acc[0], (double)l);
             if (ip == iy) atomicAdd(&a.acc[1], 1.0);
-            atomicAdd(&a.ss[a.s0], q);
+            atomicAdd(&a.ss[a.s0], (double)q);
         }
+    }
+}
+
+// sum of per-thread fp32 partials -> one atomicAdd(double) per CTA: fp32 shuffles inside a warp (<= 32 terms), fp64 across warps
+__device__ __forceinline__ void block_accumulate_fast(float v, double* out, double* scratch) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[wid] = (double)v;
+    __syncthreads();
+    if (threadIdx.x == 0 && out != nullptr) {
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < WARPS; ++i) r += scratch[i];
+        atomicAdd(out, r);
     }
 }
 
@@ -292,7 +322,7 @@ __device__ void dw_item(const b200nn_mlp_step& a, int l, int item, float scale, 
             g2 = fmaf(v, v, g2);
         }
     }
-    block_accumulate(g2, &a.gss[Ly.gi_w], sh.scratch);
+    block_accumulate_fast(g2, &a.gss[Ly.gi_w], sh.scratch);
 }
 
 // db[n] = scale * sum_m err[m][n] (layers.py:197) for 256 columns
@@ -308,7 +338,7 @@ __device__ void db_item(const b200nn_mlp_step& a, int l, int item, float scale, 
         Ly.db[n] = v;
         g2 = v * v;
     }
-    block_accumulate(g2, &a.gss[Ly.gi_b], sh.scratch);
+    block_accumulate_fast(g2, &a.gss[Ly.gi_b], sh.scratch);
 }
 
 // err_{l-1}[r0.., k0..] = act'(out_{l-1}) * scale * err_l . w_l^T for one 8 x 32 tile (layers.py:189 + the Activation backward), both slots
@@ -366,8 +396,8 @@ __device__ void dx_item(const b200nn_mlp_step& a, int l, int item, float scale, 
             Pv.err[(long long)m * K + k] = v;
         }
     }
-    block_accumulate(a0, Ly.s_out0 >= 0 ? &a.ss[Ly.s_out0] : nullptr, sh.scratch);
-    if (Ly.s_out1 >= 0) block_accumulate(a1, &a.ss[Ly.s_out1], sh.scratch);
+    block_accumulate_fast(a0, Ly.s_out0 >= 0 ? &a.ss[Ly.s_out0] : nullptr, sh.scratch);
+    if (Ly.s_out1 >= 0) block_accumulate_fast(a1, &a.ss[Ly.s_out1], sh.scratch);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_train_step_kernel(const __grid_constant__ b200nn_mlp_step a) {
@@ -377,6 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_train_step_kernel(const __grid
     Shared sh{mlp_smem, scratch, &opt_scalars};
     unsigned epoch = 0;
     const int G = gridDim.x;
+    stamp(a.sync, 0);
     // ---- step_begin: slots, accumulators, Adam's t (visible to everyone after the first barrier; nothing reads them before)
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < a.n_slots; i += THREADS) a.ss[i] = 0.0;
@@ -386,11 +417,14 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_train_step_kernel(const __grid
     // ---- warm L2: parameters and Adam moments (the only large operands: 28 B per parameter), one 128-byte line per thread and
     // tensor; the step's dependent phases then wait on L2 hits instead of HBM round trips
     {
-        const long long gt = (long long)blockIdx.x * THREADS + threadIdx.x, nt = (long long)G * THREADS;
-        for (int ti = 0; ti < a.n_params; ++ti) {
+        // warp <-> tensor (round robin), so that a thread reads ONE descriptor instead of walking the table serially
+        const int gw = blockIdx.x * WARPS + (threadIdx.x >> 5), nw = G * WARPS, lane = threadIdx.x & 31;
+        if (gw < nw - nw % a.n_params || nw < a.n_params) {
+            const int ti = gw % a.n_params;
             const b200nn_param P = a.params[ti];
             const long long lines = (P.n * 4 + 127) >> 7;
-            for (long long i = gt; i < lines; i += nt) {
+            const int per = nw >= a.n_params ? nw / a.n_params : 1;          // warps that share this tensor
+            for (long long i = (long long)(gw / a.n_params) * 32 + lane; i < lines; i += (long long)per * 32) {
                 prefetch_l2(reinterpret_cast<const char*>(P.p) + (i << 7));
                 prefetch_l2(reinterpret_cast<const char*>(P.m) + (i << 7));
                 prefetch_l2(reinterpret_cast<const char*>(P.v) + (i << 7));
@@ -462,6 +496,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_train_step_kernel(const __grid
     }
     // ---- last CTA out re-arms the barrier and the norm slots for the next launch
     __syncthreads();
+    stamp(a.sync, 2 * (int)epoch + 1);
     if (threadIdx.x == 0 && atomicAdd(&a.sync[1], 1u) == (unsigned)G - 1u) {
         for (int i = 0; i < a.n_params; ++i) a.gss[i] = 0.0;
         a.sync[0] = 0u;

@@ -497,7 +497,7 @@ class Plan:
         # optimizer table in update order (last layer first), as the layer-by-layer program builds it
         ups = [(li, L._weights, L._d_weights, L._bias, L._d_bias, ()) for li, L, _ in reversed(dense)]
         oplan = opt._make_plan(ups, self.ss, 1, nl)
-        sync = torch.zeros(2, dtype=torch.int32, device=B.device())
+        sync = torch.zeros(64, dtype=torch.int32, device=B.device())   # barrier words + phase time stamps
         errs = [None] * nl
         errs[nl - 1] = self.buf(self.pred.shape)
         for l in range(nl - 1, -1, -1):
