@@ -1100,6 +1100,9 @@ static int check_act(const char* who, int act, float alpha) {
 // the tensor-core contraction: the persistent CTA-pair kernel (gemm_tc2.cuh) unless B200NN_TC2=0 selects the first-generation one
 static int tc_gemm_any(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi,
                        int M, int N, int K, float* ws, cudaStream_t st, bool x3) {
+    // large error-compensated contractions: fp16 hi / lo planes at twice the TF32 rate (f16_split.cu)
+    if (x3 && ws != nullptr && tcapi::f16_enabled() && tcapi::f16_worth(M, N, K))
+        return tcapi::gemm2_f16x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st);
     if (tcapi::tc2_enabled())
         return x3 ? tcapi::gemm2_x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st)
                   : tcapi::gemm2_plain(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st);
@@ -1137,6 +1140,11 @@ size_t b200nn_dense_ws_bytes_math(int math, int M, int N, int K) {
         mx(tcapi::ws2(M, N, K, true));
         mx(tcapi::ws2(M, K, N, true));
         mx(tcapi::ws2(K, N, M, true));
+        auto f16 = [&](long long m, long long n, long long k) {       // partials + operand planes of the fp16-plane path
+            if (tcapi::f16_enabled() && tcapi::f16_worth(m, n, k))
+                mx((tcapi::ws2(m, n, (k + 1) / 2, true) + 255) / 256 * 256 + tcapi::f16_extra_bytes(m, n, k));
+        };
+        f16(M, N, K); f16(M, K, N); f16(K, N, M);
     }
     return r;
 }

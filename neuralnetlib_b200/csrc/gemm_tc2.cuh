@@ -83,6 +83,19 @@ __device__ __forceinline__ void tc2_commit(uint32_t bar) {
         tc::tc_commit(bar);
 }
 template <int CG>
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int CG>
 __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if constexpr (CG == 2)
         asm volatile(
@@ -172,18 +185,23 @@ __device__ __forceinline__ void epi_math(const Epilogue& e, float scale, float (
     a1 += s1;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool X3>
+// F16: both operands arrive as fp16 hi / lo PLANES (K-major, split once per call by f16_split.cu: x * s = hi + 2^-11 lo with a
+// power-of-two range scale s per tensor); 3 MMAs of kind::f16 per k-step (hi.hi into the main accumulator, lo.hi + hi.lo into the
+// second one) at TWICE the TF32 rate -- the same 22-bit products as X3 for half the tensor-pipe time, and no splitter warps.
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool X3, bool F16 = false>
 __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, Epilogue epi, int M, int N, int K, int kb_per_split, int splits,
                 float* __restrict__ ws, const ConvTma cv, int tma_out) {
     constexpr int BNH = BN / CG;                                   // B columns staged by one CTA
     constexpr uint32_t A_BYTES = BLOCK_M * 128, B_BYTES = BNH * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t LO_OFFSET = STAGES * STAGE_BYTES;           // X3: the lo tiles mirror the raw ring behind it
-    constexpr int ACC_COLS = BN * (X3 ? 2 : 1);                    // X3: main + lo-product accumulators
+    static_assert(!(X3 && F16) && !(F16 && (A_MN || B_MN)), "F16 planes are K-major and pre-split");
+    constexpr bool DUAL = X3 || F16;                               // hi and lo operand tiles, two accumulators
+    constexpr uint32_t LO_OFFSET = STAGES * STAGE_BYTES;           // DUAL: the lo tiles mirror the hi / raw ring behind it
+    constexpr int ACC_COLS = BN * (DUAL ? 2 : 1);                  // DUAL: main + lo-product accumulators
     constexpr int NUM_ACC = ACC_COLS * 2 <= 512 ? 2 : 1;
     constexpr int TMEM_COLS = ACC_COLS * NUM_ACC < 32 ? 32 : ACC_COLS * NUM_ACC;
-    constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES * (X3 ? 2 : 1);
+    constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES * (DUAL ? 2 : 1);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
@@ -267,9 +285,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint32_t own = tc::smem_u32(&full_bar[s]);
                     constexpr int LG = X3 ? 1 : CG;     // X3: loads are counted per CTA (see the splitter), else on the leader's barrier
-                    if (X3 || rank == 0) tc::mbar_expect_tx(own, STAGE_BYTES * LG);
+                    if (X3 || rank == 0) tc::mbar_expect_tx(own, STAGE_BYTES * LG * (F16 ? 2 : 1));
                     const uint32_t bar = LG == 2 ? mapa(own, 0) : own;
-                    const int k0 = kb * BLOCK_K;
+                    const int k0 = kb * BLOCK_K * (F16 ? 2 : 1);          // F16: a k-block is 64 two-byte elements
                     if (cv.mode == 1 || cv.mode == 2) {
                         // A tile = 128 consecutive pixels (whole image rows / whole images), one tap, 32 channels
                         const int dy = cv.mode == 1 ? ky - cv.pad_y : cv.pad_y - ky;
@@ -308,12 +326,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int j = 0; j < BLOCK_M / 32; ++j) tma2_load_2d<LG>(sa + j * SLAB_BYTES, &tmA, bar, m0 + j * 32, k0);
                         } else {
                             tma2_load_2d<LG>(sa, &tmA, bar, k0, m0);
+                            if constexpr (F16) tma2_load_2d<LG>(sa + LO_OFFSET, &tmA, bar, k0, m0 + cv.lo_a);
                         }
                         if constexpr (B_MN) {
 #pragma unroll
                             for (int j = 0; j < BNH / 32; ++j) tma2_load_2d<LG>(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, k0);
                         } else {
                             tma2_load_2d<LG>(sb, &tmB, bar, k0, n0);
+                            if constexpr (F16) tma2_load_2d<LG>(sb + LO_OFFSET, &tmB, bar, k0, n0 + cv.lo_b);
                         }
                     }
                 }
@@ -323,7 +343,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread of the LEADER CTA issues for the pair) =====
         if (rank == 0 && tc::elect_one()) {
-            constexpr uint32_t idesc = tc::make_idesc(BLOCK_M * CG, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = F16 ? tc::make_idesc_f16(BLOCK_M * CG, BN) : tc::make_idesc(BLOCK_M * CG, BN, A_MN, B_MN);
+            auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
+                if constexpr (F16) tc2_mma_f16<CG>(d, ad, bd, id, accum); else tc2_mma<CG>(d, ad, bd, id, accum);
+            };
             uint32_t it = 0, item = 0;
             for (int w = unit; w < total_work; w += num_units, ++item) {
                 const Work wk = decode_work(w, num_m, num_n);
@@ -344,12 +367,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
                         const uint64_t ad = A_MN ? tc::desc_mnmajor(sa, j) : tc::desc_kmajor(sa, j);
                         const uint64_t bd = B_MN ? tc::desc_mnmajor(sb, j) : tc::desc_kmajor(sb, j);
-                        tc2_mma<CG>(d_main, ad, bd, idesc, (!first || j > 0) ? 1u : 0u);
-                        if constexpr (X3) {
+                        mma(d_main, ad, bd, idesc, (!first || j > 0) ? 1u : 0u);
+                        if constexpr (DUAL) {
                             const uint64_t adl = A_MN ? tc::desc_mnmajor(sa + LO_OFFSET, j) : tc::desc_kmajor(sa + LO_OFFSET, j);
                             const uint64_t bdl = B_MN ? tc::desc_mnmajor(sb + LO_OFFSET, j) : tc::desc_kmajor(sb + LO_OFFSET, j);
-                            tc2_mma<CG>(d_main + BN, adl, bd, idesc, (!first || j > 0) ? 1u : 0u);   // A_lo . B_hi
-                            tc2_mma<CG>(d_main + BN, ad, bdl, idesc, 1u);                           // A_hi . B_lo
+                            mma(d_main + BN, adl, bd, idesc, (!first || j > 0) ? 1u : 0u);   // A_lo . B_hi
+                            mma(d_main + BN, ad, bdl, idesc, 1u);                           // A_hi . B_lo
                         }
                     }
                     tc2_commit<CG>(tc::smem_u32(&empty_bar[s]));        // frees the stage (in both CTAs) once these MMAs have read it
@@ -401,6 +424,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         const int ew = warp - 2;
         const float scale = chain_scale(epi.ss, epi.chain);
+        float f16_unscale = 1.0f;
+        if constexpr (F16) f16_unscale = __ldg(cv.inv_scale) * __ldg(cv.inv_scale + 1);
         const int am = epi.act == B200NN_ACT_NONE ? 0 : (epi.act == B200NN_ACT_RELU ? 1 : 2);
         const int mm = epi.mask_y == nullptr ? 0 : (epi.mask_act == B200NN_ACT_RELU ? 1 : 2);
         double d0 = 0.0, d1 = 0.0;
@@ -421,6 +446,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int kx = t % epi.kw, ky = t / epi.kw;
                 orow = ((long long)c * epi.kh + ky) * epi.kw + kx;
             }
+            // First-order compensation of the tensor core's truncating accumulate. Every MMA adds into the fp32 accumulator with
+            // truncation; measured (scripts/probe_trunc_bias.py, profiles/r2_trunc_bias.txt) the result is the exact sum times
+            // (1 - 1.64e-8 * MMAs chained on the main accumulator), independent of shape and of the operands' sign pattern
+            // (-4.2e-6 at 256 MMAs, -2.1e-6 at 128). Undoing that factor halves the error of the compensated modes and removes
+            // the part that compounds from layer to layer (a same-signed shrink of every activation).
+            float trunc_comp = 1.0f;
+            if constexpr (DUAL) {
+                const int kb_begin = wk.split * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+                trunc_comp = 1.0f + 1.64e-8f * (float)((kb_end - kb_begin) * (BLOCK_K / UMMA_K));
+            }
             float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
@@ -434,7 +469,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     float lo[32];
                     tc::tc_ld32(taddr + BN, lo);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += lo[i];
+                    for (int i = 0; i < 32; ++i) v[i] = (v[i] + lo[i]) * trunc_comp;
+                }
+                if constexpr (F16) {      // (hi.hi + 2^-11 (lo.hi + hi.lo)) / (s_a s_b)
+                    float lo[32];
+                    tc::tc_ld32(taddr + BN, lo);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(lo[i], 0.00048828125f, v[i]) * (f16_unscale * trunc_comp);
                 }
                 if (splits > 1) {                 // split-K partial: the raw accumulator, reduced by splitk_reduce_*
                     if (row_ok) {
@@ -593,12 +634,12 @@ static size_t ws_bytes2(long long M, long long N, long long K, bool x3) {
     return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool X3>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool X3, bool F16 = false>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Epilogue& epi, int M, int N, int K,
                    const Plan2& p, float* ws, cudaStream_t st, const ConvTma& cv, int tma_out) {
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + (BN / CG) * 128) * (X3 ? 2 : 1) + EPI_BYTES + 1024;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * 128 + (BN / CG) * 128) * ((X3 || F16) ? 2 : 1) + EPI_BYTES + 1024;
     static_assert(smem <= 227 * 1024, "ring + staging exceed the shared memory of an SM");
-    auto kern = gemm_tc2_kernel<BN, STAGES, A_MN, B_MN, CG, X3>;
+    auto kern = gemm_tc2_kernel<BN, STAGES, A_MN, B_MN, CG, X3, F16>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -621,14 +662,14 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     return B200NN_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, bool X3>
+template <int BN, bool A_MN, bool B_MN, int CG, bool X3, bool F16 = false>
 static int launch2_stages(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Epilogue& epi, int M, int N,
                           int K, const Plan2& p, float* ws, cudaStream_t st, const ConvTma& cv, int tma_out) {
-    constexpr long long stage = (long long)(BLOCK_M * 128 + (BN / CG) * 128) * (X3 ? 2 : 1);
+    constexpr long long stage = (long long)(BLOCK_M * 128 + (BN / CG) * 128) * ((X3 || F16) ? 2 : 1);
     constexpr long long fit = (227 * 1024 - 1024 - (long long)EPI_BYTES - 512) / stage;
     constexpr int S = fit > 8 ? 8 : (int)fit;
     static_assert(S >= 2, "at least a double-buffered ring");
-    return launch2<BN, S, A_MN, B_MN, CG, X3>(ta, tb, to, epi, M, N, K, p, ws, st, cv, tma_out);
+    return launch2<BN, S, A_MN, B_MN, CG, X3, F16>(ta, tb, to, epi, M, N, K, p, ws, st, cv, tma_out);
 }
 
 template <bool X3>
@@ -693,6 +734,39 @@ static int gemm2(const float* A, long long lda, bool a_mn, const float* B, long 
     else      { if (int rc = tc::make_map(&tb, B, K, N, ldb, p.bn / p.cg, false)) return rc; }
     ConvTma cv{};
     return run2<X3>(ta, tb, a_mn, b_mn, epi, M, N, K, p, ws, st, cv);
+}
+
+// D[M,N] = A.B from fp16 hi / lo planes: Ap = [hi plane (M rows) | lo plane] with the lo plane lo_a rows below, row pitch lda
+// (elements), K two-byte elements per row; Bp likewise with N rows. K4 = ceil(K / 2) is the reduction length in the 4-byte units the
+// planner counts in (a k-block is 128 bytes either way).
+template <int UNUSED = 0>   // a template so that only gemm_tc2_f16.cu instantiates the F16 kernels
+static int gemm2_f16(const void* Ap, long long lda, int lo_a, const void* Bp, long long ldb, int lo_b, const float* inv_scale,
+                     const Epilogue& epi, int M, int N, int K, float* ws, cudaStream_t st) {
+    const int K4 = (K + 1) / 2;
+    const Plan2 p = plan2(M, N, K4, true);
+    CUtensorMap ta, tb, to;
+    if (int rc = tc::make_map_f16(&ta, Ap, K, (long long)lo_a + M, lda, BLOCK_M)) return rc;
+    if (int rc = tc::make_map_f16(&tb, Bp, K, (long long)lo_b + N, ldb, p.bn / p.cg)) return rc;
+    ConvTma cv{};
+    cv.lo_a = lo_a; cv.lo_b = lo_b; cv.inv_scale = inv_scale;
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "gemm_tc2 (f16 planes): split-K needs a workspace");
+    int tma_out = 0;
+    if (int rc = make_out_map(&to, epi, M, N, p.splits, &tma_out)) return rc;
+#define TC2_F16(BN, CG) return launch2_stages<BN, false, false, CG, false, true>(ta, tb, to, epi, M, N, K4, p, ws, st, cv, tma_out);
+    if (p.cg == 2) {
+        switch (p.bn) {
+            case 64: TC2_F16(64, 2)
+            case 128: TC2_F16(128, 2)
+            default: TC2_F16(256, 2)
+        }
+    }
+    switch (p.bn) {
+        case 32: TC2_F16(32, 1)
+        case 64: TC2_F16(64, 1)
+        case 128: TC2_F16(128, 1)
+        default: TC2_F16(256, 1)
+    }
+#undef TC2_F16
 }
 
 template <bool X3>

@@ -19,6 +19,15 @@ int gemm2_plain(const float* A, long long lda, bool a_mn, const float* B, long l
                 int N, int K, float* ws, cudaStream_t st);
 int gemm2_x3(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
              int K, float* ws, cudaStream_t st);
+// TF32X3 accuracy at twice the rate for LARGE contractions: operands pre-split into fp16 hi / lo planes (f16_split.cu), three
+// kind::f16 MMAs per k-step (gemm_tc2.cuh F16 mode). ws: ws2(M, N, ceil(K / 2), true) + f16_extra_bytes(M, N, K) bytes.
+bool f16_enabled();
+bool f16_worth(long long M, long long N, long long K);
+size_t f16_extra_bytes(long long M, long long N, long long K);
+int gemm2_f16x3(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
+                int K, float* ws, cudaStream_t st);
+int gemm2_f16_planes(const void* Ap, long long lda, int lo_a, const void* Bp, long long ldb, int lo_b, const float* inv_scale,
+                     const Epilogue& epi, int M, int N, int K, float* ws, cudaStream_t st);
 // which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
 int conv1(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws, cudaStream_t st, bool x3);
 int conv2_plain(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws, cudaStream_t st);

@@ -88,6 +88,10 @@ struct ConvTma {
     int kw, taps;
     int W, H;          // image size (input = output)
     int pad_y, pad_x;
+    // fp16 hi/lo operand planes (gemm_tc2.cuh F16 mode): the lo plane of A / B starts this many rows below the hi plane in the
+    // same tensor map; inv_scale = {1 / s_a, 1 / s_b} (device) undoes the power-of-two range scaling of the planes
+    int lo_a, lo_b;
+    const float* inv_scale;
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -128,6 +132,10 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) { retu
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep) { return make_desc(tile + kstep * 1024, SLAB_BYTES, 512, 1); }
 // instruction descriptor (InstrDescriptor): c_format F32 = 1 [4,6) | a/b format TF32 = 2 [7,10) [10,13) | a_major [15] |
 // b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+// kind::f16 with fp16 operands (a / b format 0), fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -460,6 +468,21 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; box = {32, box_rows};
 // K-major operands use SWIZZLE_128B, MN-major operands the 32-byte-atom variant (see the header comment)
+// K-major fp16 operand planes: element (row, k) at base[row * ld + k]; box {64 k = 128 bytes, box_rows}, 128-byte swizzle
+static int make_map_f16(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    B200NN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200NN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed with %d (inner=%lld outer=%lld ld=%lld)", (int)r, inner, outer, ld);
+    return B200NN_OK;
+}
+
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_rows,
                     bool mn_major) {
     EncodeTiledFn fn = encode_fn();

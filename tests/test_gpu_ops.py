@@ -516,7 +516,9 @@ def test_dense_tf32_tcgen05(K, M, N, Kd):
 
 
 @pytest.mark.parametrize("M,N,Kd", [(256, 64, 6272), (512, 512, 512), (300, 260, 200), (128, 32, 64), (64, 4096, 512),
-                                    (1000, 128, 96), (256, 256, 2048), (256, 4096, 4096)])
+                                    (1000, 128, 96), (256, 256, 2048), (256, 4096, 4096),
+                                    # large contractions take the fp16 hi/lo-plane path (f16_split.cu + gemm_tc2.cuh F16 mode)
+                                    (2048, 2048, 2048), (2052, 1028, 4100)])
 def test_dense_tf32x3_tcgen05(K, M, N, Kd):
     """Error-compensated tensor-core path (math mode 2): raw + lo operand tiles, three tcgen05 MMAs per k-step. Must
     reach the FFMA path's accuracy (rel 1e-5 of the fp64 oracle), not single-pass TF32's 2e-3."""
