@@ -385,6 +385,11 @@ int b200nn_mul(const float* a, const float* b, const double* ss, uint64_t chain,
 int b200nn_avgpool2d_fwd(const b200nn_pool_geom* g, const float* x, float* y, void* stream);
 int b200nn_avgpool2d_bwd(const b200nn_pool_geom* g, const float* err, const double* ss, uint64_t chain, float* dx, double* ss_out,
                          void* stream);
+/* Autoencoder.backward_pass's clip rule (models.py:1033-1048) on one tensor: norm clip to `threshold`, clamp to [-10, 10], divide by
+ * (np.std + 1e-8); threshold <= 0 copies. scratch3: three device float64 words (zeroed by the call). in-place allowed. */
+int b200nn_ae_clip(const float* g, float* out, long long n, float threshold, double* scratch3, void* stream);
+/* out = a + s * b (the Autoencoder's scaled skip connection, models.py:1014-1019); in-place allowed */
+int b200nn_axpy(const float* a, const float* b, float s, float* out, long long n, void* stream);
 int b200nn_gap2d_fwd(const float* x, float* y, int N, int HW, int C, void* stream);
 int b200nn_gap2d_bwd(const float* err, const double* ss, uint64_t chain, float* dx, double* ss_out, int N, int HW, int C, void* stream);
 int b200nn_upsample2d_fwd(const float* x, float* y, int N, int H, int W, int C, int fh, int fw, void* stream);

@@ -139,6 +139,8 @@ _SIGNATURES = {
     "b200nn_bn_bwd_apply": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_int, c_float, _P, _P, _P]),
     "b200nn_pool_bn_bwd_partial": (c_int, [_P, _P, _P, c_u64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "b200nn_mul": (c_int, [_P, _P, _P, c_u64, _P, _P, c_ll, _P]),
+    "b200nn_ae_clip": (c_int, [_P, _P, c_ll, c_float, _P, _P]),
+    "b200nn_axpy": (c_int, [_P, _P, c_float, _P, c_ll, _P]),
     "b200nn_avgpool2d_fwd": (c_int, [C.POINTER(PoolGeom), _P, _P, _P]),
     "b200nn_avgpool2d_bwd": (c_int, [C.POINTER(PoolGeom), _P, _P, c_u64, _P, _P, _P]),
     "b200nn_gap2d_fwd": (c_int, [_P, _P, c_int, c_int, c_int, _P]),

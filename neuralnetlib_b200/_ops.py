@@ -484,3 +484,14 @@ def sgd_multi(plan: OptPlan, hyper, on_stream=None):
 def mlp_train_step(desc):
     """desc: a filled _backend.MlpStep (kept alive by the caller). One launch = one whole train step of a small MLP."""
     check(lib().b200nn_mlp_train_step(C.byref(desc), stream()))
+
+
+def ae_clip(g, out, threshold, scratch3):
+    """Autoencoder clip rule (models.py:1033-1048) on one tensor; scratch3: float64[3] device tensor."""
+    _f32(g, out)
+    check(lib().b200nn_ae_clip(ptr(g), ptr(out), g.numel(), float(threshold), ptr(scratch3), stream()))
+
+
+def axpy(a, b, s, out):
+    _f32(a, b, out)
+    check(lib().b200nn_axpy(ptr(a), ptr(b), float(s), ptr(out), a.numel(), stream()))

@@ -20,6 +20,58 @@ __global__ void __launch_bounds__(256) mul_kernel(const float* __restrict__ a, c
     if (ss_out != nullptr) block_accumulate(acc, ss_out, scratch);
 }
 
+// out = a + s * b  (Autoencoder skip connections, models.py:1014-1019)
+__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float s, float* __restrict__ out,
+                                                   long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fmaf(s, b[i], a[i]);
+}
+
+// Autoencoder.backward_pass's own clip rule (models.py:1033-1048), applied to every error tensor and every gradient:
+//   g *= min(1, threshold / ||g||);  g = clip(g, -10, 10);  g /= std(g) + 1e-8          (np.std: population, over all elements)
+// scratch[0] = sum g^2 (pass 1), scratch[1] / [2] = sum / sum of squares of the clamped tensor (pass 2), pass 3 applies.
+__global__ void __launch_bounds__(256) ae_clip_sumsq_kernel(const float* __restrict__ g, long long n, double* scratch) {
+    __shared__ double sc[32];
+    float acc = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(g[i], g[i], acc);
+    block_accumulate(acc, &scratch[0], sc);
+}
+__device__ __forceinline__ float ae_norm_scale(const double* scratch, float threshold) {
+    if (threshold <= 0.0f) return 1.0f;
+    const double nrm = sqrt(scratch[0]);
+    return nrm > (double)threshold ? (float)((double)threshold / nrm) : 1.0f;
+}
+__global__ void __launch_bounds__(256) ae_clip_stats_kernel(const float* __restrict__ g, long long n, float threshold, double* scratch) {
+    const float s = ae_norm_scale(scratch, threshold);
+    double a1 = 0.0, a2 = 0.0;       // fp64 per thread: the variance is a difference of two nearly equal sums when |mean| >> std
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)clip10(g[i] * s);
+        a1 += v; a2 += v * v;
+    }
+    // block reduction in fp64
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a1 = warp_sum(a1); a2 = warp_sum(a2);
+    __shared__ double s1[8], s2[8];
+    if (lane == 0) { s1[wid] = a1; s2[wid] = a2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < 8; ++i) { t1 += s1[i]; t2 += s2[i]; }
+        atomicAdd(&scratch[1], t1);
+        atomicAdd(&scratch[2], t2);
+    }
+}
+__global__ void __launch_bounds__(256) ae_clip_apply_kernel(const float* __restrict__ g, float* __restrict__ out, long long n, float threshold,
+                                                            const double* __restrict__ scratch) {
+    const float s = ae_norm_scale(scratch, threshold);
+    const double mean = scratch[1] / (double)n;
+    double var = scratch[2] / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = threshold > 0.0f ? (float)(1.0 / (sqrt(var) + 1e-8)) : 1.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = threshold > 0.0f ? clip10(g[i] * s) * inv : g[i];
+}
+
 // mean over every (ph x pw) window of the zero-padded input (np.mean of the padded slice: padding counts in the divisor)
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(b200nn_pool_geom g, const float* __restrict__ x, float* __restrict__ y,
                                                           long long total) {
@@ -201,6 +253,28 @@ int b200nn_mul(const float* a, const float* b, const double* ss, uint64_t chain,
     if (n == 0) return B200NN_OK;
     mul_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, ss, chain, out, ss_out, n);
     B200NN_LAUNCH_CHECK("mul");
+    return B200NN_OK;
+}
+
+int b200nn_axpy(const float* a, const float* b, float s, float* out, long long n, void* stream) {
+    B200NN_REQUIRE(a != nullptr && b != nullptr && out != nullptr && n >= 0, "axpy: bad argument");
+    if (n == 0) return B200NN_OK;
+    axpy_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, b, s, out, n);
+    B200NN_LAUNCH_CHECK("axpy");
+    return B200NN_OK;
+}
+
+int b200nn_ae_clip(const float* g, float* out, long long n, float threshold, double* scratch3, void* stream) {
+    B200NN_REQUIRE(g != nullptr && out != nullptr && scratch3 != nullptr && n >= 0, "ae_clip: bad argument");
+    if (n == 0) return B200NN_OK;
+    cudaStream_t st = as_stream(stream);
+    B200NN_CUDA(cudaMemsetAsync(scratch3, 0, 3 * sizeof(double), st));
+    ae_clip_sumsq_kernel<<<grid_for(n), 256, 0, st>>>(g, n, scratch3);
+    B200NN_LAUNCH_CHECK("ae_clip_sumsq");
+    ae_clip_stats_kernel<<<grid_for(n), 256, 0, st>>>(g, n, threshold, scratch3);
+    B200NN_LAUNCH_CHECK("ae_clip_stats");
+    ae_clip_apply_kernel<<<grid_for(n), 256, 0, st>>>(g, out, n, threshold, scratch3);
+    B200NN_LAUNCH_CHECK("ae_clip_apply");
     return B200NN_OK;
 }
 

@@ -571,3 +571,313 @@ class GAN(BaseModel):
             if verbose:
                 print()
         return history
+
+
+class Autoencoder(BaseModel):
+    """Mirror of neuralnetlib/models.py:778-1565 (the training loop) on the device kernels: encoder / decoder
+    layer lists, separate losses and optimizers, and backward_pass's OWN clip rule (models.py:1033-1048: norm clip to
+    gradient_clip_threshold, clamp to +-10, divide by np.std + 1e-8) applied to every error tensor and every gradient
+    (b200nn_ae_clip). Activations, errors, gradients and optimizer state stay in HBM; the per-layer weight update happens right
+    after each layer's backward, as in the reference. Not captured into a graph (this loop is a 'next' row, not the bench path).
+    Reference behaviours kept: the decoder is fed the raw encoder output also in variational mode (the reparameterised latent only
+    enters the loss VALUE: KL, latent penalties, models.py:1001-1010, :1124-1137); skip connections add encoder Dense outputs to
+    decoder Dense outputs of the same width in the forward only (:1014-1019), the backward ignores them."""
+
+    def __init__(self, encoder_layers: list = None, decoder_layers: list = None, gradient_clip_threshold: float = 5.0,
+                 enable_padding: bool = False, padding_size: int = 32, random_state: int | None = None,
+                 skip_connections: bool = False, l1_reg: float = 0.0, l2_reg: float = 0.0, variational: bool = False):
+        super().__init__(gradient_clip_threshold, enable_padding, padding_size, random_state)
+        self.encoder_layers = encoder_layers if encoder_layers is not None else []
+        self.decoder_layers = decoder_layers if decoder_layers is not None else []
+        self.encoder_optimizer = self.decoder_optimizer = None
+        self.encoder_loss = self.decoder_loss = None
+        self.y_true = self.predictions = self.latent_space = None
+        self.skip_connections, self.variational = skip_connections, variational
+        self.l1_reg, self.l2_reg = l1_reg, l2_reg
+        self.epsilon = 1e-7
+        self.latent_dim = None
+        self.latent_mean = self.latent_log_var = None
+        self.metrics = None
+        self._scratch = None
+
+    # ---- construction (models.py:881-974) ---------------------------------------------------------------------------
+    @staticmethod
+    def _append(lst, layer, first_must_be_input):
+        if not lst:
+            if first_must_be_input and not isinstance(layer, Input):
+                raise ValueError("The first encoder layer must be an Input layer.")
+        else:
+            prev_t, cur_t = type(lst[-1]), type(layer)
+            if cur_t in incompatibility_dict.get(prev_t, []):
+                raise ValueError(f"{cur_t.__name__} layer cannot follow {prev_t.__name__} layer.")
+        lst.append(layer)
+        act = getattr(layer, "activation", getattr(layer, "activation_function", None))
+        if act and not isinstance(layer, Activation):
+            if isinstance(act, str):
+                lst.append(Activation.from_name(act))
+            elif isinstance(act, ActivationFunction):
+                lst.append(Activation(act))
+            elif isinstance(act, Activation):
+                lst.append(act)
+            else:
+                raise ValueError(f"Invalid activation function: {act}")
+
+    def add_encoder_layer(self, layer: Layer):
+        self._append(self.encoder_layers, layer, True)
+
+    def add_decoder_layer(self, layer: Layer):
+        self._append(self.decoder_layers, layer, False)
+
+    def compile(self, encoder_loss=None, decoder_loss=None, encoder_optimizer=None, decoder_optimizer=None, verbose: bool = False,
+                metrics: list | None = None):
+        encoder_loss = decoder_loss if encoder_loss is None else encoder_loss
+        decoder_loss = encoder_loss if decoder_loss is None else decoder_loss
+        encoder_optimizer = decoder_optimizer if encoder_optimizer is None else encoder_optimizer
+        decoder_optimizer = encoder_optimizer if decoder_optimizer is None else decoder_optimizer
+        if encoder_loss is None or encoder_optimizer is None:
+            raise ValueError("At least one loss and optimizer must be specified")
+        as_loss = lambda v: v if isinstance(v, LossFunction) else LossFunction.from_name(v)        # noqa: E731
+        as_opt = lambda v: v if isinstance(v, Optimizer) else Optimizer.from_name(v)               # noqa: E731
+        self.encoder_loss, self.decoder_loss = as_loss(encoder_loss), as_loss(decoder_loss)
+        self.encoder_optimizer, self.decoder_optimizer = as_opt(encoder_optimizer), as_opt(decoder_optimizer)
+        self.metrics = metrics
+        if verbose:
+            print(str(self))
+        last = self.encoder_layers[-1]
+        # models.py:974 reads .units (variational) or .output_shape[-1]; the latter only exists on Embedding-like layers upstream
+        self.latent_dim = last.units if self.variational else (last.output_shape[-1] if hasattr(last, "output_shape")
+                                                               else getattr(last, "units", None))
+
+    def __str__(self) -> str:
+        s = f"Autoencoder(gradient_clip_threshold={self.gradient_clip_threshold}, random_state={self.random_state})\n"
+        s += "Encoder:\n" + "".join(f"  Layer {i + 1}: {l}\n" for i, l in enumerate(self.encoder_layers))
+        s += "Decoder:\n" + "".join(f"  Layer {i + 1}: {l}\n" for i, l in enumerate(self.decoder_layers))
+        return s + f"Losses: {self.encoder_loss} / {self.decoder_loss}\nOptimizers: {self.encoder_optimizer} / {self.decoder_optimizer}\n"
+
+    def summary(self):
+        print(str(self))
+
+    # ---- forward (models.py:976-1030) ---------------------------------------------------------------------------------
+    def _forward_dev(self, X, training: bool = True) -> torch.Tensor:
+        t = X if isinstance(X, torch.Tensor) else B.to_device(np.asarray(X))
+        rows = t.shape[0]
+        if self.enable_padding and rows % self.padding_size:
+            pad = (rows + self.padding_size - 1) // self.padding_size * self.padding_size
+            tp = B.zeros((pad,) + tuple(t.shape[1:]))
+            tp[:rows].copy_(t)
+            t = tp
+        skip = {}
+        for layer in self.encoder_layers:
+            t = layer.forward_pass(t, training) if isinstance(layer, Dropout) else layer.forward_pass(t)   # noqa: F405
+            if self.skip_connections and isinstance(layer, Dense):
+                skip[layer.units] = t
+        self._latent_dev = t
+        for layer in self.decoder_layers:
+            t = layer.forward_pass(t, training) if isinstance(layer, Dropout) else layer.forward_pass(t)   # noqa: F405
+            if self.skip_connections and isinstance(layer, Dense) and skip.get(layer.units) is not None:
+                s = skip[layer.units]
+                out = B.empty(tuple(t.shape))
+                ops.axpy(t.contiguous(), s.contiguous(), 1.0 / np.sqrt(layer.units), out)
+                t = out
+        return t[:rows]
+
+    def _latent_terms(self, encoded: np.ndarray):
+        """(latent_space, kl) of models.py:817-831, 1001-1007: the reparameterisation draws from default_rng(random_state) anew each call."""
+        if not self.variational:
+            self.latent_mean = self.latent_log_var = None
+            return encoded, 0.0
+        half = encoded.shape[-1] // 2
+        self.latent_mean, self.latent_log_var = encoded[:, :half], encoded[:, half:]
+        eps = np.random.default_rng(self.random_state).normal(size=self.latent_mean.shape)
+        latent = self.latent_mean + np.exp(0.5 * self.latent_log_var) * eps
+        kl = -0.5 * np.mean(1 + self.latent_log_var - np.square(self.latent_mean) - np.exp(self.latent_log_var))
+        return latent, float(kl)
+
+    def forward_pass(self, X, training: bool = True):
+        out = self._forward_dev(X, training)
+        self.latent_space, _ = self._latent_terms(B.to_host(self._latent_dev))
+        return out if isinstance(X, torch.Tensor) else B.to_host(out)
+
+    # ---- backward with the Autoencoder's clip rule (models.py:1032-1114) ------------------------------------------------
+    def _clip(self, t: torch.Tensor) -> torch.Tensor:
+        if t is None:
+            return None
+        if self._scratch is None:
+            self._scratch = B.zeros((3,), dtype=torch.float64)
+        out = B.empty(tuple(t.shape))
+        ops.ae_clip(t.contiguous(), out, float(self.gradient_clip_threshold), self._scratch)
+        return out
+
+    def _update_layer(self, layer, idx, optimizer):
+        if not hasattr(layer, "weights") or getattr(layer, "_weights", None) is None:
+            return
+        dw = self._clip(layer._d_weights)
+        if getattr(layer, "_d_bias", None) is not None:
+            optimizer.update(idx, layer._weights, dw, layer._bias, self._clip(layer._d_bias))
+        else:
+            optimizer.update(idx, layer._weights, dw)
+
+    def _backward_dev(self, error: torch.Tensor, pred: torch.Tensor = None, y: torch.Tensor = None):
+        for i, layer in enumerate(reversed(self.decoder_layers)):
+            if i == 0 and isinstance(layer, Activation):
+                name = type(layer.activation_function).__name__
+                if pred is not None and name == "Softmax" and isinstance(self.decoder_loss, CategoricalCrossentropy):
+                    error = B.to_device(B.to_host(pred) - B.to_host(y))
+                elif pred is not None and name == "Sigmoid" and isinstance(self.decoder_loss, BinaryCrossentropy):
+                    p, yy = B.to_host(pred), B.to_host(y)
+                    error = B.to_device((p - yy) / (p * (1 - p) + 1e-15))
+                # any other pair: the loss derivative passes THROUGH the last activation unchanged (models.py:1054-1062)
+            else:
+                error = layer.backward_pass(self._clip(error))
+            self._update_layer(layer, len(self.decoder_layers) - 1 - i, self.decoder_optimizer)
+        for i, layer in enumerate(reversed(self.encoder_layers)):
+            error = layer.backward_pass(self._clip(error))
+            self._update_layer(layer, len(self.encoder_layers) - 1 - i, self.encoder_optimizer)
+        return error
+
+    def backward_pass(self, error):
+        e = error if isinstance(error, torch.Tensor) else B.to_device(np.asarray(error))
+        pred = None if self.predictions is None else B.to_device(np.asarray(self.predictions))
+        y = None if self.y_true is None else B.to_device(np.asarray(self.y_true))
+        self._backward_dev(e, pred, y)
+
+    def _calculate_regularization(self) -> float:
+        reg = 0.0
+        if self.l1_reg > 0 or self.l2_reg > 0:
+            for layer in list(self.encoder_layers) + list(self.decoder_layers):
+                if hasattr(layer, "weights") and layer.weights is not None:
+                    w = np.asarray(layer.weights)
+                    reg += self.l1_reg * np.sum(np.abs(w)) if self.l1_reg > 0 else 0.0
+                    reg += self.l2_reg * np.sum(np.square(w)) if self.l2_reg > 0 else 0.0
+        return float(reg)
+
+    def _loss_and_error(self, lf, y_dev, pred_dev, want_err=True):
+        p2 = pred_dev.reshape(pred_dev.shape[0], -1)
+        y2 = y_dev.reshape(p2.shape)
+        err = B.empty(tuple(p2.shape)) if want_err else None
+        acc = B.zeros((4,), dtype=torch.float64)
+        ops.loss_fwd_bwd(lf._kind, 0, p2.contiguous(), y2.contiguous(), err, acc, None, None, 1, float(getattr(lf, "_param", 1.0)))
+        loss = float(acc.cpu()[0].item()) / lf._denominator(tuple(p2.shape))
+        return loss, (err.reshape(pred_dev.shape) if want_err else None)
+
+    def train_on_batch(self, x_batch, y_batch=None) -> float:
+        """models.py:1116-1146."""
+        x = x_batch if isinstance(x_batch, torch.Tensor) else B.to_device(np.asarray(x_batch))
+        y = x if y_batch is None else (y_batch if isinstance(y_batch, torch.Tensor) else B.to_device(np.asarray(y_batch)))
+        pred = self._forward_dev(x, True)
+        self.y_true = B.to_host(y)
+        self.predictions = B.to_host(pred)
+        self.latent_space, kl = self._latent_terms(B.to_host(self._latent_dev))
+        loss, err = self._loss_and_error(self.decoder_loss, y, pred)
+        latent_l2 = 0.0001 * float(np.mean(np.square(self.latent_space)))
+        penalty = 0.0001 * float(np.mean(np.abs(np.std(self.latent_space, axis=0) - 1.0)))
+        if self.skip_connections:
+            latent_l2 *= 0.1
+            penalty *= 0.1
+        total = loss + self._calculate_regularization() + latent_l2 + penalty + 0.01 * kl
+        if err.dim() == 1:
+            err = err.reshape(-1, 1)
+        self._backward_dev(err, pred, y)
+        return total
+
+    # ---- inference (models.py:1148-1195) --------------------------------------------------------------------------------
+    def predict(self, X, output_latent: bool = False, temperature: float = 1.0) -> np.ndarray:
+        out = self._forward_dev(np.asarray(X), False)
+        if output_latent:
+            return B.to_host(self._latent_dev)
+        dec = B.to_host(out)
+        if not np.isclose(temperature, 1.0, rtol=1e-09, atol=1e-09):
+            dec = np.exp(np.log(np.clip(dec, 1e-7, 1.0)) / temperature)
+            dec /= np.sum(dec, axis=-1, keepdims=True)
+        return dec
+
+    def evaluate(self, x_test, y_test=None, batch_size: int = 32) -> tuple:
+        x_test = np.asarray(x_test)
+        y_test = x_test if y_test is None else np.asarray(y_test)
+        total, preds = 0.0, []
+        n_batches = int(np.ceil(len(x_test) / batch_size))
+        for i in range(0, len(x_test), batch_size):
+            bx, by = x_test[i:i + batch_size], y_test[i:i + batch_size]
+            p = self._forward_dev(bx, False)
+            yd = B.to_device(by)
+            dl, _ = self._loss_and_error(self.decoder_loss, yd, p, False)
+            el, _ = self._loss_and_error(self.encoder_loss, yd, p, False)
+            total += (dl + el) / 2
+            preds.append(B.to_host(p))
+        return total / n_batches, np.vstack(preds)
+
+    def fit(self, x_train, epochs: int, batch_size: int | None = None, verbose: bool = True, metrics: list | None = None,
+            random_state: int | None = None, validation_data: tuple | None = None, validation_split: float | None = None,
+            callbacks: list = []) -> dict:
+        """models.py:1286-1539 (loss / val_loss history, per-epoch reshuffle with the same seed, callbacks)."""
+        if self.metrics is not None:
+            metrics = self.metrics
+        history = History({"loss": [], "val_loss": []})
+        if validation_data is not None and validation_split is not None:
+            raise ValueError("Cannot specify both validation_data and validation_split")
+        x_train = np.asarray(x_train)
+        if validation_data is None and validation_split is not None:
+            x_train, x_val = train_test_split(x_train, test_size=validation_split, random_state=random_state)
+            validation_data = (x_val, x_val)
+        if metrics is not None:
+            metrics = [Metric(m) for m in metrics]
+            for m in metrics:
+                history[m.name] = []
+                history[f"val_{m.name}"] = []
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            cb.on_train_begin({"history": history, "model": self})
+        seed = random_state if random_state is not None else self.random_state
+        xd = B.to_device(x_train)
+        for epoch in range(epochs):
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch, {"model": self})
+            idx = torch.from_numpy(shuffle_indices(x_train.shape[0], seed)).to(B.device())
+            t0, error, preds, inputs = time.time(), 0.0, [], []
+            step = batch_size if batch_size is not None else x_train.shape[0]
+            n_batches = int(np.ceil(x_train.shape[0] / step))
+            for bi, j in enumerate(range(0, x_train.shape[0], step)):
+                rows = idx[j:j + step]
+                xb = B.empty((rows.numel(),) + tuple(xd.shape[1:]))
+                ops.gather_rows(xd, rows, xb)
+                for cb in callbacks:
+                    cb.on_batch_begin(bi, {"batch": bi, "size": rows.numel(), "model": self})
+                be = self.train_on_batch(xb)
+                error += be
+                logs = {"batch": bi, "size": rows.numel(), "model": self, "loss": be}
+                if metrics is not None:
+                    preds.append(self.predictions); inputs.append(self.y_true)
+                    for m in metrics:
+                        logs[m.name] = m(preds[-1], inputs[-1])
+                for cb in callbacks:
+                    cb.on_batch_end(bi, logs)
+                if verbose:
+                    progress_bar(bi + 1, n_batches, message=f"Epoch {epoch + 1}/{epochs} - loss: {format_number(error / (bi + 1))} - "
+                                                            f"{time.time() - t0:.2f}s")
+            error /= n_batches
+            history["loss"].append(error)
+            epoch_logs = {"loss": error, "model": self, "history": history}
+            if metrics is not None:
+                for m in metrics:
+                    history[m.name].append(m(np.vstack(preds), np.vstack(inputs)))
+                    epoch_logs[m.name] = history[m.name][-1]
+            if validation_data is not None:
+                x_val = validation_data[0]
+                y_val = validation_data[1] if len(validation_data) > 1 else x_val
+                val_loss, val_pred = self.evaluate(x_val, y_val, batch_size or 32)
+                history["val_loss"].append(val_loss)
+                epoch_logs["val_loss"] = val_loss
+                if metrics is not None:
+                    for m in metrics:
+                        history[f"val_{m.name}"].append(m(val_pred, np.asarray(y_val)))
+            if verbose:
+                print()
+            stop = False
+            for cb in callbacks:
+                if cb.on_epoch_end(epoch, epoch_logs):
+                    stop = True
+            if stop:
+                break
+        for cb in callbacks:
+            cb.on_train_end({"history": history, "model": self})
+        return history
