@@ -34,5 +34,12 @@ def math_version() -> int:
     return _MATH_VERSION
 
 
+def invalidate_plans() -> None:
+    """A layer swapped a parameter TENSOR (assignment with a different element count): plans, captured graphs and optimizer tables
+    built on the old pointer are rebuilt at the next step (the same version counter as set_math)."""
+    global _MATH_VERSION
+    _MATH_VERSION += 1
+
+
 def get_math() -> str:
     return _MATH

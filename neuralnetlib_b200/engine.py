@@ -725,6 +725,9 @@ class Plan:
             self._acc_host = torch.zeros(2, dtype=torch.float64).pin_memory()
             self._acc_host_np = self._acc_host.numpy()
         B.check(B.lib().b200nn_read_sync(self._acc_host.data_ptr(), self.acc.data_ptr(), 16, B.stream()))
+        if self.dp is not None and self.dp.comm.peer and self.dp.comm.timeouts():
+            # a peer exchange gave up after 10 s (a rank never arrived): the sums of this step are garbage, replicas have diverged
+            raise B.B200NNError("data-parallel peer exchange timed out: a rank did not arrive; results of this step are invalid")
         return float(self._acc_host_np[0]), float(self._acc_host_np[1])
 
     def set_input(self, x):

@@ -162,6 +162,9 @@ class _ParamMixin:
             cur.copy_(B.to_device(arr).reshape(cur.shape))   # keep the pointer: captured graphs stay valid
         else:
             setattr(self, "_" + name, B.to_device(arr))
+            if cur is not None:      # the pointer changed under plans / graphs / optimizer tables that captured the old one
+                from . import invalidate_plans
+                invalidate_plans()
         self._shapes[name] = arr.shape
 
 

@@ -384,6 +384,14 @@ class Sequential(BaseModel):
             xb, yb = x_test[i:i + batch_size], y_test[i:i + batch_size]
             out = self._forward_dev(xb, training=False)
             plan = self._last_plan
+            if plan.pred.shape[0] != len(xb):
+                # enable_padding: the plan ran on zero-padded rows; the reference slices the predictions back before the loss
+                # (models.py:190-192), so the loss is taken over the real rows only (host contract of the loss, device kernel inside)
+                ph = B.to_host(out)[:len(xb)]
+                total += float(self.loss_function(np.asarray(self._dense_targets(yb, plan.pred.shape[-1])).reshape(ph.shape), ph))
+                preds.append(ph)
+                nb += 1
+                continue
             plan.set_target(np.asarray(self._dense_targets(yb, plan.pred.shape[-1])).reshape(tuple(plan.pred.shape)))
             plan.program("loss").run()
             total += float(plan.acc[0].item()) / self._loss_denominator(plan)

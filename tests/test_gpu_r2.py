@@ -317,3 +317,21 @@ def test_conv2d_column_path(N, H, W, C, F, k, s, pad, math, tol):
     h = host(ss)
     assert abs(h[1] - np.sum(rdx ** 2)) < max(10 * tol, 1e-4) * np.sum(rdx ** 2)
     assert abs(h[2] - np.sum((rdx * (x > 0)) ** 2)) < max(10 * tol, 1e-4) * np.sum((rdx * (x > 0)) ** 2)
+
+
+def test_evaluate_with_enable_padding_counts_real_rows_only():
+    """evaluate() under enable_padding (models.py:159-181, 565-601): a batch that is not a multiple of padding_size runs on
+    zero-padded rows, but loss and predictions cover the real rows only (round-1 advisor finding: it raised)."""
+    from neuralnetlib_b200 import layers as L, models as M, optimizers as Opt
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(13, 9)).astype(np.float32)
+    y = np.eye(4, dtype=np.float32)[rng.integers(0, 4, 13)]
+    out = []
+    for pad in (True, False):
+        m = M.Sequential(random_state=8, enable_padding=pad, padding_size=8)
+        m.add(L.Input(9)); m.add(L.Dense(6, activation="tanh")); m.add(L.Dense(4, activation="softmax"))
+        m.compile(loss_function="categorical_crossentropy", optimizer=Opt.SGD())
+        out.append(m.evaluate(x, y, batch_size=13))
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * max(1.0, abs(out[1][0]))
+    assert out[0][1].shape == out[1][1].shape == (13, 4)
+    assert nrel(out[0][1], out[1][1]) < 1e-6
