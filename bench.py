@@ -74,34 +74,44 @@ def load_peaks():
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 20 ms while the timed region runs."""
+    """SM clock / power / throttle reasons of one GPU, read in-process through NVML by a background thread: every 2 ms while a timed
+    region runs (Timer.time_steps switches it to `fast`), every 20 ms otherwise. The timing loop itself is never delayed (an inline
+    NVML read on one rank would skew the ranks of a data-parallel step against each other). Falls back to `nvidia-smi -lms 20`."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
         self.nvml = self.handle = None
-        try:   # NVML in-process: one sample costs a few microseconds of host time, so it can be taken between timed steps
+        self.fast = False
+        self._stop = threading.Event()
+        try:
             import pynvml
             pynvml.nvmlInit()
             self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
 
-    def sample(self):
-        """One in-process NVML sample (called from the timing loops while the device is executing the timed steps)."""
-        if self.nvml is None:
-            return
-        try:
-            n, h = self.nvml, self.handle
-            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            flag = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731
-            self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
-                              str(n.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
-        except Exception:
-            pass
+    def _sample(self):
+        n, h = self.nvml, self.handle
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731
+        self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(self.max_sm),
+                          str(n.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(0.002 if self.fast else 0.02)
 
     def start(self):
+        if self.nvml is not None:
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
@@ -131,6 +141,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
     def stop(self):
+        self._stop.set()
         if self.proc is None:
             return
         time.sleep(0.25)
@@ -306,15 +317,16 @@ class Timer:
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         self.barrier()
         out = None
-        every = max(1, K // 40)
-        for i, (s, e) in enumerate(ev):
+        if self.sampler is not None:
+            self.sampler.fast = True          # 2 ms NVML polling (background thread) while the timed steps run
+        for s, e in ev:
             self.flush.zero_()                # evict L2 (126 MB) between steps; outside the timed events
             s.record(self.stream)
             out = fn()
             e.record(self.stream)
-            if self.sampler is not None and i % every == 0:
-                self.sampler.sample()         # host-side NVML read while the device runs the queued steps; outside the events
         self.barrier()
+        if self.sampler is not None:
+            self.sampler.fast = False
         return self.reduce_max(sum(s.elapsed_time(e) for s, e in ev)) / K, out
 
     def per_op(self, prog, reps):

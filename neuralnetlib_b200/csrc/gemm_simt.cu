@@ -733,33 +733,41 @@ __global__ void __launch_bounds__(256) dense_smalln_dx_kernel(const float* __res
     epi_finish(epi, st, scratch);
 }
 
-// partial[chunk][k (+ ones row K)][n] = sum over the chunk's rows of x[m, k] * e[m, n]
+// partial[chunk][k (+ ones row K)][n] = sum over the chunk's rows of x[m, k] * e[m, n]. The error rows are staged zero-padded to NMAX
+// columns (128-bit broadcast reads, no per-class bound check: the branchy form was instruction-bound, 192 us at 8192 x 4096 x 10).
+template <int NMAX>
 __global__ void __launch_bounds__(256) dense_smalln_dw_kernel(const float* __restrict__ x, const float* __restrict__ e,
                                                               float* __restrict__ partial, int M, int N, int K,
                                                               int rows_per_chunk) {
-    __shared__ float es[64 * SMALLN_MAX];   // the chunk's error rows, staged 64 rows at a time
+    __shared__ __align__(16) float es[64 * NMAX];   // the chunk's error rows, staged 64 rows at a time
     const int k = blockIdx.x * blockDim.x + threadIdx.x;    // 0..K (K = ones row -> db)
     const int m_begin = blockIdx.y * rows_per_chunk, m_end = min(M, m_begin + rows_per_chunk);
-    float acc[SMALLN_MAX];
+    float acc[NMAX];
 #pragma unroll
-    for (int n = 0; n < SMALLN_MAX; ++n) acc[n] = 0.0f;
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.0f;
     for (int mb = m_begin; mb < m_end; mb += 64) {
         const int nr = min(64, m_end - mb);
         __syncthreads();
-        for (int i = threadIdx.x; i < nr * N; i += blockDim.x) es[i] = e[(long long)mb * N + i];
+        for (int i = threadIdx.x; i < 64 * NMAX; i += blockDim.x) {
+            const int r = i / NMAX, n = i - r * NMAX;
+            es[i] = (r < nr && n < N) ? e[(long long)(mb + r) * N + n] : 0.0f;     // rows past the chunk and columns past N: zeros
+        }
         __syncthreads();
         if (k <= K) {
-            for (int r0 = 0; r0 < nr; r0 += 8) {
-                float xv[8];
+            for (int r0 = 0; r0 < nr; r0 += 16) {
+                float xv[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)   // 8 independent loads in flight
+                for (int j = 0; j < 16; ++j)   // 16 independent loads in flight
                     xv[j] = (r0 + j < nr) ? (k < K ? x[(long long)(mb + r0 + j) * K + k] : 1.0f) : 0.0f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float* er = &es[min(r0 + j, nr - 1) * N];
+                for (int j = 0; j < 16; ++j) {
+                    const float4* er = reinterpret_cast<const float4*>(&es[min(r0 + j, 63) * NMAX]);
 #pragma unroll
-                    for (int n = 0; n < SMALLN_MAX; ++n)
-                        if (n < N) acc[n] = fmaf(xv[j], er[n], acc[n]);
+                    for (int q = 0; q < NMAX / 4; ++q) {
+                        const float4 ev = er[q];
+                        acc[4 * q] = fmaf(xv[j], ev.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv[j], ev.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(xv[j], ev.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv[j], ev.w, acc[4 * q + 3]);
+                    }
                 }
             }
         }
@@ -767,7 +775,7 @@ __global__ void __launch_bounds__(256) dense_smalln_dw_kernel(const float* __res
     if (k <= K) {
         float* dst = partial + ((long long)blockIdx.y * (K + 1) + k) * N;
 #pragma unroll
-        for (int n = 0; n < SMALLN_MAX; ++n)
+        for (int n = 0; n < NMAX; ++n)
             if (n < N) dst[n] = acc[n];
     }
 }
@@ -888,10 +896,24 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float
     for (int k0 = 0; k0 < K; k0 += HR_KC) {
         const int kc = min(HR_KC, K - k0);
         __syncthreads();
-        {   // columns >= N are staged as zeros, so the FMA loop below carries no bound checks (no branches between its loads)
+        {   // columns >= N are staged as zeros, so the FMA loop below carries no bound checks (no branches between its loads).
+            // Eight loads in flight per thread: a one-load-per-iteration loop made this staging (48 dependent L2 round trips per
+            // chunk) the whole kernel: 137-190 us whatever the batch (ncu: long_scoreboard 18.7 per issue).
             const int n = threadIdx.x % NL;
-            for (int k = threadIdx.x / NL; k < kc; k += 256 / NL)
-                if (n < NMAX) ws[k * PITCH + n] = n < N ? w[(long long)(k0 + k) * N + n] : 0.0f;
+            constexpr int KSTEP = 256 / NL;
+            for (int kb = threadIdx.x / NL; kb < kc; kb += KSTEP * 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = kb + j * KSTEP;
+                    v[j] = (k < kc && n < N) ? __ldg(w + (long long)(k0 + k) * N + n) : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = kb + j * KSTEP;
+                    if (k < kc && n < NMAX) ws[k * PITCH + n] = v[j];
+                }
+            }
         }
         __syncthreads();
 #pragma unroll 4
@@ -956,30 +978,45 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float
 
 // Large-batch dx of a small Dense: thread = one input feature k with w[k, :] in registers, CTA = 256 features x DXR rows whose
 // error rows sit in shared memory (broadcast reads); the mask load and the dx store are coalesced 1 KB runs per row.
-constexpr int DXR = 32;
+constexpr int DXR = 128;   // rows per CTA: the prologue (error rows, w[k, :] into registers) is amortised over 128 KB of traffic
 template <int NMAX>
 __global__ void __launch_bounds__(256) dense_smalln_dx_rows_kernel(const float* __restrict__ e, const float* __restrict__ w,
                                                                    Epilogue epi, int M, int N, int K) {
     __shared__ double scratch[32];
-    __shared__ float es[DXR][NMAX];
+    __shared__ __align__(16) float es[DXR][NMAX];
     EpiState st;
     epi_begin(epi, st);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int m0 = blockIdx.y * DXR, nr = min(DXR, M - m0);
-    for (int i = threadIdx.x; i < nr * N; i += blockDim.x) es[i / N][i % N] = e[(long long)m0 * N + i];
+    for (int i = threadIdx.x; i < DXR * NMAX; i += blockDim.x) {
+        const int r = i / NMAX, n = i - r * NMAX;
+        es[r][n] = (r < nr && n < N) ? e[(long long)(m0 + r) * N + n] : 0.0f;     // zero-padded: 128-bit broadcast reads below
+    }
     float wr[NMAX];
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) wr[n] = (k < K && n < N) ? w[(long long)k * N + n] : 0.0f;
     __syncthreads();
     if (k < K) {
-#pragma unroll 4
-        for (int r = 0; r < nr; ++r) {
-            float v = 0.0f;
+        constexpr int RB = 8;                        // mask loads in flight per thread
+        for (int r0 = 0; r0 < nr; r0 += RB) {
+            float mk[RB];
 #pragma unroll
-            for (int n = 0; n < NMAX; ++n) v = fmaf(es[r][n < N ? n : 0], wr[n], v);
-            const long long i = (long long)(m0 + r) * K + k;
-            const float mk = epi.mask_y != nullptr ? epi.mask_y[i] : 0.0f;
-            epi_store_premask(epi, st, m0 + r, k, v, mk);
+            for (int j = 0; j < RB; ++j)
+                mk[j] = (epi.mask_y != nullptr && r0 + j < nr) ? epi.mask_y[(long long)(m0 + r0 + j) * K + k] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                if (r0 + j < nr) {
+                    const float4* er = reinterpret_cast<const float4*>(es[r0 + j]);
+                    float v = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < NMAX / 4; ++q) {
+                        const float4 ev = er[q];
+                        v = fmaf(ev.x, wr[4 * q], v); v = fmaf(ev.y, wr[4 * q + 1], v);
+                        v = fmaf(ev.z, wr[4 * q + 2], v); v = fmaf(ev.w, wr[4 * q + 3], v);
+                    }
+                    epi_store_premask(epi, st, m0 + r0 + j, k, v, mk[j]);
+                }
+            }
         }
     }
     epi_finish(epi, st, scratch);
@@ -1268,7 +1305,9 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
             const int chunks = smalln_chunks(M);
             const int rpc = (M + chunks - 1) / chunks;
             const dim3 grid((K + 1 + 255) / 256, chunks);
-            dense_smalln_dw_kernel<<<grid, 256, 0, st>>>(x, err, ws, M, N, K, rpc);
+            if (N <= 12) dense_smalln_dw_kernel<12><<<grid, 256, 0, st>>>(x, err, ws, M, N, K, rpc);
+            else if (N <= 16) dense_smalln_dw_kernel<16><<<grid, 256, 0, st>>>(x, err, ws, M, N, K, rpc);
+            else dense_smalln_dw_kernel<32><<<grid, 256, 0, st>>>(x, err, ws, M, N, K, rpc);
             B200NN_LAUNCH_CHECK("dense_smalln_dw");
             Epilogue e = plain_epilogue(dw, N, K);
             e.ss = ss; e.chain = chain; e.db = db;
