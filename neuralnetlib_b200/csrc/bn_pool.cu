@@ -770,6 +770,156 @@ __global__ void __launch_bounds__(256) pool_bn_act_bwd_stream_apply_kernel(
     if (prev_act != B200NN_ACT_NONE && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
 }
 
+// ---- one-channel-per-thread forms of the two streaming backward kernels (round 2). The channel-quad kernels above keep six float4
+// constants per pooled position in registers (apply: 221 registers = ONE 256-thread CTA per SM, ~41 KB of loads in flight per SM,
+// 2.2 TB/s; ncu: profiles/r2_ncu_cfg3_kernels.txt). With one channel per thread the constants are 24 scalars, a warp still covers whole
+// 128-byte lines (32 consecutive channels), four batch rows are in flight per thread (20 loads) and three CTAs fit an SM. The
+// arithmetic per element is unchanged.
+constexpr int SB1_UNROLL = 4;
+
+struct SbPos1 {
+    long long pos[4];
+    long long obase;
+};
+__device__ __forceinline__ SbPos1 sb_positions1(long long idx, int W, int C) {
+    const int OW = W >> 1;
+    const int c = (int)(idx % C); long long t = idx / C;
+    const int ox = (int)(t % OW); const int oy = (int)(t / OW);
+    SbPos1 r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.pos[q] = ((long long)(2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * C + c;
+    r.obase = ((long long)oy * OW + ox) * C + c;
+    return r;
+}
+
+__global__ void __launch_bounds__(256, 3) pool_bn_bwd_stream_partial1_kernel(
+    const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, float* __restrict__ part, double* ss0, int B, int H, int W, int C, long long items) {
+    __shared__ double scratch[32];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < items;
+    const float scale = chain_scale(ss, chain);
+    const long long P = (long long)H * W * C, OP = P >> 2;
+    float a0 = 0.0f;
+    if (ok) {
+        const SbPos1 sp = sb_positions1(idx, W, C);
+        float mean[4], gq[4], bq[4], is[4], sb[4], sg[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mean[q] = save_mean[sp.pos[q]];
+            is[q] = save_invstd[sp.pos[q]];
+            gq[q] = gamma[sp.pos[q]] * is[q];
+            bq[q] = beta[sp.pos[q]];
+            sb[q] = sg[q] = 0.0f;
+        }
+        const int r0 = blockIdx.y * SB_ROWS, r1 = min(B, r0 + SB_ROWS);
+        for (int rb = r0; rb < r1; rb += SB1_UNROLL) {
+            float e[SB1_UNROLL], xv[SB1_UNROLL][4];
+#pragma unroll
+            for (int j = 0; j < SB1_UNROLL; ++j) {
+                const int r = min(rb + j, r1 - 1);
+                e[j] = err[(long long)r * OP + sp.obase];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xv[j][q] = x[(long long)r * P + sp.pos[q]];
+            }
+#pragma unroll
+            for (int j = 0; j < SB1_UNROLL; ++j) {
+                if (rb + j < r1) {
+                    const float ev = scale * e[j];
+                    float yq[4], dq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        dq[q] = clip10(xv[j][q]) - mean[q];
+                        yq[q] = fmaf(gq[q], dq[q], bq[q]);
+                    }
+                    const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float u = (yq[q] == m) ? ev : 0.0f;      /* every tied maximum, layers.py:631-637 */
+                        sb[q] += u;
+                        sg[q] = fmaf(u, dq[q], sg[q]);
+                        a0 = fmaf(u, u, a0);
+                    }
+                }
+            }
+        }
+        float* pb = part + (long long)blockIdx.y * 2 * P;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pb[sp.pos[q]] = sb[q];                       // sum U
+            pb[P + sp.pos[q]] = sg[q] * is[q];           // sum U * xhat
+        }
+    }
+    if (ss0 != nullptr) block_accumulate(a0, ss0, scratch);
+}
+
+__global__ void __launch_bounds__(256, 3) pool_bn_act_bwd_stream_apply1_kernel(
+    const float* __restrict__ x, const float* __restrict__ err, const double* __restrict__ ss, uint64_t chain,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+    const float* __restrict__ save_invstd, float* __restrict__ r0out, const float* __restrict__ dgamma,
+    const float* __restrict__ dbeta, int B, int H, int W, int C, float inv_total, int prev_act, float prev_alpha, double* ss1,
+    double* ss2, long long items) {
+    __shared__ double scratch[32];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < items;
+    const float scale = chain_scale(ss, chain);
+    const long long P = (long long)H * W * C, OP = P >> 2;
+    float a1 = 0.0f, a2 = 0.0f;
+    if (ok) {
+        const SbPos1 sp = sb_positions1(idx, W, C);
+        float mean[4], gq[4], bq[4], ka[4], kb[4], isv[4];   // dx = g * (U - xhat * kb - ka), ka = dbeta / N, kb = dgamma / N
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mean[q] = save_mean[sp.pos[q]];
+            isv[q] = save_invstd[sp.pos[q]];
+            gq[q] = gamma[sp.pos[q]] * isv[q];
+            bq[q] = beta[sp.pos[q]];
+            ka[q] = dbeta[sp.pos[q]] * inv_total;
+            kb[q] = dgamma[sp.pos[q]] * inv_total;
+        }
+        const int r0 = blockIdx.y * SB_ROWS, r1 = min(B, r0 + SB_ROWS);
+        for (int rb = r0; rb < r1; rb += SB1_UNROLL) {
+            float e[SB1_UNROLL], xraw[SB1_UNROLL][4];
+#pragma unroll
+            for (int j = 0; j < SB1_UNROLL; ++j) {
+                const int r = min(rb + j, r1 - 1);
+                e[j] = err[(long long)r * OP + sp.obase];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xraw[j][q] = x[(long long)r * P + sp.pos[q]];
+            }
+#pragma unroll
+            for (int j = 0; j < SB1_UNROLL; ++j) {
+                if (rb + j < r1) {
+                    const float ev = scale * e[j];
+                    float yq[4], xh[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float d = clip10(xraw[j][q]) - mean[q];
+                        yq[q] = fmaf(gq[q], d, bq[q]);
+                        xh[q] = d * isv[q];
+                    }
+                    const float m = fmaxf(fmaxf(yq[0], yq[1]), fmaxf(yq[2], yq[3]));
+                    float* rb_out = r0out + (long long)(rb + j) * P;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float u = (yq[q] == m) ? ev : 0.0f;
+                        float d = gq[q] * (u - xh[q] * kb[q] - ka[q]);                       /* layers.py:1264-1274 */
+                        a1 = fmaf(d, d, a1);
+                        if (prev_act != B200NN_ACT_NONE) {
+                            d *= act_grad_from_y(prev_act, xraw[j][q], prev_alpha);           /* layers.py:237 */
+                            a2 = fmaf(d, d, a2);
+                        }
+                        rb_out[sp.pos[q]] = d;
+                    }
+                }
+            }
+        }
+    }
+    if (ss1 != nullptr) block_accumulate(a1, ss1, scratch);
+    if (prev_act != B200NN_ACT_NONE && ss2 != nullptr) block_accumulate(a2, ss2, scratch);
+}
+
 // Forward statistics, streaming form: ONE sweep over x. Thread = 4 adjacent positions (float4), blockIdx.y = a chunk of
 // SS_ROWS batch rows; per chunk the sums are taken about a per-position shift K = clip(x[first row of the chunk]) so that
 // sum((x - K)^2) - sum(x - K)^2 / n loses nothing to cancellation (a one-pass variance about zero would); the chunks are then
@@ -1047,6 +1197,16 @@ int b200nn_pool_bn_act_bwd_apply(const float* x, const float* err, const double*
 }
 
 // ---- streaming forms (large batches; any batch size, C % 4 == 0) -----------------------------------------------------------
+// one channel per thread when a warp then covers whole 128-byte lines (C % 32 == 0); B200NN_STREAM_SCALAR=0 keeps the quad kernels
+static bool stream_scalar_form(int C) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200NN_STREAM_SCALAR");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && C % 32 == 0;
+}
+
 static int check_stream_block(const char* who, int B, int H, int W, int C, const void* a, const void* b, const void* c) {
     B200NN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0,
                    "%s: needs even H, W and C %% 4 == 0 (got %dx%dx%d)", who, H, W, C);
@@ -1070,8 +1230,14 @@ int b200nn_pool_bn_bwd_stream_partial(const float* x, const float* err, const do
     const int chunks = (B + SB_ROWS - 1) / SB_ROWS;
     const dim3 grid((unsigned)((items + 255) / 256), (unsigned)chunks);
     cudaStream_t st = as_stream(stream);
-    pool_bn_bwd_stream_partial_kernel<<<grid, 256, 0, st>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, ws, ss_out0, B, H,
-                                                          W, C, items);
+    if (stream_scalar_form(C)) {
+        const dim3 grid1((unsigned)((items * 4 + 255) / 256), (unsigned)chunks);
+        pool_bn_bwd_stream_partial1_kernel<<<grid1, 256, 0, st>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, ws, ss_out0, B, H,
+                                                                W, C, items * 4);
+    } else {
+        pool_bn_bwd_stream_partial_kernel<<<grid, 256, 0, st>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, ws, ss_out0, B, H,
+                                                              W, C, items);
+    }
     B200NN_LAUNCH_CHECK("pool_bn_bwd_stream_partial");
     stream_reduce2_kernel<<<(unsigned)((2 * P / 4 + 255) / 256), 256, 0, st>>>(ws, chunks, P, dbeta, dgamma);
     B200NN_LAUNCH_CHECK("stream_reduce2");
@@ -1087,6 +1253,12 @@ int b200nn_pool_bn_act_bwd_stream_apply(const float* x, const float* err, const 
     B200NN_REQUIRE(dgamma != nullptr && dbeta != nullptr && B_total >= B, "pool_bn_act_bwd_stream_apply: bad argument");
     const long long items = (long long)(H / 2) * (W / 2) * (C / 4);
     const dim3 grid((unsigned)((items + 255) / 256), (unsigned)((B + SB_ROWS - 1) / SB_ROWS));
+    if (stream_scalar_form(C)) {
+        const dim3 grid1((unsigned)((items * 4 + 255) / 256), (unsigned)((B + SB_ROWS - 1) / SB_ROWS));
+        pool_bn_act_bwd_stream_apply1_kernel<<<grid1, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd,
+                                                                                r0, dgamma, dbeta, B, H, W, C, 1.0f / (float)B_total,
+                                                                                prev_act, prev_alpha, ss_out1, ss_out2, items * 4);
+    } else
     pool_bn_act_bwd_stream_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, err, ss, chain, gamma, beta, save_mean, save_invstd, r0,
                                                                            dgamma, dbeta, B, H, W, C, 1.0f / (float)B_total, prev_act,
                                                                            prev_alpha, ss_out1, ss_out2, items);
