@@ -100,6 +100,13 @@ class ClockSampler:
         self.rows.append([str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(self.max_sm),
                           str(n.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
 
+    def sample_inline(self):
+        if self.nvml is not None:
+            try:
+                self._sample()
+            except Exception:
+                pass
+
     def _poll(self):
         while not self._stop.is_set():
             try:
@@ -324,6 +331,8 @@ class Timer:
             s.record(self.stream)
             out = fn()
             e.record(self.stream)
+        if self.sampler is not None:
+            self.sampler.sample_inline()      # every step is enqueued, the device is still running them: one guaranteed sample under load
         self.barrier()
         if self.sampler is not None:
             self.sampler.fast = False

@@ -129,14 +129,15 @@ __global__ void __launch_bounds__(256) bn_fwd_apply_kernel(const float* __restri
     for (int r = ry; r < B; r += BN_ROWG) yc[(long long)r * P] = g * (clip10(xc[(long long)r * P]) - mean) + b;
 }
 
-// BatchNorm apply + MaxPool 2x2/s2 from rank-summed moments: a thread owns (window, channel quad) and FB_APPLY_ROWS batch rows
+// BatchNorm apply + MaxPool 2x2/s2 from rank-summed moments: a thread owns (window, channel quad) and `rows_per_chunk` batch rows
+// (8, or 32 at large batch: the prologue finalises 16 positions' moments in fp64 and is worth amortising)
 constexpr int FB_APPLY_ROWS = 8;
 __global__ void __launch_bounds__(256) bn_pool_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ rmean,
                                                             float* __restrict__ rvar, float* __restrict__ save_mean,
                                                             float* __restrict__ save_invstd, const double* __restrict__ stats,
                                                             float* __restrict__ y, int B, int H, int W, int C, double n_total,
-                                                            float momentum, float eps, long long total) {
+                                                            float momentum, float eps, long long total, int rows_per_chunk) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int CQ = C >> 2, OW = W >> 1, OH = H >> 1;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) bn_pool_apply_kernel(const float* __restr
         }
     }
     const long long OP = (long long)OH * OW * C, obase = ((long long)oy * OW + ox) * C + c;
-    const int r0 = chunk * FB_APPLY_ROWS, r1 = min(B, r0 + FB_APPLY_ROWS);
+    const int r0 = chunk * rows_per_chunk, r1 = min(B, r0 + rows_per_chunk);
 #pragma unroll 4
     for (int r = r0; r < r1; ++r) {
         const float* xr = x + (long long)r * P;
@@ -951,15 +952,26 @@ __global__ void __launch_bounds__(256) stream_stats_combine_kernel(const float* 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     double n = 0.0, mean = 0.0, M2 = 0.0;
-    for (int c = 0; c < chunks; ++c) {
-        const float* pb = part + (long long)c * 3 * P + i;
-        const double nc = (double)min(SS_ROWS, B - c * SS_ROWS);
-        const double K = (double)pb[0], S1 = (double)pb[P], S2 = (double)pb[2 * P];
-        const double mc = K + S1 / nc, m2c = fmax(S2 - S1 * S1 / nc, 0.0);
-        const double tot = n + nc, delta = mc - mean;
-        mean += delta * nc / tot;
-        M2 += m2c + delta * delta * n * nc / tot;
-        n = tot;
+    for (int c0 = 0; c0 < chunks; c0 += 8) {      // the loads of eight chunks in flight before the (serial, fp64) merge consumes them
+        float kv[8], s1v[8], s2v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* pb = part + (long long)min(c0 + j, chunks - 1) * 3 * P + i;
+            kv[j] = pb[0]; s1v[j] = pb[P]; s2v[j] = pb[2 * P];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            if (c < chunks) {
+                const double nc = (double)min(SS_ROWS, B - c * SS_ROWS);
+                const double K = (double)kv[j], S1 = (double)s1v[j], S2 = (double)s2v[j];
+                const double mc = K + S1 / nc, m2c = fmax(S2 - S1 * S1 / nc, 0.0);
+                const double tot = n + nc, delta = mc - mean;
+                mean += delta * nc / tot;
+                M2 += m2c + delta * delta * n * nc / tot;
+                n = tot;
+            }
+        }
     }
     const double S = mean * n;
     stats[i] = S;                       // sum clip(x)
@@ -1156,13 +1168,18 @@ int b200nn_bn_pool_fwd_apply(const float* x, const float* gamma, const float* be
                    "bn_pool_fwd_apply: needs even H, W and C %% 4 == 0 (got %dx%dx%d)", H, W, C);
     B200NN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_pool)) & 15) == 0,
                    "bn_pool_fwd_apply: x and y must be 16-byte aligned");
-    const long long chunks = (B + FB_APPLY_ROWS - 1) / FB_APPLY_ROWS;
-    const long long total = chunks * (H / 2) * (W / 2) * (C / 4);
+    // rows per thread: 32 or 16 while that still leaves >= 2 CTAs per SM, else 8
+    const long long windows = (long long)(H / 2) * (W / 2) * (C / 4);
+    int rpc = FB_APPLY_ROWS;
+    for (int cand = 32; cand > FB_APPLY_ROWS; cand >>= 1)
+        if ((long long)((B + cand - 1) / cand) * windows >= 2LL * 256 * kNumSMs) { rpc = cand; break; }
+    const long long chunks = (B + rpc - 1) / rpc;
+    const long long total = chunks * windows;
     const long long blocks = (total + 255) / 256;
     B200NN_REQUIRE(blocks < (1LL << 31), "bn_pool_fwd_apply: grid too large");
     bn_pool_apply_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, gamma, beta, running_mean, running_var, save_mean,
                                                                    save_invstd, stats, y_pool, B, H, W, C, (double)B_total,
-                                                                   momentum, eps, total);
+                                                                   momentum, eps, total, rpc);
     B200NN_LAUNCH_CHECK("bn_pool_fwd_apply");
     return B200NN_OK;
 }
