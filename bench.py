@@ -727,7 +727,8 @@ def run_b200(args):
         dist.barrier()
     if rank != 0:
         sys.stdout.flush()
-        os._exit(0)   # the captured step graphs still hold the NCCL communicator: let process exit reclaim it
+        _dp_teardown(dist)
+        return 0
 
     if world == 1 and not args.no_cpu_baseline:
         budget_steps = 24
@@ -738,8 +739,23 @@ def run_b200(args):
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
-        os._exit(0)
+        _dp_teardown(dist)
     return 0
+
+
+def _dp_teardown(dist):
+    """Orderly exit of a data-parallel rank: plans / graphs were dropped per leg, so the communicators can be destroyed and the process
+    group closed. A watchdog ends the process if NCCL's destroy does not return within 20 s (the line is already printed)."""
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        from neuralnetlib_b200 import parallel
+        parallel.shutdown()
+        dist.destroy_process_group()
+    except Exception as e:   # noqa: BLE001
+        print(f"[bench] teardown: {e!r}", file=sys.stderr)
+    watchdog.cancel()
 
 
 def main():

@@ -107,6 +107,14 @@ class Sequential(BaseModel):
         self._plans = {}
         self._last_plan = None
 
+    def __del__(self):
+        # a model that goes out of scope must not leave captured graphs behind: under data parallelism they reference the NCCL
+        # communicator, whose destruction waits for them
+        try:
+            self._drop_plans()
+        except Exception:   # noqa: BLE001  (interpreter shutdown: the library may be gone already)
+            pass
+
     def _plan(self, batch_shape, training: bool) -> Plan:
         from . import math_version
         if getattr(self, "_plans_math", None) != math_version():   # set_math() after the first step: the mode is frozen into a plan

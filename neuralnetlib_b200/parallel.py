@@ -81,6 +81,24 @@ def all_gather_bytes(payload: bytes, group=None) -> list[bytes]:
 
 
 # ---- communicator -----------------------------------------------------------------------------------------------------
+import weakref
+
+_LIVE_COMMS = []     # every Communicator of this process, for shutdown()
+_LIVE_MODELS = weakref.WeakSet()   # every model made data parallel (their plans hold graphs that reference a communicator)
+
+
+def shutdown(models=()):
+    """Orderly teardown of the data-parallel state of this process: drop the plans (and with them the captured step graphs, which
+    reference the NCCL communicator) of `models`, drain the device, destroy every communicator. Call on every rank, then
+    torch.distributed.destroy_process_group()."""
+    for m in list(models) + list(_LIVE_MODELS):
+        if hasattr(m, "_drop_plans"):
+            m._drop_plans()
+    torch.cuda.synchronize()
+    while _LIVE_COMMS:
+        _LIVE_COMMS.pop().destroy()
+
+
 class Communicator:
     """b200nn_comm (include/b200nn.h): NCCL communicator + optional CUDA-IPC symmetric buffer for one-shot exchanges.
     Bootstrapped over an initialised torch.distributed process group (torchrun)."""
@@ -119,6 +137,7 @@ class Communicator:
         if use_peer and (self.world > 1 or use_peer == "force"):   # "force": map the symmetric buffer even for a world of one (tests)
             self._open_peer(sym_bytes or int(os.environ.get("B200NN_SYM_BYTES", str(256 << 20))))
         dist.barrier(group)
+        _LIVE_COMMS.append(self)
 
     def _open_peer(self, sym_bytes):
         lib = B.lib()
@@ -219,6 +238,7 @@ def make_data_parallel(model, comm: Communicator | None = None, group=None):
         comm = Communicator(group)
     model._dp = DataParallel(comm) if comm.world > 1 else None
     model._drop_plans()
+    _LIVE_MODELS.add(model)
     return model
 
 
@@ -234,5 +254,6 @@ def make_gan_data_parallel(gan, comm: Communicator | None = None, group=None):
     for net in (gan.generator, gan.discriminator):
         net._dp = DataParallel(comm) if comm.world > 1 else None
         net._drop_plans()
+        _LIVE_MODELS.add(net)
     gan._dp = gan.discriminator._dp
     return gan

@@ -169,9 +169,16 @@ def main():
     if rank == 0:
         print(f"DP_OK world={world} peer={comm.peer} nccl={comm.nccl_version} median-errs={out}")
     sys.stdout.flush()
-    # no ncclCommDestroy here: the captured step graphs still reference the communicator, and NCCL's destroy waits for them;
-    # process exit reclaims everything
-    os._exit(0)
+    # orderly teardown: drop the plans (the captured step graphs reference the communicator), drain the device, destroy the
+    # communicators, close the process group; a watchdog ends the process if NCCL's destroy does not return
+    import threading
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    from neuralnetlib_b200 import parallel
+    parallel.shutdown()
+    dist.destroy_process_group()
+    watchdog.cancel()
 
 
 if __name__ == "__main__":
