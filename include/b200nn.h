@@ -346,6 +346,9 @@ int b200nn_comm_region_create(b200nn_comm* comm, size_t bytes, int* site_out, si
 /* buf[0..n) <- sum over ranks, in place. dtype 0 = float32, 1 = float64. site >= 0: one-shot peer-memory exchange
  * through that site; site < 0: ncclAllReduce. */
 int b200nn_comm_allreduce_sum(b200nn_comm* comm, int site, void* buf, long long n, int dtype, void* stream);
+/* two payloads in one latency exchange (site >= 0 only; (n_a rounded up to even) + 2 n_b <= 1024 words, site payload >= 8 bytes per
+ * word): n_a float32 values and n_b float64 values, each summed over the ranks in rank order like b200nn_comm_allreduce_sum */
+int b200nn_comm_allreduce_sum2(b200nn_comm* comm, int site, float* a, int n_a, double* b, int n_b, void* stream);
 
 /* ---- BatchNormalization under data parallelism: each batch-coupled kernel splits at its reduction ---------------
  * forward:  b200nn_bn_stats_partial  ->  sum `stats` over ranks (fp64)  ->  b200nn_bn_fwd_apply | b200nn_bn_pool_fwd_apply

@@ -132,6 +132,7 @@ _SIGNATURES = {
     "b200nn_comm_timeouts": (c_int, [_P]),
     "b200nn_comm_site_create": (c_int, [_P, c_size_t, C.POINTER(c_int)]),
     "b200nn_comm_allreduce_sum": (c_int, [_P, c_int, _P, c_ll, c_int, _P]),
+    "b200nn_comm_allreduce_sum2": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P]),
     "b200nn_bn_stats_partial": (c_int, [_P, _P, c_int, c_ll, _P]),
     "b200nn_bn_fwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_ll, c_ll, c_float, c_float, _P]),
     "b200nn_bn_pool_fwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_ll, c_float, c_float, _P]),

@@ -202,6 +202,61 @@ __global__ void __launch_bounds__(1024) exchange_sum_ll_kernel(PeerPtrs peers, i
     }
 }
 
+// Two payloads in ONE latency exchange: n_a float32 words followed (from an even word index) by n_b float64 values. The train step's
+// last small gradient bucket and its clip slots / loss accumulators then cross the GPUs in one NVLink round trip instead of two
+// back-to-back kernels (~9 us per step at config 2).
+__global__ void __launch_bounds__(1024) exchange_sum_ll2_kernel(PeerPtrs peers, int rank, int world, int site, size_t data_off,
+                                                                size_t rank_words, float* __restrict__ a, int n_a,
+                                                                double* __restrict__ b, int n_b) {
+    SymHeader* me = reinterpret_cast<SymHeader*>(peers.p[rank]);
+    const unsigned seq = *reinterpret_cast<volatile unsigned*>(&me->seq[site]) + 1u;
+    const unsigned par = seq & 1u;
+    const int lane = threadIdx.x;
+    const int b0 = (n_a + 1) & ~1;                       // first word of the float64 segment (even, so pairs sit in one warp)
+    const int nwords = b0 + 2 * n_b;
+    const bool in_a = lane < n_a, in_b = lane >= b0 && lane < nwords, live = in_a || in_b;
+    unsigned mine = 0;
+    if (in_a) mine = __float_as_uint(a[lane]);
+    if (in_b) mine = reinterpret_cast<const unsigned*>(b)[lane - b0];
+    if (live) {
+        for (int p = 0; p < world; ++p) {
+            uint2* dst = reinterpret_cast<uint2*>(peers.p[p] + data_off) + ((size_t)par * world + rank) * rank_words + lane;
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(mine), "r"(seq) : "memory");
+        }
+    }
+    float tf = 0.0f;
+    double td = 0.0;
+    for (int r = 0; r < world; ++r) {
+        unsigned vx = 0, vy = 0;
+        if (live) {
+            const uint2* src = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + ((size_t)par * world + r) * rank_words + lane;
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(src) : "memory");
+                if (vy == seq) break;
+                if ((++spins & 0x3ffu) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
+                }
+            }
+        }
+        __syncwarp();
+        tf += __uint_as_float(vx);
+        const unsigned hi = __shfl_down_sync(0xffffffffu, vx, 1);      // word 2i low, 2i + 1 high (b0 is even)
+        td += __hiloint2double((int)hi, (int)vx);
+    }
+    if (in_a) a[lane] = tf;
+    if (in_b && ((lane - b0) & 1) == 0) b[(lane - b0) >> 1] = td;
+    __syncthreads();
+    if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned*>(&me->seq[site]) = seq;
+    }
+}
+
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -378,6 +433,21 @@ int b200nn_comm_allreduce_sum(b200nn_comm* c, int site, void* buf, long long n, 
         exchange_sum_kernel<double><<<(int)ctas, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site],
                                                                                  c->site_stride[site], static_cast<double*>(buf), n, vec_ok);
     B200NN_LAUNCH_CHECK("exchange_sum");
+    return B200NN_OK;
+}
+
+int b200nn_comm_allreduce_sum2(b200nn_comm* c, int site, float* a, int n_a, double* b, int n_b, void* stream) {
+    B200NN_REQUIRE(c != nullptr && a != nullptr && b != nullptr && n_a > 0 && n_b > 0, "comm_allreduce_sum2: bad argument");
+    if (c->world == 1) return B200NN_OK;
+    const size_t words = (size_t)((n_a + 1) & ~1) + 2 * (size_t)n_b;
+    B200NN_REQUIRE(c->peer_ready && site >= 0 && site < c->n_sites && words <= 1024 && c->site_stride[site] >= 8 * words,
+                   "comm_allreduce_sum2: %zu words do not fit the latency path of site %d", words, site);
+    PeerPtrs pp;
+    for (int p = 0; p < MAX_WORLD; ++p) pp.p[p] = p < c->world ? c->peer[p] : nullptr;
+    const int threads = (int)((words + 31) / 32 * 32);
+    exchange_sum_ll2_kernel<<<1, threads, 0, as_stream(stream)>>>(pp, c->rank, c->world, site, c->site_off[site], c->site_stride[site] / 8,
+                                                                a, n_a, b, n_b);
+    B200NN_LAUNCH_CHECK("exchange_sum_ll2");
     return B200NN_OK;
 }
 

@@ -140,7 +140,7 @@ class Plan:
             return None
         return ("range", self._raw_begin, self.n_slots - self._raw_begin)
 
-    def _sync_slots(self, first, final=False):
+    def _sync_slots(self, first, final=False, mergeable=False):
         """Sum the clip slots [first, n_slots) produced by the op(s) just emitted over the ranks: the reference's clips
         act on whole-batch tensors (models.py:214), so their norms are global. Slots already exchanged (sync_slots_now
         called from inside a layer's hook) are skipped. With deferred clips nothing is exchanged between the backward
@@ -151,7 +151,11 @@ class Plan:
             first = getattr(self, "_slots_synced", 0)   # nothing was exchanged since the backward began
         first = max(first, getattr(self, "_slots_synced", 0))
         if self.dp is not None:
-            if self._acc_pending and first == 0:
+            if self._acc_pending and first == 0 and final and mergeable and getattr(self, "_merge_final", False):
+                # train step with deferred clips: this exchange can share ONE NVLink round trip with the last small gradient
+                # bucket (_grad_exchange emits it)
+                self._final_slots = self._ssacc[0:4 + self.n_slots]
+            elif self._acc_pending and first == 0:
                 self.allreduce(self._ssacc[0:4 + self.n_slots], "slot_exchange")   # accumulators sit right in front of slot 0
             else:
                 if self._acc_pending:
@@ -316,8 +320,14 @@ class Plan:
                                                       need_dx_c)
                 if raw and cur is not None:
                     cur = _Err(cur.t, ())
-                # the block's kernels apply their pending chain to dw / db themselves (the reduce launch), also when deferred
-                layers[ci]._grad_pending = None
+                # the block's kernels apply their pending chain to dw / db themselves (the reduce launch), also when deferred --
+                # unless the block left it to the optimizer (last op of a data-parallel train step, see _plan_backward_block)
+                dchain = self.state[ci].pop("wgrad_chain_deferred", None)
+                if dchain is not None:
+                    layers[ci]._grad_pending = (self.ss, dchain[1], dchain[2])
+                    self._upd_chain[ci] = dchain
+                else:
+                    layers[ci]._grad_pending = None
                 if not compute_only:
                     updates.append(ci)
                     self._grad_bucket_ready(layers[ci])
@@ -358,7 +368,7 @@ class Plan:
                 i = j - 1
             else:
                 i -= 1
-        self._sync_slots(first, final=True)
+        self._sync_slots(first, final=True, mergeable=True)
         if raw and cur is not None:
             cur = _Err(cur.t, self.pending_chain())   # whoever materialises the input error applies the whole chain
         return updates, cur
@@ -376,6 +386,9 @@ class Plan:
             return
         while self._buckets_done < len(dp.buckets) and (final or dp.bucket_layers[self._buckets_done] is layer):
             lo, hi, _ = dp.buckets[self._buckets_done]
+            if (not final and getattr(self, "_merge_final", False) and self._buckets_done == len(dp.buckets) - 1
+                    and (hi - lo) * 4 <= 3072 and dp.comm.peer):
+                return    # the last small bucket of a train step travels together with the clip slots (_grad_exchange)
             self._buckets_done += 1
             t = dp.flat[lo:hi]
             site = dp.comm.site(t.numel() * 4) if t.numel() * 4 <= (64 << 10) else -1
@@ -432,7 +445,24 @@ class Plan:
 
     def _grad_exchange(self, updates):
         """Before the optimizer: flush the buckets not yet issued and join the side stream."""
-        if self.dp is None or not updates:
+        if self.dp is None:
+            return
+        pend, self._final_slots = getattr(self, "_final_slots", None), None
+        if pend is not None:
+            dp, merged = self.dp, False
+            if updates and dp.buckets is not None and self._buckets_done == len(dp.buckets) - 1 and dp.comm.peer:
+                lo, hi, _ = dp.buckets[-1]
+                t = dp.flat[lo:hi]
+                words = ((t.numel() + 1) & ~1) + 2 * pend.numel()
+                if words <= 1024:
+                    site = dp.comm.site(4 * words)
+                    if site >= 0:
+                        self.emit(lambda: dp.comm.allreduce2(t, pend, site), "grad_slot_exchange", (t, pend))
+                        self._buckets_done += 1
+                        merged = True
+            if not merged:
+                self.allreduce(pend, "slot_exchange")
+        if not updates:
             return
         self._grad_bucket_ready(None, final=True)
         if self._side_used:
@@ -607,7 +637,9 @@ class Plan:
                     self.allreduce(self.ss[s0:s0 + 1], "slot_exchange")
                 self._slots_synced = self.n_slots
             self._early_setup(True)
+            self._merge_final = self.defer_clips and self.dp is not None
             updates, _ = self._build_backward(_Err(err0, (s0,)), False, False, False)
+            self._merge_final = False
             if head_state is not None:
                 del head_state["dw_partial"]   # other programs of this plan (public backward_pass) run the plain Dense backward
             self._grad_exchange(updates)

@@ -593,8 +593,15 @@ class Conv2D(Layer, _ParamMixin):
             dgp, dbp = bn._d_gamma.data_ptr(), bn._d_beta.data_ptr()
             ctx.emit(lambda: ops.convblock_bwd(g, x, w, b, kind, alpha, gm, bt, sm, si, et, ss, chain, dgp, dbp, None, None, r_out, 3,
                                                b_total, s0, s1, s2, (), ctx.ws, peer), "convblock_bwd_peer", (x, et, r_out))
-            ctx.sync_slots_now()   # the weight gradient owes the three clips just produced: their norms are global
-            ctx.emit(lambda: ops.convblock_wgrad_reduce(g, ctx.ws, ss, chain_out, dw, db), "convblock_reduce", (dw,))
+            if getattr(ctx, "_merge_final", False) and ctx.defer_clips and not need_dx:
+                # last backward op of a train step: the reduce emits the RAW weight gradient and the optimizer applies the whole
+                # pending chain (as for every other deferred gradient), so that the clip norms and this gradient can cross the GPUs
+                # in ONE exchange instead of norms -> scaled reduce -> gradient
+                st["wgrad_chain_deferred"] = chain_out
+                ctx.emit(lambda: ops.convblock_wgrad_reduce(g, ctx.ws, ss, (), dw, db), "convblock_reduce", (dw,))
+            else:
+                ctx.sync_slots_now()   # the weight gradient owes the three clips just produced: their norms are global
+                ctx.emit(lambda: ops.convblock_wgrad_reduce(g, ctx.ws, ss, chain_out, dw, db), "convblock_reduce", (dw,))
         elif ctx.dp is not None:
             sums, b_total = bn._dp_sums(ctx), x.shape[0] * ctx.world
             dgp, dbp = sums.data_ptr() + 4 * P, sums.data_ptr()

@@ -182,6 +182,13 @@ class Communicator:
         B.check(B.lib().b200nn_comm_allreduce_sum(self.handle, int(site), t.data_ptr(), t.numel(),
                                                   0 if t.dtype == torch.float32 else 1, B.stream() if stream is None else stream))
 
+    def allreduce2(self, a: torch.Tensor, b: torch.Tensor, site: int, stream: int | None = None):
+        """One latency exchange for a float32 tensor and a float64 tensor (b200nn_comm_allreduce_sum2)."""
+        if self.world == 1:
+            return
+        B.check(B.lib().b200nn_comm_allreduce_sum2(self.handle, int(site), a.data_ptr(), a.numel(), b.data_ptr(), b.numel(),
+                                                   B.stream() if stream is None else stream))
+
     def timeouts(self) -> int:
         return int(B.lib().b200nn_comm_timeouts(self.handle))
 
