@@ -1540,6 +1540,289 @@ __global__ void __launch_bounds__(256) conv_fewf_fwd_kernel(b200nn_conv_geom g, 
     }
 }
 
+// The same with lane <-> CHANNEL QUAD (C / 4 a power of two <= 32, 3 x 3 taps): the C / 4 lanes of a pixel read its 4 C bytes as one
+// contiguous run, so a warp load covers whole lines (the thread-per-pixel form above reads 16 bytes of 32 different lines per
+// instruction: 132 us per launch for the generator's 28x28x32 -> 1 output layer at batch 512); the lane's 9 x 4 x F weights sit in
+// registers, all nine tap loads of a pixel are in flight together, the lanes of a pixel are folded with log2(C / 4) shuffles.
+template <int FM>
+__global__ void __launch_bounds__(256) conv_fewf_fwd2_kernel(b200nn_conv_geom g, const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y, int act, float alpha,
+                                                             long long n_pix) {
+    const int C4 = g.C >> 2, F = g.F;
+    const int cq = threadIdx.x % C4;                       // channel quad of this lane
+    const int ppw = 32 / C4;                               // pixels per warp
+    float wr[9][4][FM];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                wr[tap][j][f] = f < F ? w[((long long)((cq * 4 + j) * g.kh + tap / 3) * g.kw + tap % 3) * F + f] : 0.0f;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int sub = (threadIdx.x & 31) / C4;               // which of the warp's pixels
+    for (long long p0 = warp * ppw; p0 < n_pix; p0 += n_warps * ppw) {
+        const long long p = p0 + sub;
+        const bool pok = p < n_pix;
+        const int ox = (int)(p % g.OW); long long t = p / g.OW;
+        const int oy = (int)(t % g.OH); const int n = (int)(t / g.OH);
+        float4 v[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int iy = oy * g.sh - g.ph + tap / 3, ix = ox * g.sw - g.pw + tap % 3;
+            v[tap] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+                v[tap] = *reinterpret_cast<const float4*>(x + (((long long)n * g.H + iy) * g.W + ix) * g.C + cq * 4);
+        }
+        float acc[FM];
+#pragma unroll
+        for (int f = 0; f < FM; ++f) acc[f] = 0.0f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int f = 0; f < FM; ++f) {
+                acc[f] = fmaf(v[tap].x, wr[tap][0][f], acc[f]); acc[f] = fmaf(v[tap].y, wr[tap][1][f], acc[f]);
+                acc[f] = fmaf(v[tap].z, wr[tap][2][f], acc[f]); acc[f] = fmaf(v[tap].w, wr[tap][3][f], acc[f]);
+            }
+#pragma unroll
+        for (int f = 0; f < FM; ++f)
+            for (int o = 1; o < C4; o <<= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+        if (pok && cq == 0) {
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                if (f < F) y[p * F + f] = act_apply(act, acc[f] + (bias != nullptr ? bias[f] : 0.0f), alpha);
+        }
+    }
+}
+// ---- band kernels: 3 x 3, stride 1, 'same' (pad 1), F <= 2, C / 4 a power of two <= 32 (the generator's output layer) -------------
+// A CTA stages a band of FB_RB output rows of one image plus its one-row / one-column halo in shared memory, so the nine taps of a
+// pixel are shared-memory reads: HBM / L2 see x 1.5 times instead of 9 (the lane <-> channel-quad form above is L2-bound at 9x).
+constexpr int FB_RB = 4;
+
+template <int FM>
+__global__ void __launch_bounds__(256) conv_fewf_band_fwd_kernel(b200nn_conv_geom g, const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y, int act, float alpha) {
+    extern __shared__ __align__(16) float fb_tile[];       // [(FB_RB + 2)][(W + 2)][C]
+    const int C = g.C, C4 = C >> 2, F = g.F, W = g.W, H = g.H, WP = W + 2;
+    const int bands = (H + FB_RB - 1) / FB_RB;
+    const int n = blockIdx.x / bands, y0 = (blockIdx.x % bands) * FB_RB;
+    const int cq = threadIdx.x % C4, ppw = 32 / C4, sub = (threadIdx.x & 31) / C4, warp = threadIdx.x >> 5;
+    float wr[9][4][FM];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                wr[tap][j][f] = f < F ? w[((long long)((cq * 4 + j) * 3 + tap / 3) * 3 + tap % 3) * F + f] : 0.0f;
+    const int row4 = WP * C4;                               // float4 per tile row
+    for (int i = threadIdx.x; i < (FB_RB + 2) * row4; i += blockDim.x) {
+        const int r = i / row4, rem = i - r * row4, px = rem / C4, c4 = rem - px * C4;
+        const int iy = y0 - 1 + r, ix = px - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const float4*>(x + (((long long)n * H + iy) * W + ix) * C + c4 * 4);
+        reinterpret_cast<float4*>(fb_tile)[i] = v;
+    }
+    __syncthreads();
+    const int rows = min(FB_RB, H - y0), npix = rows * W;
+    for (int p0 = warp * ppw; p0 < npix; p0 += 8 * ppw) {
+        const int p = p0 + sub;
+        const bool pok = p < npix;
+        const int oy = p / W, ox = p - oy * W;
+        float acc[FM];
+#pragma unroll
+        for (int f = 0; f < FM; ++f) acc[f] = 0.0f;
+        if (pok) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float4 v = reinterpret_cast<const float4*>(fb_tile)[((oy + tap / 3) * WP + ox + tap % 3) * C4 + cq];
+#pragma unroll
+                for (int f = 0; f < FM; ++f) {
+                    acc[f] = fmaf(v.x, wr[tap][0][f], acc[f]); acc[f] = fmaf(v.y, wr[tap][1][f], acc[f]);
+                    acc[f] = fmaf(v.z, wr[tap][2][f], acc[f]); acc[f] = fmaf(v.w, wr[tap][3][f], acc[f]);
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < FM; ++f)
+            for (int o = 1; o < C4; o <<= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+        if (pok && cq == 0) {
+            const long long po = ((long long)n * H + y0 + oy) * W + ox;
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                if (f < F) y[po * F + f] = act_apply(act, acc[f] + (bias != nullptr ? bias[f] : 0.0f), alpha);
+        }
+    }
+}
+
+// weight + bias gradient: persistent CTAs walk (image, band) items; lane (pixel slot, channel quad) accumulates its 9 x 4 x F outputs
+// in registers over all its pixels; one partial per CTA in the reference's row order (c,ky,kx) (+ the bias row) -> splitk_reduce.
+template <int FM>
+__global__ void __launch_bounds__(256) conv_fewf_band_wgrad_kernel(b200nn_conv_geom g, const float* __restrict__ x, const float* __restrict__ err,
+                                                                   float* __restrict__ partial) {
+    extern __shared__ __align__(16) float fb_tile[];       // x tile [(FB_RB + 2)][(W + 2)][C] | e tile [FB_RB][W][FM] | red[8][9 C FM]
+    const int C = g.C, C4 = C >> 2, F = g.F, W = g.W, H = g.H, WP = W + 2;
+    const int bands = (H + FB_RB - 1) / FB_RB, items = g.N * bands;
+    const int cq = threadIdx.x % C4, ppw = 32 / C4, sub = (threadIdx.x & 31) / C4, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* et = fb_tile + (FB_RB + 2) * WP * C;
+    float* red = et + FB_RB * W * FM;
+    float acc[9][4][FM], bsum[FM];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f) acc[tap][j][f] = 0.0f;
+#pragma unroll
+    for (int f = 0; f < FM; ++f) bsum[f] = 0.0f;
+    const int row4 = WP * C4;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / bands, y0 = (item % bands) * FB_RB;
+        const int rows = min(FB_RB, H - y0), npix = rows * W;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (FB_RB + 2) * row4; i += blockDim.x) {
+            const int r = i / row4, rem = i - r * row4, px = rem / C4, c4 = rem - px * C4;
+            const int iy = y0 - 1 + r, ix = px - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const float4*>(x + (((long long)n * H + iy) * W + ix) * C + c4 * 4);
+            reinterpret_cast<float4*>(fb_tile)[i] = v;
+        }
+        for (int i = threadIdx.x; i < npix * FM; i += blockDim.x) {
+            const int p = i / FM, f = i - p * FM;
+            et[i] = f < F ? err[(((long long)n * H + y0) * W + p) * F + f] : 0.0f;
+        }
+        __syncthreads();
+        for (int p0 = warp * ppw; p0 < npix; p0 += 8 * ppw) {
+            const int p = p0 + sub;
+            if (p < npix) {
+                const int oy = p / W, ox = p - oy * W;
+                float e[FM];
+#pragma unroll
+                for (int f = 0; f < FM; ++f) e[f] = et[p * FM + f];
+                if (cq == 0) {
+#pragma unroll
+                    for (int f = 0; f < FM; ++f) bsum[f] += e[f];
+                }
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float4 v = reinterpret_cast<const float4*>(fb_tile)[((oy + tap / 3) * WP + ox + tap % 3) * C4 + cq];
+#pragma unroll
+                    for (int f = 0; f < FM; ++f) {
+                        acc[tap][0][f] = fmaf(v.x, e[f], acc[tap][0][f]); acc[tap][1][f] = fmaf(v.y, e[f], acc[tap][1][f]);
+                        acc[tap][2][f] = fmaf(v.z, e[f], acc[tap][2][f]); acc[tap][3][f] = fmaf(v.w, e[f], acc[tap][3][f]);
+                    }
+                }
+            }
+        }
+    }
+    // fold the pixel slots of a warp (lanes C4 apart), then the warps through shared memory
+    __syncthreads();
+    const int K = 9 * C;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f) {
+                float v = acc[tap][j][f];
+                for (int o = C4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane < C4) red[(warp * K + ((cq * 4 + j) * 9 + tap)) * FM + f] = v;      // row (c, ky, kx): the reference order
+            }
+    __shared__ float bred[8][FM];
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+        float v = bsum[f];
+        for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) bred[warp][f] = v;
+    }
+    __syncthreads();
+    float* pb = partial + (long long)blockIdx.x * (K + 1) * F;
+    for (int i = threadIdx.x; i < K * FM; i += blockDim.x) {
+        const int row = i / FM, f = i - row * FM;
+        float t = 0.0f;
+        for (int wv = 0; wv < 8; ++wv) t += red[(wv * K + row) * FM + f];
+        if (f < F) pb[(long long)row * F + f] = t;
+    }
+    if (threadIdx.x < FM && (int)threadIdx.x < F) {
+        float t = 0.0f;
+        for (int wv = 0; wv < 8; ++wv) t += bred[wv][threadIdx.x];
+        pb[(long long)K * F + threadIdx.x] = t;
+    }
+}
+
+// data gradient: thread = (input pixel, channel quad), the nine error taps are scalar loads that hit L1, no stride arithmetic
+template <int FM>
+__global__ void __launch_bounds__(256) conv_fewf_band_dx_kernel(b200nn_conv_geom g, const float* __restrict__ err, const float* __restrict__ w,
+                                                                Epilogue epi, long long total4) {
+    __shared__ double scratch[32];
+    const int C4 = g.C >> 2, F = g.F, W = g.W, H = g.H;
+    const int cq = threadIdx.x % C4;
+    float wr[9][4][FM];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < FM; ++f)
+                wr[tap][j][f] = f < F ? w[((long long)((cq * 4 + j) * 3 + tap / 3) * 3 + tap % 3) * F + f] : 0.0f;
+    EpiState st;
+    epi_begin(epi, st);
+    // blockDim.x is a multiple of C4, so a thread keeps its channel quad over the grid-stride loop
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i / C4;
+        const int ix = (int)(t % W); t /= W;
+        const int iy = (int)(t % H); const long long n = t / H;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int oy = iy + 1 - tap / 3, ox = ix + 1 - tap % 3;
+            if (oy >= 0 && oy < H && ox >= 0 && ox < W) {
+                const float* ep = err + ((n * H + oy) * W + ox) * F;
+#pragma unroll
+                for (int f = 0; f < FM; ++f) {
+                    if (f < F) {
+                        const float e = __ldg(ep + f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = fmaf(e, wr[tap][j][f], acc[j]);
+                    }
+                }
+            }
+        }
+        float v[4] = {acc[0] * st.scale, acc[1] * st.scale, acc[2] * st.scale, acc[3] * st.scale};
+        float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (epi.mask_y != nullptr) mk = *reinterpret_cast<const float4*>(epi.mask_y + i * 4);
+        const float m[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            st.a0 = fmaf(v[j], v[j], st.a0);
+            if (epi.mask_y != nullptr) {
+                v[j] *= act_grad_from_y(epi.mask_act, m[j], epi.mask_alpha);
+                st.a1 = fmaf(v[j], v[j], st.a1);
+            }
+        }
+        *reinterpret_cast<float4*>(epi.out + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    epi_finish(epi, st, scratch);
+}
+
+static bool conv_fewf_band_ok(const b200nn_conv_geom* g) {
+    const int C4 = g->C >> 2;
+    return g->kh == 3 && g->kw == 3 && g->sh == 1 && g->sw == 1 && g->ph == 1 && g->pw == 1 && g->OH == g->H && g->OW == g->W &&
+           g->C % 4 == 0 && C4 >= 1 && C4 <= 32 && (C4 & (C4 - 1)) == 0 && g->F <= 2 &&
+           (size_t)((FB_RB + 2) * (g->W + 2) * g->C + FB_RB * g->W * 2 + 8 * 9 * g->C * 2) * sizeof(float) <= 46 * 1024;
+}
+static size_t conv_fewf_band_smem(const b200nn_conv_geom* g, bool wgrad) {
+    size_t fl = (size_t)(FB_RB + 2) * (g->W + 2) * g->C;
+    if (wgrad) fl += (size_t)FB_RB * g->W * 2 + (size_t)8 * 9 * g->C * 2;
+    return fl * sizeof(float);
+}
+static int conv_fewf_band_groups() { return kNumSMs * 2; }
+
+static bool conv_fewf_fwd2_ok(const b200nn_conv_geom* g) {
+    const int C4 = g->C >> 2;
+    return g->kh == 3 && g->kw == 3 && g->C % 4 == 0 && C4 >= 1 && C4 <= 32 && (C4 & (C4 - 1)) == 0 && g->F <= 2;
+}
+
 // dx[n,iy,ix,c] = scale * sum_{ky,kx,f} err[n,oy,ox,f] * W[c,ky,kx,f] (+ activation backward, sum-of-squares slots).
 // thread = (input pixel, channel quad); works for few filters (scalar err loads) and any C % 4 == 0
 __global__ void __launch_bounds__(256) conv_fewf_dx_kernel(b200nn_conv_geom g, const float* __restrict__ err, const float* __restrict__ w,
@@ -1773,7 +2056,9 @@ size_t b200nn_conv2d_ws_bytes(const b200nn_conv_geom* g) {
         r = r > d ? r : d;
     }
     if (conv_fewf_ok(g)) {
-        const size_t d = (size_t)conv_fewf_groups(g) * (Kf + 1) * g->F * sizeof(float);
+        size_t d = (size_t)conv_fewf_groups(g) * (Kf + 1) * g->F * sizeof(float);
+        r = r > d ? r : d;
+        d = (size_t)conv_fewf_band_groups() * (Kf + 1) * g->F * sizeof(float);
         r = r > d ? r : d;
     }
     if (smallk3::ok(g)) {
@@ -1805,6 +2090,23 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
     if (conv_fewf_ok(g) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {       // a handful of filters: direct kernel, every math mode
         long long blocks = ((long long)M + 255) / 256;
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        if (conv_fewf_band_ok(g)) {
+            const int bands = (g->H + FB_RB - 1) / FB_RB;
+            const size_t smem = conv_fewf_band_smem(g, false);
+            if (g->F == 1) conv_fewf_band_fwd_kernel<1><<<g->N * bands, 256, smem, as_stream(stream)>>>(*g, x, w, b, y, act, alpha);
+            else conv_fewf_band_fwd_kernel<2><<<g->N * bands, 256, smem, as_stream(stream)>>>(*g, x, w, b, y, act, alpha);
+            B200NN_LAUNCH_CHECK("conv_fewf_band_fwd");
+            return B200NN_OK;
+        }
+        if (conv_fewf_fwd2_ok(g) && M >= 4096) {
+            const long long warps = ((long long)M + (32 / (g->C >> 2)) - 1) / (32 / (g->C >> 2));
+            long long b2 = (warps + 7) / 8;
+            if (b2 > kNumSMs * 8) b2 = kNumSMs * 8;
+            if (g->F == 1) conv_fewf_fwd2_kernel<1><<<(int)b2, 256, 0, as_stream(stream)>>>(*g, x, w, b, y, act, alpha, M);
+            else conv_fewf_fwd2_kernel<2><<<(int)b2, 256, 0, as_stream(stream)>>>(*g, x, w, b, y, act, alpha, M);
+            B200NN_LAUNCH_CHECK("conv_fewf_fwd2");
+            return B200NN_OK;
+        }
         conv_fewf_fwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(*g, x, w, b, y, act, alpha, M);
         B200NN_LAUNCH_CHECK("conv_fewf_fwd");
         return B200NN_OK;
@@ -1880,7 +2182,17 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
     }
     if (conv_fewf_ok(g) && ws != nullptr && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
         // a handful of filters: direct bandwidth kernels in every math mode
-        if (dw != nullptr) {
+        const bool band = conv_fewf_band_ok(g);
+        if (dw != nullptr && band) {
+            const int groups = conv_fewf_band_groups();
+            Epilogue e = plain_epilogue(dw, g->F, Kf);
+            e.ss = ss; e.chain = chain; e.db = db;
+            const size_t smem = conv_fewf_band_smem(g, true);
+            if (g->F == 1) conv_fewf_band_wgrad_kernel<1><<<groups, 256, smem, st>>>(*g, x, err, ws);
+            else conv_fewf_band_wgrad_kernel<2><<<groups, 256, smem, st>>>(*g, x, err, ws);
+            B200NN_LAUNCH_CHECK("conv_fewf_band_wgrad");
+            if (int rc = launch_splitk_reduce(ws, groups, Kf + 1, g->F, e, st)) return rc;
+        } else if (dw != nullptr) {
             const int groups = conv_fewf_groups(g);
             const int warps = groups * (g->C / 4);
             Epilogue e = plain_epilogue(dw, g->F, Kf);
@@ -1897,7 +2209,9 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
             const long long t4 = (long long)Mi * g->C / 4;
             long long b2 = (t4 + 255) / 256;
             if (b2 > kNumSMs * 16) b2 = kNumSMs * 16;
-            conv_fewf_dx_kernel<<<(int)b2, 256, 0, st>>>(*g, err, w, e, t4);
+            if (band && g->F == 1) conv_fewf_band_dx_kernel<1><<<(int)b2, 256, 0, st>>>(*g, err, w, e, t4);
+            else if (band) conv_fewf_band_dx_kernel<2><<<(int)b2, 256, 0, st>>>(*g, err, w, e, t4);
+            else conv_fewf_dx_kernel<<<(int)b2, 256, 0, st>>>(*g, err, w, e, t4);
             B200NN_LAUNCH_CHECK("conv_fewf_dx");
         }
         return B200NN_OK;

@@ -207,7 +207,11 @@ def test_conv2d_golden(K, golden, gi):
                                                (8, 13, 13, 32, 64, 3, 2, "same"), (4, 28, 28, 32, 1, 3, 1, "same"),
                                                # large-batch small-K kernels (conv_smallk3.cuh): ragged last tile, generic K, strides
                                                (7, 30, 30, 2, 64, 3, 1, "valid"), (6, 31, 29, 1, 32, 5, 1, "same"),
-                                               (33, 28, 28, 1, 64, 3, 2, "same"), (12, 32, 32, 3, 32, 3, 1, "same")])
+                                               (33, 28, 28, 1, 64, 3, 2, "same"), (12, 32, 32, 3, 32, 3, 1, "same"),
+                                               # few-filter kernels with lane <-> channel quad (conv_fewf_fwd2)
+                                               (8, 28, 28, 32, 1, 3, 1, "same"), (24, 28, 28, 16, 2, 3, 2, "same"),
+                                               # band kernels (3 x 3 / stride 1 / 'same' / F <= 2): ragged last band, two filters
+                                               (5, 12, 20, 16, 2, 3, 1, "same"), (3, 10, 9, 8, 1, 3, 1, "same")])
 def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
     rng = np.random.default_rng(H * 31 + C)
     x = rng.normal(size=(N, H, W, C)).astype(np.float32)
