@@ -167,30 +167,46 @@ __global__ void __launch_bounds__(1024) exchange_sum_ll_kernel(PeerPtrs peers, i
             asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(mine), "r"(seq) : "memory");
         }
     }
-    T total = T(0);
-    for (int r = 0; r < world; ++r) {
-        unsigned vx = 0, vy = 0;
-        if (lane < nwords) {
-            const uint2* src = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + ((size_t)par * world + r) * rank_words + lane;
-            unsigned spins = 0;
-            unsigned long long t0 = 0;
-            for (;;) {
-                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(src) : "memory");
-                if (vy == seq) break;
-                if ((++spins & 0x3ffu) == 0) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
-                }
+    // every rank's word is polled in the same sweep (loads in flight together: one round trip per sweep, not per rank)
+    unsigned wv[MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) wv[r] = 0;
+    if (lane < nwords) {
+        const uint2* base = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + (size_t)par * world * rank_words + lane;
+        unsigned got = 0, spins = 0;
+        const unsigned full = (1u << world) - 1u;
+        unsigned long long t0 = 0;
+        for (;;) {
+            unsigned vx[MAX_WORLD], vy[MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) {
+                vx[r] = 0; vy[r] = 0;
+                if (r < world && !((got >> r) & 1u))
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx[r]), "=r"(vy[r]) : "l"(base + (size_t)r * rank_words) : "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r)
+                if (r < world && !((got >> r) & 1u) && vy[r] == seq) { got |= 1u << r; wv[r] = vx[r]; }
+            if (got == full) break;
+            if ((++spins & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
             }
         }
-        __syncwarp();
-        if (WPE == 1) {
-            total += static_cast<T>(__uint_as_float(vx));
-        } else {                                         // lane 2i holds the low word, lane 2i+1 the high word
-            const unsigned hi = __shfl_down_sync(0xffffffffu, vx, 1);
-            total += static_cast<T>(__hiloint2double((int)hi, (int)vx));
+    }
+    __syncwarp();
+    T total = T(0);
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) {          // sums in rank order: bit-identical on every rank
+        if (r < world) {
+            if (WPE == 1) {
+                total += static_cast<T>(__uint_as_float(wv[r]));
+            } else {                                 // lane 2i holds the low word, lane 2i+1 the high word
+                const unsigned hi = __shfl_down_sync(0xffffffffu, wv[r], 1);
+                total += static_cast<T>(__hiloint2double((int)hi, (int)wv[r]));
+            }
         }
     }
     if (WPE == 1) { if (lane < n) buf[lane] = total; }
@@ -224,29 +240,44 @@ __global__ void __launch_bounds__(1024) exchange_sum_ll2_kernel(PeerPtrs peers, 
             asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(mine), "r"(seq) : "memory");
         }
     }
-    float tf = 0.0f;
-    double td = 0.0;
-    for (int r = 0; r < world; ++r) {
-        unsigned vx = 0, vy = 0;
-        if (live) {
-            const uint2* src = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + ((size_t)par * world + r) * rank_words + lane;
-            unsigned spins = 0;
-            unsigned long long t0 = 0;
-            for (;;) {
-                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(src) : "memory");
-                if (vy == seq) break;
-                if ((++spins & 0x3ffu) == 0) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
-                }
+    unsigned wv[MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) wv[r] = 0;
+    if (live) {
+        const uint2* base = reinterpret_cast<const uint2*>(peers.p[rank] + data_off) + (size_t)par * world * rank_words + lane;
+        unsigned got = 0, spins = 0;
+        const unsigned full = (1u << world) - 1u;
+        unsigned long long t0 = 0;
+        for (;;) {
+            unsigned vx[MAX_WORLD], vy[MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r) {
+                vx[r] = 0; vy[r] = 0;
+                if (r < world && !((got >> r) & 1u))
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx[r]), "=r"(vy[r]) : "l"(base + (size_t)r * rank_words) : "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < MAX_WORLD; ++r)
+                if (r < world && !((got >> r) & 1u) && vy[r] == seq) { got |= 1u << r; wv[r] = vx[r]; }
+            if (got == full) break;
+            if ((++spins & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WAIT_TIMEOUT_NS) { atomicAdd(&me->timeouts, 1u); break; }
             }
         }
-        __syncwarp();
-        tf += __uint_as_float(vx);
-        const unsigned hi = __shfl_down_sync(0xffffffffu, vx, 1);      // word 2i low, 2i + 1 high (b0 is even)
-        td += __hiloint2double((int)hi, (int)vx);
+    }
+    __syncwarp();
+    float tf = 0.0f;
+    double td = 0.0;
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) {
+        if (r < world) {
+            tf += __uint_as_float(wv[r]);
+            const unsigned hi = __shfl_down_sync(0xffffffffu, wv[r], 1);      // word 2i low, 2i + 1 high (b0 is even)
+            td += __hiloint2double((int)hi, (int)wv[r]);
+        }
     }
     if (in_a) a[lane] = tf;
     if (in_b && ((lane - b0) & 1) == 0) b[(lane - b0) >> 1] = td;

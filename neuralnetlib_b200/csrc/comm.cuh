@@ -65,6 +65,7 @@ struct PeerRegion {
     int rank, world, site;
     size_t off;          // byte offset of the region in every rank's symmetric buffer
     unsigned stagger_ns; // start offset between CTAs that share an SM (peer-fused kernels)
+    int poll_all;        // 1: poll every rank's word in the same sweep (loads in flight together); 0: rank by rank
 };
 
 }  // namespace b200nn
