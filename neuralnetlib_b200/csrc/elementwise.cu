@@ -4,6 +4,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
 #include "opt_common.cuh"
 
@@ -11,6 +15,8 @@ namespace b200nn {
 
 static thread_local char g_last_error[512] = {0};
 static long long g_launches = 0;
+static std::mutex g_graph_mu;
+static std::unordered_map<void*, long long> g_graph_kernels;   // graph exec -> kernel nodes (see b200nn_graph_end)
 
 void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
 
@@ -578,6 +584,16 @@ int b200nn_graph_begin(void* stream) {
 int b200nn_graph_end(void* stream, void** graph_exec_out) {
     cudaGraph_t graph = nullptr;
     B200NN_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
+    // kernel nodes of the captured step: b200nn_graph_launch adds them to the launch count (b200nn_launch_count counts KERNELS)
+    size_t n_nodes = 0, n_kernels = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0) {
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        if (cudaGraphGetNodes(graph, nodes.data(), &n_nodes) == cudaSuccess)
+            for (size_t i = 0; i < n_nodes; ++i) {
+                cudaGraphNodeType t;
+                if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++n_kernels;
+            }
+    }
     cudaGraphExec_t exec = nullptr;
     cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -585,17 +601,34 @@ int b200nn_graph_end(void* stream, void** graph_exec_out) {
         set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         return B200NN_ECUDA;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        g_graph_kernels[exec] = (long long)n_kernels;
+    }
     *graph_exec_out = exec;
     return B200NN_OK;
 }
 
 int b200nn_graph_launch(void* graph_exec, void* stream) {
     B200NN_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+    long long n = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        auto it = g_graph_kernels.find(graph_exec);
+        if (it != g_graph_kernels.end()) n = it->second;
+    }
+    __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED);
     return B200NN_OK;
 }
 
 int b200nn_graph_destroy(void* graph_exec) {
-    if (graph_exec != nullptr) B200NN_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+    if (graph_exec != nullptr) {
+        {
+            std::lock_guard<std::mutex> lk(g_graph_mu);
+            g_graph_kernels.erase(graph_exec);
+        }
+        B200NN_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+    }
     return B200NN_OK;
 }
 
