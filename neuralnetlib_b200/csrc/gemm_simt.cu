@@ -478,6 +478,35 @@ __global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __res
     }
 }
 
+// column sums, 128-bit form for NARROW matrices (F / 4 divides 256: conv bias gradients with 32..512 filters): thread = (column quad,
+// row lane), 256 / (F / 4) row lanes per CTA, eight row loads in flight per thread, row lanes folded through shared memory
+__global__ void __launch_bounds__(256) colsum_partial4r_kernel(const float* __restrict__ x, long long R, int F, float* __restrict__ partial) {
+    __shared__ float4 red[256];
+    const int F4 = F >> 2, RL = 256 / F4;
+    const int c = threadIdx.x % F4, ty = threadIdx.x / F4;
+    const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = r0 + ty; r < r1; r += 8LL * RL) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = r + (long long)j * RL < r1 ? x4[(r + (long long)j * RL) * F4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (ty == 0) {
+        for (int l = 1; l < RL; ++l) { const float4 t = red[l * F4 + c]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        reinterpret_cast<float4*>(partial + (long long)blockIdx.x * F)[c] = s;
+    }
+}
+static bool colsum4r_ok(const void* x, const void* ws, int F) {
+    const int F4 = F >> 2;
+    return (F & 3) == 0 && F4 >= 1 && F4 <= 256 && 256 % F4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0;
+}
+
 // column sums of a [R, F] matrix with the lazy clip multiplier: out[f] = scale * sum_r x[r, f].
 // partial: the 256 threads of a CTA form (256 / FT) row lanes x FT columns (FT = min(F rounded up to 32, 256)); each thread
 // keeps four independent accumulators over its rows, the row lanes are folded through shared memory.
@@ -1430,7 +1459,9 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         if (db != nullptr) {   // layers.py:197
             int nb = (M + 7) / 8;   // >= 8 rows per CTA; threads run over the columns
             if (nb > kNumSMs * 2) nb = kNumSMs * 2;
-            if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0)
+            if (colsum4r_ok(err, ws, N))
+                colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
+            else if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0)
                 colsum_partial4_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
             else
                 colsum_partial_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
@@ -2233,7 +2264,8 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
             if (db != nullptr) {   // layers.py:513
                 int nb = (Mo + 7) / 8;
                 if (nb > kNumSMs * 2) nb = kNumSMs * 2;
-                colsum_partial_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
+                if (colsum4r_ok(err, ws, g->F)) colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
+                else colsum_partial_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
                 B200NN_LAUNCH_CHECK("conv2d_db_partial");
                 colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(ws, nb, g->F, ss, chain, db);
                 B200NN_LAUNCH_CHECK("conv2d_db_final");
@@ -2525,7 +2557,8 @@ int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const
             const long long R = (long long)g->N * g->OH * g->OW;
             int nb = (int)((R + 63) / 64);
             if (nb > kNumSMs * 2) nb = kNumSMs * 2;
-            colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, gws);
+            if (colsum4r_ok(err, gws, g->F)) colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, R, g->F, gws);
+            else colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, gws);
             B200NN_LAUNCH_CHECK("convt_db_partial");
             colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(gws, nb, g->F, ss, chain, db);
             B200NN_LAUNCH_CHECK("convt_db_final");
@@ -2556,7 +2589,8 @@ int b200nn_convt_bwd(int math, const b200nn_convt_geom* g, const float* x, const
         const long long R = (long long)g->N * g->OH * g->OW;
         int nb = (int)((R + 63) / 64);
         if (nb > kNumSMs * 2) nb = kNumSMs * 2;
-        colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
+        if (colsum4r_ok(err, ws, g->F)) colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
+        else colsum_partial_kernel<<<nb, 256, 0, st>>>(err, R, g->F, ws);
         B200NN_LAUNCH_CHECK("convt_db_partial");
         colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(ws, nb, g->F, ss, chain, db);
         B200NN_LAUNCH_CHECK("convt_db_final");
