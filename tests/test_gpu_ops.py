@@ -154,7 +154,8 @@ def test_dense_oracle(K, M, N, Kd, act):
     xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
     wsb = K.ops.dense_ws_bytes(M, N, Kd)
     ws = K.empty((max(wsb // 4, 1),))
-    y = K.empty((M, N))
+    G = Guarded(K)                      # the skinny-slab and small-N kernels index shared / global memory by hand
+    y = G((M, N))
     K.ops.dense_fwd(0, xd, wd, bd, y, ACTS[act], alpha, ws)
     x64, w64 = x.astype(np.float64), w.astype(np.float64)
     ref = O.act_fwd(act, O.dense_fwd(x64, w64, b.astype(np.float64)), alpha)
@@ -162,10 +163,11 @@ def test_dense_oracle(K, M, N, Kd, act):
     # backward with a clip chain and the fused backward of a preceding activation (mask from x)
     ss = K.ss()
     K.ops.sumsq(ed, ss, 0)
-    dx, dw, db = K.empty((M, Kd)), K.empty((Kd, N)), K.empty((N,))
+    dx, dw, db = G((M, Kd)), G((Kd, N)), G((N,))
     xpos = np.maximum(x, 0)  # pretend x is a ReLU output
     xpd = K.dev(xpos)
     K.ops.dense_bwd(0, xpd, wd, ed, ss, (0,), dx, dw, db, ACTS["relu"], 0.0, 1, 2, ws)
+    G.check()
     e64 = O.clip_l2(err.astype(np.float64))
     rdx, rdw, rdb = O.dense_bwd(xpos.astype(np.float64), w64, e64)
     hss = K.host(ss)
@@ -221,13 +223,15 @@ def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
     err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
     xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
     ws = K.empty((max(K.ops.conv2d_ws_bytes(geom) // 4, 1),))
-    y = K.empty((N, oh, ow, F))
+    G = Guarded(K)                      # small-K tile GEMMs, few-filter / band kernels: hand-indexed shared memory and tails
+    y = G((N, oh, ow, F))
     K.ops.conv2d_fwd(0, geom, xd, wd, bd, y, 1, 0.0, ws)
     ref = np.maximum(O.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), pad), 0)
     assert nrel(K.host(y), ref) < TOL
     ss = K.ss(); K.ops.sumsq(ed, ss, 0)
-    dx, dw, db = K.empty(x.shape), K.empty(w.shape), K.empty((F,))
+    dx, dw, db = G(x.shape), G(w.shape), G((F,))
     K.ops.conv2d_bwd(0, geom, xd, wd, ed, ss, (0,), dx, dw, db, 0, 0.0, 1, None, ws)
+    G.check()
     rdx, rdw, rdb = O.conv2d_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (s, s), pad)
     assert nrel(K.host(dx), rdx) < TOL
     assert nrel(K.host(dw), rdw) < TOL
@@ -457,9 +461,11 @@ def test_fused_bn_pool_block(K, Bn, H, W, C):
     beta.reshape(H, W, C)[:2, :2, 0] = 0.25; gamma.reshape(H, W, C)[:2, :2, 0] = 1.0
     xd, gd, bd = K.dev(x), K.dev(gamma), K.dev(beta)
     rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
-    sm, si = K.empty((P,)), K.empty((P,))
-    yp = K.empty((Bn, H // 2, W // 2, C))
+    G = Guarded(K)                      # sentinel guard bands around every output: the kernels index shared / global memory by hand
+    sm, si = G((P,)), G((P,))
+    yp = G((Bn, H // 2, W // 2, C))
     K.ops.bn_pool_fwd_train(xd, gd, bd, rm, rv, sm, si, yp, 0.9, 1e-5)
+    G.check()
     shp = (H, W, C)
     g64, b64 = gamma.astype(np.float64).reshape(shp), beta.astype(np.float64).reshape(shp)
     x64 = x.astype(np.float64)
@@ -469,8 +475,9 @@ def test_fused_bn_pool_block(K, Bn, H, W, C):
     assert nrel(K.host(rm).reshape(shp), rrm) < TOL and nrel(K.host(rv).reshape(shp), rrv) < TOL
     e = rng.normal(size=ryp.shape).astype(np.float32)
     ed = K.dev(e); ss = K.ss(); K.ops.sumsq(ed, ss, 0)
-    r0, dg, dbt = K.empty(x.shape), K.empty((P,)), K.empty((P,))
+    r0, dg, dbt = G(x.shape), G((P,)), G((P,))
     K.ops.pool_bn_act_bwd(xd, ed, ss, (0,), gd, bd, sm, si, r0, dg, dbt, 1, 0.0, 1, 2, 3)
+    G.check()
     # reference chain: clip -> pool bwd -> clip -> bn bwd -> clip -> relu' ; the kernel emits the unclipped
     # intermediates plus their sums of squares, the chain (1, 2, 3) reproduces the clips
     U = O.maxpool_bwd(ybn, O.clip_l2(e.astype(np.float64)), (2, 2), (2, 2))
@@ -583,18 +590,19 @@ def test_convblock_first_block(K, Bn, H, W, C, F, act):
     # reference: clip(U) -> bn bwd -> clip -> act bwd -> clip -> conv bwd
     Rc = O.clip_l2(O.act_bwd(act, pre, O.clip_l2(O.bn_bwd(O.clip_l2(U), g64, cache, 1e-5)[0]), alpha))
     _, rdw, rdbias = O.conv2d_bwd(x64, w64, Rc, (1, 1), "same")
-    ws = K.empty((max(K.ops.convblock_ws_bytes(g) // 4, 1),))
+    G = Guarded(K)                      # guard bands around every output and the workspace of the first-block kernels
+    ws = G((max(K.ops.convblock_ws_bytes(g) // 4, 1),))
     for modes in ((0,), (1, 2)):
         rm, rv = K.B.zeros((P,)), K.B.to_device(np.ones(P))
-        sm, si = K.empty((P,)), K.empty((P,))
-        yp = K.empty((Bn, H // 2, W // 2, F))
+        sm, si = G((P,)), G((P,))
+        yp = G((Bn, H // 2, W // 2, F))
         stats = K.B.zeros((2 * P,), dtype=K.torch.float64)
         for md in modes:
             K.ops.convblock_fwd(g, xd, wd, bd, kind, alpha, gd, btd, rm, rv, sm, si, stats, md, Bn, yp if md != 1 else None, 0.9, 1e-5)
         assert nrel(K.host(yp), ryp) < 2e-5, modes
         assert nrel(K.host(rm).reshape(shp), rrm) < TOL and nrel(K.host(rv).reshape(shp), rrv) < TOL
         ed = K.dev(e); ss = K.ss(); K.ops.sumsq(ed, ss, 0)
-        dg, dbt, dw, db, r = K.empty((P,)), K.empty((P,)), K.empty((3, 3, C, F)), K.empty((F,)), K.empty((Bn, H, W, F))
+        dg, dbt, dw, db, r = G((P,)), G((P,)), G((3, 3, C, F)), G((F,)), G((Bn, H, W, F))
         s2 = 3 if act != "linear" else None
         cout = (1, 2, 3) if act != "linear" else (1, 2)
         if modes == (0,):
@@ -615,6 +623,7 @@ def test_convblock_first_block(K, Bn, H, W, C, F, act):
         assert nrel(K.host(dw), rdw) < 3e-5, modes
         # with a linear activation the bias gradient is sum over the batch of a BatchNorm backward output == 0 identically
         assert np.abs(K.host(db) - rdbias.reshape(-1)).max() < 3e-5 * max(np.abs(rdbias).max(), np.abs(rdw).max())
+        G.check()
 
 
 def test_convblock_peer_fused_world_of_one(K):
