@@ -176,8 +176,13 @@ def test_train_on_batch_oracle_full_size(cfg, batch, steps, tol):
         assert len(theirs) == len(mine) > 0
         assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss)), (s, loss, rloss)
         for (li, layer), rl in zip(mine, theirs):
-            grads_close(layer.d_weights, rl["dw"], tol, (s, li, "dw"))
-            grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), tol, (s, li, "db"))
+            if li > last_pool and cfg in (2, 3):
+                # above the last pool no discrete decision of a pool feeds the gradient: the plain norm-relative bound holds
+                assert nrel(layer.d_weights, rl["dw"]) < max(tol, 5e-5), (s, li, "dw", nrel(layer.d_weights, rl["dw"]))
+                assert nrel(layer.d_bias.reshape(-1), rl["db"].reshape(-1)) < max(tol, 5e-5), (s, li, "db")
+            else:
+                grads_close(layer.d_weights, rl["dw"], tol, (s, li, "dw"))
+                grads_close(layer.d_bias.reshape(-1), rl["db"].reshape(-1), tol, (s, li, "db"))
             d = np.abs(layer.weights - rl["w"])
             # below a max-pool an isolated near-tie flip perturbs one filter's gradient by ~1e-3 (grads_close), hence its
             # Adam update by ~1e-3 * lr: those layers are held to 90 % of the elements instead of 99.9 %
