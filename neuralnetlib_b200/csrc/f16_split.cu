@@ -102,6 +102,23 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const float* __restrict
     }
 }
 
+// forward-convolution weights w[(c, tap), F] (the reference's K order, layers.py:470) -> K-major planes [F][(tap, c)]: the k order
+// of the implicit-GEMM producer (one tap's channels are consecutive); one thread per plane element, a few hundred KB at most
+__global__ void __launch_bounds__(256) split_conv_w_fwd_kernel(const float* __restrict__ w, int C, int taps, int F, __half* __restrict__ planes,
+                                                               const unsigned* __restrict__ maxbits, float* __restrict__ inv_out) {
+    float inv;
+    const float s = plane_scale(*maxbits, inv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *inv_out = inv;
+    const long long K = (long long)taps * C, total = K * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i / K), k = (int)(i - (long long)f * K), tap = k / C, c = k - tap * C;
+        __half h, l;
+        split1(__ldg(w + ((long long)c * taps + tap) * F + f), s, h, l);
+        planes[i] = h;
+        planes[total + i] = l;
+    }
+}
+
 static inline long long pitch_of(long long k) { return (k + 7) / 8 * 8; }
 
 }  // namespace f16
@@ -164,6 +181,58 @@ int gemm2_f16x3(const float* A, long long lda, bool a_mn, const float* B, long l
     if (int rc = prepare(A, lda, M, K, a_mn, pa, words, inv, st)) return rc;
     if (int rc = prepare(B, ldb, N, K, b_mn, pb, words + 1, inv + 1, st)) return rc;
     return gemm2_f16_planes(pa, pitch, M, pb, pitch, N, inv, epi, M, N, K, ws, st);
+}
+
+// ---- implicit-GEMM convolution (cfg3's conv2 / conv3 in TF32X3 mode: layers.py:471-477 forward, :513-528 data gradient) ------------
+// 0: off, 1 (default): where it pays, 2: wherever the geometry allows (tests)
+static int conv_f16_mode() {
+    const char* e = getenv("B200NN_F16CONV");
+    return e != nullptr ? atoi(e) : 1;
+}
+
+bool conv_f16_worth(int which, const b200nn_conv_geom* g) {
+    const int mode = conv_f16_mode();
+    if (mode == 0 || !f16_enabled() || (which != 1 && which != 2)) return false;
+    const long long Ck = which == 1 ? g->C : g->F, Nn = which == 1 ? g->F : g->C;
+    if (Ck % 64 != 0) return false;
+    const long long P = (long long)g->N * g->H * g->W, K = (long long)g->kh * g->kw * Ck;
+    return mode >= 2 || P * Nn * K >= (1LL << 32);
+}
+
+// both operands' planes (the larger of the forward and the data-gradient pair) + the scale words
+size_t conv_f16_extra_bytes(const b200nn_conv_geom* g) {
+    const long long P = (long long)g->N * g->H * g->W, taps = (long long)g->kh * g->kw;
+    const long long cmax = g->C > g->F ? g->C : g->F;
+    return (size_t)(2 * P * cmax + 2 * taps * g->C * g->F) * sizeof(__half) + 1024;
+}
+
+int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const float* w, const Epilogue& epi, float* ws, cudaStream_t st) {
+    B200NN_REQUIRE(ws != nullptr, "conv2_f16x3: needs a workspace");
+    const int taps = g->kh * g->kw, Ck = which == 1 ? g->C : g->F, Nn = which == 1 ? g->F : g->C;
+    const long long P = (long long)g->N * g->H * g->W, K = (long long)taps * Ck;
+    const size_t part = (ws2(P, Nn, K / 2, true) + 255) / 256 * 256;
+    char* base = reinterpret_cast<char*>(ws) + part;
+    __half* pa = reinterpret_cast<__half*>(base);                              // [2 N][H][W][Ck]
+    __half* pb = pa + 2 * P * Ck;                                              // [2 Nn][K]
+    unsigned* words = reinterpret_cast<unsigned*>(pb + 2 * (long long)Nn * K);
+    float* inv = reinterpret_cast<float*>(words + 2);
+    if (int rc = prepare(a, Ck, (int)P, Ck, false, pa, words, inv, st)) return rc;
+    if (which == 2) {
+        // err . W^T contracts over (tap, f): the weights as stored, seen as the matrix [C][(tap, f)]
+        if (int rc = prepare(w, K, Nn, (int)K, false, pb, words + 1, inv + 1, st)) return rc;
+    } else {
+        B200NN_CUDA(cudaMemsetAsync(words + 1, 0, sizeof(unsigned), st));
+        const long long total = K * Nn;
+        int blocks = (int)((total / 4 + 255) / 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        f16::maxabs_kernel<<<blocks, 256, 0, st>>>(w, g->F, (int)K, g->F, words + 1);
+        B200NN_LAUNCH_CHECK("f16_maxabs");
+        blocks = (int)((total + 255) / 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        f16::split_conv_w_fwd_kernel<<<blocks, 256, 0, st>>>(w, g->C, taps, g->F, pb, words + 1, inv + 1);
+        B200NN_LAUNCH_CHECK("f16_split_conv_w");
+    }
+    return conv2_f16_planes(which, g, pa, pb, K, inv, epi, ws, st);
 }
 
 }  // namespace tcapi

@@ -1261,6 +1261,8 @@ static int tc_gemm_any(const float* A, long long lda, bool a_mn, const float* B,
 // which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
 static int tc_conv_any(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws,
                        cudaStream_t st, bool x3) {
+    // large error-compensated forward / data-gradient convolutions: fp16 hi / lo planes at twice the TF32 rate (f16_split.cu)
+    if (x3 && ws != nullptr && tcapi::tc2_enabled() && tcapi::conv_f16_worth(which, g)) return tcapi::conv2_f16x3(which, g, a, b, epi, ws, st);
     if (tcapi::tc2_enabled()) return x3 ? tcapi::conv2_x3(which, g, a, b, epi, ws, st) : tcapi::conv2_plain(which, g, a, b, epi, ws, st);
     return tcapi::conv1(which, g, a, b, epi, ws, st, x3);
 }
@@ -2137,6 +2139,15 @@ size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g) {
         size_t t = tcapi::conv_ws1(g, math == B200NN_MATH_TF32X3);
         const size_t t2 = tcapi::conv_ws2(g, math == B200NN_MATH_TF32X3);
         t = t > t2 ? t : t2;
+        if (math == B200NN_MATH_TF32X3 && tcapi::tc2_enabled()) {      // partials + operand planes of the fp16-plane path
+            const long long P = (long long)g->N * g->H * g->W, taps = (long long)g->kh * g->kw;
+            for (int which = 1; which <= 2; ++which) {
+                if (!tcapi::conv_f16_worth(which, g)) continue;
+                const long long Ck = which == 1 ? g->C : g->F, Nn = which == 1 ? g->F : g->C;
+                const size_t f = (tcapi::ws2(P, Nn, taps * Ck / 2, true) + 255) / 256 * 256 + tcapi::conv_f16_extra_bytes(g);
+                t = t > f ? t : f;
+            }
+        }
         const size_t d = (size_t)kNumSMs * 2 * g->F * sizeof(float);   // column-sum partials for db
         r = r > t ? r : t;
         r = r > d ? r : d;

@@ -260,7 +260,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // feeds the whole SM); tap / channel / pixel positions advance incrementally
                 int tap = 0, c0 = 0, ky = 0, kx = 0, img = 0, y0 = 0, x0 = 0;
                 if (cv.mode == 1 || cv.mode == 2) {
-                    const int k0 = kb_begin * BLOCK_K, HW = cv.H * cv.W;
+                    const int k0 = kb_begin * BLOCK_K * (F16 ? 2 : 1), HW = cv.H * cv.W;
                     tap = k0 / cv.C; c0 = k0 - tap * cv.C; ky = tap / cv.kw; kx = tap - ky * cv.kw;
                     img = m0 / HW; y0 = (m0 - img * HW) / cv.W;
                 } else if (cv.mode == 3) {
@@ -293,13 +293,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const int dy = cv.mode == 1 ? ky - cv.pad_y : cv.pad_y - ky;
                         const int dx = cv.mode == 1 ? kx - cv.pad_x : cv.pad_x - kx;
                         tma2_load_4d<LG>(sa, &tmA, bar, c0, dx, y0 + dy, img);
-                        if constexpr (B_MN) {
+                        if constexpr (F16) {
+                            // fp16 planes: 64 channels of one tap per k-block; the lo images follow the hi images in the same
+                            // map; the weights are a plain K-major plane matrix [filters | channels][(tap, channel)]
+                            tma2_load_4d<LG>(sa + LO_OFFSET, &tmA, bar, c0, dx, y0 + dy, img + cv.lo_a);
+                            tma2_load_2d<LG>(sb, &tmB, bar, k0, n0);
+                            tma2_load_2d<LG>(sb + LO_OFFSET, &tmB, bar, k0, n0 + cv.lo_b);
+                        } else if constexpr (B_MN) {
 #pragma unroll
                             for (int j = 0; j < BNH / 32; ++j) tma2_load_3d<LG>(sb + j * SLAB_BYTES, &tmB, bar, n0 + j * 32, tap, c0);
                         } else {
                             tma2_load_3d<LG>(sb, &tmB, bar, c0, tap, n0);
                         }
-                        c0 += BLOCK_K;
+                        c0 += BLOCK_K * (F16 ? 2 : 1);
                         if (c0 >= cv.C) {
                             c0 = 0; ++tap;
                             if (++kx == cv.kw) { kx = 0; ++ky; }
@@ -736,22 +742,9 @@ static int gemm2(const float* A, long long lda, bool a_mn, const float* B, long 
     return run2<X3>(ta, tb, a_mn, b_mn, epi, M, N, K, p, ws, st, cv);
 }
 
-// D[M,N] = A.B from fp16 hi / lo planes: Ap = [hi plane (M rows) | lo plane] with the lo plane lo_a rows below, row pitch lda
-// (elements), K two-byte elements per row; Bp likewise with N rows. K4 = ceil(K / 2) is the reduction length in the 4-byte units the
-// planner counts in (a k-block is 128 bytes either way).
 template <int UNUSED = 0>   // a template so that only gemm_tc2_f16.cu instantiates the F16 kernels
-static int gemm2_f16(const void* Ap, long long lda, int lo_a, const void* Bp, long long ldb, int lo_b, const float* inv_scale,
-                     const Epilogue& epi, int M, int N, int K, float* ws, cudaStream_t st) {
-    const int K4 = (K + 1) / 2;
-    const Plan2 p = plan2(M, N, K4, true);
-    CUtensorMap ta, tb, to;
-    if (int rc = tc::make_map_f16(&ta, Ap, K, (long long)lo_a + M, lda, BLOCK_M)) return rc;
-    if (int rc = tc::make_map_f16(&tb, Bp, K, (long long)lo_b + N, ldb, p.bn / p.cg)) return rc;
-    ConvTma cv{};
-    cv.lo_a = lo_a; cv.lo_b = lo_b; cv.inv_scale = inv_scale;
-    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "gemm_tc2 (f16 planes): split-K needs a workspace");
-    int tma_out = 0;
-    if (int rc = make_out_map(&to, epi, M, N, p.splits, &tma_out)) return rc;
+static int dispatch2_f16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Epilogue& epi, int M, int N, int K4,
+                         const Plan2& p, float* ws, cudaStream_t st, const ConvTma& cv, int tma_out) {
 #define TC2_F16(BN, CG) return launch2_stages<BN, false, false, CG, false, true>(ta, tb, to, epi, M, N, K4, p, ws, st, cv, tma_out);
     if (p.cg == 2) {
         switch (p.bn) {
@@ -767,6 +760,46 @@ static int gemm2_f16(const void* Ap, long long lda, int lo_a, const void* Bp, lo
         default: TC2_F16(256, 1)
     }
 #undef TC2_F16
+}
+
+// D[M,N] = A.B from fp16 hi / lo planes: Ap = [hi plane (M rows) | lo plane] with the lo plane lo_a rows below, row pitch lda
+// (elements), K two-byte elements per row; Bp likewise with N rows. K4 = ceil(K / 2) is the reduction length in the 4-byte units the
+// planner counts in (a k-block is 128 bytes either way).
+template <int UNUSED = 0>
+static int gemm2_f16(const void* Ap, long long lda, int lo_a, const void* Bp, long long ldb, int lo_b, const float* inv_scale,
+                     const Epilogue& epi, int M, int N, int K, float* ws, cudaStream_t st) {
+    const int K4 = (K + 1) / 2;
+    const Plan2 p = plan2(M, N, K4, true);
+    CUtensorMap ta, tb, to;
+    if (int rc = tc::make_map_f16(&ta, Ap, K, (long long)lo_a + M, lda, BLOCK_M)) return rc;
+    if (int rc = tc::make_map_f16(&tb, Bp, K, (long long)lo_b + N, ldb, p.bn / p.cg)) return rc;
+    ConvTma cv{};
+    cv.lo_a = lo_a; cv.lo_b = lo_b; cv.inv_scale = inv_scale;
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "gemm_tc2 (f16 planes): split-K needs a workspace");
+    int tma_out = 0;
+    if (int rc = make_out_map(&to, epi, M, N, p.splits, &tma_out)) return rc;
+    return dispatch2_f16(ta, tb, to, epi, M, N, K4, p, ws, st, cv, tma_out);
+}
+
+// implicit-GEMM convolution from fp16 planes (forward: which = 1, Ap = planes of x; data gradient: which = 2, Ap = planes of err).
+// Ap = [hi images (g->N) | lo images][H][W][Ck] two-byte elements, Ck = channels along K (C_in resp. F), a multiple of 64;
+// Bp = K-major weight planes [hi rows (Nn) | lo rows][K = (tap, channel)] with row pitch ldb, Nn = F resp. C_in.
+template <int UNUSED = 0>
+static int conv2_f16(int which, const b200nn_conv_geom* g, const void* Ap, const void* Bp, long long ldb, const float* inv_scale,
+                     const Epilogue& epi, float* ws, cudaStream_t st) {
+    const int Ck = which == 1 ? g->C : g->F, Nn = which == 1 ? g->F : g->C;
+    const int M = g->N * g->H * g->W, K = g->kh * g->kw * Ck, K4 = K / 2;
+    B200NN_REQUIRE((which == 1 || which == 2) && Ck % 64 == 0, "conv2_f16: forward / data gradient with 64 | channels only");
+    const Plan2 p = plan2(M, Nn, K4, true);
+    CUtensorMap ta, tb, to;
+    if (int rc = tc::make_image_map_f16(&ta, Ap, 2 * g->N, g->H, g->W, Ck, BLOCK_M)) return rc;
+    if (int rc = tc::make_map_f16(&tb, Bp, K, 2LL * Nn, ldb, p.bn / p.cg)) return rc;
+    ConvTma cv = tc::conv_tma(which, g, Ck);
+    cv.lo_a = g->N; cv.lo_b = Nn; cv.inv_scale = inv_scale;
+    B200NN_REQUIRE(p.splits == 1 || ws != nullptr, "conv2_f16: split-K needs a workspace");
+    int tma_out = 0;
+    if (int rc = make_out_map(&to, epi, M, Nn, p.splits, &tma_out)) return rc;
+    return dispatch2_f16(ta, tb, to, epi, M, Nn, K4, p, ws, st, cv, tma_out);
 }
 
 template <bool X3>

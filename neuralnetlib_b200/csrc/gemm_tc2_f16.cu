@@ -11,5 +11,10 @@ int gemm2_f16_planes(const void* Ap, long long lda, int lo_a, const void* Bp, lo
     return tc2::gemm2_f16(Ap, lda, lo_a, Bp, ldb, lo_b, inv_scale, epi, M, N, K, ws, st);
 }
 
+int conv2_f16_planes(int which, const b200nn_conv_geom* g, const void* Ap, const void* Bp, long long ldb, const float* inv_scale,
+                     const Epilogue& epi, float* ws, cudaStream_t st) {
+    return tc2::conv2_f16(which, g, Ap, Bp, ldb, inv_scale, epi, ws, st);
+}
+
 }  // namespace tcapi
 }  // namespace b200nn

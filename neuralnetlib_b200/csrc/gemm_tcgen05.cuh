@@ -666,6 +666,24 @@ static int make_image_map(CUtensorMap* map, const float* t, int Nimg, int H, int
     return make_map_nd(map, t, 4, dims, strides, box, mn_major);
 }
 
+// the same over fp16 operand planes t[Nimg, H, W, Cn] (gemm_tc2.cuh F16 mode): 64 channels = 128 bytes per box row
+static int make_image_map_f16(CUtensorMap* map, const void* t, int Nimg, int H, int W, int Cn, int pixels) {
+    EncodeTiledFn fn = encode_fn();
+    B200NN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)Cn, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cn * 2, (cuuint64_t)W * Cn * 2, (cuuint64_t)H * W * Cn * 2};
+    const int bx = W < pixels ? W : pixels;
+    const int by = H < pixels / bx ? H : pixels / bx;
+    const int bb = pixels / (bx * by);
+    const cuuint32_t box[4] = {64, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bb};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(t), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200NN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16 images) failed with %d", (int)r);
+    return B200NN_OK;
+}
+
 // 3-D map over the weights w[(c, tap), F]: (f, tap, c)
 static int make_weight_map(CUtensorMap* map, const float* w, int taps, int C, int F, int box_c, bool mn_major) {
     const cuuint64_t dims[3] = {(cuuint64_t)F, (cuuint64_t)taps, (cuuint64_t)C};

@@ -280,6 +280,44 @@ def test_conv2d_tcgen05_implicit_gemm(K, N, H, W, C, F, k, act, math, tol):
         assert nrel(K.host(y1), ref) > 20 * nrel(K.host(y), ref)
 
 
+@pytest.mark.parametrize("N,H,W,C,F,k,act", [(8, 16, 16, 64, 128, 3, 1), (37, 8, 8, 128, 256, 3, 1), (7, 64, 8, 64, 64, 1, 0),
+                                             (5, 4, 4, 192, 64, 3, 1), (3, 32, 32, 64, 64, 5, 1)])
+def test_conv2d_tcgen05_f16_planes(K, monkeypatch, N, H, W, C, F, k, act):
+    """tf32x3 forward / data-gradient convolution from fp16 hi / lo operand planes (f16_split.cu conv2_f16x3: the image operand as
+    hi / lo IMAGES behind one 4-D TMA map, the weights as a K-major plane matrix in the producer's (tap, channel) order), forced on
+    small geometries with B200NN_F16CONV=2: the FFMA path's 1e-5 against the fp64 oracle, guard bands around outputs and the
+    workspace the sizing call promises, and a different bit pattern from the in-kernel 3xTF32 split (so the planes really ran)."""
+    rng = np.random.default_rng(H * 17 + C + k)
+    x = np.maximum(rng.normal(size=(N, H, W, C)), 0).astype(np.float32)
+    w = (rng.normal(size=(k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    geom, oh, ow = _conv_geom(K, N, H, W, C, F, k, k, 1, 1, "same")
+    err = (1e-3 * rng.normal(size=(N, oh, ow, F))).astype(np.float32)      # a small-magnitude operand: the range scale matters
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    ref = O.conv2d_fwd(x64, w64, b.astype(np.float64), (1, 1), "same")
+    ref = np.maximum(ref, 0) if act else ref
+    rdx, rdw, rdb = O.conv2d_bwd(x64, w64, O.clip_l2(err.astype(np.float64)), (1, 1), "same")
+    out = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("B200NN_F16CONV", mode)
+        G = Guarded(K)
+        ws = G((max(K.ops.conv2d_ws_bytes(geom, 2) // 4, 1),))
+        y = G((N, oh, ow, F))
+        K.ops.conv2d_fwd(2, geom, xd, wd, bd, y, act, 0.0, ws)
+        ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+        dx, dw, db = G(x.shape), G(w.shape), G((F,))
+        K.ops.conv2d_bwd(2, geom, xd, wd, ed, ss, (0,), dx, dw, db, 1, 0.0, 1, 2, ws)
+        G.check()
+        assert nrel(K.host(y), ref) < 1e-5, mode
+        assert nrel(K.host(dx), rdx * (x > 0)) < 1e-5, mode
+        assert nrel(K.host(dw), rdw) < 1e-5, mode
+        h = K.host(ss)
+        assert abs(h[1] - np.sum(rdx ** 2)) < 1e-4 * np.sum(rdx ** 2)
+        out[mode] = (K.host(y).copy(), K.host(dx).copy())
+    assert not np.array_equal(out["2"][0], out["0"][0]) and not np.array_equal(out["2"][1], out["0"][1])
+
+
 def _convt_geom(K, N, H, W, C, F, kh, kw, sh, sw, pad):
     oh, ow, pt, pb, pl, pr = O.convT_geometry(H, W, kh, kw, sh, sw, pad)
     return K.B.ConvTGeom(N, H, W, C, F, kh, kw, sh, sw, pt, pl, oh, ow), oh, ow
