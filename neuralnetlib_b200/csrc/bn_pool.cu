@@ -947,35 +947,56 @@ __global__ void __launch_bounds__(256) bn_stats_stream_kernel(const float* __res
     *reinterpret_cast<float4*>(pb + 2 * P) = s2;
 }
 
+// Chan's pairwise merge of two (count, mean, M2) summaries; an empty side leaves the other unchanged
+struct Moments {
+    double n, mean, M2;
+};
+__device__ __forceinline__ Moments merge_moments(const Moments& a, const Moments& b) {
+    if (b.n == 0.0) return a;
+    if (a.n == 0.0) return b;
+    Moments r;
+    r.n = a.n + b.n;
+    const double delta = b.mean - a.mean, f = b.n / r.n;
+    r.mean = a.mean + delta * f;
+    r.M2 = a.M2 + b.M2 + delta * delta * a.n * f;
+    return r;
+}
+
 __global__ void __launch_bounds__(256) stream_stats_combine_kernel(const float* __restrict__ part, int chunks, int B, long long P,
                                                                    double* __restrict__ stats) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    double n = 0.0, mean = 0.0, M2 = 0.0;
-    for (int c0 = 0; c0 < chunks; c0 += 8) {      // the loads of eight chunks in flight before the (serial, fp64) merge consumes them
+    Moments tot = {0.0, 0.0, 0.0};
+    for (int c0 = 0; c0 < chunks; c0 += 8) {
+        // eight chunks at a time: their loads in flight together, their summaries formed independently, then merged as a
+        // balanced tree (depth 3 instead of a serial chain of eight fp64 divide chains); fixed order, so every run and every
+        // replica forms the same bits
         float kv[8], s1v[8], s2v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float* pb = part + (long long)min(c0 + j, chunks - 1) * 3 * P + i;
             kv[j] = pb[0]; s1v[j] = pb[P]; s2v[j] = pb[2 * P];
         }
+        Moments m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = c0 + j;
-            if (c < chunks) {
-                const double nc = (double)min(SS_ROWS, B - c * SS_ROWS);
-                const double K = (double)kv[j], S1 = (double)s1v[j], S2 = (double)s2v[j];
-                const double mc = K + S1 / nc, m2c = fmax(S2 - S1 * S1 / nc, 0.0);
-                const double tot = n + nc, delta = mc - mean;
-                mean += delta * nc / tot;
-                M2 += m2c + delta * delta * n * nc / tot;
-                n = tot;
-            }
+            const double nc = c < chunks ? (double)min(SS_ROWS, B - c * SS_ROWS) : 0.0;
+            const double K = (double)kv[j], S1 = (double)s1v[j], S2 = (double)s2v[j];
+            const double inv = nc > 0.0 ? 1.0 / nc : 0.0;
+            m[j].n = nc;
+            m[j].mean = K + S1 * inv;
+            m[j].M2 = fmax(S2 - S1 * S1 * inv, 0.0);
         }
+#pragma unroll
+        for (int step = 1; step < 8; step *= 2)
+#pragma unroll
+            for (int j = 0; j + step < 8; j += 2 * step) m[j] = merge_moments(m[j], m[j + step]);
+        tot = merge_moments(tot, m[0]);
     }
-    const double S = mean * n;
-    stats[i] = S;                       // sum clip(x)
-    stats[P + i] = M2 + S * S / n;      // sum clip(x)^2, formed from the exact M2 (see bn_stats_partial_kernel)
+    const double S = tot.mean * tot.n;
+    stats[i] = S;                               // sum clip(x)
+    stats[P + i] = tot.M2 + S * S / tot.n;      // sum clip(x)^2, formed from the exact M2 (see bn_stats_partial_kernel)
 }
 
 static int check_fused_block(const char* who, int B, int H, int W, int C) {
