@@ -131,7 +131,9 @@ struct CbBuf {   // per staging buffer: patch[CB_MAXB][STRIDE] | aux[CB_FPC * CB
 template <int C, int ACT>
 __device__ __forceinline__ void cb_conv(const float* __restrict__ p, const float (&wr)[9 * C], float bias, int act, float alpha,
                                         float (&S)[4]) {
-    S[0] = S[1] = S[2] = S[3] = bias;
+    // packed FFMA2 (fma.rn.f32x2, sm_100): the two outputs of a window row share the tap weight, so one instruction does both
+    // fused multiply-adds — the same roundings as two scalar FFMAs, half the FMA-pipe slots (scripts/ffma2_probe.cu: 46 -> 66 TFLOP/s)
+    float2 S01 = make_float2(bias, bias), S23 = S01;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         float rows[4][4];
@@ -145,12 +147,12 @@ __device__ __forceinline__ void cb_conv(const float* __restrict__ p, const float
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const float wv = wr[(c * 3 + ky) * 3 + kx];
-                S[0] = fmaf(rows[ky][kx], wv, S[0]);
-                S[1] = fmaf(rows[ky][kx + 1], wv, S[1]);
-                S[2] = fmaf(rows[ky + 1][kx], wv, S[2]);
-                S[3] = fmaf(rows[ky + 1][kx + 1], wv, S[3]);
+                const float2 w2 = make_float2(wv, wv);
+                S01 = __ffma2_rn(make_float2(rows[ky][kx], rows[ky][kx + 1]), w2, S01);
+                S23 = __ffma2_rn(make_float2(rows[ky + 1][kx], rows[ky + 1][kx + 1]), w2, S23);
             }
     }
+    S[0] = S01.x; S[1] = S01.y; S[2] = S23.x; S[3] = S23.y;
 #pragma unroll
     for (int q = 0; q < 4; ++q) S[q] = cb_act<ACT>(S[q], act, alpha);     // layers.py:231-234 (auto-appended Activation)
 }

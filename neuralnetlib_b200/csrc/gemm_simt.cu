@@ -2238,7 +2238,7 @@ int b200nn_conv2d_fwd(int math, const b200nn_conv_geom* g, const float* x, const
         return b200nn_dense_fwd(math, cw.col, cw.wp, b, y, M, g->F, K, act, alpha, cw.rest, stream);
     }
     if (smallk3::ok(g) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
-        smallk3::launch_fwd(g, x, w, b, y, act, alpha, M, as_stream(stream));
+        smallk3::launch_fwd(g, x, w, b, y, act, alpha, M, as_stream(stream), math == B200NN_MATH_TF32X3 ? 2 : (math == B200NN_MATH_TF32 ? 1 : 0));
         B200NN_LAUNCH_CHECK("conv2d_smallk_fwd3");
         return B200NN_OK;
     }
@@ -2364,7 +2364,8 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
         Epilogue e = plain_epilogue(dw, g->F, Kf);
         e.ss = ss; e.chain = chain; e.db = db;
         e.row_mode = 1; e.kh = g->kh; e.kw = g->kw; e.C = g->C;
-        B200NN_REQUIRE(smallk3::launch_wgrad(g, x, err, ws, Mo, st) == 0, "conv2d_smallk_wgrad3: cannot configure shared memory");
+        B200NN_REQUIRE(smallk3::launch_wgrad(g, x, err, ws, Mo, st, math == B200NN_MATH_TF32X3 ? 2 : (math == B200NN_MATH_TF32 ? 1 : 0)) == 0,
+                       "conv2d_smallk_wgrad3: cannot configure shared memory");
         B200NN_LAUNCH_CHECK("conv2d_smallk_wgrad3");
         if (int rc = launch_splitk_reduce(ws, nb, Kf + 1, g->F, e, st)) return rc;
     } else if (dw != nullptr && smallk_wgrad_ok(g) && ws != nullptr && (reinterpret_cast<uintptr_t>(err) & 15) == 0) {

@@ -240,6 +240,43 @@ def test_conv2d_oracle(K, N, H, W, C, F, k, s, pad):
 
 
 @pytest.mark.parametrize("math,tol", [(2, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize("N,H,W,C,F,k,s,pad", [(7, 30, 30, 2, 64, 3, 1, "valid"), (6, 31, 29, 1, 32, 5, 1, "same"),
+                                               (33, 28, 28, 1, 64, 3, 2, "same"), (12, 32, 32, 3, 32, 3, 1, "same"),
+                                               (9, 32, 32, 3, 64, 3, 1, "same")])
+def test_conv2d_smallk_tensor_modes(K, monkeypatch, N, H, W, C, F, k, s, pad, math, tol):
+    """Small-K (first-layer) convolutions in the tensor-core math modes: the mma.sync TF32 / 3xTF32 tile kernels of
+    conv_smallk3.cuh (ragged last tile, K = 9 / 18 / 25 / 27 padded to 32, strides, both filter counts) against the fp64 oracle;
+    tf32x3 must meet the FFMA path's 1e-5, and differ in bits from the FFMA result (the tensor cores really ran). The 3xTF32 kernels
+    are off by default (no faster than the FFMA kernels, see conv_smallk3.cuh) and forced here with B200NN_SMALLK_MMA=2."""
+    monkeypatch.setenv("B200NN_SMALLK_MMA", "2")
+    rng = np.random.default_rng(H * 13 + C + F)
+    x = rng.normal(size=(N, H, W, C)).astype(np.float32)
+    w = (rng.normal(size=(k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    b = rng.normal(size=(F,)).astype(np.float32)
+    geom, oh, ow = _conv_geom(K, N, H, W, C, F, k, k, s, s, pad)
+    err = rng.normal(size=(N, oh, ow, F)).astype(np.float32)
+    xd, wd, bd, ed = K.dev(x), K.dev(w), K.dev(b), K.dev(err)
+    G = Guarded(K)
+    ws = G((max(K.ops.conv2d_ws_bytes(geom, math) // 4, 1),))
+    y = G((N, oh, ow, F))
+    K.ops.conv2d_fwd(math, geom, xd, wd, bd, y, 1, 0.0, ws)
+    ref = np.maximum(O.conv2d_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (s, s), pad), 0)
+    assert nrel(K.host(y), ref) < tol
+    ss = K.ss(); K.ops.sumsq(ed, ss, 0)
+    dx, dw, db = G(x.shape), G(w.shape), G((F,))
+    K.ops.conv2d_bwd(math, geom, xd, wd, ed, ss, (0,), dx, dw, db, 0, 0.0, 1, None, ws)
+    G.check()
+    rdx, rdw, rdb = O.conv2d_bwd(x.astype(np.float64), w.astype(np.float64), O.clip_l2(err.astype(np.float64)), (s, s), pad)
+    assert nrel(K.host(dx), rdx) < tol
+    assert nrel(K.host(dw), rdw) < tol
+    assert nrel(K.host(db), rdb) < max(tol, 1e-5)
+    y0 = K.empty((N, oh, ow, F)); K.ops.conv2d_fwd(0, geom, xd, wd, bd, y0, 1, 0.0, ws)
+    assert not np.array_equal(K.host(y0), K.host(y))
+    if math == 1:
+        assert nrel(K.host(y), ref) > 20 * nrel(K.host(y0), ref)
+
+
+@pytest.mark.parametrize("math,tol", [(2, 1e-5), (1, 2e-3)])
 @pytest.mark.parametrize("N,H,W,C,F,k,act", [(8, 16, 16, 64, 128, 3, 1), (37, 8, 8, 128, 256, 3, 1), (45, 4, 4, 32, 32, 3, 0),
                                              (3, 32, 32, 32, 96, 5, 1), (2, 4, 128, 32, 64, 3, 0), (7, 64, 8, 64, 32, 1, 1)])
 def test_conv2d_tcgen05_implicit_gemm(K, N, H, W, C, F, k, act, math, tol):
