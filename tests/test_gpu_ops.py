@@ -745,3 +745,20 @@ def test_convblock_peer_fused_world_of_one(K):
         for a_, b_ in zip(got, ref):
             assert nrel(a_, b_) < 2e-6, rnd
     assert comm.timeouts() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [8192, 200704, 200705, 12288 + 3, 5_000_000])
+def test_upload_pinned_and_pageable(K, n):
+    """b200nn_upload (the batch upload of Sequential.train_on_batch) from pinned and from pageable host memory, odd byte counts
+    included: the same bytes on the device, nothing written outside the destination."""
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=(n,)).astype(np.float32)
+    pinned = K.torch.empty(n, dtype=K.torch.float32).pin_memory()
+    pinned.numpy()[:] = a
+    for src in (pinned.numpy(), a):
+        G = Guarded(K)
+        dst = G((n,))
+        K.B.check(K.B.lib().b200nn_upload(dst.data_ptr(), src.__array_interface__["data"][0], src.nbytes, K.B.stream()))
+        G.check()
+        assert np.array_equal(dst.cpu().numpy(), a)
