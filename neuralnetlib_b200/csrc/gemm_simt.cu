@@ -965,8 +965,11 @@ __global__ void __launch_bounds__(256) dense_softmax_cce_rows_kernel(const float
             }
         }
         __syncthreads();
-#pragma unroll 4
-        for (int kk = lane; kk < kc; kk += 32) {     // unrolled: 4 x R independent 128-byte row loads in flight per warp
+        // unrolled: 4 x R (8 x R for one or two rows per warp: small batches have one CTA per SM, and four loads per warp left the
+        // kernel waiting on HBM round trips) independent 128-byte row loads in flight per warp
+        constexpr int UNR = R <= 2 ? 8 : 4;
+#pragma unroll UNR
+        for (int kk = lane; kk < kc; kk += 32) {
             float xv[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) xv[r] = __ldg(xr[r] + k0 + kk);
@@ -1075,14 +1078,14 @@ __global__ void __launch_bounds__(256) dense_smalln_dx_rows_kernel(const float* 
 // the bytes in flight per thread (the scalar form above keeps 24 KB per SM in flight and runs at 2 TB/s on config 4's 268 MB).
 template <int NMAX>
 __global__ void __launch_bounds__(256) dense_smalln_dx_rows4_kernel(const float* __restrict__ e, const float* __restrict__ w,
-                                                                    Epilogue epi, int M, int N, int K) {
+                                                                    Epilogue epi, int M, int N, int K, int rpc) {
     __shared__ double scratch[32];
     __shared__ __align__(16) float es[DXR][NMAX];
     EpiState st;
     epi_begin(epi, st);
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int m0 = blockIdx.y * DXR, nr = min(DXR, M - m0);
-    for (int i = threadIdx.x; i < DXR * NMAX; i += blockDim.x) {
+    const int m0 = blockIdx.y * rpc, nr = min(rpc, M - m0);      // rpc <= DXR rows per CTA (fewer at small batches: see the launch)
+    for (int i = threadIdx.x; i < rpc * NMAX; i += blockDim.x) {
         const int r = i / NMAX, n = i - r * NMAX;
         es[r][n] = (r < nr && n < N) ? e[(long long)(m0 + r) * N + n] : 0.0f;
     }
@@ -1436,9 +1439,18 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
                 const bool quad = (K & 3) == 0 && N <= 16 && e.bias == nullptr && e.act == B200NN_ACT_NONE && (e.ldo & 3) == 0 &&
                                   ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(e.mask_y)) & 15) == 0;
                 if (quad) {
-                    const dim3 grid4((K / 4 + 255) / 256, (M + DXR - 1) / DXR);
-                    if (N <= 12) dense_smalln_dx_rows4_kernel<12><<<grid4, 256, 0, st>>>(err, w, e, M, N, K);
-                    else dense_smalln_dx_rows4_kernel<16><<<grid4, 256, 0, st>>>(err, w, e, M, N, K);
+                    // 128 rows per CTA amortise the prologue at config 4's batch; a small batch (config 3: 1024 rows -> 32 CTAs) gets
+                    // fewer rows per CTA so that two CTAs per SM are in flight
+                    const int gx = (K / 4 + 255) / 256;
+                    int rpc = DXR;
+                    if ((long long)gx * ((M + DXR - 1) / DXR) < 2 * kNumSMs) {
+                        const int want = (2 * kNumSMs + gx - 1) / gx;                 // row blocks wanted
+                        rpc = ((M + want - 1) / want + 15) / 16 * 16;
+                        rpc = rpc < 16 ? 16 : (rpc > DXR ? DXR : rpc);
+                    }
+                    const dim3 grid4(gx, (M + rpc - 1) / rpc);
+                    if (N <= 12) dense_smalln_dx_rows4_kernel<12><<<grid4, 256, 0, st>>>(err, w, e, M, N, K, rpc);
+                    else dense_smalln_dx_rows4_kernel<16><<<grid4, 256, 0, st>>>(err, w, e, M, N, K, rpc);
                 } else if (N <= 12) dense_smalln_dx_rows_kernel<12><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
                 else if (N <= 16) dense_smalln_dx_rows_kernel<16><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
                 else dense_smalln_dx_rows_kernel<32><<<grid, 256, 0, st>>>(err, w, e, M, N, K);
