@@ -146,14 +146,18 @@ bool f16_worth(long long M, long long N, long long K) {
 }
 
 // one operand: fp32 [rows_src][cols_src] (pitch ld) -> planes with `mn` rows and K = the other dimension
-static int prepare(const float* src, long long ld, int mn, int K, bool transposed, __half* planes, unsigned* maxbits, float* inv,
-                   cudaStream_t st) {
+// premax (optional): a word that already holds the bit pattern of max |src| (the max pass is skipped)
+static int prepare(const float* src, long long ld, int mn, int K, bool transposed, __half* planes, unsigned* maxbits_own, float* inv,
+                   cudaStream_t st, const unsigned* premax = nullptr) {
     const int R = transposed ? K : mn, C = transposed ? mn : K;      // source shape
-    B200NN_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), st));
     long long blocks = ((long long)R * (C / 4) + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    f16::maxabs_kernel<<<(int)blocks, 256, 0, st>>>(src, ld, R, C, maxbits);
-    B200NN_LAUNCH_CHECK("f16_maxabs");
+    const unsigned* maxbits = premax != nullptr ? premax : maxbits_own;
+    if (premax == nullptr) {
+        B200NN_CUDA(cudaMemsetAsync(maxbits_own, 0, sizeof(unsigned), st));
+        f16::maxabs_kernel<<<(int)blocks, 256, 0, st>>>(src, ld, R, C, maxbits_own);
+        B200NN_LAUNCH_CHECK("f16_maxabs");
+    }
     const long long pitch = f16::pitch_of(K);
     if (!transposed) {
         f16::split_rows_kernel<<<(int)blocks, 256, 0, st>>>(src, ld, R, C, planes, pitch, maxbits, inv);
@@ -169,7 +173,7 @@ static int prepare(const float* src, long long ld, int mn, int K, bool transpose
 // D[M,N] = A.B with fp32-grade products on the fp16 tensor pipe. a_mn: A stored [K][M] (ld = lda) else [M][K]; b_mn: B stored
 // [K][N] else [N][K]. `ws`: ws2(M, N, ceil(K/2), x3) bytes of split-K partials followed by f16_extra_bytes(M, N, K).
 int gemm2_f16x3(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
-                int K, float* ws, cudaStream_t st) {
+                int K, float* ws, cudaStream_t st, const unsigned* premax_a, const unsigned* premax_b) {
     B200NN_REQUIRE(ws != nullptr, "gemm2_f16x3: needs a workspace");
     const size_t part = (ws2(M, N, (K + 1) / 2, true) + 255) / 256 * 256;
     char* base = reinterpret_cast<char*>(ws) + part;
@@ -178,8 +182,8 @@ int gemm2_f16x3(const float* A, long long lda, bool a_mn, const float* B, long l
     __half* pb = pa + 2LL * M * pitch;
     unsigned* words = reinterpret_cast<unsigned*>(pb + 2LL * N * pitch);       // [0] max bits of A, [1] of B, [2..3] inverse scales
     float* inv = reinterpret_cast<float*>(words + 2);
-    if (int rc = prepare(A, lda, M, K, a_mn, pa, words, inv, st)) return rc;
-    if (int rc = prepare(B, ldb, N, K, b_mn, pb, words + 1, inv + 1, st)) return rc;
+    if (int rc = prepare(A, lda, M, K, a_mn, pa, words, inv, st, premax_a)) return rc;
+    if (int rc = prepare(B, ldb, N, K, b_mn, pb, words + 1, inv + 1, st, premax_b)) return rc;
     return gemm2_f16_planes(pa, pitch, M, pb, pitch, N, inv, epi, M, N, K, ws, st);
 }
 
@@ -206,7 +210,8 @@ size_t conv_f16_extra_bytes(const b200nn_conv_geom* g) {
     return (size_t)(2 * P * cmax + 2 * taps * g->C * g->F) * sizeof(__half) + 1024;
 }
 
-int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const float* w, const Epilogue& epi, float* ws, cudaStream_t st) {
+int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const float* w, const Epilogue& epi, float* ws, cudaStream_t st,
+                const unsigned* premax_a) {
     B200NN_REQUIRE(ws != nullptr, "conv2_f16x3: needs a workspace");
     const int taps = g->kh * g->kw, Ck = which == 1 ? g->C : g->F, Nn = which == 1 ? g->F : g->C;
     const long long P = (long long)g->N * g->H * g->W, K = (long long)taps * Ck;
@@ -216,7 +221,7 @@ int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const floa
     __half* pb = pa + 2 * P * Ck;                                              // [2 Nn][K]
     unsigned* words = reinterpret_cast<unsigned*>(pb + 2 * (long long)Nn * K);
     float* inv = reinterpret_cast<float*>(words + 2);
-    if (int rc = prepare(a, Ck, (int)P, Ck, false, pa, words, inv, st)) return rc;
+    if (int rc = prepare(a, Ck, (int)P, Ck, false, pa, words, inv, st, premax_a)) return rc;
     if (which == 2) {
         // err . W^T contracts over (tap, f): the weights as stored, seen as the matrix [C][(tap, f)]
         if (int rc = prepare(w, K, Nn, (int)K, false, pb, words + 1, inv + 1, st)) return rc;

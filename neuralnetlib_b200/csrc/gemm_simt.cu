@@ -460,8 +460,26 @@ int launch_splitk_reduce(const float* ws, int splits, int M, int N, const Epilog
 
 // column sums, 128-bit form (F % 4 == 0, 16-byte aligned rows): thread = a quad of columns, eight row loads in flight (the scalar form
 // below keeps four 4-byte loads in flight: 67 us for 134 MB at config 4)
-__global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __restrict__ x, long long R, int F, float* __restrict__ partial) {
+// maxbits (optional): the CTA's max |x| over finite elements is folded into *maxbits with atomicMax (bit pattern; zeroed by the caller) --
+// the range scale of the fp16 operand planes (f16_split.cu) as a by-product of the pass that reads the error matrix anyway
+__device__ __forceinline__ float absmax4(float m, const float4& v) {
+    return fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+__device__ __forceinline__ void publish_absmax(float m, unsigned* maxbits) {
+    __shared__ unsigned sm_max[8];
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm_max[threadIdx.x >> 5] = __float_as_uint(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned r = 0;
+        for (int i = 0; i < 8; ++i) r = max(r, sm_max[i]);        // non-negative floats order like their bit patterns
+        if (r != 0 && r < 0x7f800000u) atomicMax(maxbits, r);      // NaN / Inf never become the scale (as f16::maxabs_kernel)
+    }
+}
+__global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __restrict__ x, long long R, int F, float* __restrict__ partial,
+                                                              unsigned* maxbits = nullptr) {
     const int F4 = F >> 2;
+    float mx = 0.0f;
     const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -472,16 +490,19 @@ __global__ void __launch_bounds__(256) colsum_partial4_kernel(const float* __res
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = r + j < r1 ? x4[(r + j) * F4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; mx = absmax4(mx, v[j]); }
         }
         reinterpret_cast<float4*>(partial + (long long)blockIdx.x * F)[c] = s;
     }
+    if (maxbits != nullptr) publish_absmax(mx, maxbits);
 }
 
 // column sums, 128-bit form for NARROW matrices (F / 4 divides 256: conv bias gradients with 32..512 filters): thread = (column quad,
 // row lane), 256 / (F / 4) row lanes per CTA, eight row loads in flight per thread, row lanes folded through shared memory
-__global__ void __launch_bounds__(256) colsum_partial4r_kernel(const float* __restrict__ x, long long R, int F, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) colsum_partial4r_kernel(const float* __restrict__ x, long long R, int F, float* __restrict__ partial,
+                                                               unsigned* maxbits = nullptr) {
     __shared__ float4 red[256];
+    float mx = 0.0f;
     const int F4 = F >> 2, RL = 256 / F4;
     const int c = threadIdx.x % F4, ty = threadIdx.x / F4;
     const long long rows_per_block = (R + gridDim.x - 1) / gridDim.x;
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(256) colsum_partial4r_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = r + (long long)j * RL < r1 ? x4[(r + (long long)j * RL) * F4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+        for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; mx = absmax4(mx, v[j]); }
     }
     red[threadIdx.x] = s;
     __syncthreads();
@@ -501,6 +522,7 @@ __global__ void __launch_bounds__(256) colsum_partial4r_kernel(const float* __re
         for (int l = 1; l < RL; ++l) { const float4 t = red[l * F4 + c]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
         reinterpret_cast<float4*>(partial + (long long)blockIdx.x * F)[c] = s;
     }
+    if (maxbits != nullptr) publish_absmax(mx, maxbits);
 }
 static bool colsum4r_ok(const void* x, const void* ws, int F) {
     const int F4 = F >> 2;
@@ -1251,11 +1273,13 @@ static int check_act(const char* who, int act, float alpha) {
 }
 
 // the tensor-core contraction: the persistent CTA-pair kernel (gemm_tc2.cuh) unless B200NN_TC2=0 selects the first-generation one
+// premax_a / premax_b (optional): device words that already hold the bit pattern of max |A| / max |B| (see publish_absmax)
 static int tc_gemm_any(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi,
-                       int M, int N, int K, float* ws, cudaStream_t st, bool x3) {
+                       int M, int N, int K, float* ws, cudaStream_t st, bool x3, const unsigned* premax_a = nullptr,
+                       const unsigned* premax_b = nullptr) {
     // large error-compensated contractions: fp16 hi / lo planes at twice the TF32 rate (f16_split.cu)
     if (x3 && ws != nullptr && tcapi::f16_enabled() && tcapi::f16_worth(M, N, K))
-        return tcapi::gemm2_f16x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st);
+        return tcapi::gemm2_f16x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st, premax_a, premax_b);
     if (tcapi::tc2_enabled())
         return x3 ? tcapi::gemm2_x3(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st)
                   : tcapi::gemm2_plain(A, lda, a_mn, B, ldb, b_mn, epi, M, N, K, ws, st);
@@ -1263,9 +1287,10 @@ static int tc_gemm_any(const float* A, long long lda, bool a_mn, const float* B,
 }
 // which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
 static int tc_conv_any(int which, const b200nn_conv_geom* g, const float* a, const float* b, const Epilogue& epi, float* ws,
-                       cudaStream_t st, bool x3) {
+                       cudaStream_t st, bool x3, const unsigned* premax_a = nullptr) {
     // large error-compensated forward / data-gradient convolutions: fp16 hi / lo planes at twice the TF32 rate (f16_split.cu)
-    if (x3 && ws != nullptr && tcapi::tc2_enabled() && tcapi::conv_f16_worth(which, g)) return tcapi::conv2_f16x3(which, g, a, b, epi, ws, st);
+    if (x3 && ws != nullptr && tcapi::tc2_enabled() && tcapi::conv_f16_worth(which, g))
+        return tcapi::conv2_f16x3(which, g, a, b, epi, ws, st, premax_a);
     if (tcapi::tc2_enabled()) return x3 ? tcapi::conv2_x3(which, g, a, b, epi, ws, st) : tcapi::conv2_plain(which, g, a, b, epi, ws, st);
     return tcapi::conv1(which, g, a, b, epi, ws, st, x3);
 }
@@ -1300,8 +1325,15 @@ size_t b200nn_dense_ws_bytes_math(int math, int M, int N, int K) {
                 mx((tcapi::ws2(m, n, (k + 1) / 2, true) + 255) / 256 * 256 + tcapi::f16_extra_bytes(m, n, k));
         };
         f16(M, N, K); f16(M, K, N); f16(K, N, M);
+        r = (r + 255) / 256 * 256 + 256;      // the last 256 bytes: max word of the error matrix (publish_absmax -> operand planes)
     }
     return r;
+}
+// where b200nn_dense_bwd keeps max |err| between its column-sum pass and the fp16-plane contractions: the tail of the workspace the
+// sizing call above promises (every other user of the workspace stays below it)
+static unsigned* dense_max_word(int math, int M, int N, int K, float* ws) {
+    if (math != B200NN_MATH_TF32X3 || ws == nullptr) return nullptr;
+    return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + b200nn_dense_ws_bytes_math(math, M, N, K) - 256);
 }
 
 size_t b200nn_dense_ws_bytes(int M, int N, int K) {
@@ -1469,14 +1501,21 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         return skinny::launch_bwd(x, w, err, ss, chain, dx, dw, db, M, N, K, prev_act, prev_alpha, ss_out0, ss_out1, st);
     const bool use_tc = math != B200NN_MATH_FP32 && dense_tc_ok(x, w, err, M, N, K) && ws != nullptr;
     const bool x3 = math == B200NN_MATH_TF32X3;
+    // max |err| for the fp16 operand planes of the weight / data gradient, taken by the column-sum pass that reads err anyway
+    unsigned* errmax = nullptr;
     if (dw != nullptr && use_tc) {
         if (db != nullptr) {   // layers.py:197
             int nb = (M + 7) / 8;   // >= 8 rows per CTA; threads run over the columns
             if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+            const bool quad = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0;
+            if (x3 && quad && tcapi::f16_enabled() && (tcapi::f16_worth(K, N, M) || (dx != nullptr && tcapi::f16_worth(M, K, N)))) {
+                errmax = dense_max_word(math, M, N, K, ws);
+                B200NN_CUDA(cudaMemsetAsync(errmax, 0, sizeof(unsigned), st));
+            }
             if (colsum4r_ok(err, ws, N))
-                colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
-            else if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0)
-                colsum_partial4_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
+                colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, M, N, ws, errmax);
+            else if (quad)
+                colsum_partial4_kernel<<<nb, 256, 0, st>>>(err, M, N, ws, errmax);
             else
                 colsum_partial_kernel<<<nb, 256, 0, st>>>(err, M, N, ws);
             B200NN_LAUNCH_CHECK("dense_db_partial");
@@ -1485,7 +1524,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         }
         Epilogue e = plain_epilogue(dw, N, K);   // dw[K,N] = x^T . err : both operands MN-major, no transposed copies
         e.ss = ss; e.chain = chain;
-        if (int rc = tc_gemm_any(x, K, true, err, N, true, e, K, N, M, ws, st, x3)) return rc;
+        if (int rc = tc_gemm_any(x, K, true, err, N, true, e, K, N, M, ws, st, x3, nullptr, errmax)) return rc;
     } else if (dw != nullptr) {  // dw[K,N] (+ db row) = x^T[K(+1), M] . err[M,N]
         ColMajorOnesA af{x, K, K, M, db != nullptr ? 1 : 0};
         RowMajorB bf{err, N, M, N};
@@ -1497,7 +1536,7 @@ int b200nn_dense_bwd(int math, const float* x, const float* w, const float* err,
         Epilogue e = plain_epilogue(dx, K, M);
         dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
         if (use_tc) {
-            if (int rc = tc_gemm_any(err, N, false, w, N, false, e, M, K, N, ws, st, x3)) return rc;
+            if (int rc = tc_gemm_any(err, N, false, w, N, false, e, M, K, N, ws, st, x3, errmax, nullptr)) return rc;
         } else {
             RowMajorA af{err, N, M, N};
             ColMajorB bf{w, N, N, K};
@@ -2163,6 +2202,7 @@ size_t b200nn_conv2d_ws_bytes_math(int math, const b200nn_conv_geom* g) {
         const size_t d = (size_t)kNumSMs * 2 * g->F * sizeof(float);   // column-sum partials for db
         r = r > t ? r : t;
         r = r > d ? r : d;
+        if (math == B200NN_MATH_TF32X3) r = (r + 255) / 256 * 256 + 256;   // the last 256 bytes: max word of the error tensor (conv2d_bwd)
     }
     return r;
 }
@@ -2283,11 +2323,16 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
     if (math != B200NN_MATH_FP32 && ws != nullptr && tcapi::conv_ok(g, x, w, err) &&
         ((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
         const bool x3 = math == B200NN_MATH_TF32X3;
+        unsigned* errmax = nullptr;     // max |err| for the fp16 image planes of the data gradient, from the column-sum pass
         if (dw != nullptr) {
             if (db != nullptr) {   // layers.py:513
                 int nb = (Mo + 7) / 8;
                 if (nb > kNumSMs * 2) nb = kNumSMs * 2;
-                if (colsum4r_ok(err, ws, g->F)) colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
+                if (x3 && dx != nullptr && colsum4r_ok(err, ws, g->F) && tcapi::tc2_enabled() && tcapi::conv_f16_worth(2, g)) {
+                    errmax = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + b200nn_conv2d_ws_bytes_math(math, g) - 256);
+                    B200NN_CUDA(cudaMemsetAsync(errmax, 0, sizeof(unsigned), st));
+                }
+                if (colsum4r_ok(err, ws, g->F)) colsum_partial4r_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws, errmax);
                 else colsum_partial_kernel<<<nb, 256, 0, st>>>(err, Mo, g->F, ws);
                 B200NN_LAUNCH_CHECK("conv2d_db_partial");
                 colsum_final_kernel<<<(g->F + 31) / 32, 256, 0, st>>>(ws, nb, g->F, ss, chain, db);
@@ -2301,7 +2346,7 @@ int b200nn_conv2d_bwd(int math, const b200nn_conv_geom* g, const float* x, const
         if (dx != nullptr) {
             Epilogue e = plain_epilogue(dx, g->C, Mi);
             dx_epilogue(e, ss, chain, x, prev_act, prev_alpha, ss_out0, ss_out1);
-            if (int rc = tc_conv_any(2, g, err, w, e, ws, st, x3)) return rc;
+            if (int rc = tc_conv_any(2, g, err, w, e, ws, st, x3, errmax)) return rc;
         }
         return B200NN_OK;
     }

@@ -24,8 +24,10 @@ int gemm2_x3(const float* A, long long lda, bool a_mn, const float* B, long long
 bool f16_enabled();
 bool f16_worth(long long M, long long N, long long K);
 size_t f16_extra_bytes(long long M, long long N, long long K);
+// premax_a / premax_b (optional): device words already holding the bit pattern of max |A| / max |B| over finite elements (the max pass
+// of that operand is skipped)
 int gemm2_f16x3(const float* A, long long lda, bool a_mn, const float* B, long long ldb, bool b_mn, const Epilogue& epi, int M, int N,
-                int K, float* ws, cudaStream_t st);
+                int K, float* ws, cudaStream_t st, const unsigned* premax_a = nullptr, const unsigned* premax_b = nullptr);
 int gemm2_f16_planes(const void* Ap, long long lda, int lo_a, const void* Bp, long long ldb, int lo_b, const float* inv_scale,
                      const Epilogue& epi, int M, int N, int K, float* ws, cudaStream_t st);
 // the same for the implicit-GEMM convolution (forward and data gradient with 64 | channels along K): the image operand is split
@@ -33,7 +35,8 @@ int gemm2_f16_planes(const void* Ap, long long lda, int lo_a, const void* Bp, lo
 // ws: ws2(P, Nn, K / 2, true) + conv_f16_extra_bytes(g) bytes.
 bool conv_f16_worth(int which, const b200nn_conv_geom* g);
 size_t conv_f16_extra_bytes(const b200nn_conv_geom* g);
-int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const float* w, const Epilogue& epi, float* ws, cudaStream_t st);
+int conv2_f16x3(int which, const b200nn_conv_geom* g, const float* a, const float* w, const Epilogue& epi, float* ws, cudaStream_t st,
+                const unsigned* premax_a = nullptr);
 int conv2_f16_planes(int which, const b200nn_conv_geom* g, const void* Ap, const void* Bp, long long ldb, const float* inv_scale,
                      const Epilogue& epi, float* ws, cudaStream_t st);
 // which: 1 forward (a = x, b = w), 2 data gradient (a = err, b = w), 3 weight gradient (a = x, b = err)
