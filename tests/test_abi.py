@@ -68,3 +68,31 @@ def test_workspace_sizing_per_math_mode():
     assert lib.b200nn_conv2d_ws_bytes_math(0, ctypes.byref(ok)) == lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
     for math in (1, 2):
         assert lib.b200nn_conv2d_ws_bytes_math(math, ctypes.byref(ok)) >= lib.b200nn_conv2d_ws_bytes(ctypes.byref(ok))
+
+
+def test_workspace_sizing_fp16_plane_convolution(monkeypatch):
+    """Host-only: a tf32x3 convolution that takes the fp16-plane form (config 3's conv2 at batch 1024) gets room for the hi / lo
+    image planes of its larger operand and both weight plane matrices, plus the 256-byte tail that carries max |err| from the
+    column-sum pass to the data gradient; B200NN_F16CONV=0 switches the planes off, and a geometry below the worth threshold
+    keeps the in-kernel split's sizing unless the planes are forced (B200NN_F16CONV=2)."""
+    from neuralnetlib_b200 import _backend as B
+    lib = B.lib()
+    big = B.ConvGeom(1024, 16, 16, 64, 128, 3, 3, 1, 1, 1, 1, 16, 16)
+    small = B.ConvGeom(8, 16, 16, 64, 128, 3, 3, 1, 1, 1, 1, 16, 16)
+    P, taps = 1024 * 16 * 16, 9
+    planes = (2 * P * max(64, 128) + 2 * taps * 64 * 128) * 2      # one image operand at a time (x forward, err backward)
+    monkeypatch.delenv("B200NN_F16CONV", raising=False)
+    with_planes = lib.b200nn_conv2d_ws_bytes_math(2, ctypes.byref(big))
+    assert with_planes >= planes + 256
+    assert with_planes % 256 == 0
+    monkeypatch.setenv("B200NN_F16CONV", "0")
+    without = lib.b200nn_conv2d_ws_bytes_math(2, ctypes.byref(big))
+    assert without < planes and without >= lib.b200nn_conv2d_ws_bytes_math(1, ctypes.byref(big))
+    small_off = lib.b200nn_conv2d_ws_bytes_math(2, ctypes.byref(small))
+    monkeypatch.delenv("B200NN_F16CONV")
+    assert lib.b200nn_conv2d_ws_bytes_math(2, ctypes.byref(small)) == small_off          # below the threshold: no planes by default
+    monkeypatch.setenv("B200NN_F16CONV", "2")
+    assert lib.b200nn_conv2d_ws_bytes_math(2, ctypes.byref(small)) >= (2 * 8 * 256 * 128 + 2 * taps * 64 * 128) * 2
+    # Dense: the tail word is part of every tf32x3 sizing
+    assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) % 256 == 0
+    assert lib.b200nn_dense_ws_bytes_math(2, 8192, 4096, 4096) >= 2 * (8192 + 4096) * 4096 * 2 + 256
